@@ -1,0 +1,158 @@
+/*
+ * dppo_b200.h -- C ABI of libdppo_b200.so, the B200 (sm_100a) DPPO update engine.
+ *
+ * The reference (oswsnqc/Tensorflow-DPPO) has no FFI: its boundary for this path is the
+ * Python/TensorFlow graph surface.  Every entry point below names the reference interface it
+ * replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference adds to call them from PPO.py / Chief.py / Worker.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; dppo_last_error() gives the message
+ *     (thread-local, valid until the next call on that thread);
+ *   - all tensor arguments are RAW DEVICE POINTERS owned by the caller, fp32, contiguous,
+ *     row-major, 16-byte aligned; nothing is retained after the call except inside dppo_ctx;
+ *   - every launch takes the CUDA stream (cudaStream_t as void*) to enqueue on and is
+ *     asynchronous; no call allocates device memory (the caller passes the workspace whose size
+ *     dppo_workspace_bytes() reports) and none synchronises the host, except dppo_create,
+ *     dppo_comm_init/destroy and the *_host entry point;
+ *   - one dppo_ctx per GPU / process; a ctx is not thread-safe;
+ *   - layouts: rollout buffers are time-major, sample row b = t*N + n; weights are [in,out]
+ *     row-major (TF `kernel`); the flat parameter / gradient vector is
+ *     [W1,b1,...,WL,bL,Wv,bv,Wp,bp] (Model.py:12-14,17 creation order, trunk generalised to L
+ *     hidden layers).  Head outputs: v[B], pdflat[B,2A] = [mean | logstd] (distributions.py:187).
+ */
+#ifndef DPPO_B200_H
+#define DPPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPPO_MAX_HIDDEN 8
+#define DPPO_NUM_LOSS_SLOTS 8          /* policy, value, entropy, total, mean_kl, clip_frac, vclip_frac, rows */
+#define DPPO_NCCL_UNIQUE_ID_BYTES 128
+
+/* GAE modes (Worker.py:82-92) */
+#define DPPO_GAE_REFERENCE 0   /* mask 1-done[t+1]; bootstrap predv[T-1]*(1-done[T-1]) -- as written */
+#define DPPO_GAE_STANDARD  1   /* mask 1-done[t];   bootstrap last_v*(1-last_done)                     */
+
+/* arithmetic of the dense layers */
+#define DPPO_GEMM_FP32_SIMT 0  /* exact fp32 FMA (parity path, every shape)                         */
+#define DPPO_GEMM_TF32X3    1  /* tcgen05 kind::tf32, 3-term split (fp32-accurate tensor-core path)  */
+#define DPPO_GEMM_BF16      2  /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (config 4)         */
+
+typedef struct dppo_ctx dppo_ctx;
+
+typedef struct dppo_config {
+    int32_t obs_dim;                    /* env.observation_space.shape[0]   (PPO.py:13,17)        */
+    int32_t act_dim;                    /* env.action_space.shape[0]        (distributions.py:234) */
+    int32_t n_hidden;                   /* trunk depth L (Model.py:12 has L=1, width 16)           */
+    int32_t hidden[DPPO_MAX_HIDDEN];    /* trunk widths                                            */
+    int32_t max_rows;                   /* largest B (= T*N rows) any call will pass               */
+    int32_t device;                     /* CUDA device ordinal                                     */
+    int32_t gemm_mode;                  /* DPPO_GEMM_*                                             */
+    float   entcoeff;                   /* parameter_dict['ENTCOEFF']   (main.py:15, PPO.py:11)    */
+    float   vcoeff;                     /* parameter_dict['VCOEFF']     (main.py:16, PPO.py:12)    */
+    float   clip_param;                 /* parameter_dict['CLIP_PARAM'] (main.py:17, PPO.py:10,19) */
+} dppo_config;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* dppo_last_error(void);
+int         dppo_version(void);
+
+/* number of fp32 parameters of one net (pi or oldpi): tf.get_collection(TRAINABLE_VARIABLES,
+ * scope) flattened -- Model.py:17 */
+int64_t dppo_param_count(const dppo_config* cfg);
+/* offsets[i] of the 2*(L+2) tensors in the flat vector, Model.py:17 order; returns their count */
+int     dppo_param_offsets(const dppo_config* cfg, int64_t* offsets, int capacity);
+/* length of the gradient buffer dppo_loss_grad writes: n_params + DPPO_NUM_LOSS_SLOTS (the loss
+ * scalars ride at the tail so that ONE allreduce averages both -- SURVEY 8(e)) */
+int64_t dppo_grad_buffer_len(const dppo_config* cfg);
+/* bytes of device workspace dppo_create needs for this config */
+size_t  dppo_workspace_bytes(const dppo_config* cfg);
+
+/* replaces: tf.Session() + the PPO graph construction (main.py:31, PPO.py:8-53) */
+int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes, dppo_ctx** out);
+int dppo_destroy(dppo_ctx* ctx);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* replaces Worker.py:82-92 for N rollouts at once.  rew/predv/done/adv_out/ret_out are [T,N]
+ * time-major (done is 0/1 as fp32).  last_v/last_done ([N]) are read in STANDARD mode only and
+ * may be NULL in REFERENCE mode.  normalize!=0 applies Worker.py:92 per rollout (column). */
+int dppo_gae(dppo_ctx* ctx, const float* rew, const float* predv, const float* done,
+             const float* last_v, const float* last_done, int T, int N, double gamma, double lam,
+             int mode, int normalize, float* adv_out, float* ret_out, void* stream);
+
+/* replaces sess.run([pipredv, piPD.flatparam()], {s: obs}) -- Model.py:11-15 via PPO.py:21,
+ * Worker.py:146.  v_out[B], pdflat_out[B,2A]; either may be NULL. */
+int dppo_forward(dppo_ctx* ctx, const float* params, const float* obs, int B,
+                 float* v_out, float* pdflat_out, void* stream);
+
+/* replaces sess.run([policyLoss, valueLoss, entropyLoss, total_loss, gradient], feed_dict) for
+ * one worker tower: pi forward, oldpi forward (PPO.py:21-22), DiagGaussianPd logp/entropy
+ * (distributions.py:195-203), the clipped losses (PPO.py:29-40) and compute_gradients w.r.t.
+ * pipara (PPO.py:46).  obs[B,obs_dim], act[B,act_dim], adv[B], ret[B].
+ * grad_out has dppo_grad_buffer_len() floats: d total_loss / d params, then the
+ * DPPO_NUM_LOSS_SLOTS scalars.  losses_out (8 floats) may be NULL. */
+int dppo_loss_grad(dppo_ctx* ctx, const float* params_pi, const float* params_old,
+                   const float* obs, const float* act, const float* adv, const float* ret,
+                   int B, float l_mul, float* losses_out, float* grad_out, void* stream);
+
+/* replaces PPO._average_gradients (PPO.py:55-65; towers fed by Chief.py:54-64): in-place mean
+ * over ranks of buf[0:n] with ncclAllReduce(ncclAvg) on NVLink/NVSwitch. */
+int dppo_comm_unique_id(void* id_out_128_bytes);
+int dppo_comm_init(dppo_ctx* ctx, int rank, int world, const void* id_128_bytes);
+int dppo_comm_destroy(dppo_ctx* ctx);
+int dppo_allreduce_avg(dppo_ctx* ctx, float* buf, int64_t n, void* stream);
+
+/* replaces Optimizer.apply_gradients (PPO.py:20,53): tf.train.AdamOptimizer step in TF-1.x
+ * form, lr = LEARNING_RATE*l_mul, step = t after increment (1-based). */
+int dppo_adam_apply(dppo_ctx* ctx, float* params, const float* grad, float* m, float* v,
+                    int64_t n, int step, float lr, float beta1, float beta2, float eps,
+                    void* stream);
+
+/* replaces sync_pis (PPO.py:47): oldpi <- pi */
+int dppo_sync_old(dppo_ctx* ctx, const float* params_pi, float* params_old, void* stream);
+
+/* replaces sess.run([ca, pipredv], {s: obs}) for a batch of states: pi forward +
+ * DiagGaussianPd.sample (PPO.py:23, distributions.py:204-205, Worker.py:146).
+ * action_out[B,A], v_out[B]; Philox counter = (seed, offset). */
+int dppo_act(dppo_ctx* ctx, const float* params, const float* obs, int B, uint64_t seed,
+             uint64_t offset, float* action_out, float* v_out, void* stream);
+
+/* the whole update from HOST buffers (what Chief._train feeds through feed_dict,
+ * Chief.py:54-64): pinned host rollout -> chunked H2D overlapped with GAE + loss_grad ->
+ * (allreduce if a communicator exists) -> losses back to host.  Synchronises `stream`.
+ * params_pi/params_old/grad_out are device pointers; everything *_h is host memory. */
+int dppo_update_host(dppo_ctx* ctx, const float* params_pi, const float* params_old,
+                     const float* obs_h, const float* act_h, const float* rew_h,
+                     const float* predv_h, const float* done_h, int T, int N,
+                     double gamma, double lam, int gae_mode, float l_mul,
+                     float* losses_out_h, float* grad_out, void* stream);
+
+/* ---- launch accounting -------------------------------------------------------------------------
+ * Every kernel the library launches is counted per family; with enable_timing != 0 each launch
+ * is also bracketed by CUDA events on its own stream (used by bench.py for the roofline line).
+ * Families, in order: gae, gemm_nn (forward), gemm_nt (dX), gemm_tn (dW), loss, finalize, misc,
+ * adam, allreduce, tc_gemm.  dppo_profile_read synchronises the recorded events and returns the
+ * number of families written. */
+#define DPPO_PROFILE_KINDS 10
+int dppo_profile_reset(int enable_timing);
+int dppo_profile_read(int64_t* launches, double* ms, int capacity);
+
+/* ---- unit-test hooks (exported so the parity tests can exercise kernels in isolation) ------ */
+/* C[M,N] = epilogue(A . B).  mode 0: A[M,K] B[K,N] (+bias, relu flag);  mode 1: A[M,K] B[N,K]^T,
+ * C *= (mask[M,N] > 0) when mask != NULL;  mode 2: C[K?]: A[Kr,M]^T . B[Kr,N] with split-K over Kr
+ * (deterministic), bias_out[N] = column sums of B when non-NULL. */
+int dppo_dbg_gemm(dppo_ctx* ctx, int mode, int M, int N, int K, const float* A, const float* B,
+                  float* C, const float* bias, const float* mask, int relu, float* bias_out,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPPO_B200_H */

@@ -460,3 +460,62 @@ def cpu_update_torch(theta_pi, theta_old, buf, T, N, lay: Layout, hp: HParams, l
         grads.append(t_pi.grad.numpy())
         losses.append([pl.item(), vl.item(), el.item(), tot.item()])
     return np.mean(np.array(losses), axis=0), tower_mean(grads)
+
+
+# --------------------------------------------------------------------------
+# branch-robust synthetic buffers for parity tests
+# --------------------------------------------------------------------------
+def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, hp: HParams = HParams(),
+                  margin=1e-4, seed=99):
+    """The PPO loss is discontinuous in its inputs where tf.minimum / tf.maximum / clip switch
+    branch (PPO.py:33-39).  A row that sits within fp32 rounding of such a switch makes the
+    fp32 device result and the fp64 oracle legitimately pick different branches (a 1/sqrt(B)
+    relative change of the gradient), which says nothing about parity.  This helper edits the
+    SYNTHETIC act / ret of the few rows within ``margin`` of a switch so that none is left:
+      * |ratio - (1 +- c)| < margin                -> resample the action row;
+      * ||v - v_old| - c| < margin (clip edge)     -> put the return on the far side of v_old, where
+                                                      both branches have the same gradient 2(v-R);
+      * outside the clip and |vf1 - vf2| < margin  -> resample the return.
+    Returns (act, ret, n_edited)."""
+    rng = np.random.default_rng(seed)
+    act = np.array(act, np.float32, copy=True); ret = np.array(ret, np.float32, copy=True).reshape(-1)
+    v, flat, _ = mlp_forward(theta_pi, obs, lay)
+    v_old, flat_old, _ = mlp_forward(theta_old, obs, lay)
+    c = hp.CLIP_PARAM * l_mul
+    dv = v - v_old
+    edited = 0
+    for _ in range(50):
+        a64 = act.astype(np.float64); r64 = ret.astype(np.float64)
+        ratio = np.exp(dg_logp(flat, a64) - dg_logp(flat_old, a64))
+        bad_r = (np.abs(ratio - (1 - c)) < margin) | (np.abs(ratio - (1 + c)) < margin)
+        edge = np.abs(np.abs(dv) - c) < margin
+        vclip = v_old + np.clip(dv, -c, c)
+        vf1 = np.square(v - r64); vf2 = np.square(vclip - r64)
+        on_far_side = np.sign(dv) * (v_old - r64) > 0.5
+        bad_edge = edge & ~on_far_side
+        bad_v = (np.abs(dv) > c) & ~edge & (np.abs(vf1 - vf2) < margin * (1 + vf1))
+        n = int(bad_r.sum() + bad_edge.sum() + bad_v.sum())
+        if n == 0:
+            break
+        edited += n
+        act[bad_r] = rng.standard_normal((int(bad_r.sum()), act.shape[1])).astype(np.float32)
+        sgn = np.where(dv[bad_edge] >= 0, 1.0, -1.0)
+        ret[bad_edge] = (v_old[bad_edge] - sgn * (1.0 + np.abs(rng.standard_normal(int(bad_edge.sum()))))).astype(np.float32)
+        ret[bad_v] = rng.standard_normal(int(bad_v.sum())).astype(np.float32)
+    else:
+        raise RuntimeError("sanitize_rows did not converge")
+    return act, ret, edited
+
+
+def make_case(T, N, obs_dim, hidden, act_dim, seed=1234, l_mul=0.7, trunk_std=1.0, head_std=0.1, delta=0.02,
+              hp: HParams = HParams()):
+    """Frozen synthetic update case: buffer, GAE'd advantages/returns (oracle),
+    pi != oldpi parameters, with branch-ambiguous rows removed.  Everything fp32."""
+    lay = make_layout(obs_dim, hidden, act_dim)
+    buf = make_buffer(T, N, obs_dim, act_dim, seed)
+    th_pi, th_old = make_params_pair(lay, trunk_std, head_std, delta)
+    adv, ret = gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], hp.GAMMA, hp.LAM)
+    act, ret2, edited = sanitize_rows(th_pi, th_old, buf["obs"], buf["act"], adv.reshape(-1), ret.reshape(-1),
+                                      l_mul, lay, hp)
+    return dict(lay=lay, buf=buf, theta_pi=th_pi, theta_old=th_old, adv=adv.reshape(-1).astype(np.float32),
+                ret=ret2.astype(np.float32), act=act, l_mul=l_mul, edited=edited, T=T, N=N)

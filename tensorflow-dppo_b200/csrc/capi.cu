@@ -1,0 +1,474 @@
+// C ABI of libdppo_b200.so (include/dppo_b200.h): context, workspace carving and the
+// stream-ordered orchestration of the update path
+//     GAE (Worker.py:82-92) -> pi & oldpi forward (Model.py:11-15, PPO.py:21-22)
+//     -> loss + d_out (PPO.py:29-40,46) -> dense backward -> split-K finalize
+//     -> allreduce (PPO.py:55-65) -> Adam (PPO.py:53).
+#include "common.cuh"
+#include <string.h>
+#include <math.h>
+#include <new>
+
+namespace dppo {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- profiler ----------------------------------------------------------------------------------
+struct ProfState {
+    bool timing = false;
+    long long launches[KK_COUNT] = {0};
+    double ms[KK_COUNT] = {0};
+    static constexpr int kMaxSlots = 8192;
+    cudaEvent_t ev0[kMaxSlots], ev1[kMaxSlots];
+    int kind_of[kMaxSlots];
+    int created = 0, used = 0;
+};
+static ProfState g_prof;
+
+ProfScope::ProfScope(int k, cudaStream_t s) : kind(k), st(s), slot(-1) {
+    g_prof.launches[k]++;
+    if (!g_prof.timing || g_prof.used >= ProfState::kMaxSlots) return;
+    if (g_prof.used >= g_prof.created) {
+        if (cudaEventCreate(&g_prof.ev0[g_prof.created]) != cudaSuccess) return;
+        if (cudaEventCreate(&g_prof.ev1[g_prof.created]) != cudaSuccess) return;
+        g_prof.created++;
+    }
+    slot = g_prof.used++;
+    g_prof.kind_of[slot] = k;
+    cudaEventRecord(g_prof.ev0[slot], st);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof.ev1[slot], st);
+}
+
+int comm_unique_id(void* out);
+int comm_init(dppo_ctx* ctx, int rank, int world, const void* id_bytes);
+int comm_destroy(dppo_ctx* ctx);
+int allreduce_avg(dppo_ctx* ctx, float* buf, int64_t n, cudaStream_t st);
+
+int make_shape(const dppo_config* cfg, NetShape* s) {
+    DPPO_REQUIRE(cfg != nullptr, "null config");
+    DPPO_REQUIRE(cfg->obs_dim >= 1 && cfg->act_dim >= 1, "obs_dim=%d act_dim=%d must be >= 1", cfg->obs_dim, cfg->act_dim);
+    DPPO_REQUIRE(cfg->n_hidden >= 0 && cfg->n_hidden <= kMaxLayers, "n_hidden=%d out of [0,%d]", cfg->n_hidden, kMaxLayers);
+    s->obs = cfg->obs_dim; s->act = cfg->act_dim; s->L = cfg->n_hidden; s->P = 1 + 2 * cfg->act_dim;
+    int64_t off = 0;
+    int fan_in = cfg->obs_dim;
+    for (int l = 0; l < s->L; ++l) {
+        DPPO_REQUIRE(cfg->hidden[l] >= 1, "hidden[%d]=%d must be >= 1", l, cfg->hidden[l]);
+        s->h[l] = cfg->hidden[l];
+        s->w_off[l] = off; off += (int64_t)fan_in * s->h[l];
+        s->b_off[l] = off; off += s->h[l];
+        fan_in = s->h[l];
+    }
+    s->w_off[s->L] = off; off += (int64_t)fan_in * s->P;
+    s->b_off[s->L] = off; off += s->P;
+    s->n_params = off;
+    return 0;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// one pass computes the size (base == nullptr) or carves the pointers
+static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Workspace* ws) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> char* {
+        char* p = base ? base + off : nullptr;
+        off += align_up(bytes);
+        return p;
+    };
+    const size_t R = (size_t)cfg->max_rows;
+    const int H = s.in_dim(s.L);
+    const size_t head = ((size_t)H * s.P + s.P) * sizeof(float);
+    Workspace w{};
+    w.head_pi = (float*)take(head);
+    w.head_old = (float*)take(head);
+    for (int l = 0; l < s.L; ++l) w.act_pi[l] = (float*)take(R * s.h[l] * sizeof(float));
+    const size_t hm = (size_t)(s.hmax() > 0 ? s.hmax() : 1);
+    w.scratch[0] = (float*)take(R * hm * sizeof(float));
+    w.scratch[1] = (float*)take(R * hm * sizeof(float));
+    w.out_pi = (float*)take(R * s.P * sizeof(float));
+    w.out_old = (float*)take(R * s.P * sizeof(float));
+    w.d_out = (float*)take(R * s.P * sizeof(float));
+    const size_t stride = (size_t)((s.n_params + 3) & ~3LL);
+    w.partial = (float*)take((size_t)kSplitK * stride * sizeof(float));
+    const size_t tiles = (R + kLossTileRows - 1) / kLossTileRows + 64;
+    w.loss_part = (double*)take(tiles * kLossSlots * sizeof(double));
+    w.gae_adv = (float*)take(R * sizeof(float));
+    w.gae_ret = (float*)take(R * sizeof(float));
+    w.stage_floats = R * ((size_t)s.obs + s.act + 3);
+    w.stage = (float*)take(w.stage_floats * sizeof(float));
+    if (ws) *ws = w;
+    return off;
+}
+
+// ---- forward of pi (and oldpi) over rows [0, rows) of obs ------------------------------------
+static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
+                        int rows, cudaStream_t st) {
+    const NetShape& s = c->shape;
+    Workspace& w = c->ws;
+    const int nets = params_old ? 2 : 1;
+    if (int r = launch_pack_heads(s, params_pi, params_old, w.head_pi, w.head_old, st)) return r;
+    const float* in0 = obs; const float* in1 = obs;
+    for (int l = 0; l < s.L; ++l) {
+        float* o0 = w.act_pi[l];
+        float* o1 = w.scratch[l & 1];
+        if (int r = gemm_nn_dual(rows, s.h[l], s.in_dim(l), in0, in1, s.in_dim(l),
+                                 params_pi + s.w_off[l], params_old ? params_old + s.w_off[l] : nullptr, s.h[l],
+                                 o0, o1, s.h[l], params_pi + s.b_off[l],
+                                 params_old ? params_old + s.b_off[l] : nullptr, 1, nets, st)) return r;
+        in0 = o0; in1 = o1;
+    }
+    const int H = s.in_dim(s.L);
+    return gemm_nn_dual(rows, s.P, H, in0, in1, H, w.head_pi, w.head_old, s.P, w.out_pi, w.out_old, s.P,
+                        w.head_pi + (size_t)H * s.P, w.head_old + (size_t)H * s.P, 0, nets, st);
+}
+
+// ---- fwd + loss + bwd over one block of rows; dW/db land in the split-K partial buffer --------
+static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
+                          const float* act, const float* adv, const float* ret, int rows, int tile0,
+                          int B_total, float l_mul, int accumulate, cudaStream_t st) {
+    const NetShape& s = c->shape;
+    Workspace& w = c->ws;
+    if (int r = forward_nets(c, params_pi, params_old, obs, rows, st)) return r;
+    const float inv_B = 1.0f / (float)B_total;
+    const float clip = c->cfg.clip_param * l_mul;                       // PPO.py:19
+    if (int r = launch_loss(s, w.out_pi, w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
+                            c->cfg.vcoeff, w.d_out, w.loss_part, st)) return r;
+
+    const int64_t stride = (s.n_params + 3) & ~3LL;
+    GemmEpi tn; tn.accumulate = accumulate; tn.slice_stride = stride;
+    const int H = s.in_dim(s.L);
+    const float* head_in = s.L ? w.act_pi[s.L - 1] : obs;
+    // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
+    tn.bias_out = w.partial + s.b_off[s.L];
+    if (int r = gemm_tn_splitk(H, s.P, rows, head_in, H, w.d_out, s.P, w.partial + s.w_off[s.L], s.P, tn, st)) return r;
+    if (s.L == 0) return 0;
+    // dh_L = (d_out . Wh^T) * [h_L > 0]
+    int cur = 0;
+    {
+        GemmEpi nt; nt.mask = w.act_pi[s.L - 1];
+        if (int r = gemm_nt(rows, H, s.P, w.d_out, s.P, w.head_pi, s.P, w.scratch[cur], H, nt, st)) return r;
+    }
+    for (int l = s.L - 1; l >= 0; --l) {
+        const float* dY = w.scratch[cur];
+        const float* x_in = l ? w.act_pi[l - 1] : obs;
+        tn.bias_out = w.partial + s.b_off[l];
+        if (int r = gemm_tn_splitk(s.in_dim(l), s.h[l], rows, x_in, s.in_dim(l), dY, s.h[l],
+                                   w.partial + s.w_off[l], s.h[l], tn, st)) return r;
+        if (l > 0) {
+            GemmEpi nt; nt.mask = w.act_pi[l - 1];
+            if (int r = gemm_nt(rows, s.h[l - 1], s.h[l], dY, s.h[l], params_pi + s.w_off[l], s.h[l],
+                                w.scratch[cur ^ 1], s.h[l - 1], nt, st)) return r;
+            cur ^= 1;
+        }
+    }
+    return 0;
+}
+
+__global__ void reduce_slices_kernel(const float* __restrict__ part, int n_slices, long long stride, long long n,
+                                     float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < n_slices; ++k) s += part[(size_t)k * stride + i];
+        out[i] = s;
+    }
+}
+
+}  // namespace dppo
+
+using namespace dppo;
+
+#define CTX_GUARD(ctx)                                                     \
+    DPPO_REQUIRE((ctx) != nullptr, "null dppo_ctx");                       \
+    DPPO_CHECK_CUDA(cudaSetDevice((ctx)->cfg.device))
+
+extern "C" {
+
+const char* dppo_last_error(void) { return g_err; }
+int dppo_version(void) { return 100; }
+
+int64_t dppo_param_count(const dppo_config* cfg) {
+    NetShape s;
+    if (make_shape(cfg, &s)) return -1;
+    return s.n_params;
+}
+
+int dppo_param_offsets(const dppo_config* cfg, int64_t* offsets, int capacity) {
+    NetShape s;
+    if (int r = make_shape(cfg, &s)) return r;
+    const int n = 2 * (s.L + 2);
+    DPPO_REQUIRE(offsets && capacity >= n, "dppo_param_offsets: need capacity %d", n);
+    for (int l = 0; l < s.L; ++l) { offsets[2 * l] = s.w_off[l]; offsets[2 * l + 1] = s.b_off[l]; }
+    const int64_t H = s.in_dim(s.L), head = s.w_off[s.L];
+    offsets[2 * s.L + 0] = head;                         // Wv [H,1]
+    offsets[2 * s.L + 1] = head + H;                     // bv [1]
+    offsets[2 * s.L + 2] = head + H + 1;                 // Wp [H,2A]
+    offsets[2 * s.L + 3] = head + H + 1 + 2 * s.act * H; // bp [2A]
+    return n;
+}
+
+int64_t dppo_grad_buffer_len(const dppo_config* cfg) {
+    const int64_t n = dppo_param_count(cfg);
+    return n < 0 ? n : n + kLossSlots;
+}
+
+size_t dppo_workspace_bytes(const dppo_config* cfg) {
+    NetShape s;
+    if (make_shape(cfg, &s)) return 0;
+    if (cfg->max_rows < 1) { set_error("max_rows=%d must be >= 1", cfg->max_rows); return 0; }
+    return carve(cfg, s, nullptr, nullptr);
+}
+
+int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes, dppo_ctx** out) {
+    DPPO_REQUIRE(out != nullptr, "dppo_create: null out");
+    *out = nullptr;
+    NetShape s;
+    if (int r = make_shape(cfg, &s)) return r;
+    DPPO_REQUIRE(cfg->max_rows >= 1, "max_rows=%d must be >= 1", cfg->max_rows);
+    DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT,
+                 "gemm_mode=%d is not built in this library version (only DPPO_GEMM_FP32_SIMT=0)", cfg->gemm_mode);
+    int ndev = 0;
+    DPPO_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    DPPO_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d CUDA devices)", cfg->device, ndev);
+    DPPO_CHECK_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    DPPO_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    DPPO_REQUIRE(prop.major == 10, "libdppo_b200 is built for sm_100a only; device %d is sm_%d%d", cfg->device,
+                 prop.major, prop.minor);
+    const size_t need = carve(cfg, s, nullptr, nullptr);
+    DPPO_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: %zu < %zu bytes",
+                 workspace_bytes, need);
+    DPPO_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    dppo_ctx* c = new (std::nothrow) dppo_ctx();
+    DPPO_REQUIRE(c != nullptr, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg; c->shape = s; c->workspace = workspace; c->workspace_bytes = workspace_bytes;
+    c->num_sms = prop.multiProcessorCount;
+    carve(cfg, s, (char*)workspace, &c->ws);
+    c->world = 1;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 64 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->losses_pinned, kLossSlots * sizeof(float));
+    if (e != cudaSuccess) {
+        set_error("dppo_create: %s", cudaGetErrorString(e));
+        delete c;
+        return -2;
+    }
+    *out = c;
+    return 0;
+}
+
+int dppo_destroy(dppo_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    comm_destroy(c);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 64; ++i) if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
+    if (c->done_ev) cudaEventDestroy(c->done_ev);
+    if (c->losses_pinned) cudaFreeHost(c->losses_pinned);
+    delete c;
+    return 0;
+}
+
+int dppo_gae(dppo_ctx* c, const float* rew, const float* predv, const float* done, const float* last_v,
+             const float* last_done, int T, int N, double gamma, double lam, int mode, int normalize,
+             float* adv_out, float* ret_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(rew && predv && done && adv_out && ret_out, "dppo_gae: null buffer");
+    return launch_gae(rew, predv, done, last_v, last_done, T, N, gamma, lam, mode, normalize, adv_out, ret_out,
+                      (cudaStream_t)stream);
+}
+
+int dppo_forward(dppo_ctx* c, const float* params, const float* obs, int B, float* v_out, float* pdflat_out,
+                 void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params && obs, "dppo_forward: null buffer");
+    DPPO_REQUIRE(B >= 0 && B <= c->cfg.max_rows, "dppo_forward: B=%d exceeds max_rows=%d", B, c->cfg.max_rows);
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = forward_nets(c, params, nullptr, obs, B, st)) return r;
+    return launch_split_heads(c->shape, c->ws.out_pi, B, v_out, pdflat_out, st);
+}
+
+int dppo_act(dppo_ctx* c, const float* params, const float* obs, int B, uint64_t seed, uint64_t offset,
+             float* action_out, float* v_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params && obs && action_out, "dppo_act: null buffer");
+    DPPO_REQUIRE(B >= 0 && B <= c->cfg.max_rows, "dppo_act: B=%d exceeds max_rows=%d", B, c->cfg.max_rows);
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = forward_nets(c, params, nullptr, obs, B, st)) return r;
+    return launch_sample(c->shape, c->ws.out_pi, B, seed, offset, action_out, v_out, st);
+}
+
+int dppo_loss_grad(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
+                   const float* act, const float* adv, const float* ret, int B, float l_mul, float* losses_out,
+                   float* grad_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params_pi && params_old && obs && act && adv && ret && grad_out, "dppo_loss_grad: null buffer");
+    DPPO_REQUIRE(B >= 1 && B <= c->cfg.max_rows, "dppo_loss_grad: B=%d out of [1, max_rows=%d]", B, c->cfg.max_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, adv, ret, B, 0, B, l_mul, 0, st)) return r;
+    const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
+    return launch_finalize(c->shape, c->ws.partial, kSplitK, c->ws.loss_part, tiles, 1.0f / (float)B,
+                           c->cfg.entcoeff, c->cfg.vcoeff, B, grad_out, losses_out, st);
+}
+
+int dppo_comm_unique_id(void* id_out) {
+    DPPO_REQUIRE(id_out != nullptr, "dppo_comm_unique_id: null buffer");
+    return comm_unique_id(id_out);
+}
+int dppo_comm_init(dppo_ctx* c, int rank, int world, const void* id) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(id != nullptr, "dppo_comm_init: null id");
+    return comm_init(c, rank, world, id);
+}
+int dppo_comm_destroy(dppo_ctx* c) {
+    DPPO_REQUIRE(c != nullptr, "null dppo_ctx");
+    return comm_destroy(c);
+}
+int dppo_allreduce_avg(dppo_ctx* c, float* buf, int64_t n, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(buf != nullptr && n >= 0, "dppo_allreduce_avg: bad buffer");
+    return allreduce_avg(c, buf, n, (cudaStream_t)stream);
+}
+
+int dppo_adam_apply(dppo_ctx* c, float* params, const float* grad, float* m, float* v, int64_t n, int step,
+                    float lr, float beta1, float beta2, float eps, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params && grad && m && v && n >= 0, "dppo_adam_apply: bad buffer");
+    return launch_adam(params, grad, m, v, n, step, lr, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int dppo_sync_old(dppo_ctx* c, const float* params_pi, float* params_old, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params_pi && params_old, "dppo_sync_old: null buffer");
+    ProfScope ps(KK_MISC, (cudaStream_t)stream);
+    DPPO_CHECK_CUDA(cudaMemcpyAsync(params_old, params_pi, (size_t)c->shape.n_params * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs_h,
+                     const float* act_h, const float* rew_h, const float* predv_h, const float* done_h, int T,
+                     int N, double gamma, double lam, int gae_mode, float l_mul, float* losses_out_h,
+                     float* grad_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params_pi && params_old && obs_h && act_h && rew_h && predv_h && done_h && grad_out,
+                 "dppo_update_host: null buffer");
+    DPPO_REQUIRE(gae_mode == DPPO_GAE_REFERENCE, "dppo_update_host: only DPPO_GAE_REFERENCE (last_v is not fed)");
+    const long long B64 = (long long)T * N;
+    DPPO_REQUIRE(T >= 1 && N >= 1 && B64 <= c->cfg.max_rows, "dppo_update_host: T*N=%lld exceeds max_rows=%d", B64,
+                 c->cfg.max_rows);
+    const int B = (int)B64;
+    const NetShape& s = c->shape;
+    Workspace& w = c->ws;
+    cudaStream_t st = (cudaStream_t)stream, cp = c->copy_stream;
+    float* d_obs = w.stage;
+    float* d_act = d_obs + (size_t)B * s.obs;
+    float* d_rew = d_act + (size_t)B * s.act;
+    float* d_pv = d_rew + B;
+    float* d_done = d_pv + B;
+
+    // the copy stream must not overwrite staging that earlier work on `st` still reads
+    DPPO_CHECK_CUDA(cudaEventRecord(c->done_ev, st));
+    DPPO_CHECK_CUDA(cudaStreamWaitEvent(cp, c->done_ev, 0));
+    // small arrays first: GAE needs whole rollouts
+    DPPO_CHECK_CUDA(cudaMemcpyAsync(d_rew, rew_h, (size_t)B * 4, cudaMemcpyHostToDevice, cp));
+    DPPO_CHECK_CUDA(cudaMemcpyAsync(d_pv, predv_h, (size_t)B * 4, cudaMemcpyHostToDevice, cp));
+    DPPO_CHECK_CUDA(cudaMemcpyAsync(d_done, done_h, (size_t)B * 4, cudaMemcpyHostToDevice, cp));
+    DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[0], cp));
+    // row chunks of the big arrays; chunk c's fwd+loss+bwd overlaps chunk c+1's H2D copy
+    int n_chunks = 8;
+    int rows_per = ((B + n_chunks - 1) / n_chunks + kLossTileRows - 1) / kLossTileRows * kLossTileRows;
+    if (rows_per < 4096) rows_per = (4096 < B ? 4096 : (B + kLossTileRows - 1) / kLossTileRows * kLossTileRows);
+    n_chunks = (B + rows_per - 1) / rows_per;
+    DPPO_REQUIRE(n_chunks <= 63, "dppo_update_host: too many chunks");
+    for (int k = 0; k < n_chunks; ++k) {
+        const int r0 = k * rows_per, rows = (B - r0 < rows_per) ? B - r0 : rows_per;
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(d_obs + (size_t)r0 * s.obs, obs_h + (size_t)r0 * s.obs,
+                                        (size_t)rows * s.obs * 4, cudaMemcpyHostToDevice, cp));
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(d_act + (size_t)r0 * s.act, act_h + (size_t)r0 * s.act,
+                                        (size_t)rows * s.act * 4, cudaMemcpyHostToDevice, cp));
+        DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[k + 1], cp));
+    }
+    DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));
+    if (int r = launch_gae(d_rew, d_pv, d_done, nullptr, nullptr, T, N, gamma, lam, gae_mode, 1, w.gae_adv,
+                           w.gae_ret, st)) return r;
+    for (int k = 0; k < n_chunks; ++k) {
+        const int r0 = k * rows_per, rows = (B - r0 < rows_per) ? B - r0 : rows_per;
+        DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[k + 1], 0));
+        if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.act,
+                                   w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, st))
+            return r;
+    }
+    const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
+    if (int r = launch_finalize(s, w.partial, kSplitK, w.loss_part, tiles, 1.0f / (float)B, c->cfg.entcoeff,
+                                c->cfg.vcoeff, B, grad_out, nullptr, st)) return r;
+    if (c->nccl_comm && c->world > 1)
+        if (int r = allreduce_avg(c, grad_out, s.n_params + kLossSlots, st)) return r;
+    DPPO_CHECK_CUDA(cudaMemcpyAsync(c->losses_pinned, grad_out + s.n_params, kLossSlots * sizeof(float),
+                                    cudaMemcpyDeviceToHost, st));
+    DPPO_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (losses_out_h) memcpy(losses_out_h, c->losses_pinned, kLossSlots * sizeof(float));
+    return 0;
+}
+
+int dppo_profile_reset(int enable_timing) {
+    // fold finished timings, then reset
+    for (int i = 0; i < g_prof.used; ++i) cudaEventSynchronize(g_prof.ev1[i]);
+    g_prof.used = 0;
+    for (int k = 0; k < KK_COUNT; ++k) { g_prof.launches[k] = 0; g_prof.ms[k] = 0.0; }
+    g_prof.timing = enable_timing != 0;
+    return 0;
+}
+
+int dppo_profile_read(int64_t* launches, double* ms, int capacity) {
+    DPPO_REQUIRE(launches && ms && capacity >= KK_COUNT, "dppo_profile_read: need capacity %d", (int)KK_COUNT);
+    for (int i = 0; i < g_prof.used; ++i) {
+        DPPO_CHECK_CUDA(cudaEventSynchronize(g_prof.ev1[i]));
+        float t = 0.f;
+        DPPO_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]));
+        g_prof.ms[g_prof.kind_of[i]] += (double)t;
+    }
+    g_prof.used = 0;
+    for (int k = 0; k < KK_COUNT; ++k) { launches[k] = g_prof.launches[k]; ms[k] = g_prof.ms[k]; }
+    return KK_COUNT;
+}
+
+int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, const float* B, float* C,
+                  const float* bias, const float* mask, int relu, float* bias_out, void* stream) {
+    CTX_GUARD(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmEpi e; e.bias = bias; e.relu = relu; e.mask = mask;
+    if (mode == 0) return gemm_nn(M, N, K, A, K, B, N, C, N, e, st);
+    if (mode == 1) return gemm_nt(M, N, K, A, K, B, K, C, N, e, st);
+    if (mode == 2) {
+        // C[M,N] = A[K,M]^T . B[K,N]; partial slices live in the ctx workspace
+        const int64_t need = (int64_t)M * N + N;
+        const int64_t stride = (need + 3) & ~3LL;
+        DPPO_REQUIRE(stride * kSplitK <= ((c->shape.n_params + 3) & ~3LL) * kSplitK,
+                     "dppo_dbg_gemm: M*N+N=%lld exceeds the partial buffer (n_params=%lld)", (long long)need,
+                     (long long)c->shape.n_params);
+        e.slice_stride = stride; e.bias_out = bias_out ? c->ws.partial + (int64_t)M * N : nullptr;
+        if (int r = gemm_tn_splitk(M, N, K, A, M, B, N, c->ws.partial, N, e, st)) return r;
+        ProfScope ps(KK_MISC, st);
+        reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, kSplitK, stride, (long long)M * N, C);
+        DPPO_LAUNCH_CHECK();
+        if (bias_out) {
+            reduce_slices_kernel<<<4, 256, 0, st>>>(c->ws.partial + (int64_t)M * N, kSplitK, stride, N, bias_out);
+            DPPO_LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    DPPO_REQUIRE(false, "dppo_dbg_gemm: bad mode %d", mode);
+}
+
+}  // extern "C"

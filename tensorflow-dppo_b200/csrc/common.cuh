@@ -1,0 +1,143 @@
+// Shared declarations of libdppo_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/dppo_b200.h"
+
+namespace dppo {
+
+void set_error(const char* fmt, ...);
+
+#define DPPO_CHECK_CUDA(expr)                                                             \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            dppo::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                            cudaGetErrorString(_e));                                      \
+            return -2;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+#define DPPO_REQUIRE(cond, ...)                                                           \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            dppo::set_error(__VA_ARGS__);                                                 \
+            return -1;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+#define DPPO_LAUNCH_CHECK() DPPO_CHECK_CUDA(cudaGetLastError())
+
+constexpr int kMaxLayers = DPPO_MAX_HIDDEN;
+constexpr int kLossSlots = DPPO_NUM_LOSS_SLOTS;
+constexpr int kLossTileRows = 128;          // rows per CTA of the loss kernel
+constexpr int kSplitK = 32;                 // dW split-K slices (deterministic two-stage reduce)
+
+// Internal parameter layout: identical to the public one for the trunk; the two heads are packed
+// into ONE [H_L, P] matrix (P = 1 + 2A: value | mean | logstd) + bias[P], so that the heads are a
+// single GEMM.  Same total size as the public head block.
+struct NetShape {
+    int obs, act, L, P;
+    int h[kMaxLayers];
+    int64_t w_off[kMaxLayers + 1];   // trunk W_l offsets, [L] = packed head W
+    int64_t b_off[kMaxLayers + 1];   // trunk b_l offsets, [L] = packed head b
+    int64_t n_params;
+    int in_dim(int l) const { return l == 0 ? obs : h[l - 1]; }
+    int out_dim(int l) const { return l == L ? P : h[l]; }
+    int hmax() const { int m = 0; for (int i = 0; i < L; ++i) m = h[i] > m ? h[i] : m; return m; }
+};
+
+int make_shape(const dppo_config* cfg, NetShape* s);
+
+struct Workspace {
+    // all device pointers into the caller's workspace
+    float* head_pi;      // packed head W|b of pi      [H_L*P + P]
+    float* head_old;     // packed head W|b of oldpi
+    float* act_pi[kMaxLayers];   // post-ReLU activations of pi, layer l: [max_rows, h[l]]
+    float* scratch[2];   // oldpi activations / dh ping-pong: [max_rows, hmax]
+    float* out_pi;       // [max_rows, P]
+    float* out_old;      // [max_rows, P]
+    float* d_out;        // [max_rows, P]
+    float* partial;      // [kSplitK, n_params] dW/db split-K partials (internal layout)
+    double* loss_part;   // [loss_tiles_max, kLossSlots]
+    float* gae_adv;      // [max_rows] used by dppo_update_host
+    float* gae_ret;      // [max_rows]
+    float* stage;        // device staging for dppo_update_host: obs|act|rew|predv|done
+    size_t stage_floats;
+};
+
+}  // namespace dppo
+
+struct dppo_ctx {
+    dppo_config cfg;
+    dppo::NetShape shape;
+    dppo::Workspace ws;
+    void* workspace;
+    size_t workspace_bytes;
+    int num_sms;
+    // communicator (comm.cu)
+    void* nccl_comm;
+    int rank, world;
+    // update_host plumbing
+    cudaStream_t copy_stream;
+    cudaEvent_t chunk_ev[64];
+    cudaEvent_t done_ev;
+    float* losses_pinned;
+};
+
+namespace dppo {
+
+// ---- launch accounting (dppo_profile_*): every kernel launch of the library passes through a
+// ProfScope; counters are always on, CUDA-event timing only when enabled (bench.py's roofline pass)
+enum KernelKind { KK_GAE = 0, KK_GEMM_NN, KK_GEMM_NT, KK_GEMM_TN, KK_LOSS, KK_FINALIZE, KK_MISC, KK_ADAM,
+                  KK_ALLREDUCE, KK_TC_GEMM, KK_COUNT };
+struct ProfScope {
+    int kind; cudaStream_t st; int slot;
+    ProfScope(int kind, cudaStream_t st);
+    ~ProfScope();
+};
+
+// ---- kernels' host launchers (one per .cu) ----
+int launch_gae(const float* rew, const float* predv, const float* done, const float* last_v,
+               const float* last_done, int T, int N, double gamma, double lam, int mode,
+               int normalize, float* adv, float* ret, cudaStream_t st);
+
+// C = epi(A.B) family, see sgemm.cu
+struct GemmEpi {
+    const float* bias = nullptr;   // [N] added before relu (NN)
+    int relu = 0;
+    const float* mask = nullptr;   // [M,N] (ld = ldc): C *= (mask > 0)   (NT)
+    float* bias_out = nullptr;     // TN: column sums of B -> partial slices, stride = slice_stride
+    int accumulate = 0;            // TN: partial += instead of =
+    int64_t slice_stride = 0;      // TN: floats between split-K slices of C / bias_out
+};
+int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const GemmEpi& e, cudaStream_t st);
+// nets (1 or 2) independent products sharing shapes (pi and oldpi forward in one launch)
+int gemm_nn_dual(int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0,
+                 const float* B1, int ldb, float* C0, float* C1, int ldc, const float* bias0,
+                 const float* bias1, int relu, int nets, cudaStream_t st);
+int gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const GemmEpi& e, cudaStream_t st);
+// C[s][M,N] (+)= A[k, M]^T . B[k, N] over k in slice s of [0,K); kSplitK slices
+int gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                   int ldc, const GemmEpi& e, cudaStream_t st);
+
+int launch_pack_heads(const NetShape& s, const float* params_pi, const float* params_old,
+                      float* head_pi, float* head_old, cudaStream_t st);
+int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
+                const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
+                float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st);
+int launch_finalize(const NetShape& s, const float* partial, int n_slices, const double* loss_part,
+                    int n_loss_tiles, float inv_B, float entcoeff, float vcoeff, int rows_total,
+                    float* grad_out, float* losses_out, cudaStream_t st);
+int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
+                       cudaStream_t st);
+int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,
+                float b1, float b2, float eps, cudaStream_t st);
+int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,
+                  float* action, float* v_out, cudaStream_t st);
+
+}  // namespace dppo

@@ -1,0 +1,371 @@
+// K4: DiagGaussianPd + PPO clipped loss forward/backward on the head outputs, plus the small
+// elementwise kernels around it (head packing, split-K finalize, Adam, sampling).
+//
+// Reference math: /root/reference/Others/distributions.py:184-208 (DiagGaussianPd),
+// /root/reference/PPO.py:19,29-40 (losses), PPO.py:46 (gradient; closed form per SURVEY
+// Appendix B, with TensorFlow's tie rules for minimum / maximum / clip_by_value).
+#include "common.cuh"
+
+namespace dppo {
+
+// ---------------------------------------------------------------------------------------------
+// head packing: public [Wv(H) | bv | Wp(H,2A) | bp(2A)]  ->  internal [Wh(H,P) | bh(P)]
+// (Model.py:13-14 creates two dense layers on the same input; one GEMM serves both.)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_heads_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                  float* __restrict__ h0, float* __restrict__ h1, int H, int A,
+                                  long long head_off) {
+    const int P = 1 + 2 * A;
+    const int total = H * P + P;
+    const float* src = (blockIdx.y == 0 ? p0 : p1);
+    float* dst = (blockIdx.y == 0 ? h0 : h1);
+    if (src == nullptr) return;
+    src += head_off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v;
+        if (i < H * P) {
+            const int k = i / P, c = i % P;
+            v = (c == 0) ? src[k] : src[H + 1 + k * 2 * A + (c - 1)];
+        } else {
+            const int c = i - H * P;
+            v = (c == 0) ? src[H] : src[H + 1 + 2 * A * H + (c - 1)];
+        }
+        dst[i] = v;
+    }
+}
+
+int launch_pack_heads(const NetShape& s, const float* params_pi, const float* params_old,
+                      float* head_pi, float* head_old, cudaStream_t st) {
+    const int H = s.in_dim(s.L);
+    const int total = H * s.P + s.P;
+    dim3 grid((total + 255) / 256, 2);
+    ProfScope ps(KK_MISC, st);
+    pack_heads_kernel<<<grid, 256, 0, st>>>(params_pi, params_old, head_pi, head_old, H, s.act,
+                                            (long long)s.w_off[s.L]);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss forward + d(total)/d(head outputs)
+// ---------------------------------------------------------------------------------------------
+// One CTA = kLossTileRows rows.  The [rows,P] head tiles and the [rows,A] action tile are
+// staged through shared memory with fully coalesced float loads (P = 1+2A is odd, so the
+// row-strided per-thread reads that follow are bank-conflict free), one thread then owns one
+// row, and d_out goes back through the same smem tile to a coalesced store.  The seven batch sums
+// (surrogate, value, entropy, kl, clip counters) are reduced with warp shuffles, then across the
+// 4 warps, and land as fp64 partials per tile; finalize_kernel adds the tiles in a fixed order.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kLossTileRows)
+ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_old,
+                const float* __restrict__ act, const float* __restrict__ adv,
+                const float* __restrict__ ret, int rows, int A, int tile0, float inv_B, float clip,
+                float entcoeff, float vcoeff, float* __restrict__ d_out,
+                double* __restrict__ loss_part) {
+    extern __shared__ float smem[];
+    const int P = 1 + 2 * A;
+    float* s_pi = smem;                              // [R][P]   (becomes d_out)
+    float* s_old = s_pi + kLossTileRows * P;         // [R][P]
+    float* s_act = s_old + kLossTileRows * P;        // [R][A]
+    __shared__ double s_red[kLossTileRows / 32][kLossSlots];
+
+    const int row0 = blockIdx.x * kLossTileRows;
+    const int nrows = min(kLossTileRows, rows - row0);
+    const int tid = threadIdx.x;
+
+    {   // coalesced tile loads
+        const float* gp = out_pi + (size_t)row0 * P;
+        const float* go = out_old + (size_t)row0 * P;
+        for (int i = tid; i < nrows * P; i += kLossTileRows) { s_pi[i] = __ldg(gp + i); s_old[i] = __ldg(go + i); }
+        const float* ga = act + (size_t)row0 * A;
+        for (int i = tid; i < nrows * A; i += kLossTileRows) s_act[i] = __ldg(ga + i);
+    }
+    __syncthreads();
+
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (tid < nrows) {
+        float* o = s_pi + tid * P;
+        const float* q = s_old + tid * P;
+        const float* a = s_act + tid * A;
+        const float advb = __ldg(adv + row0 + tid);
+        const float R = __ldg(ret + row0 + tid);
+
+        // log ratio = logp_pi(a) - logp_old(a), accumulated per component so that the shared
+        // 0.5*log(2pi)*A term cancels exactly (distributions.py:195-198, PPO.py:31)
+        float logratio = 0.f, sum_ls = 0.f, kl = 0.f;
+        for (int k = 0; k < A; ++k) {
+            const float mu = o[1 + k], ls = o[1 + A + k];
+            const float muo = q[1 + k], lso = q[1 + A + k];
+            const float z = (a[k] - mu) * expf(-ls);
+            const float zo = (a[k] - muo) * expf(-lso);
+            logratio += 0.5f * (zo * zo - z * z) + (lso - ls);
+            sum_ls += ls;
+            // KL(old || new), distributions.py:199-201 (diagnostic only)
+            const float dm = muo - mu;
+            kl += (ls - lso) + (expf(2.f * lso) + dm * dm) * 0.5f * expf(-2.f * ls) - 0.5f;
+        }
+        const float ratio = expf(logratio);
+        const float ent = sum_ls + (float)A * 1.4189385332046727f;     // 0.5*log(2*pi*e), :202-203
+        const float surr1 = ratio * advb;                                // PPO.py:32
+        const float rc = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+        const float surr2 = rc * advb;                                   // PPO.py:33
+        const bool first = (surr1 <= surr2);                             // tf.minimum -> x iff x<=y
+        const float g_logp = first ? (-advb * inv_B) * ratio : 0.f;
+
+        const float v = o[0], vo = q[0];
+        const float dv = v - vo;
+        const float vclip = vo + fminf(fmaxf(dv, -clip), clip);         // PPO.py:37
+        const float e1 = (v - R) * (v - R);                              // PPO.py:36
+        const float e2 = (vclip - R) * (vclip - R);                      // PPO.py:38
+        const bool vfirst = (e1 >= e2);                                  // tf.maximum -> x iff x>=y
+        const bool inclip = (dv >= -clip) && (dv <= clip);
+        const float g_v = vcoeff * inv_B * (vfirst ? 2.f * (v - R) : (inclip ? 2.f * (vclip - R) : 0.f));
+
+        acc[0] = -(double)fminf(surr1, surr2);                           // PPO.py:34
+        acc[1] = (double)fmaxf(e1, e2);                                  // PPO.py:39
+        acc[2] = (double)ent;                                            // PPO.py:29-30
+        acc[3] = (double)kl;
+        acc[4] = first ? 0.0 : 1.0;
+        acc[5] = vfirst ? 0.0 : 1.0;
+        acc[6] = 1.0;
+
+        // d total / d [v | mean | logstd]  
+        const float ent_g = entcoeff * inv_B;
+        for (int k = 0; k < A; ++k) {
+            const float mu = o[1 + k], ls = o[1 + A + k];
+            const float inv_std = expf(-ls);
+            const float z = (a[k] - mu) * inv_std;
+            o[1 + k] = g_logp * z * inv_std;
+            o[1 + A + k] = g_logp * (z * z - 1.f) - ent_g;
+        }
+        o[0] = g_v;
+    }
+    __syncthreads();
+    {   // coalesced d_out store
+        float* gd = d_out + (size_t)row0 * P;
+        for (int i = tid; i < nrows * P; i += kLossTileRows) gd[i] = s_pi[i];
+    }
+    // block reduction of the batch sums
+    const int warp = tid / 32, lane = tid % 32;
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+        const double w = warp_sum(acc[s]);
+        if (lane == 0) s_red[warp][s] = w;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLossTileRows / 32; ++w) t += s_red[w][tid];
+        loss_part[(size_t)(tile0 + blockIdx.x) * kLossSlots + tid] = t;
+    }
+}
+
+int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
+                const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
+                float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st) {
+    if (rows == 0) return 0;
+    const size_t smem = (size_t)kLossTileRows * (2 * s.P + s.act) * sizeof(float);
+    DPPO_REQUIRE(smem <= 200 * 1024, "loss kernel: act_dim=%d needs %zu B of shared memory", s.act, smem);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(ppo_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = (rows + kLossTileRows - 1) / kLossTileRows;
+    ProfScope ps(KK_LOSS, st);
+    ppo_loss_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, act, adv, ret, rows, s.act, tile0,
+                                                       inv_B, clip, entcoeff, vcoeff, d_out, loss_part);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: deterministic split-K reduction of dW/db partials (internal layout) into the public
+// flat gradient (PPO.py:46 order), + the loss scalars at the tail.
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_kernel(const float* __restrict__ partial, int n_slices, long long slice_stride,
+                                long long n_params, long long head_off, int H, int A,
+                                const double* __restrict__ loss_part, int n_tiles, float entcoeff,
+                                float vcoeff, float* __restrict__ grad_out, float* __restrict__ losses_out) {
+    const int P = 1 + 2 * A;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += stride) {
+        float s = 0.f;
+        for (int k = 0; k < n_slices; ++k) s += __ldg(partial + (size_t)k * slice_stride + i);
+        long long pub = i;
+        if (i >= head_off) {
+            const long long r = i - head_off;
+            if (r < (long long)H * P) {
+                const int k = (int)(r / P), c = (int)(r % P);
+                pub = head_off + (c == 0 ? k : (long long)H + 1 + (long long)k * 2 * A + (c - 1));
+            } else {
+                const int c = (int)(r - (long long)H * P);
+                pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + 2LL * A * H + (c - 1));
+            }
+        }
+        grad_out[pub] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        double acc[7];
+#pragma unroll
+        for (int s = 0; s < 7; ++s) acc[s] = 0.0;
+        for (int t = threadIdx.x; t < n_tiles; t += 32)
+#pragma unroll
+            for (int s = 0; s < 7; ++s) acc[s] += loss_part[(size_t)t * kLossSlots + s];
+#pragma unroll
+        for (int s = 0; s < 7; ++s) acc[s] = warp_sum(acc[s]);
+        if (threadIdx.x == 0) {
+            const double n = acc[6] > 0 ? acc[6] : 1.0;
+            float o[kLossSlots];
+            o[0] = (float)(acc[0] / n);                       // policyLoss   PPO.py:34
+            o[1] = (float)((double)vcoeff * acc[1] / n);      // valueLoss    PPO.py:39
+            o[2] = (float)(-(double)entcoeff * acc[2] / n);   // entropyLoss  PPO.py:35
+            o[3] = o[0] + o[2] + o[1];                        // total_loss   PPO.py:40
+            o[4] = (float)(acc[3] / n);                       // mean KL(old||new)
+            o[5] = (float)(acc[4] / n);                       // fraction of rows on the clipped surrogate
+            o[6] = (float)(acc[5] / n);                       // fraction of rows on the clipped value branch
+            o[7] = (float)acc[6];                             // rows
+#pragma unroll
+            for (int s = 0; s < kLossSlots; ++s) {
+                grad_out[n_params + s] = o[s];
+                if (losses_out) losses_out[s] = o[s];
+            }
+        }
+    }
+}
+
+int launch_finalize(const NetShape& s, const float* partial, int n_slices, const double* loss_part,
+                    int n_loss_tiles, float inv_B, float entcoeff, float vcoeff, int rows_total,
+                    float* grad_out, float* losses_out, cudaStream_t st) {
+    (void)inv_B; (void)rows_total;
+    const long long stride = (s.n_params + 3) & ~3LL;
+    const int H = s.in_dim(s.L);
+    int grid = (int)((s.n_params + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    ProfScope ps(KK_FINALIZE, st);
+    finalize_kernel<<<grid, 256, 0, st>>>(partial, n_slices, stride, s.n_params, (long long)s.w_off[s.L], H,
+                                          s.act, loss_part, n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[rows,P] -> v[rows], pdflat[rows,2A]
+// ---------------------------------------------------------------------------------------------
+__global__ void split_heads_kernel(const float* __restrict__ out, long long total, int P,
+                                   float* __restrict__ v_out, float* __restrict__ pd_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / P; const int c = (int)(i % P);
+        const float x = __ldg(out + i);
+        if (c == 0) { if (v_out) v_out[r] = x; }
+        else if (pd_out) pd_out[r * (P - 1) + (c - 1)] = x;
+    }
+}
+
+int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
+                       cudaStream_t st) {
+    if (rows == 0) return 0;
+    const long long total = (long long)rows * s.P;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    ProfScope ps(KK_MISC, st);
+    split_heads_kernel<<<grid, 256, 0, st>>>(out, total, s.P, v_out, pd_out);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: tf.train.AdamOptimizer apply (PPO.py:20,53), TF-1.x form:
+//   lr_t = lr*sqrt(1-b2^t)/(1-b1^t);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//   theta -= lr_t * m / (sqrt(v) + eps)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,
+                float b1, float b2, float eps, cudaStream_t st) {
+    DPPO_REQUIRE(step >= 1, "dppo_adam_apply: step=%d must be >= 1 (t after increment)", step);
+    if (n == 0) return 0;
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_ADAM, st);
+    adam_kernel<<<grid, 256, 0, st>>>(params, grad, m, v, (long long)n, (float)lr_t, b1, b2, eps);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DiagGaussianPd.sample (distributions.py:204-205): a = mean + exp(logstd) * N(0,1)
+// Philox4x32-10 counter RNG (key = seed, counter = (offset, row, quad)), Box-Muller.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void sample_kernel(const float* __restrict__ out, int rows, int A, uint64_t seed, uint64_t offset,
+                              float* __restrict__ action, float* __restrict__ v_out) {
+    const int P = 1 + 2 * A;
+    const int quads = (A + 3) / 4;
+    const long long total = (long long)rows * quads;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int r = (int)(i / quads), q = (int)(i % quads);
+        uint32_t c[4] = {(uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)r, (uint32_t)q};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        float z[4];
+        {
+            const float r0 = sqrtf(-2.f * logf(u01(c[0]))), r1 = sqrtf(-2.f * logf(u01(c[2])));
+            float s0, c0, s1, c1;
+            sincosf(6.283185307179586f * u01(c[1]), &s0, &c0);
+            sincosf(6.283185307179586f * u01(c[3]), &s1, &c1);
+            z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+        }
+        const float* o = out + (size_t)r * P;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = q * 4 + e;
+            if (k < A) action[(size_t)r * A + k] = o[1 + k] + expf(o[1 + A + k]) * z[e];
+        }
+        if (q == 0 && v_out) v_out[r] = o[0];
+    }
+}
+
+int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,
+                  float* action, float* v_out, cudaStream_t st) {
+    if (rows == 0) return 0;
+    const long long total = (long long)rows * ((s.act + 3) / 4);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    ProfScope ps(KK_MISC, st);
+    sample_kernel<<<grid, 256, 0, st>>>(out, rows, s.act, seed, offset, action, v_out);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace dppo

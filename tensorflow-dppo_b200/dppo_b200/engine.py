@@ -1,0 +1,212 @@
+"""DppoEngine: thin host wrapper over the C ABI (include/dppo_b200.h).
+
+It owns the dppo_ctx and its workspace (a torch uint8 CUDA tensor -- device memory container
+only), validates tensors, passes raw ``data_ptr()``s and the current CUDA stream, and raises
+``RuntimeError`` with ``dppo_last_error()`` on any non-zero return.  No computation happens in
+Python or in torch ops.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .layout import ParamLayout
+
+
+class DppoEngine:
+    """One engine per GPU / process (the replacement of one tf.Session + PPO graph,
+    /root/reference/main.py:31, PPO.py:8-53)."""
+
+    LOSS_NAMES = ("policyLoss", "valueLoss", "entropyLoss", "total_loss", "mean_kl", "clip_frac",
+                  "vclip_frac", "rows")
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden: Sequence[int], max_rows: int, device: int = 0,
+                 entcoeff: float = 0.01, vcoeff: float = 0.5, clip_param: float = 0.2,
+                 gemm_mode: int = L.GEMM_FP32_SIMT):
+        self.lib = L.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("DppoEngine needs a CUDA device (sm_100a); there is no CPU path")
+        if len(hidden) > L.MAX_HIDDEN:
+            raise ValueError(f"at most {L.MAX_HIDDEN} hidden layers")
+        self.layout = ParamLayout(obs_dim, hidden, act_dim)
+        cfg = L.DppoConfig()
+        cfg.obs_dim, cfg.act_dim, cfg.n_hidden = obs_dim, act_dim, len(hidden)
+        for i, h in enumerate(hidden):
+            cfg.hidden[i] = int(h)
+        cfg.max_rows, cfg.device, cfg.gemm_mode = int(max_rows), int(device), int(gemm_mode)
+        cfg.entcoeff, cfg.vcoeff, cfg.clip_param = entcoeff, vcoeff, clip_param
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.obs_dim, self.act_dim, self.hidden, self.max_rows = obs_dim, act_dim, tuple(hidden), int(max_rows)
+        self.n_params = int(self.lib.dppo_param_count(C.byref(cfg)))
+        if self.n_params != self.layout.n_params:
+            raise RuntimeError("C and Python parameter layouts disagree")
+        self.grad_len = int(self.lib.dppo_grad_buffer_len(C.byref(cfg)))
+        nbytes = int(self.lib.dppo_workspace_bytes(C.byref(cfg)))
+        if nbytes == 0:
+            raise RuntimeError("dppo_workspace_bytes: " + L.last_error(self.lib))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ctx = C.c_void_p()
+        self._check(self.lib.dppo_create(C.byref(cfg), self.workspace.data_ptr(), nbytes, C.byref(ctx)))
+        self.ctx = ctx
+        self.world = 1
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"libdppo_b200 error {rc}: {L.last_error(self.lib)}")
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev(self, t: torch.Tensor, numel: Optional[int] = None, name: str = "tensor"):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError(f"{name}: expected a contiguous float32 CUDA tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name}: on {t.device}, engine is on {self.device}")
+        if numel is not None and t.numel() != numel:
+            raise ValueError(f"{name}: expected {numel} elements, got {t.numel()}")
+        return t.data_ptr()
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx.value:
+            self.lib.dppo_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def new_grad_buffer(self):
+        return torch.zeros(self.grad_len, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ hot path
+    def gae(self, rew, predv, done, gamma: float, lam: float, mode: int = L.GAE_REFERENCE, normalize: bool = True,
+            last_v=None, last_done=None, adv_out=None, ret_out=None):
+        """[T,N] time-major buffers -> (adv, ret).  Worker.py:82-92."""
+        T, N = rew.shape
+        adv = adv_out if adv_out is not None else torch.empty_like(rew)
+        ret = ret_out if ret_out is not None else torch.empty_like(rew)
+        self._check(self.lib.dppo_gae(
+            self.ctx, self._dev(rew, T * N, "rew"), self._dev(predv, T * N, "predv"), self._dev(done, T * N, "done"),
+            self._dev(last_v, N, "last_v") if last_v is not None else None,
+            self._dev(last_done, N, "last_done") if last_done is not None else None,
+            T, N, float(gamma), float(lam), int(mode), int(bool(normalize)),
+            self._dev(adv, T * N, "adv_out"), self._dev(ret, T * N, "ret_out"), self._stream()))
+        return adv, ret
+
+    def forward(self, params, obs):
+        """(v[B], pdflat[B,2A]) = Model.FC forward.  Model.py:11-15."""
+        B = obs.shape[0]
+        v = torch.empty(B, dtype=torch.float32, device=self.device)
+        pd = torch.empty(B, 2 * self.act_dim, dtype=torch.float32, device=self.device)
+        self._check(self.lib.dppo_forward(self.ctx, self._dev(params, self.n_params, "params"),
+                                          self._dev(obs, B * self.obs_dim, "obs"), B, v.data_ptr(), pd.data_ptr(),
+                                          self._stream()))
+        return v, pd
+
+    def act(self, params, obs, seed: int, offset: int):
+        """(action[B,A], v[B]) = piPD.sample(), pipredv.  PPO.py:23, Worker.py:146."""
+        B = obs.shape[0]
+        a = torch.empty(B, self.act_dim, dtype=torch.float32, device=self.device)
+        v = torch.empty(B, dtype=torch.float32, device=self.device)
+        self._check(self.lib.dppo_act(self.ctx, self._dev(params, self.n_params, "params"),
+                                      self._dev(obs, B * self.obs_dim, "obs"), B, int(seed), int(offset),
+                                      a.data_ptr(), v.data_ptr(), self._stream()))
+        return a, v
+
+    def loss_grad(self, params_pi, params_old, obs, act, adv, ret, l_mul: float, grad_out=None, losses_out=None):
+        """One worker tower: losses + d total_loss / d pipara.  PPO.py:21-46.
+        Returns (losses[8], grad_buffer[n_params + 8])."""
+        B = obs.shape[0]
+        g = grad_out if grad_out is not None else self.new_grad_buffer()
+        self._check(self.lib.dppo_loss_grad(
+            self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
+            self._dev(obs, B * self.obs_dim, "obs"), self._dev(act, B * self.act_dim, "act"),
+            self._dev(adv, B, "adv"), self._dev(ret, B, "ret"), B, float(l_mul),
+            self._dev(losses_out, L.NUM_LOSS_SLOTS, "losses_out") if losses_out is not None else None,
+            self._dev(g, self.grad_len, "grad_out"), self._stream()))
+        return g[self.n_params:], g
+
+    # ------------------------------------------------------------------ collective + optimiser
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = L.load_library()
+        buf = C.create_string_buffer(L.NCCL_UNIQUE_ID_BYTES)
+        rc = lib.dppo_comm_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"dppo_comm_unique_id: {L.last_error(lib)}")
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, L.NCCL_UNIQUE_ID_BYTES)
+        self._check(self.lib.dppo_comm_init(self.ctx, rank, world, buf))
+        self.world = world
+
+    def allreduce_avg(self, buf, n: Optional[int] = None):
+        """In-place mean over ranks.  PPO._average_gradients, PPO.py:55-65."""
+        n = buf.numel() if n is None else n
+        self._dev(buf, None, "buf")
+        self._check(self.lib.dppo_allreduce_avg(self.ctx, buf.data_ptr(), n, self._stream()))
+        return buf
+
+    def adam_apply(self, params, grad, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
+        """tf.train.AdamOptimizer.apply_gradients.  PPO.py:20,53."""
+        n = self.n_params
+        self._dev(grad, None, "grad")
+        self._check(self.lib.dppo_adam_apply(self.ctx, self._dev(params, n, "params"), grad.data_ptr(),
+                                             self._dev(m, n, "m"), self._dev(v, n, "v"), n, int(step), float(lr),
+                                             beta1, beta2, eps, self._stream()))
+
+    def sync_old(self, params_pi, params_old):
+        """oldpi <- pi.  PPO.py:47."""
+        self._check(self.lib.dppo_sync_old(self.ctx, self._dev(params_pi, self.n_params, "params_pi"),
+                                           self._dev(params_old, self.n_params, "params_old"), self._stream()))
+
+    # ------------------------------------------------------------------ host-buffer entry (e2e)
+    def update_host(self, params_pi, params_old, obs_h, act_h, rew_h, predv_h, done_h, gamma, lam, l_mul,
+                    grad_out=None, gae_mode: int = L.GAE_REFERENCE):
+        """Whole update from pinned HOST buffers (what Chief._train feeds, Chief.py:54-64):
+        chunked H2D overlapped with GAE + loss_grad (+ allreduce), losses read back.  Synchronises."""
+        T, N = rew_h.shape
+        B = T * N
+        for name, t, n in (("obs_h", obs_h, B * self.obs_dim), ("act_h", act_h, B * self.act_dim),
+                           ("rew_h", rew_h, B), ("predv_h", predv_h, B), ("done_h", done_h, B)):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+                raise TypeError(f"{name}: expected a contiguous float32 host tensor with {n} elements")
+            if not t.is_pinned():
+                raise TypeError(f"{name}: host buffers must be pinned (torch.Tensor.pin_memory())")
+        g = grad_out if grad_out is not None else self.new_grad_buffer()
+        losses = (C.c_float * L.NUM_LOSS_SLOTS)()
+        self._check(self.lib.dppo_update_host(
+            self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
+            obs_h.data_ptr(), act_h.data_ptr(), rew_h.data_ptr(), predv_h.data_ptr(), done_h.data_ptr(), T, N,
+            float(gamma), float(lam), int(gae_mode), float(l_mul), losses, self._dev(g, self.grad_len, "grad_out"),
+            self._stream()))
+        return list(losses), g
+
+    # ------------------------------------------------------------------ launch accounting
+    def profile_reset(self, timing: bool = False):
+        self._check(self.lib.dppo_profile_reset(int(timing)))
+
+    def profile_read(self):
+        """{family: (launches, total_ms)} since the last reset."""
+        n = len(L.PROFILE_KINDS)
+        cnt = (C.c_int64 * n)(); ms = (C.c_double * n)()
+        k = self.lib.dppo_profile_read(cnt, ms, n)
+        if k < 0:
+            self._check(k)
+        return {name: (int(cnt[i]), float(ms[i])) for i, name in enumerate(L.PROFILE_KINDS)}
+
+    # ------------------------------------------------------------------ unit-test hook
+    def dbg_gemm(self, mode, A, B, M, N, K, bias=None, mask=None, relu=False, want_bias_out=False):
+        Cm = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        bo = torch.empty(N, dtype=torch.float32, device=self.device) if want_bias_out else None
+        self._check(self.lib.dppo_dbg_gemm(self.ctx, mode, M, N, K, self._dev(A, None, "A"), self._dev(B, None, "B"),
+                                           Cm.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                           mask.data_ptr() if mask is not None else None, int(relu),
+                                           bo.data_ptr() if bo is not None else None, self._stream()))
+        return (Cm, bo) if want_bias_out else Cm

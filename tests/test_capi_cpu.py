@@ -1,0 +1,108 @@
+"""No-GPU checks of the boundary: the C-ABI library loads, exports every symbol that
+include/dppo_b200.h declares, and its host-only entry points (layout / workspace sizing /
+argument validation) agree with the oracle's layout.  No compute call is made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import dppo_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dppo_b200 import build
+    build.build()
+    from dppo_b200 import _lib
+    return _lib.load_library()
+
+
+def _cfg(obs, hidden, act, max_rows=1024):
+    from dppo_b200._lib import DppoConfig
+    c = DppoConfig()
+    c.obs_dim, c.act_dim, c.n_hidden, c.max_rows = obs, act, len(hidden), max_rows
+    for i, h in enumerate(hidden):
+        c.hidden[i] = h
+    c.entcoeff, c.vcoeff, c.clip_param = 0.01, 0.5, 0.2
+    return c
+
+
+def test_header_symbols_all_exported(lib):
+    from dppo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dppo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dppo_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (dppo_[a-z_0-9]+)", nm))
+    assert declared <= exported, f"declared but not exported: {declared - exported}"
+    assert declared == set(_lib.EXPORTED), "ctypes prototypes out of sync with the header"
+    assert lib.dppo_version() >= 100
+
+
+@pytest.mark.parametrize("obs,hidden,act,n", [(3, (16,), 1, 115), (17, (256, 256), 6, 73741),
+                                               (376, (256, 256), 17, 171299), (376, (1024,) * 4, 17, 3570723),
+                                               (5, (), 2, 30)])
+def test_param_layout_matches_oracle(lib, obs, hidden, act, n):
+    from dppo_b200 import ParamLayout
+    c = _cfg(obs, hidden, act)
+    assert lib.dppo_param_count(C.byref(c)) == n
+    assert lib.dppo_grad_buffer_len(C.byref(c)) == n + 8
+    lay = O.make_layout(obs, hidden, act)
+    offs = (C.c_int64 * 32)()
+    k = lib.dppo_param_offsets(C.byref(c), offs, 32)
+    assert k == 2 * (len(hidden) + 2)
+    assert list(offs[:k]) == [e[2] for e in lay.entries]
+    pl = ParamLayout(obs, hidden, act)
+    assert pl.n_params == n and pl.offsets() == list(offs[:k])
+    assert [e.shape for e in pl.entries] == [e[1] for e in lay.entries]
+
+
+def test_workspace_and_validation(lib):
+    from dppo_b200._lib import last_error
+    c = _cfg(376, (256, 256), 17, max_rows=131072)
+    nbytes = lib.dppo_workspace_bytes(C.byref(c))
+    # at least: 2 pi activations + 2 scratch [B,256] + 3 head tiles [B,35]
+    assert nbytes > 131072 * 4 * (4 * 256 + 3 * 35)
+    assert nbytes < 4 << 30
+    bad = _cfg(0, (16,), 1)
+    assert lib.dppo_param_count(C.byref(bad)) == -1 and "obs_dim" in last_error(lib)
+    bad = _cfg(3, (16,) * 8, 1)
+    bad.n_hidden = 9
+    assert lib.dppo_param_count(C.byref(bad)) == -1 and "n_hidden" in last_error(lib)
+    # no device here: create must fail loudly, not fall back
+    ctx = C.c_void_p()
+    import torch
+    if not torch.cuda.is_available():
+        rc = lib.dppo_create(C.byref(c), None, 0, C.byref(ctx))
+        assert rc != 0 and ctx.value is None and last_error(lib)
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    from dppo_b200 import DppoEngine
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DppoEngine(3, 1, (16,), 800)
+
+
+def test_missing_library_is_loud(tmp_path):
+    from dppo_b200 import _lib
+    with pytest.raises(_lib.LibraryMissing):
+        _lib.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under tensorflow-dppo_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "tensorflow-dppo_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in txt.replace("# oracle-free", ""), f"{fn} mentions the oracle"

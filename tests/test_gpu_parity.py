@@ -1,0 +1,371 @@
+"""GPU parity tests: every kernel of the update path, called through the C ABI, against the
+oracle (and the committed reference-generated goldens).  fp32 tolerance from BASELINE.json
+north_star: 1e-5 (relative to the tensor's max magnitude; stated per assert)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dppo_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _engine(obs, hidden, act, max_rows, **kw):
+    from dppo_b200 import DppoEngine
+    return DppoEngine(obs, act, hidden, max_rows, **kw)
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).cuda()
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+
+def per_tensor_rel_err(got, ref, lay):
+    worst = {}
+    for name, shape, off in lay.entries:
+        n = int(np.prod(shape))
+        worst[name] = rel_err(got[off:off + n], ref[off:off + n])
+    return worst
+
+
+# ------------------------------------------------------------------------------- GAE
+def test_gae_matches_reference_goldens(golden_dir):
+    """Worker.py:82-92 executed verbatim (tests/golden/gae_ref.npz) vs dppo_gae, one rollout per call."""
+    g = np.load(os.path.join(golden_dir, "gae_ref.npz"))
+    eng = _engine(3, (16,), 1, 4096)
+    for i in range(int(g["n_cases"])):
+        r = g[f"c{i}_r"].astype(np.float32); pv = g[f"c{i}_predv"]; d = g[f"c{i}_done"]
+        if not np.array_equal(r.astype(np.float64), g[f"c{i}_r"]):
+            continue
+        T = len(r)
+        adv, ret = eng.gae(dev(r[:, None]), dev(pv[:, None]), dev(d[:, None]), 0.99, 0.95)
+        adv = adv.cpu().numpy()[:, 0]; ret = ret.cpu().numpy()[:, 0]
+        ref_adv = g[f"c{i}_adv"]
+        np.testing.assert_allclose(ret, g[f"c{i}_etr"].astype(np.float32), rtol=0, atol=1e-6, err_msg=f"case {i}")
+        ok = np.isfinite(ref_adv)
+        if ok.all():
+            np.testing.assert_allclose(adv, ref_adv, rtol=2e-6, atol=2e-6, err_msg=f"case {i} T={T}")
+        else:           # degenerate std == 0 cases: the reference yields nan/inf, so must we
+            assert not np.isfinite(adv[~ok]).any()
+
+
+@pytest.mark.parametrize("T,N", [(200, 4), (2048, 64), (2048, 32), (1, 3), (17, 9), (1000, 13), (4100, 8)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gae_batch_vs_oracle(T, N, mode):
+    rng = np.random.default_rng(T * 1000 + N)
+    rew = rng.standard_normal((T, N)).astype(np.float32)
+    pv = rng.standard_normal((T, N)).astype(np.float32)
+    done = (rng.random((T, N)) < 0.02).astype(np.float32)
+    lv = rng.standard_normal(N).astype(np.float32); ld = (rng.random(N) < 0.3).astype(np.float32)
+    eng = _engine(3, (16,), 1, max(T * N, 128))
+    norm = T > 1
+    adv, ret = eng.gae(dev(rew), dev(pv), dev(done), 0.99, 0.95, mode=mode, normalize=norm,
+                       last_v=dev(lv), last_done=dev(ld))
+    with np.errstate(all="ignore"):
+        a_ref, r_ref = O.gae_batch(rew, pv, done, 0.99, 0.95, mode, lv, ld, normalize=norm)
+    np.testing.assert_allclose(ret.cpu().numpy(), r_ref, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(adv.cpu().numpy(), a_ref, rtol=3e-6, atol=3e-6)
+    # raw (un-normalised) advantages are bit-exact fp32 roundings of the fp64 scan
+    adv_raw, _ = eng.gae(dev(rew), dev(pv), dev(done), 0.99, 0.95, mode=mode, normalize=False,
+                         last_v=dev(lv), last_done=dev(ld))
+    a_raw_ref, _ = O.gae_batch(rew, pv, done, 0.99, 0.95, mode, lv, ld, normalize=False)
+    assert np.mean(adv_raw.cpu().numpy() != a_raw_ref) < 1e-3          # fma re-association: rare 1-ulp flips
+    np.testing.assert_allclose(adv_raw.cpu().numpy(), a_raw_ref, rtol=2e-7, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------- GEMM building blocks
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (1000, 256, 376), (777, 35, 256), (130, 3, 16), (64, 16, 3),
+                                   (4096, 256, 256), (129, 257, 33)])
+def test_gemm_modes(M, N, K):
+    eng = _engine(376, (256, 256), 17, 4096)
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((K, N)); bias = rng.standard_normal(N)
+    ref = np.maximum(A.astype(np.float32).astype(np.float64) @ B.astype(np.float32).astype(np.float64)
+                     + bias.astype(np.float32), 0)
+    got = eng.dbg_gemm(0, dev(A), dev(B), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(got, ref) < 2e-6, "NN"
+    # NT with mask:  C = (A . Bt^T) * [mask > 0]
+    Bt = rng.standard_normal((N, K)); mask = rng.standard_normal((M, N))
+    ref = (A.astype(np.float32).astype(np.float64) @ Bt.astype(np.float32).astype(np.float64).T) * (mask.astype(np.float32) > 0)
+    got = eng.dbg_gemm(1, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    assert rel_err(got, ref) < 2e-6, "NT"
+    # TN split-K:  C[M2,N] = X[Kr,M2]^T . G[Kr,N],  bias_out = colsum(G); needs M2*N+N <= n_params
+    M2 = min(K, 300); Kr = M
+    X = rng.standard_normal((Kr, M2)); G = rng.standard_normal((Kr, N))
+    X64 = X.astype(np.float32).astype(np.float64); G64 = G.astype(np.float32).astype(np.float64)
+    got, bo = eng.dbg_gemm(2, dev(X), dev(G), M2, N, Kr, want_bias_out=True)
+    assert rel_err(got.cpu().numpy(), X64.T @ G64) < 2e-6, "TN"
+    assert rel_err(bo.cpu().numpy(), G64.sum(0)) < 2e-6, "TN bias"
+
+
+# ------------------------------------------------------------------------------- forward
+def test_forward_matches_reference_model_fc_golden(golden_dir):
+    """Model().FC executed from the reference source (tests/golden/model_fc_ref.npz)."""
+    g = np.load(os.path.join(golden_dir, "model_fc_ref.npz"))
+    for tag, obs_dim, A in (("pend", 3, 1), ("cheetah", 17, 6)):
+        s = g[f"{tag}_s"].astype(np.float32)
+        eng = _engine(obs_dim, (16,), A, 256)
+        v, pd = eng.forward(dev(g[f"{tag}_theta"]), dev(s))
+        lay = O.make_layout(obs_dim, (16,), A)
+        v_ref, flat_ref, _ = O.mlp_forward(g[f"{tag}_theta"].astype(np.float32), s, lay)
+        np.testing.assert_allclose(v.cpu().numpy(), v_ref, rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(pd.cpu().numpy(), flat_ref, rtol=1e-5, atol=1e-8)
+        # and against the reference's own numbers (inputs there were fp64: looser)
+        np.testing.assert_allclose(v.cpu().numpy(), g[f"{tag}_predv"][:, 0, 0], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("obs,hidden,A,B", [(3, (16,), 1, 800), (17, (256, 256), 6, 4096), (376, (256, 256), 17, 2048),
+                                            (5, (), 2, 300), (33, (64, 48, 40, 24), 4, 1000),
+                                            (376, (1024, 1024, 1024, 1024), 17, 512)])
+def test_forward_vs_oracle(obs, hidden, A, B):
+    lay = O.make_layout(obs, hidden, A)
+    th, _ = O.make_params_pair(lay)
+    x = np.random.default_rng(0).standard_normal((B, obs)).astype(np.float32)
+    eng = _engine(obs, hidden, A, B)
+    v, pd = eng.forward(dev(th), dev(x))
+    v_ref, flat_ref, _ = O.mlp_forward(th, x, lay)
+    assert rel_err(v.cpu().numpy(), v_ref) < TOL
+    assert rel_err(pd.cpu().numpy(), flat_ref) < TOL
+
+
+# ------------------------------------------------------------------------------- loss on reference goldens
+def _identity_head_params(P, second_half):
+    """L=0 net over obs = [head_pi | head_old] (2P wide) whose heads copy one half of the input."""
+    A = (P - 1) // 2
+    lay = O.make_layout(2 * P, (), A)
+    th = np.zeros(lay.n_params, np.float32)
+    p = O.unflatten(th, lay)
+    base = P if second_half else 0
+    p["Wv"][base + 0, 0] = 1.0
+    for j in range(2 * A):
+        p["Wp"][base + 1 + j, j] = 1.0
+    return lay, th
+
+
+def test_loss_matches_reference_ppo_lines_golden(golden_dir):
+    """PPO.py:29-40 executed from the reference source (tests/golden/ppo_loss_ref.npz): feed its head
+    values through identity heads so the device loss kernel sees exactly those numbers."""
+    g = np.load(os.path.join(golden_dir, "ppo_loss_ref.npz"))
+    for tag in "abc":
+        flat, flat_old = g[f"{tag}_flat"], g[f"{tag}_flat_old"]
+        B, A2 = flat.shape
+        P = 1 + A2
+        obs = np.concatenate([g[f"{tag}_v"][:, None], flat, g[f"{tag}_v_old"][:, None], flat_old], 1).astype(np.float32)
+        lay, th_pi = _identity_head_params(P, False)
+        _, th_old = _identity_head_params(P, True)
+        eng = _engine(2 * P, (), A2 // 2, B)
+        losses, _ = eng.loss_grad(dev(th_pi), dev(th_old), dev(obs), dev(g[f"{tag}_act"]), dev(g[f"{tag}_adv"]),
+                                  dev(g[f"{tag}_etr"]), float(g[f"{tag}_l_mul"]))
+        got = losses.cpu().numpy()
+        np.testing.assert_allclose(got[:4], g[f"{tag}_losses"], rtol=2e-5, atol=2e-6)   # inputs rounded to fp32
+
+
+def test_diag_gaussian_kl_entropy_golden(golden_dir):
+    """DiagGaussianPd.kl / .entropy from the reference class (tests/golden/distgauss_ref.npz)."""
+    g = np.load(os.path.join(golden_dir, "distgauss_ref.npz"))
+    for A in (1, 6, 17):
+        fp, fq, xs = g[f"A{A}_p"], g[f"A{A}_q"], g[f"A{A}_x"]
+        B = fp.shape[0]; P = 1 + 2 * A
+        z = np.zeros((B, 1))
+        obs = np.concatenate([z, fq, z, fp], 1).astype(np.float32)      # pi = q, old = p  ->  KL(p || q)
+        lay, th_pi = _identity_head_params(P, False)
+        _, th_old = _identity_head_params(P, True)
+        eng = _engine(2 * P, (), A, B)
+        losses, _ = eng.loss_grad(dev(th_pi), dev(th_old), dev(obs), dev(xs), dev(np.zeros(B)), dev(np.zeros(B)), 1.0)
+        got = losses.cpu().numpy()
+        assert abs(got[4] - g[f"A{A}_kl"].mean()) < 2e-6 * max(1.0, abs(g[f"A{A}_kl"].mean()))
+        ent_q = O.dg_entropy(fq.astype(np.float32).astype(np.float64)).mean()
+        assert abs(got[2] - (-0.01 * ent_q)) < 1e-6
+
+
+# ------------------------------------------------------------------------------- loss + gradient
+CASES = [
+    ("pendulum-cfg1", 200, 4, 3, (16,), 1),          # BASELINE configs[0]
+    ("cheetah-slice", 256, 32, 17, (256, 256), 6),
+    ("humanoid-slice", 128, 64, 376, (256, 256), 17),
+    ("odd-shapes", 37, 5, 11, (24, 40, 8), 3),
+    ("no-hidden", 64, 4, 5, (), 2),
+    ("deep-1024-slice", 16, 64, 376, (1024, 1024, 1024, 1024), 17),
+]
+
+
+@pytest.mark.parametrize("name,T,N,obs,hidden,A", CASES)
+def test_loss_grad_vs_oracle(name, T, N, obs, hidden, A):
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]; B = T * N
+    eng = _engine(obs, hidden, A, B)
+    losses, g = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(c["buf"]["obs"]), dev(c["act"]),
+                              dev(c["adv"]), dev(c["ret"]), c["l_mul"])
+    l_ref, g_ref, aux = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"], c["act"], c["adv"], c["ret"],
+                                        c["l_mul"], lay)
+    got_l = losses.cpu().numpy(); got_g = g.cpu().numpy()[:lay.n_params]
+    np.testing.assert_allclose(got_l[:4], l_ref, rtol=TOL, atol=TOL)
+    assert abs(got_l[4] - aux["mean_kl"]) < 1e-5 * max(1, aux["mean_kl"])
+    assert abs(got_l[5] - aux["clip_frac"]) < 1e-9 + 1.0 / B and abs(got_l[6] - aux["vclip_frac"]) < 1e-9 + 1.0 / B
+    assert got_l[7] == B
+    errs = per_tensor_rel_err(got_g, g_ref, lay)
+    assert max(errs.values()) < TOL, errs
+    # branch coverage of the case itself
+    assert aux["clip_frac"] > 0.01 and all(0.1 < float((h > 0).mean()) < 0.9 for h in aux["hs"])
+
+
+def test_loss_grad_reference_regime_pi_equals_old():
+    """The reference's own regime (Appendix A-D9): pi == oldpi, normc(0.01) init -> ratio == 1, clips idle."""
+    lay = O.make_layout(17, (256, 256), 6)
+    th = O.init_params(lay, np.random.default_rng(3))
+    buf = O.make_buffer(64, 16, 17, 6, 5)
+    adv, ret = O.gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], 0.99, 0.95)
+    eng = _engine(17, (256, 256), 6, 1024)
+    losses, g = eng.loss_grad(dev(th), dev(th), dev(buf["obs"]), dev(buf["act"]), dev(adv.reshape(-1)),
+                              dev(ret.reshape(-1)), 1.0)
+    l_ref, g_ref, aux = O.ppo_loss_grad(th, th, buf["obs"], buf["act"], adv.reshape(-1), ret.reshape(-1), 1.0, lay)
+    got = losses.cpu().numpy()
+    np.testing.assert_allclose(got[:4], l_ref, rtol=TOL, atol=TOL)
+    assert got[5] == 0 and got[6] == 0 and abs(got[4]) < 1e-7
+    assert max(per_tensor_rel_err(g.cpu().numpy()[:lay.n_params], g_ref, lay).values()) < TOL
+
+
+def test_loss_grad_properties_full_size_humanoid():
+    """BASELINE configs[2] at full size (T=2048, N=64, obs 376, act 17, 2x256) through
+    size-independent properties: (i) the gradient of the whole batch equals the mean of the gradients
+    of its two halves (tower mean, PPO.py:55-65), (ii) deterministic re-execution is bit-identical,
+    (iii) a slice of rows agrees with the fp64 oracle."""
+    T, N, obs, hidden, A = 2048, 64, 376, (256, 256), 17
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    B = T * N
+    eng = _engine(obs, hidden, A, B)
+    d_rew, d_pv, d_done = dev(buf["rew"]), dev(buf["predv"]), dev(buf["done"])
+    adv, ret = eng.gae(d_rew, d_pv, d_done, 0.99, 0.95)
+    d_obs, d_act = dev(buf["obs"]), dev(buf["act"])
+    d_pi, d_old = dev(th_pi), dev(th_old)
+    adv = adv.reshape(-1); ret = ret.reshape(-1)
+    _, g_all = eng.loss_grad(d_pi, d_old, d_obs, d_act, adv, ret, 0.7)
+    g_all = g_all.clone()
+    _, g_again = eng.loss_grad(d_pi, d_old, d_obs, d_act, adv, ret, 0.7)
+    assert torch.equal(g_all, g_again), "update is not deterministic"
+    h = B // 2
+    _, g0 = eng.loss_grad(d_pi, d_old, d_obs[:h], d_act[:h], adv[:h], ret[:h], 0.7); g0 = g0.clone()
+    _, g1 = eng.loss_grad(d_pi, d_old, d_obs[h:], d_act[h:], adv[h:], ret[h:], 0.7)
+    mean = 0.5 * (g0.double() + g1.double()).cpu().numpy()
+    n = lay.n_params
+    assert max(per_tensor_rel_err(g_all.cpu().numpy()[:n], mean[:n], lay).values()) < TOL
+    np.testing.assert_allclose(g_all.cpu().numpy()[n:n + 7], mean[n:n + 7], rtol=TOL, atol=TOL)
+    # (iii) 8192-row slice against the oracle, with branch-ambiguous rows edited out
+    s = slice(0, 8192)
+    a_np = adv[s].cpu().numpy(); r_np = ret[s].cpu().numpy()
+    act_s, ret_s, _ = O.sanitize_rows(th_pi, th_old, buf["obs"][s], buf["act"][s], a_np, r_np, 0.7, lay)
+    losses, g_s = eng.loss_grad(d_pi, d_old, d_obs[s], dev(act_s), adv[s].contiguous(), dev(ret_s), 0.7)
+    l_ref, g_ref, _ = O.ppo_loss_grad(th_pi, th_old, buf["obs"][s], act_s, a_np, ret_s, 0.7, lay)
+    np.testing.assert_allclose(losses.cpu().numpy()[:4], l_ref, rtol=TOL, atol=TOL)
+    assert max(per_tensor_rel_err(g_s.cpu().numpy()[:n], g_ref, lay).values()) < TOL
+
+
+def test_full_size_cheetah_vs_oracle():
+    """BASELINE configs[1] at full size: T=2048, N=32, obs 17, act 6, 2x256, B=65536 rows."""
+    c = O.make_case(2048, 32, 17, (256, 256), 6)
+    lay = c["lay"]
+    eng = _engine(17, (256, 256), 6, 65536)
+    adv_d, ret_d = eng.gae(dev(c["buf"]["rew"]), dev(c["buf"]["predv"]), dev(c["buf"]["done"]), 0.99, 0.95)
+    np.testing.assert_allclose(adv_d.cpu().numpy().reshape(-1), c["adv"], rtol=3e-6, atol=3e-6)
+    losses, g = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(c["buf"]["obs"]), dev(c["act"]),
+                              dev(c["adv"]), dev(c["ret"]), c["l_mul"])
+    l_ref, g_ref, _ = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"], c["act"], c["adv"], c["ret"],
+                                      c["l_mul"], lay)
+    np.testing.assert_allclose(losses.cpu().numpy()[:4], l_ref, rtol=TOL, atol=TOL)
+    assert max(per_tensor_rel_err(g.cpu().numpy()[:lay.n_params], g_ref, lay).values()) < TOL
+
+
+# ------------------------------------------------------------------------------- Adam / sync / allreduce / act
+def test_adam_sync_allreduce_world1():
+    lay = O.make_layout(17, (256, 256), 6)
+    n = lay.n_params
+    rng = np.random.default_rng(0)
+    th = rng.standard_normal(n).astype(np.float32); g = (rng.standard_normal(n) * 1e-2).astype(np.float32)
+    eng = _engine(17, (256, 256), 6, 256)
+    p, m, v = dev(th), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    th_ref, m_ref, v_ref = th.astype(np.float64), np.zeros(n), np.zeros(n)
+    for step in (1, 2, 3):
+        eng.adam_apply(p, dev(g), m, v, step, 2e-5 * 0.7)
+        th_ref, m_ref, v_ref = O.adam_tf(th_ref, g, m_ref, v_ref, step, 2e-5 * 0.7)
+    upd = p.cpu().numpy().astype(np.float64) - th
+    assert rel_err(upd, th_ref - th) < 1e-3          # update itself, fp32 params: 1e-7 absolute on O(1) values
+    np.testing.assert_allclose(p.cpu().numpy(), th_ref, rtol=0, atol=2e-7)
+    np.testing.assert_allclose(m.cpu().numpy(), m_ref, rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(v.cpu().numpy(), v_ref, rtol=1e-5, atol=1e-15)
+    old = torch.zeros(n, device="cuda")
+    eng.sync_old(p, old)
+    assert torch.equal(old, p)
+    # world = 1 communicator: average of one tower is the tower
+    eng.comm_init(0, 1, eng.unique_id())
+    buf = dev(g).clone()
+    eng.allreduce_avg(buf)
+    torch.cuda.synchronize()
+    assert torch.equal(buf, dev(g))
+
+
+def test_act_sampling_moments_and_monte_carlo_identity():
+    """DiagGaussianPd.sample (distributions.py:204-205) + the reference self-check identity
+    entropy == -E[logp] (distributions.py:279-283), N=100000, 3 sigma."""
+    A = 4; P = 1 + 2 * A
+    pdparam = np.array([-.2, .3, .4, -.5, .1, -.5, .1, 0.8])
+    Nn = 100000
+    lay, th = _identity_head_params(P, False)
+    obs = np.zeros((Nn, 2 * P), np.float32); obs[:, 1:P] = pdparam
+    eng = _engine(2 * P, (), A, Nn)
+    a, v = eng.act(dev(th), dev(obs), seed=1234, offset=0)
+    a2, _ = eng.act(dev(th), dev(obs), seed=1234, offset=0)
+    a3, _ = eng.act(dev(th), dev(obs), seed=1234, offset=1)
+    assert torch.equal(a, a2) and not torch.equal(a, a3)
+    X = a.cpu().numpy().astype(np.float64)
+    M = np.repeat(pdparam[None], Nn, 0)
+    ll = O.dg_logp(M, X)
+    assert abs(O.dg_entropy(M).mean() + ll.mean()) < 3 * ll.std() / math.sqrt(Nn)
+    np.testing.assert_allclose(X.mean(0), pdparam[:A], atol=4 * np.exp(pdparam[A:]).max() / math.sqrt(Nn))
+    np.testing.assert_allclose(X.std(0), np.exp(pdparam[A:]), rtol=0.02)
+    assert float(v.abs().max()) == 0.0
+
+
+def test_update_host_equals_device_path():
+    """dppo_update_host (pinned host rollout, chunked H2D overlapped with compute) must produce
+    the same losses/gradient as gae + loss_grad on device-resident buffers."""
+    T, N, obs, hidden, A = 512, 64, 376, (256, 256), 17
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    eng = _engine(obs, hidden, A, T * N)
+    d_pi, d_old = dev(th_pi), dev(th_old)
+    adv, ret = eng.gae(dev(buf["rew"]), dev(buf["predv"]), dev(buf["done"]), 0.99, 0.95)
+    l_dev, g_dev = eng.loss_grad(d_pi, d_old, dev(buf["obs"]), dev(buf["act"]), adv.reshape(-1), ret.reshape(-1), 0.7)
+    g_dev = g_dev.clone()
+    pin = {k: torch.from_numpy(v).pin_memory() for k, v in buf.items()}
+    l_h, g_h = eng.update_host(d_pi, d_old, pin["obs"], pin["act"], pin["rew"], pin["predv"], pin["done"],
+                               0.99, 0.95, 0.7)
+    n = lay.n_params
+    assert max(per_tensor_rel_err(g_h.cpu().numpy()[:n], g_dev.cpu().numpy()[:n], lay).values()) < 2e-6
+    np.testing.assert_allclose(np.array(l_h), g_dev.cpu().numpy()[n:], rtol=1e-6, atol=1e-7)
+
+
+def test_errors_are_loud():
+    eng = _engine(3, (16,), 1, 128)
+    lay = O.make_layout(3, (16,), 1)
+    th = dev(np.zeros(lay.n_params))
+    with pytest.raises(RuntimeError, match="max_rows"):
+        eng.forward(th, dev(np.zeros((256, 3))))
+    with pytest.raises((TypeError, ValueError)):
+        eng.forward(th.cpu(), dev(np.zeros((8, 3))))
+    with pytest.raises(RuntimeError, match="communicator"):
+        eng.allreduce_avg(th)
+    with pytest.raises(RuntimeError, match="STANDARD"):
+        z = dev(np.zeros((4, 2)))
+        eng.gae(z, z, z, 0.99, 0.95, mode=1)
