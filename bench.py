@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec through one DPPO update on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload humanoid-cfg3] [--impl reference]
+
+A "step" = one update over one frozen synthetic rollout buffer per rank:
+    GAE scan -> pi & oldpi forward -> clipped PPO loss -> backward -> gradient allreduce (N>1)
+    -> Adam apply                                   (reference: Worker.py:82-92, PPO.py:21-65)
+`value`  : all ranks' env-steps / max-over-ranks device time, inputs resident in HBM.
+`e2e`    : the same update through dppo_update_host with PINNED HOST buffers -- the rollout's
+           H2D copies (chunked, overlapped with compute) and the D2H of the losses are inside the
+           timed region.
+`roofline`: dominant kernel family, timed live with CUDA events around every launch of the family
+           (library launch accounting, dppo_profile_*), algorithmic FLOPs / that time.
+`cpu_baseline` / `--impl reference`: the reference-equivalent CPU restatement (oracle/, PyTorch-CPU
+           fp32, tower-structured like the reference graph; TensorFlow itself is not installable here).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tensorflow-dppo_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "env_steps_per_sec_through_ppo_update"
+UNIT = "env-steps/s"
+
+
+def flops_per_step(obs, hidden, act):
+    """F = 2f + f_b, f = 2*sum(in*out) (fused heads, pi AND oldpi), f_b = 2f - 2*obs*H1."""
+    P = 1 + 2 * act
+    dims = [obs] + list(hidden)
+    f = 2 * (sum(dims[i] * dims[i + 1] for i in range(len(hidden))) + dims[-1] * P)
+    fb = 2 * f - 2 * obs * (hidden[0] if hidden else P)
+    return 2 * f + fb
+
+
+def bytes_per_step(obs, act):
+    """every input read once, outputs written once, GAE outputs re-read: 4*obs + 4*A + 28."""
+    return 4 * obs + 4 * act + 28
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained",
+                    d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons while the GPU is under load."""
+    Q = ("clocks.sm,clocks.max.sm,utilization.gpu,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                util = float(f[2])
+                if util >= 50:
+                    sm.append(float(f[0])); smax.append(float(f[1]))
+                    for n, v in zip(names, f[4:8]):
+                        if v == "Active":
+                            reasons.add(n)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples_under_load": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, steps, warmup, sample_rows=131072):
+    """The reference-equivalent CPU path on a bounded sample of the workload (first sample_T time
+    steps of every rollout).  Returns (env-steps/s, cores, description, ms_per_step)."""
+    import numpy as np
+    import torch
+    from dppo_b200.synthetic import WORKLOADS
+    from oracle import dppo_oracle as O
+    T, N, obs, act, hidden = WORKLOADS[workload]
+    Ts = max(1, min(T, sample_rows // N))
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    lay = O.make_layout(obs, hidden, act)
+    buf = O.make_buffer(Ts, N, obs, act, 1234)
+    th_pi, th_old = O.make_params_pair(lay)
+    hp = O.HParams()
+    towers = max(1, min(N, 8))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        losses, g = O.cpu_update_torch(th_pi, th_old, buf, Ts, N, lay, hp, 0.7, towers)
+        m = np.zeros(lay.n_params); v = np.zeros(lay.n_params)
+        O.adam_tf(th_pi, g, m, v, 1, hp.LEARNING_RATE * 0.7, dtype=np.float32)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    rows = Ts * N
+    desc = (f"first {Ts} of {T} time steps x {N} rollouts = {rows} rows/step of {workload}; PyTorch-CPU fp32 "
+            f"restatement of the reference graph ({towers} towers: pi+oldpi fwd, loss, autodiff bwd, tower mean, "
+            f"TF-Adam; vectorised GAE), {cores} threads")
+    return rows * len(times) / total, cores, desc, 1e3 * total / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from dppo_b200.synthetic import WORKLOADS
+    T, N, obs, act, hidden = WORKLOADS[args.workload]
+    steps = min(args.steps, 10)
+    val, cores, desc, ms = cpu_reference_run(args.workload, steps, min(args.warmup, 2))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
+                   "hidden": list(hidden)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from dppo_b200 import DppoEngine
+    from dppo_b200.dist import init_engine_comm, max_over_ranks
+    from dppo_b200.synthetic import WORKLOADS, rollout_buffer, params_pair
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    T, N, obs, act, hidden = WORKLOADS[args.workload]
+    B = T * N
+    gamma, lam, l_mul, lr = 0.99, 0.95, 0.7, 2e-5
+    eng = DppoEngine(obs, act, hidden, B, device=local)
+    if world > 1:
+        init_engine_comm(eng, rank, world)
+    host = rollout_buffer(T, N, obs, act, seed=1234 + rank, pin=True)      # weak scaling: own buffer per rank
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    p_pi_h, p_old_h = params_pair(eng.layout)
+    p_pi, p_old = p_pi_h.to(dev), p_old_h.to(dev)
+    p_init = p_pi.clone()
+    m = torch.zeros(eng.n_params, device=dev); v = torch.zeros(eng.n_params, device=dev)
+    grad = eng.new_grad_buffer()
+    adv = torch.empty(T, N, device=dev); ret = torch.empty(T, N, device=dev)
+    state = {"t": 0}
+
+    def step_device():
+        eng.gae(d["rew"], d["predv"], d["done"], gamma, lam, adv_out=adv, ret_out=ret)
+        eng.loss_grad(p_pi, p_old, d["obs"], d["act"], adv.view(-1), ret.view(-1), l_mul, grad_out=grad)
+        if world > 1:
+            eng.allreduce_avg(grad)
+        state["t"] += 1
+        eng.adam_apply(p_pi, grad, m, v, state["t"], lr * l_mul)
+
+    def step_host():
+        losses, _ = eng.update_host(p_pi, p_old, host["obs"], host["act"], host["rew"], host["predv"], host["done"],
+                                    gamma, lam, l_mul, grad_out=grad)          # allreduce inside when world > 1
+        state["t"] += 1
+        eng.adam_apply(p_pi, grad, m, v, state["t"], lr * l_mul)
+        return losses
+
+    def reset_state():
+        p_pi.copy_(p_init); m.zero_(); v.zero_(); state["t"] = 0
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms, device=dev)
+
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    for _ in range(W):
+        step_device()
+    if rank == 0:
+        sampler.start()
+    eng.profile_reset(False)
+    ms_total = timed(step_device, K)
+    launches = sum(c for c, _ in eng.profile_read().values())
+    value = world * B * K / (ms_total * 1e-3)
+
+    # --- roofline pass: the same K steps with CUDA events around every library launch -----------
+    reset_state()
+    eng.profile_reset(True)
+    ms_prof = timed(step_device, K)
+    prof = eng.profile_read()
+    eng.profile_reset(False)
+    fam_ms = {k: ms for k, (c, ms) in prof.items() if c}
+    gemm_ms = sum(fam_ms.get(k, 0.0) for k in ("gemm_nn", "gemm_nt", "gemm_tn", "tc_gemm"))
+    gemm_launches = sum(prof[k][0] for k in ("gemm_nn", "gemm_nt", "gemm_tn", "tc_gemm"))
+    peaks = load_peaks()
+    F = flops_per_step(obs, hidden, act) * B
+    achieved_tf = F * K / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    alg_bytes = bytes_per_step(obs, act) * B
+    hbm_gbs = alg_bytes * K / (ms_total * 1e-3) / 1e9
+
+    # --- e2e pass: pinned host buffers through dppo_update_host ---------------------------------
+    reset_state()
+    for _ in range(2):
+        step_host()
+    ms_e2e = timed(step_host, K)
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, cores, desc, _ = cpu_reference_run(args.workload, steps=3, warmup=1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
+                       "hidden": list(hidden), "rows_per_gpu": B, "parallelism": f"dp{world}",
+                       "gemm": "fp32 SIMT FFMA (1e-5 parity path)",
+                       "l2": f"inputs larger than L2: obs buffer {B * obs * 4 / 1e6:.0f} MB + activations "
+                             f"{B * sum(hidden) * 4 * 2 / 1e6:.0f} MB stream through HBM every step (L2 126 MB)",
+                       "step": "gae + pi/oldpi fwd + loss + bwd + allreduce(N>1) + adam"},
+            "roofline": {
+                "kernel": "sgemm_kernel (fwd NN / dX NT / dW TN families)", "bound": "tensor",
+                "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                "note": "algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
+                        "this path runs the GEMMs as fp32 FFMA (fp32 FMA pipe, ~70 TFLOP/s), not on tensor cores",
+                "launches_per_step": gemm_launches / K, "ms_per_step": gemm_ms / K,
+                "share_of_step": gemm_ms / ms_prof if ms_prof else None,
+                "family_ms_per_step": {k: v_ / K for k, v_ in fam_ms.items()},
+                "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
+                        "note": "algorithmic bytes of the whole update (1600 B/env-step at cfg3) over the step time"},
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(B * (obs + act + 3) * 4), "d2h_bytes_per_step": 32,
+                    "api": "DppoEngine.update_host -> dppo_update_host (pinned host rollout, 8-way chunked H2D "
+                           "overlapped with fwd/loss/bwd) + adam_apply"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="humanoid-cfg3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

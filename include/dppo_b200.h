@@ -124,6 +124,12 @@ int dppo_sync_old(dppo_ctx* ctx, const float* params_pi, float* params_old, void
 int dppo_act(dppo_ctx* ctx, const float* params, const float* obs, int B, uint64_t seed,
              uint64_t offset, float* action_out, float* v_out, void* stream);
 
+/* replaces the DiagGaussianPd methods as stand-alone graph ops (distributions.py:193-205) on a
+ * [B,2A] flat parameter tensor: op 0 neglogp(arg=x[B,A]) -> out[B]; 1 entropy -> out[B];
+ * 2 kl(arg=other flat[B,2A]) -> out[B]; 3 sample (Philox seed/offset) -> out[B,A]; 4 mode -> out[B,A]. */
+int dppo_diag_gaussian(dppo_ctx* ctx, int op, const float* flat, const float* arg, int B, int A,
+                       uint64_t seed, uint64_t offset, float* out, void* stream);
+
 /* the whole update from HOST buffers (what Chief._train feeds through feed_dict,
  * Chief.py:54-64): pinned host rollout -> chunked H2D overlapped with GAE + loss_grad ->
  * (allreduce if a communicator exists) -> losses back to host.  Synchronises `stream`.

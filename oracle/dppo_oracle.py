@@ -212,7 +212,7 @@ def ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret, l_mul, hp: HP
     aux = dict(
         mean_kl=float(np.mean(dg_kl(flat_old, flat))),            # distributions.py:199-201 (diagnostic)
         clip_frac=float(np.mean(surr1 > surr2)),
-        vclip_frac=float(np.mean(vf1 < vf2)),
+        vclip_frac=float(np.mean((vf1 < vf2) & ~in_clip)),   # clipped value branch selected with the clip active
         ratio=ratio,
     )
     losses = np.array([policy_loss, value_loss, entropy_loss, total])

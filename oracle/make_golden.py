@@ -84,12 +84,13 @@ def gae_cases():
                   np.array([0, 0, 1, 0, 0, 0], bool)))
     for T, p in [(200, 1 / 50), (200, 1 / 50), (200, 0.0), (200, 1 / 10), (2, 0.0), (7, 0.5),
                  (2048, 1 / 200), (2048, 1 / 200), (33, 1.0), (513, 1 / 20)]:
-        r = rng.standard_normal(T)
+        r = rng.standard_normal(T).astype(np.float32).astype(np.float64)   # fp32-representable rewards
         v = rng.standard_normal(T)
         d = rng.random(T) < p
         cases.append((r, v, d))
     # done on the very last step (bootstrap masked) and on the first step
-    r = rng.standard_normal(50); v = rng.standard_normal(50); d = np.zeros(50, bool); d[-1] = True
+    r = rng.standard_normal(50).astype(np.float32).astype(np.float64); v = rng.standard_normal(50)
+    d = np.zeros(50, bool); d[-1] = True
     cases.append((r, v, d))
     d = np.zeros(50, bool); d[0] = True
     cases.append((r.copy(), v.copy(), d))

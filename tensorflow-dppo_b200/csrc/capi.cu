@@ -421,6 +421,13 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
     return 0;
 }
 
+int dppo_diag_gaussian(dppo_ctx* c, int op, const float* flat, const float* arg, int B, int A, uint64_t seed,
+                       uint64_t offset, float* out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(B >= 0 && A >= 1, "dppo_diag_gaussian: B=%d A=%d", B, A);
+    return launch_diag_gaussian(op, flat, arg, B, A, seed, offset, out, (cudaStream_t)stream);
+}
+
 int dppo_profile_reset(int enable_timing) {
     // fold finished timings, then reset
     for (int i = 0; i < g_prof.used; ++i) cudaEventSynchronize(g_prof.ev1[i]);

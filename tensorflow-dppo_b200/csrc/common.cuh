@@ -137,6 +137,8 @@ int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_o
                        cudaStream_t st);
 int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,
                 float b1, float b2, float eps, cudaStream_t st);
+int launch_diag_gaussian(int op, const float* flat, const float* arg, int B, int A, uint64_t seed, uint64_t offset,
+                         float* out, cudaStream_t st);
 int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,
                   float* action, float* v_out, cudaStream_t st);
 

@@ -131,7 +131,7 @@ ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_
         acc[2] = (double)ent;                                            // PPO.py:29-30
         acc[3] = (double)kl;
         acc[4] = first ? 0.0 : 1.0;
-        acc[5] = vfirst ? 0.0 : 1.0;
+        acc[5] = (!vfirst && !inclip) ? 1.0 : 0.0;                       // clipped value branch selected, clip active
         acc[6] = 1.0;
 
         // d total / d [v | mean | logstd]  
@@ -354,6 +354,62 @@ __global__ void sample_kernel(const float* __restrict__ out, int rows, int A, ui
         }
         if (q == 0 && v_out) v_out[r] = o[0];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone DiagGaussianPd methods on a [B,2A] flat parameter tensor (distributions.py:193-205):
+// op 0 neglogp(x)  1 entropy  2 kl(other)  3 sample  4 mode.   One thread per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void diag_gaussian_kernel(int op, const float* __restrict__ flat, const float* __restrict__ arg,
+                                     int B, int A, uint64_t seed, uint64_t offset, float* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const float* f = flat + (size_t)r * 2 * A;
+    if (op == 0) {            // :195-198
+        const float* x = arg + (size_t)r * A;
+        float s2 = 0.f, sl = 0.f;
+        for (int k = 0; k < A; ++k) { const float z = (x[k] - f[k]) * expf(-f[A + k]); s2 += z * z; sl += f[A + k]; }
+        out[r] = 0.5f * s2 + 0.9189385332046727f * (float)A + sl;
+    } else if (op == 1) {     // :202-203
+        float sl = 0.f;
+        for (int k = 0; k < A; ++k) sl += f[A + k];
+        out[r] = sl + 1.4189385332046727f * (float)A;
+    } else if (op == 2) {     // :199-201   KL(self || other)
+        const float* q = arg + (size_t)r * 2 * A;
+        float kl = 0.f;
+        for (int k = 0; k < A; ++k) {
+            const float dm = f[k] - q[k];
+            kl += (q[A + k] - f[A + k]) + (expf(2.f * f[A + k]) + dm * dm) * 0.5f * expf(-2.f * q[A + k]) - 0.5f;
+        }
+        out[r] = kl;
+    } else if (op == 3) {     // :204-205
+        for (int q4 = 0; q4 < (A + 3) / 4; ++q4) {
+            uint32_t c[4] = {(uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)r, (uint32_t)q4};
+            philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+            const float r0 = sqrtf(-2.f * logf(u01(c[0]))), r1 = sqrtf(-2.f * logf(u01(c[2])));
+            float s0, c0, s1, c1;
+            sincosf(6.283185307179586f * u01(c[1]), &s0, &c0);
+            sincosf(6.283185307179586f * u01(c[3]), &s1, &c1);
+            const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+            for (int e = 0; e < 4; ++e) {
+                const int k = q4 * 4 + e;
+                if (k < A) out[(size_t)r * A + k] = f[k] + expf(f[A + k]) * z[e];
+            }
+        }
+    } else {                  // :193-194
+        for (int k = 0; k < A; ++k) out[(size_t)r * A + k] = f[k];
+    }
+}
+
+int launch_diag_gaussian(int op, const float* flat, const float* arg, int B, int A, uint64_t seed, uint64_t offset,
+                         float* out, cudaStream_t st) {
+    DPPO_REQUIRE(op >= 0 && op <= 4, "dppo_diag_gaussian: bad op %d", op);
+    DPPO_REQUIRE(flat && out && (arg || (op != 0 && op != 2)), "dppo_diag_gaussian: null buffer");
+    if (B == 0) return 0;
+    ProfScope ps(KK_MISC, st);
+    diag_gaussian_kernel<<<(B + 127) / 128, 128, 0, st>>>(op, flat, arg, B, A, seed, offset, out);
+    DPPO_LAUNCH_CHECK();
+    return 0;
 }
 
 int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,

@@ -131,10 +131,10 @@ __global__ void __launch_bounds__(kThreads, 2) sgemm_kernel(const GemmArgs g) {
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    float bsum[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) bsum[j] = 0.f;
-    const bool do_bias = (EPI == EPI_TN) && (g.bias_out != nullptr) && (blockIdx.y == 0) && (ty == 0);
+    // colsum(dY): thread `tid` of the first row-tile's CTAs owns column n0+tid of the B tile and adds it
+    // up straight from shared memory, Kahan-compensated (the sum cancels heavily over rows)
+    float csum = 0.f, ccomp = 0.f;
+    const bool do_bias = (EPI == EPI_TN) && (g.bias_out != nullptr) && (blockIdx.y == 0) && (tid < BN);
 
     float4 ra[BM / 64], rb[BN / 64];
     const int ntiles = (k_end - k_begin + BK - 1) / BK;
@@ -177,10 +177,15 @@ __global__ void __launch_bounds__(kThreads, 2) sgemm_kernel(const GemmArgs g) {
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-            if (EPI == EPI_TN) {
-                if (do_bias) {
+        }
+        if (EPI == EPI_TN) {
+            if (do_bias) {
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) bsum[j] += b[j];
+                for (int k = 0; k < BK; ++k) {
+                    const float y = Bs[buf][k][tid] - ccomp;
+                    const float t2 = csum + y;
+                    ccomp = (t2 - csum) - y;
+                    csum = t2;
                 }
             }
         }
@@ -239,11 +244,8 @@ __global__ void __launch_bounds__(kThreads, 2) sgemm_kernel(const GemmArgs g) {
     if (EPI == EPI_TN) {
         if (do_bias) {
             float* bo = g.bias_out + (size_t)slice * g.slice_stride;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int n = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
-                if (n < g.N) bo[n] = g.accumulate ? bo[n] + bsum[j] : bsum[j];
-            }
+            const int n = n0 + tid;
+            if (n < g.N) bo[n] = g.accumulate ? bo[n] + csum : csum;
         }
     }
 }

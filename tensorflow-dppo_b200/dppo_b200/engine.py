@@ -188,6 +188,20 @@ class DppoEngine:
             self._stream()))
         return list(losses), g
 
+    # ------------------------------------------------------------------ DiagGaussianPd methods
+    PD_OPS = {"neglogp": 0, "entropy": 1, "kl": 2, "sample": 3, "mode": 4}
+
+    def diag_gaussian(self, op: str, flat, arg=None, seed: int = 0, offset: int = 0):
+        """distributions.py:193-205 on a [B,2A] flat tensor; returns [B] or [B,A]."""
+        B, A2 = flat.shape
+        A = A2 // 2
+        out = torch.empty((B, A) if op in ("sample", "mode") else (B,), dtype=torch.float32, device=self.device)
+        self._check(self.lib.dppo_diag_gaussian(
+            self.ctx, self.PD_OPS[op], self._dev(flat, B * A2, "flat"),
+            self._dev(arg, None, "arg") if arg is not None else None, B, A, int(seed), int(offset),
+            out.data_ptr(), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ launch accounting
     def profile_reset(self, timing: bool = False):
         self._check(self.lib.dppo_profile_reset(int(timing)))
