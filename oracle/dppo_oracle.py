@@ -354,8 +354,11 @@ def tower_mean(grads: List[np.ndarray]) -> np.ndarray:
 def adam_tf(theta, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float64):
     """tf.train.AdamOptimizer (PPO.py:20,53), TF-1.x epsilon-hat form; t is the step AFTER increment."""
     theta = np.asarray(theta, dtype); g = np.asarray(g, dtype)
-    m = beta1 * np.asarray(m, dtype) + (1 - beta1) * g
-    v = beta2 * np.asarray(v, dtype) + (1 - beta2) * g * g
+    # TF casts beta1/beta2 to the variable dtype (fp32) before forming (1 - beta): keep that rounding
+    b1 = float(np.float32(beta1)); b2 = float(np.float32(beta2))
+    omb1 = float(np.float32(1) - np.float32(beta1)); omb2 = float(np.float32(1) - np.float32(beta2))
+    m = b1 * np.asarray(m, dtype) + omb1 * g
+    v = b2 * np.asarray(v, dtype) + omb2 * g * g
     lr_t = dtype(lr) * np.sqrt(1 - dtype(beta2) ** t) / (1 - dtype(beta1) ** t)
     theta = theta - lr_t * m / (np.sqrt(v) + eps)
     return theta, m, v
@@ -465,6 +468,30 @@ def cpu_update_torch(theta_pi, theta_old, buf, T, N, lay: Layout, hp: HParams, l
 # --------------------------------------------------------------------------
 # branch-robust synthetic buffers for parity tests
 # --------------------------------------------------------------------------
+def sanitize_obs(theta_pi, obs, lay: Layout, margin=2e-5, seed=98):
+    """ReLU is the other discontinuity of the backward pass: tf.nn.relu's gradient is [h > 0], so a
+    pre-activation within fp32 rounding of zero flips one element of dh between the fp32 device
+    result and the fp64 oracle.  Resample the SYNTHETIC observation rows that have any pi
+    pre-activation with |z| < margin until none is left.  Returns (obs, n_resampled)."""
+    rng = np.random.default_rng(seed)
+    obs = np.array(obs, np.float32, copy=True)
+    p = unflatten(np.asarray(theta_pi, np.float64), lay)
+    rows = np.arange(obs.shape[0]); total = 0
+    for _ in range(200):
+        h = obs[rows].astype(np.float64)
+        bad = np.zeros(len(rows), bool)
+        for l in range(len(lay.hidden)):
+            z = h @ p[f"W{l + 1}"] + p[f"b{l + 1}"]
+            bad |= (np.abs(z) < margin).any(axis=1)
+            h = np.maximum(z, 0)
+        rows = rows[bad]
+        if len(rows) == 0:
+            return obs, total
+        total += len(rows)
+        obs[rows] = rng.standard_normal((len(rows), obs.shape[1])).astype(np.float32)
+    raise RuntimeError("sanitize_obs did not converge")
+
+
 def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, hp: HParams = HParams(),
                   margin=1e-4, seed=99):
     """The PPO loss is discontinuous in its inputs where tf.minimum / tf.maximum / clip switch
@@ -515,7 +542,8 @@ def make_case(T, N, obs_dim, hidden, act_dim, seed=1234, l_mul=0.7, trunk_std=1.
     buf = make_buffer(T, N, obs_dim, act_dim, seed)
     th_pi, th_old = make_params_pair(lay, trunk_std, head_std, delta)
     adv, ret = gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], hp.GAMMA, hp.LAM)
+    buf["obs"], n_obs = sanitize_obs(th_pi, buf["obs"], lay)
     act, ret2, edited = sanitize_rows(th_pi, th_old, buf["obs"], buf["act"], adv.reshape(-1), ret.reshape(-1),
                                       l_mul, lay, hp)
     return dict(lay=lay, buf=buf, theta_pi=th_pi, theta_old=th_old, adv=adv.reshape(-1).astype(np.float32),
-                ret=ret2.astype(np.float32), act=act, l_mul=l_mul, edited=edited, T=T, N=N)
+                ret=ret2.astype(np.float32), act=act, l_mul=l_mul, edited=edited + n_obs, T=T, N=N)

@@ -69,6 +69,21 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
     s->w_off[s->L] = off; off += (int64_t)fan_in * s->P;
     s->b_off[s->L] = off; off += s->P;
     s->n_params = off;
+    // split-K plan: as many slices as keep (output tiles x slices) within one wave of 2 CTAs/SM
+    int64_t poff = 0;
+    for (int l = 0; l <= s->L; ++l) {
+        const int in = s->in_dim(l), out = s->out_dim(l);
+        const int bn = out > 64 ? 128 : 64;
+        const int tiles = ((in + 127) / 128) * ((out + bn - 1) / bn);
+        int sl = (2 * kPlanSMs) / tiles;
+        if (sl < 1) sl = 1;
+        if (sl > kMaxSplitK) sl = kMaxSplitK;
+        s->slices[l] = sl;
+        s->region[l] = (((int64_t)in * out + out) + 3) & ~3LL;
+        s->part_off[l] = poff;
+        poff += (int64_t)sl * s->region[l];
+    }
+    s->partial_floats = poff;
     return 0;
 }
 
@@ -95,8 +110,7 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     w.out_pi = (float*)take(R * s.P * sizeof(float));
     w.out_old = (float*)take(R * s.P * sizeof(float));
     w.d_out = (float*)take(R * s.P * sizeof(float));
-    const size_t stride = (size_t)((s.n_params + 3) & ~3LL);
-    w.partial = (float*)take((size_t)kSplitK * stride * sizeof(float));
+    w.partial = (float*)take((size_t)s.partial_floats * sizeof(float));
     const size_t tiles = (R + kLossTileRows - 1) / kLossTileRows + 64;
     w.loss_part = (double*)take(tiles * kLossSlots * sizeof(double));
     w.gae_adv = (float*)take(R * sizeof(float));
@@ -141,13 +155,13 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     if (int r = launch_loss(s, w.out_pi, w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
                             c->cfg.vcoeff, w.d_out, w.loss_part, st)) return r;
 
-    const int64_t stride = (s.n_params + 3) & ~3LL;
-    GemmEpi tn; tn.accumulate = accumulate; tn.slice_stride = stride;
+    GemmEpi tn; tn.accumulate = accumulate;
     const int H = s.in_dim(s.L);
     const float* head_in = s.L ? w.act_pi[s.L - 1] : obs;
     // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
-    tn.bias_out = w.partial + s.b_off[s.L];
-    if (int r = gemm_tn_splitk(H, s.P, rows, head_in, H, w.d_out, s.P, w.partial + s.w_off[s.L], s.P, tn, st)) return r;
+    float* pw = w.partial + s.part_off[s.L];
+    tn.slice_stride = s.region[s.L]; tn.slices = s.slices[s.L]; tn.bias_out = pw + (size_t)H * s.P;
+    if (int r = gemm_tn_splitk(H, s.P, rows, head_in, H, w.d_out, s.P, pw, s.P, tn, st)) return r;
     if (s.L == 0) return 0;
     // dh_L = (d_out . Wh^T) * [h_L > 0]
     int cur = 0;
@@ -158,9 +172,10 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     for (int l = s.L - 1; l >= 0; --l) {
         const float* dY = w.scratch[cur];
         const float* x_in = l ? w.act_pi[l - 1] : obs;
-        tn.bias_out = w.partial + s.b_off[l];
-        if (int r = gemm_tn_splitk(s.in_dim(l), s.h[l], rows, x_in, s.in_dim(l), dY, s.h[l],
-                                   w.partial + s.w_off[l], s.h[l], tn, st)) return r;
+        pw = w.partial + s.part_off[l];
+        tn.slice_stride = s.region[l]; tn.slices = s.slices[l]; tn.bias_out = pw + (size_t)s.in_dim(l) * s.h[l];
+        if (int r = gemm_tn_splitk(s.in_dim(l), s.h[l], rows, x_in, s.in_dim(l), dY, s.h[l], pw, s.h[l], tn, st))
+            return r;
         if (l > 0) {
             GemmEpi nt; nt.mask = w.act_pi[l - 1];
             if (int r = gemm_nt(rows, s.h[l - 1], s.h[l], dY, s.h[l], params_pi + s.w_off[l], s.h[l],
@@ -317,8 +332,8 @@ int dppo_loss_grad(dppo_ctx* c, const float* params_pi, const float* params_old,
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, adv, ret, B, 0, B, l_mul, 0, st)) return r;
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    return launch_finalize(c->shape, c->ws.partial, kSplitK, c->ws.loss_part, tiles, 1.0f / (float)B,
-                           c->cfg.entcoeff, c->cfg.vcoeff, B, grad_out, losses_out, st);
+    return launch_finalize(c->shape, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
+                           losses_out, st);
 }
 
 int dppo_comm_unique_id(void* id_out) {
@@ -386,10 +401,13 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
     DPPO_CHECK_CUDA(cudaMemcpyAsync(d_done, done_h, (size_t)B * 4, cudaMemcpyHostToDevice, cp));
     DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[0], cp));
     // row chunks of the big arrays; chunk c's fwd+loss+bwd overlaps chunk c+1's H2D copy
-    int n_chunks = 8;
-    int rows_per = ((B + n_chunks - 1) / n_chunks + kLossTileRows - 1) / kLossTileRows * kLossTileRows;
-    if (rows_per < 4096) rows_per = (4096 < B ? 4096 : (B + kLossTileRows - 1) / kLossTileRows * kLossTileRows);
-    n_chunks = (B + rows_per - 1) / rows_per;
+    // chunk = one full wave of forward CTAs (2 CTAs/SM x 148 SMs over the widest layer's column tiles)
+    int col_tiles = 1;
+    for (int l = 0; l < s.L; ++l) { const int t = (s.h[l] + 127) / 128; if (t > col_tiles) col_tiles = t; }
+    int rows_per = (2 * kPlanSMs / col_tiles) * 128;
+    if (rows_per < 4096) rows_per = 4096;
+    while ((B + rows_per - 1) / rows_per > 32) rows_per *= 2;
+    int n_chunks = (B + rows_per - 1) / rows_per;
     DPPO_REQUIRE(n_chunks <= 63, "dppo_update_host: too many chunks");
     for (int k = 0; k < n_chunks; ++k) {
         const int r0 = k * rows_per, rows = (B - r0 < rows_per) ? B - r0 : rows_per;
@@ -410,8 +428,8 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
             return r;
     }
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    if (int r = launch_finalize(s, w.partial, kSplitK, w.loss_part, tiles, 1.0f / (float)B, c->cfg.entcoeff,
-                                c->cfg.vcoeff, B, grad_out, nullptr, st)) return r;
+    if (int r = launch_finalize(s, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out, nullptr,
+                                st)) return r;
     if (c->nccl_comm && c->world > 1)
         if (int r = allreduce_avg(c, grad_out, s.n_params + kLossSlots, st)) return r;
     DPPO_CHECK_CUDA(cudaMemcpyAsync(c->losses_pinned, grad_out + s.n_params, kLossSlots * sizeof(float),
@@ -461,16 +479,17 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         // C[M,N] = A[K,M]^T . B[K,N]; partial slices live in the ctx workspace
         const int64_t need = (int64_t)M * N + N;
         const int64_t stride = (need + 3) & ~3LL;
-        DPPO_REQUIRE(stride * kSplitK <= ((c->shape.n_params + 3) & ~3LL) * kSplitK,
-                     "dppo_dbg_gemm: M*N+N=%lld exceeds the partial buffer (n_params=%lld)", (long long)need,
-                     (long long)c->shape.n_params);
-        e.slice_stride = stride; e.bias_out = bias_out ? c->ws.partial + (int64_t)M * N : nullptr;
+        int slices = (int)(c->shape.partial_floats / stride);
+        if (slices > 37) slices = 37;
+        DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N=%lld exceeds the partial buffer (%lld floats)",
+                     (long long)need, (long long)c->shape.partial_floats);
+        e.slice_stride = stride; e.slices = slices; e.bias_out = bias_out ? c->ws.partial + (int64_t)M * N : nullptr;
         if (int r = gemm_tn_splitk(M, N, K, A, M, B, N, c->ws.partial, N, e, st)) return r;
         ProfScope ps(KK_MISC, st);
-        reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, kSplitK, stride, (long long)M * N, C);
+        reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
         DPPO_LAUNCH_CHECK();
         if (bias_out) {
-            reduce_slices_kernel<<<4, 256, 0, st>>>(c->ws.partial + (int64_t)M * N, kSplitK, stride, N, bias_out);
+            reduce_slices_kernel<<<4, 256, 0, st>>>(c->ws.partial + (int64_t)M * N, slices, stride, N, bias_out);
             DPPO_LAUNCH_CHECK();
         }
         return 0;

@@ -33,7 +33,8 @@ void set_error(const char* fmt, ...);
 constexpr int kMaxLayers = DPPO_MAX_HIDDEN;
 constexpr int kLossSlots = DPPO_NUM_LOSS_SLOTS;
 constexpr int kLossTileRows = 128;          // rows per CTA of the loss kernel
-constexpr int kSplitK = 32;                 // dW split-K slices (deterministic two-stage reduce)
+constexpr int kMaxSplitK = 148;             // upper bound of dW split-K slices per layer
+constexpr int kPlanSMs = 148;               // B200: the split-K plan fills 2 CTAs/SM x 148 SMs in whole waves
 
 // Internal parameter layout: identical to the public one for the trunk; the two heads are packed
 // into ONE [H_L, P] matrix (P = 1 + 2A: value | mean | logstd) + bias[P], so that the heads are a
@@ -44,6 +45,12 @@ struct NetShape {
     int64_t w_off[kMaxLayers + 1];   // trunk W_l offsets, [L] = packed head W
     int64_t b_off[kMaxLayers + 1];   // trunk b_l offsets, [L] = packed head b
     int64_t n_params;
+    // dW/db split-K plan (deterministic two-stage reduction): layer l's partials are slices[l] copies of
+    // its contiguous [W_l | b_l] region (region[l] floats, padded to 4), starting at part_off[l]
+    int slices[kMaxLayers + 1];
+    int64_t region[kMaxLayers + 1];
+    int64_t part_off[kMaxLayers + 1];
+    int64_t partial_floats;
     int in_dim(int l) const { return l == 0 ? obs : h[l - 1]; }
     int out_dim(int l) const { return l == L ? P : h[l]; }
     int hmax() const { int m = 0; for (int i = 0; i < L; ++i) m = h[i] > m ? h[i] : m; return m; }
@@ -60,7 +67,7 @@ struct Workspace {
     float* out_pi;       // [max_rows, P]
     float* out_old;      // [max_rows, P]
     float* d_out;        // [max_rows, P]
-    float* partial;      // [kSplitK, n_params] dW/db split-K partials (internal layout)
+    float* partial;      // split-K partials, see NetShape::part_off
     double* loss_part;   // [loss_tiles_max, kLossSlots]
     float* gae_adv;      // [max_rows] used by dppo_update_host
     float* gae_ret;      // [max_rows]
@@ -112,6 +119,7 @@ struct GemmEpi {
     float* bias_out = nullptr;     // TN: column sums of B -> partial slices, stride = slice_stride
     int accumulate = 0;            // TN: partial += instead of =
     int64_t slice_stride = 0;      // TN: floats between split-K slices of C / bias_out
+    int slices = 1;                // TN: number of split-K slices
 };
 int gemm_nn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const GemmEpi& e, cudaStream_t st);
@@ -121,7 +129,7 @@ int gemm_nn_dual(int M, int N, int K, const float* A0, const float* A1, int lda,
                  const float* bias1, int relu, int nets, cudaStream_t st);
 int gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
             const GemmEpi& e, cudaStream_t st);
-// C[s][M,N] (+)= A[k, M]^T . B[k, N] over k in slice s of [0,K); kSplitK slices
+// C[s][M,N] (+)= A[k, M]^T . B[k, N] over k in slice s of [0,K); e.slices slices
 int gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                    int ldc, const GemmEpi& e, cudaStream_t st);
 
@@ -130,9 +138,8 @@ int launch_pack_heads(const NetShape& s, const float* params_pi, const float* pa
 int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
                 const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st);
-int launch_finalize(const NetShape& s, const float* partial, int n_slices, const double* loss_part,
-                    int n_loss_tiles, float inv_B, float entcoeff, float vcoeff, int rows_total,
-                    float* grad_out, float* losses_out, cudaStream_t st);
+int launch_finalize(const NetShape& s, const float* partial, const double* loss_part, int n_loss_tiles,
+                    float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st);
 int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
                        cudaStream_t st);
 int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,

@@ -189,15 +189,26 @@ int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, co
 // finalize: deterministic split-K reduction of dW/db partials (internal layout) into the public
 // flat gradient (PPO.py:46 order), + the loss scalars at the tail.
 // ---------------------------------------------------------------------------------------------
-__global__ void finalize_kernel(const float* __restrict__ partial, int n_slices, long long slice_stride,
-                                long long n_params, long long head_off, int H, int A,
-                                const double* __restrict__ loss_part, int n_tiles, float entcoeff,
-                                float vcoeff, float* __restrict__ grad_out, float* __restrict__ losses_out) {
+struct FinalizePlan {
+    int n_regions;
+    long long w_off[kMaxLayers + 1];      // internal offset of region l (= [W_l | b_l], contiguous)
+    long long region[kMaxLayers + 1];     // slice stride of region l
+    long long part_off[kMaxLayers + 1];   // where region l's slices start in the partial buffer
+    int slices[kMaxLayers + 1];
+};
+
+__global__ void finalize_kernel(const float* __restrict__ partial, FinalizePlan plan, long long n_params,
+                                long long head_off, int H, int A, const double* __restrict__ loss_part, int n_tiles,
+                                float entcoeff, float vcoeff, float* __restrict__ grad_out,
+                                float* __restrict__ losses_out) {
     const int P = 1 + 2 * A;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += stride) {
+        int l = 0;
+        while (l + 1 < plan.n_regions && i >= plan.w_off[l + 1]) ++l;
+        const float* src = partial + plan.part_off[l] + (i - plan.w_off[l]);
         float s = 0.f;
-        for (int k = 0; k < n_slices; ++k) s += __ldg(partial + (size_t)k * slice_stride + i);
+        for (int k = 0; k < plan.slices[l]; ++k) s += __ldg(src + (size_t)k * plan.region[l]);
         long long pub = i;
         if (i >= head_off) {
             const long long r = i - head_off;
@@ -240,18 +251,21 @@ __global__ void finalize_kernel(const float* __restrict__ partial, int n_slices,
     }
 }
 
-int launch_finalize(const NetShape& s, const float* partial, int n_slices, const double* loss_part,
-                    int n_loss_tiles, float inv_B, float entcoeff, float vcoeff, int rows_total,
-                    float* grad_out, float* losses_out, cudaStream_t st) {
-    (void)inv_B; (void)rows_total;
-    const long long stride = (s.n_params + 3) & ~3LL;
+int launch_finalize(const NetShape& s, const float* partial, const double* loss_part, int n_loss_tiles,
+                    float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st) {
+    FinalizePlan plan;
+    plan.n_regions = s.L + 1;
+    for (int l = 0; l <= s.L; ++l) {
+        plan.w_off[l] = s.w_off[l]; plan.region[l] = s.region[l];
+        plan.part_off[l] = s.part_off[l]; plan.slices[l] = s.slices[l];
+    }
     const int H = s.in_dim(s.L);
     int grid = (int)((s.n_params + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
     ProfScope ps(KK_FINALIZE, st);
-    finalize_kernel<<<grid, 256, 0, st>>>(partial, n_slices, stride, s.n_params, (long long)s.w_off[s.L], H,
-                                          s.act, loss_part, n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out);
+    finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.act, loss_part,
+                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out);
     DPPO_LAUNCH_CHECK();
     return 0;
 }

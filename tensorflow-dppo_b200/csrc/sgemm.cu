@@ -314,15 +314,16 @@ int gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B,
     g.A[0] = A; g.B[0] = B; g.C[0] = C; g.bias_out = e.bias_out;
     g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.nets = 1;
     g.accumulate = e.accumulate; g.slice_stride = e.slice_stride;
-    int kps = (K + kSplitK - 1) / kSplitK;
+    const int slices = e.slices < 1 ? 1 : e.slices;
+    int kps = (K + slices - 1) / slices;
     kps = ((kps + BK - 1) / BK) * BK;
     if (kps == 0) kps = BK;
     g.k_per_slice = kps;       // slices past K see an empty range and write zeros (or keep +=)
     fill_vec_flags(g);
     // slice_stride must keep 16-B alignment of every slice for the vector epilogue
     if (g.slice_stride % 4 != 0) g.vecC = 0;
-    if (N > 64) return launch<8, 8, false, false, EPI_TN>(g, kSplitK, st);
-    return launch<8, 4, false, false, EPI_TN>(g, kSplitK, st);
+    if (N > 64) return launch<8, 8, false, false, EPI_TN>(g, slices, st);
+    return launch<8, 4, false, false, EPI_TN>(g, slices, st);
 }
 
 }  // namespace dppo

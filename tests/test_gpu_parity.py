@@ -265,9 +265,10 @@ def test_loss_grad_properties_full_size_humanoid():
     # (iii) 8192-row slice against the oracle, with branch-ambiguous rows edited out
     s = slice(0, 8192)
     a_np = adv[s].cpu().numpy(); r_np = ret[s].cpu().numpy()
-    act_s, ret_s, _ = O.sanitize_rows(th_pi, th_old, buf["obs"][s], buf["act"][s], a_np, r_np, 0.7, lay)
-    losses, g_s = eng.loss_grad(d_pi, d_old, d_obs[s], dev(act_s), adv[s].contiguous(), dev(ret_s), 0.7)
-    l_ref, g_ref, _ = O.ppo_loss_grad(th_pi, th_old, buf["obs"][s], act_s, a_np, ret_s, 0.7, lay)
+    obs_s, _ = O.sanitize_obs(th_pi, buf["obs"][s], lay)
+    act_s, ret_s, _ = O.sanitize_rows(th_pi, th_old, obs_s, buf["act"][s], a_np, r_np, 0.7, lay)
+    losses, g_s = eng.loss_grad(d_pi, d_old, dev(obs_s), dev(act_s), adv[s].contiguous(), dev(ret_s), 0.7)
+    l_ref, g_ref, _ = O.ppo_loss_grad(th_pi, th_old, obs_s, act_s, a_np, ret_s, 0.7, lay)
     np.testing.assert_allclose(losses.cpu().numpy()[:4], l_ref, rtol=TOL, atol=TOL)
     assert max(per_tensor_rel_err(g_s.cpu().numpy()[:n], g_ref, lay).values()) < TOL
 

@@ -191,7 +191,8 @@ def test_adam_tf_form_and_tower_mean():
     th1, m1, v1 = O.adam_tf(th, g, m, v, 1, 2e-5 * 0.7)
     # step 1 of TF Adam: lr_t = lr*sqrt(1-b2)/(1-b1); update = lr_t * m/(sqrt(v)+eps)
     lr_t = 2e-5 * 0.7 * math.sqrt(1 - 0.999) / (1 - 0.9)
-    np.testing.assert_allclose(th1, th - lr_t * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-8), rtol=1e-12)
+    omb1 = float(np.float32(1) - np.float32(0.9)); omb2 = float(np.float32(1) - np.float32(0.999))   # TF: fp32 betas
+    np.testing.assert_allclose(th1, th - lr_t * (omb1 * g) / (np.sqrt(omb2 * g * g) + 1e-8), rtol=1e-12)
     # differs from torch.optim.Adam's epsilon placement only at O(eps): sanity against torch
     tt = torch.tensor(th, requires_grad=True)
     opt = torch.optim.Adam([tt], lr=2e-5 * 0.7, eps=1e-8)
