@@ -398,3 +398,62 @@ def test_diag_gaussian_methods_golden(golden_dir):
     ent = eng.diag_gaussian("entropy", M).double().cpu().numpy().mean()
     kl = eng.diag_gaussian("kl", M, M2).double().cpu().numpy().mean()
     assert abs(kl - (-ent - llq.mean())) < 3 * llq.std() / math.sqrt(Nn)
+
+
+# ------------------------------------------------------------------------------- multi-GPU (NCCL over NVLink)
+def _multi_gpu_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from dppo_b200 import DppoEngine
+    from dppo_b200.dist import init_engine_comm, shard_rollouts
+    T, N, obs, hidden, A = 128, 16, 17, (64, 64), 6
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]
+    lo, hi = shard_rollouts(N, rank, world)
+    rows = (np.arange(T)[:, None] * N + np.arange(lo, hi)[None, :]).reshape(-1)
+    eng = DppoEngine(obs, A, hidden, len(rows), device=rank)
+    init_engine_comm(eng, rank, world)
+    d = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).cuda(rank)   # noqa: E731
+    p_pi = d(c["theta_pi"])
+    _, g = eng.loss_grad(p_pi, d(c["theta_old"]), d(c["buf"]["obs"][rows]), d(c["act"][rows]), d(c["adv"][rows]),
+                         d(c["ret"][rows]), c["l_mul"])
+    eng.allreduce_avg(g)                                           # PPO._average_gradients across ranks
+    m = torch.zeros(lay.n_params, device=f"cuda:{rank}"); v = torch.zeros_like(m)
+    eng.adam_apply(p_pi, g, m, v, 1, 2e-5 * c["l_mul"])
+    torch.cuda.synchronize()
+    np.save(os.path.join(out_dir, f"g_{rank}.npy"), g.cpu().numpy())
+    np.save(os.path.join(out_dir, f"p_{rank}.npy"), p_pi.cpu().numpy())
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_allreduce_equals_tower_mean(tmp_path):
+    """N ranks, one tower each: the NCCL-averaged gradient equals the oracle's tower mean (PPO.py:55-65)
+    and every rank ends with bit-identical parameters (no chief->worker broadcast needed)."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_multi_gpu_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    T, N, obs, hidden, A = 128, 16, 17, (64, 64), 6
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]
+    from dppo_b200.dist import shard_rollouts
+    towers = []
+    for r in range(world):
+        lo, hi = shard_rollouts(N, r, world)
+        rows = (np.arange(T)[:, None] * N + np.arange(lo, hi)[None, :]).reshape(-1)
+        losses, g, _ = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"][rows], c["act"][rows],
+                                       c["adv"][rows], c["ret"][rows], c["l_mul"], lay)
+        towers.append(np.concatenate([g, losses]))
+    ref = O.tower_mean(towers)
+    gs = [np.load(tmp_path / f"g_{r}.npy") for r in range(world)]
+    ps = [np.load(tmp_path / f"p_{r}.npy") for r in range(world)]
+    for r in range(1, world):
+        np.testing.assert_array_equal(gs[0], gs[r]); np.testing.assert_array_equal(ps[0], ps[r])
+    n = lay.n_params
+    assert max(per_tensor_rel_err(gs[0][:n], ref[:n], lay).values()) < TOL
+    np.testing.assert_allclose(gs[0][n:n + 4], ref[n:], rtol=TOL, atol=TOL)
