@@ -207,7 +207,7 @@ def run_b200(args):
     T, N, obs, act, hidden = WORKLOADS[args.workload]
     B = T * N
     gamma, lam, l_mul, lr = 0.99, 0.95, 0.7, 2e-5
-    eng = DppoEngine(obs, act, hidden, B, device=local)
+    eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode={"simt": 0, "tf32x3": 1}[args.gemm])
     if world > 1:
         init_engine_comm(eng, rank, world)
     host = rollout_buffer(T, N, obs, act, seed=1234 + rank, pin=True)      # weak scaling: own buffer per rank
@@ -302,17 +302,20 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
                        "hidden": list(hidden), "rows_per_gpu": B, "parallelism": f"dp{world}",
-                       "gemm": "fp32 SIMT FFMA (1e-5 parity path)",
+                       "gemm": {"simt": "fp32 SIMT FFMA", "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators"}[args.gemm],
                        "l2": f"inputs larger than L2: obs buffer {B * obs * 4 / 1e6:.0f} MB + activations "
                              f"{B * sum(hidden) * 4 * 2 / 1e6:.0f} MB stream through HBM every step (L2 126 MB)",
                        "step": "gae + pi/oldpi fwd + loss + bwd + allreduce(N>1) + adam"},
             "roofline": {
-                "kernel": "sgemm_kernel (fwd NN / dX NT / dW TN families)", "bound": "tensor",
+                "kernel": ("tc_gemm_kernel (tcgen05 fwd / dX / dW)" if args.gemm == "tf32x3" else
+                           "sgemm_kernel (fwd NN / dX NT / dW TN families)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "note": "algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
-                        "this path runs the GEMMs as fp32 FFMA (fp32 FMA pipe, ~70 TFLOP/s), not on tensor cores",
+                "note": ("algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
+                         + ("fp32-parity path: every algorithmic MAC is issued as 3 TF32 MMAs (half the bf16 rate each), so the "
+                            "ceiling of this fraction is 1/6" if args.gemm == "tf32x3" else
+                            "this path runs the GEMMs as fp32 FFMA (fp32 FMA pipe, ~74 TFLOP/s), not on tensor cores")),
                 "launches_per_step": gemm_launches / K, "ms_per_step": gemm_ms / K,
                 "share_of_step": gemm_ms / ms_prof if ms_prof else None,
                 "family_ms_per_step": {k: v_ / K for k, v_ in fam_ms.items()},
@@ -341,6 +344,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="humanoid-cfg3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3"],
+                    help="dense-layer arithmetic: fp32 FFMA, or tcgen05 kind::tf32 with the 3-term fp32-accurate split")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -76,8 +76,16 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
         const int bn = out > 64 ? 128 : 64;
         const int tiles = ((in + 127) / 128) * ((out + bn - 1) / bn);
         int sl = (2 * kPlanSMs) / tiles;
-        if (sl < 1) sl = 1;
-        if (sl > kMaxSplitK) sl = kMaxSplitK;
+        if (cfg->gemm_mode == DPPO_GEMM_TF32X3) {
+            // tensor-core accumulators truncate on every add: bound the rows one CTA reduces (<= 512, i.e. 64
+            // MMA steps); the cross-slice sum in finalize_kernel is round-to-nearest fp32
+            sl = (cfg->max_rows + 511) / 512;
+            if (sl < 1) sl = 1;
+            if (sl > 512) sl = 512;
+        } else {
+            if (sl < 1) sl = 1;
+            if (sl > kMaxSplitK) sl = kMaxSplitK;
+        }
         s->slices[l] = sl;
         s->region[l] = (((int64_t)in * out + out) + 3) & ~3LL;
         s->part_off[l] = poff;
@@ -103,6 +111,10 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     Workspace w{};
     w.head_pi = (float*)take(head);
     w.head_old = (float*)take(head);
+    if (cfg->gemm_mode != DPPO_GEMM_FP32_SIMT) {
+        w.wt_pi = (float*)take((size_t)s.n_params * sizeof(float));
+        w.wt_old = (float*)take((size_t)s.n_params * sizeof(float));
+    }
     for (int l = 0; l < s.L; ++l) w.act_pi[l] = (float*)take(R * s.h[l] * sizeof(float));
     const size_t hm = (size_t)(s.hmax() > 0 ? s.hmax() : 1);
     w.scratch[0] = (float*)take(R * hm * sizeof(float));
@@ -129,6 +141,22 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
     const int nets = params_old ? 2 : 1;
     if (int r = launch_pack_heads(s, params_pi, params_old, w.head_pi, w.head_old, st)) return r;
     const float* in0 = obs; const float* in1 = obs;
+    if (c->cfg.gemm_mode == DPPO_GEMM_TF32X3) {
+        // tensor cores: B operand K-major = transposed kernels, refreshed from the current parameters
+        if (int r = tc_transpose_weights(s, params_pi, w.head_pi, w.wt_pi, params_old, w.head_old, w.wt_old, st)) return r;
+        for (int l = 0; l <= s.L; ++l) {
+            const bool head = (l == s.L);
+            float* o0 = head ? w.out_pi : w.act_pi[l];
+            float* o1 = head ? w.out_old : w.scratch[l & 1];
+            const int in = s.in_dim(l), out = s.out_dim(l);
+            const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
+            const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
+            if (int r = tc_gemm_kk(3, 0, rows, out, in, in0, in1, in, w.wt_pi + s.w_off[l], w.wt_old + s.w_off[l], in,
+                                   o0, o1, out, b0, b1, head ? 0 : 1, nullptr, nets, st)) return r;
+            in0 = o0; in1 = o1;
+        }
+        return 0;
+    }
     for (int l = 0; l < s.L; ++l) {
         float* o0 = w.act_pi[l];
         float* o1 = w.scratch[l & 1];
@@ -159,27 +187,38 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const int H = s.in_dim(s.L);
     const float* head_in = s.L ? w.act_pi[s.L - 1] : obs;
     // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
-    float* pw = w.partial + s.part_off[s.L];
-    tn.slice_stride = s.region[s.L]; tn.slices = s.slices[s.L]; tn.bias_out = pw + (size_t)H * s.P;
-    if (int r = gemm_tn_splitk(H, s.P, rows, head_in, H, w.d_out, s.P, pw, s.P, tn, st)) return r;
+    const bool tcore = (c->cfg.gemm_mode == DPPO_GEMM_TF32X3);
+    // dW_l (+ db_l) into layer l's split-K partial region
+    auto dense_dw = [&](int l, const float* x_in, const float* dY) -> int {
+        const int in = s.in_dim(l), out = s.out_dim(l);
+        float* p = w.partial + s.part_off[l];
+        if (tcore) {
+            if (int r = tc_gemm_tn_splitk(3, in, out, rows, x_in, in, dY, out, p, out, s.slices[l], s.region[l],
+                                          accumulate, st)) return r;
+            return tc_colsum(dY, rows, out, out, s.slices[l], p + (size_t)in * out, s.region[l], accumulate, st);
+        }
+        tn.slice_stride = s.region[l]; tn.slices = s.slices[l]; tn.bias_out = p + (size_t)in * out;
+        return gemm_tn_splitk(in, out, rows, x_in, in, dY, out, p, out, tn, st);
+    };
+    // dX = (dY . W^T) * [h > 0]   (W is [n_out_of_this_product, k] row-major = K-major B operand)
+    auto dense_dx = [&](int M_, int N_, int K_, const float* dY, const float* W, float* dX, const float* mask) -> int {
+        if (tcore) return tc_gemm_kk(3, 1, M_, N_, K_, dY, nullptr, K_, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr,
+                                     0, mask, 1, st);
+        GemmEpi nt; nt.mask = mask;
+        return gemm_nt(M_, N_, K_, dY, K_, W, K_, dX, N_, nt, st);
+    };
+    if (int r = dense_dw(s.L, head_in, w.d_out)) return r;
     if (s.L == 0) return 0;
     // dh_L = (d_out . Wh^T) * [h_L > 0]
     int cur = 0;
-    {
-        GemmEpi nt; nt.mask = w.act_pi[s.L - 1];
-        if (int r = gemm_nt(rows, H, s.P, w.d_out, s.P, w.head_pi, s.P, w.scratch[cur], H, nt, st)) return r;
-    }
+    if (int r = dense_dx(rows, H, s.P, w.d_out, w.head_pi, w.scratch[cur], w.act_pi[s.L - 1])) return r;
     for (int l = s.L - 1; l >= 0; --l) {
         const float* dY = w.scratch[cur];
         const float* x_in = l ? w.act_pi[l - 1] : obs;
-        pw = w.partial + s.part_off[l];
-        tn.slice_stride = s.region[l]; tn.slices = s.slices[l]; tn.bias_out = pw + (size_t)s.in_dim(l) * s.h[l];
-        if (int r = gemm_tn_splitk(s.in_dim(l), s.h[l], rows, x_in, s.in_dim(l), dY, s.h[l], pw, s.h[l], tn, st))
-            return r;
+        if (int r = dense_dw(l, x_in, dY)) return r;
         if (l > 0) {
-            GemmEpi nt; nt.mask = w.act_pi[l - 1];
-            if (int r = gemm_nt(rows, s.h[l - 1], s.h[l], dY, s.h[l], params_pi + s.w_off[l], s.h[l],
-                                w.scratch[cur ^ 1], s.h[l - 1], nt, st)) return r;
+            if (int r = dense_dx(rows, s.h[l - 1], s.h[l], dY, params_pi + s.w_off[l], w.scratch[cur ^ 1],
+                                 w.act_pi[l - 1])) return r;
             cur ^= 1;
         }
     }
@@ -246,8 +285,9 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     NetShape s;
     if (int r = make_shape(cfg, &s)) return r;
     DPPO_REQUIRE(cfg->max_rows >= 1, "max_rows=%d must be >= 1", cfg->max_rows);
-    DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT,
-                 "gemm_mode=%d is not built in this library version (only DPPO_GEMM_FP32_SIMT=0)", cfg->gemm_mode);
+    DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT || cfg->gemm_mode == DPPO_GEMM_TF32X3,
+                 "gemm_mode=%d is not built in this library version (DPPO_GEMM_FP32_SIMT=0, DPPO_GEMM_TF32X3=1)",
+                 cfg->gemm_mode);
     int ndev = 0;
     DPPO_CHECK_CUDA(cudaGetDeviceCount(&ndev));
     DPPO_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d CUDA devices)", cfg->device, ndev);
@@ -473,6 +513,33 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
     CTX_GUARD(c);
     cudaStream_t st = (cudaStream_t)stream;
     GemmEpi e; e.bias = bias; e.relu = relu; e.mask = mask;
+    if (mode >= 16) {
+        // tensor-core products: terms = 3 (modes 16..18) or 1 (modes 32..34).
+        // 16/32: C = relu?(A[M,K].Bt[N,K]^T + bias); 17/33: same product, C *= (mask>0); 18/34: C = A[K,M]^T.B[K,N]
+        const int terms = mode >= 32 ? 1 : 3, sub = mode & 15;
+        if (sub == 0) return tc_gemm_kk(terms, 0, M, N, K, A, nullptr, K, B, nullptr, K, C, nullptr, N, bias, nullptr, relu,
+                                        nullptr, 1, st);
+        if (sub == 1) return tc_gemm_kk(terms, 1, M, N, K, A, nullptr, K, B, nullptr, K, C, nullptr, N, nullptr, nullptr, 0,
+                                        mask, 1, st);
+        if (sub == 2) {
+            const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
+            int slices = (int)(c->shape.partial_floats / stride);
+            if (slices > 5) slices = 5;
+            DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
+            if (int r = tc_gemm_tn_splitk(terms, M, N, K, A, M, B, N, c->ws.partial, N, slices, stride, 0, st)) return r;
+            if (bias_out)
+                if (int r = tc_colsum(B, K, N, N, slices, c->ws.partial + (int64_t)M * N, stride, 0, st)) return r;
+            ProfScope ps(KK_MISC, st);
+            reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
+            DPPO_LAUNCH_CHECK();
+            if (bias_out) {
+                reduce_slices_kernel<<<4, 256, 0, st>>>(c->ws.partial + (int64_t)M * N, slices, stride, N, bias_out);
+                DPPO_LAUNCH_CHECK();
+            }
+            return 0;
+        }
+        DPPO_REQUIRE(false, "dppo_dbg_gemm: bad tensor-core mode %d", mode);
+    }
     if (mode == 0) return gemm_nn(M, N, K, A, K, B, N, C, N, e, st);
     if (mode == 1) return gemm_nt(M, N, K, A, K, B, K, C, N, e, st);
     if (mode == 2) {

@@ -62,6 +62,8 @@ struct Workspace {
     // all device pointers into the caller's workspace
     float* head_pi;      // packed head W|b of pi      [H_L*P + P]
     float* head_old;     // packed head W|b of oldpi
+    float* wt_pi;        // tensor-core path: transposed kernels Wt[out][in] of pi (internal layout offsets)
+    float* wt_old;       // ... of oldpi
     float* act_pi[kMaxLayers];   // post-ReLU activations of pi, layer l: [max_rows, h[l]]
     float* scratch[2];   // oldpi activations / dh ping-pong: [max_rows, hmax]
     float* out_pi;       // [max_rows, P]
@@ -132,6 +134,17 @@ int gemm_nt(int M, int N, int K, const float* A, int lda, const float* B, int ld
 // C[s][M,N] (+)= A[k, M]^T . B[k, N] over k in slice s of [0,K); e.slices slices
 int gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                    int ldc, const GemmEpi& e, cudaStream_t st);
+
+// tensor-core products (tc_gemm.cu)
+int tc_gemm_kk(int terms, int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0,
+               const float* B1, int ldb, float* C0, float* C1, int ldc, const float* bias0, const float* bias1,
+               int relu, const float* mask, int nets, cudaStream_t st);
+int tc_gemm_tn_splitk(int terms, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                      int slices, long long slice_stride, int accumulate, cudaStream_t st);
+int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,
+              cudaStream_t st);
+int tc_transpose_weights(const NetShape& s, const float* params_pi, const float* head_pi, float* wt_pi,
+                         const float* params_old, const float* head_old, float* wt_old, cudaStream_t st);
 
 int launch_pack_heads(const NetShape& s, const float* params_pi, const float* params_old,
                       float* head_pi, float* head_old, cudaStream_t st);

@@ -1,0 +1,503 @@
+// Tensor-core dense layers: tcgen05.mma kind::tf32 with TMEM accumulators (sm_100a).
+//
+// Same three products as sgemm.cu (forward NN, dX NT, dW TN -- /root/reference/Model.py:12-14 and
+// the auto-diff of PPO.py:46), but on the 5th-generation tensor cores.  fp32 parity (1e-5) is kept
+// with the 3-term TF32 split  a = a_hi + a_lo (both round-to-nearest tf32):
+//        A.B  ~=  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi        (fp32 accumulate in TMEM)
+// whose dropped term a_lo.b_lo is ~2^-22 relative.  TERMS = 1 is plain TF32 (used by tests to
+// validate layouts, not by the update path).
+//
+// CTA = 9 warps.  Warps 0-7 stream fp32 operand tiles global -> registers -> (split) -> shared
+// memory in the canonical UMMA layouts (K-major SWIZZLE_128B, or MN-major SWIZZLE_128B_BASE32B for
+// the dW product where the reduction dimension is the slow axis of both operands), signalling an
+// mbarrier per stage; warp 8 owns TMEM and issues the MMAs from one thread, releasing stages with
+// tcgen05.commit; after the K loop warps 0-7 read the accumulator tile back with tcgen05.ld
+// (warp w -> TMEM lanes 32*(w%4).., columns split by w/4) and apply the fused epilogue.
+#include "common.cuh"
+
+namespace dppo {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int BK = 32;           // 32 tf32 = 128 B = one swizzle row; 4 MMAs of K=8 per block
+constexpr int kLoadWarps = 8;
+constexpr int kLoadThreads = kLoadWarps * 32;
+constexpr int kThreads = kLoadThreads + 32;
+
+enum { EPI_NN = 0, EPI_NT = 1, EPI_TN = 2 };
+
+struct TcArgs {
+    const float* A[2]; const float* B[2]; float* C[2]; const float* bias[2];
+    const float* mask;
+    int M, N, K;
+    int lda, ldb, ldc;
+    int tiles_n, nets;
+    int relu, accumulate;
+    int k_per_slice;
+    long long slice_stride;
+    int vecA, vecB, vecC;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D=f32, A=B=tf32, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout_type <<61
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+constexpr uint32_t kLayoutSW128 = 2;          // K-major, 16-B swizzle granule, 8-row atoms
+constexpr uint32_t kLayoutSW128Base32 = 1;    // MN-major fp32/tf32, 32-B granule, 4-row atoms
+
+// ---- tile movers -----------------------------------------------------------------------------------
+// One operand tile is R (128 or BN) x BK fp32 = R*128 B.  Each loader thread owns R/32 16-B chunks.
+template <int R, bool MN_MAJOR>
+__device__ __forceinline__ void tile_load(float4 (&reg)[R / 32], const float* __restrict__ P, int ld, int r0, int rdim,
+                                          int k0, int kend, int vec, int tid) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+        const int q = tid + i * kLoadThreads;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!MN_MAJOR) {                       // element (r,k) at P[r*ld + k]
+            const int r = r0 + (q >> 3), k = k0 + (q & 7) * 4;
+            if (r < rdim && k < kend) {
+                const float* p = P + (size_t)r * ld + k;
+                if (vec && k + 3 < kend) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    v.x = __ldg(p);
+                    if (k + 1 < kend) v.y = __ldg(p + 1);
+                    if (k + 2 < kend) v.z = __ldg(p + 2);
+                    if (k + 3 < kend) v.w = __ldg(p + 3);
+                }
+            }
+        } else {                               // element (r,k) at P[k*ld + r]
+            const int k = k0 + q / (R / 4), r = r0 + (q % (R / 4)) * 4;
+            if (k < kend && r < rdim) {
+                const float* p = P + (size_t)k * ld + r;
+                if (vec && r + 3 < rdim) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    v.x = __ldg(p);
+                    if (r + 1 < rdim) v.y = __ldg(p + 1);
+                    if (r + 2 < rdim) v.z = __ldg(p + 2);
+                    if (r + 3 < rdim) v.w = __ldg(p + 3);
+                }
+            }
+        }
+        reg[i] = v;
+    }
+}
+
+template <int R, bool MN_MAJOR, int TERMS>
+__device__ __forceinline__ void tile_store(const float4 (&reg)[R / 32], uint8_t* hi, uint8_t* lo, int tid) {
+#pragma unroll
+    for (int i = 0; i < R / 32; ++i) {
+        const int q = tid + i * kLoadThreads;
+        uint32_t off;
+        if (!MN_MAJOR) {
+            const int r = q >> 3, c = q & 7;
+            off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+        } else {
+            const int kr = q / (R / 4), cc = q % (R / 4);
+            const int atom = cc >> 3, c = cc & 7;
+            off = (uint32_t)atom * (BK * 128u) + (uint32_t)kr * 128u + (uint32_t)((((c >> 1) ^ (kr & 3)) << 5) | ((c & 1) << 4));
+        }
+        const float4 v = reg[i];
+        uint4 h;
+        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        if (TERMS == 3) {
+            uint4 l;
+            l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
+            l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
+            *reinterpret_cast<uint4*>(lo + off) = l;
+        }
+    }
+}
+
+template <int BN, int TERMS>
+struct SmemPlan {
+    static constexpr int kATile = BM * 128, kBTile = BN * 128;
+    static constexpr int kStage = TERMS == 3 ? 2 * (kATile + kBTile) : (kATile + kBTile);
+    static constexpr int kStages = (200 * 1024) / kStage >= 4 ? 4 : (200 * 1024) / kStage;
+    static constexpr int kBytes = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+template <int BN, bool MN_MAJOR, int TERMS, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
+    using Plan = SmemPlan<BN, TERMS>;
+    constexpr int STAGES = Plan::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Plan::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int net = blockIdx.x / g.tiles_n;
+    const int n0 = (blockIdx.x % g.tiles_n) * BN;
+    const int m0 = blockIdx.y * BM;
+    const int slice = blockIdx.z;
+    const int k_begin = slice * g.k_per_slice;
+    const int k_end = min(g.K, k_begin + g.k_per_slice);
+    const int nkb = max(0, (k_end - k_begin + BK - 1) / BK);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoadThreads); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    // TMEM: [0,BN) main accumulator (A_hi.B_hi); [BN,2BN) correction accumulator (A_lo.B_hi + A_hi.B_lo).
+    // The tensor core truncates when it adds into an fp32 accumulator; keeping the 2^-11-scaled correction
+    // terms out of the main accumulator cuts its number of truncating adds by 3 (precision).
+    constexpr uint32_t kTmemCols = (TERMS == 3 ? 2 : 1) * (BN < 32 ? 32 : BN);
+    if (warp == kLoadWarps) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kLoadWarps) {
+        // ================= operand movers =================
+        const float* __restrict__ A = g.A[net];
+        const float* __restrict__ B = g.B[net];
+        float4 ra[BM / 32], rb[BN / 32];
+        if (nkb > 0) {
+            tile_load<BM, MN_MAJOR>(ra, A, g.lda, m0, g.M, k_begin, k_end, g.vecA, tid);
+            tile_load<BN, MN_MAJOR>(rb, B, g.ldb, n0, g.N, k_begin, k_end, g.vecB, tid);
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            float4 na[BM / 32], nb[BN / 32];
+            if (kb + 1 < nkb) {
+                const int k0 = k_begin + (kb + 1) * BK;
+                tile_load<BM, MN_MAJOR>(na, A, g.lda, m0, g.M, k0, k_end, g.vecA, tid);
+                tile_load<BN, MN_MAJOR>(nb, B, g.ldb, n0, g.N, k0, k_end, g.vecB, tid);
+            }
+            mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+            uint8_t* st = smem + s * Plan::kStage;
+            uint8_t* a_hi = st;
+            uint8_t* a_lo = st + Plan::kATile;
+            uint8_t* b_hi = st + (TERMS == 3 ? 2 : 1) * Plan::kATile;
+            uint8_t* b_lo = b_hi + Plan::kBTile;
+            tile_store<BM, MN_MAJOR, TERMS>(ra, a_hi, a_lo, tid);
+            tile_store<BN, MN_MAJOR, TERMS>(rb, b_hi, b_lo, tid);
+            fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[s]);
+            if (kb + 1 < nkb) {
+#pragma unroll
+                for (int i = 0; i < BM / 32; ++i) ra[i] = na[i];
+#pragma unroll
+                for (int i = 0; i < BN / 32; ++i) rb[i] = nb[i];
+            }
+        }
+
+        // ================= epilogue =================
+        float* __restrict__ C = g.C[net];
+        if (EPI == EPI_TN) C += (size_t)slice * g.slice_stride;
+        const float* __restrict__ bias = g.bias[net];
+        const int q = warp & 3, half = warp >> 2;
+        const int m = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
+        constexpr int kColsPerHalf = BN / 2 < 32 ? 32 : BN / 2;
+#pragma unroll 1
+        for (int cb = half * kColsPerHalf; cb < (half + 1) * kColsPerHalf && cb < BN; cb += 32) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                if (TERMS == 3) {
+                    uint32_t w2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cb), w2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w2[j]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            const int nb0 = n0 + cb;
+            if (m < g.M && nb0 < g.N) {          // predicated (no divergent `continue`: tcgen05.ld is warp-collective)
+                float* cp = C + (size_t)m * g.ldc + nb0;
+                const float* mp = (EPI == EPI_NT && g.mask) ? g.mask + (size_t)m * g.ldc + nb0 : nullptr;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const int n = nb0 + j4 * 4;
+                    const int nv = min(4, g.N - n);
+                    if (nv > 0) {
+                        float x[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j4 * 4 + e]);
+                        if (EPI == EPI_NN) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv) {
+                                    const float y = x[e] + (bias ? __ldg(bias + n + e) : 0.f);
+                                    x[e] = g.relu ? fmaxf(y, 0.f) : y;
+                                }
+                        } else if (EPI == EPI_NT) {
+                            if (mp) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (e < nv) x[e] = (__ldg(mp + j4 * 4 + e) > 0.f) ? x[e] : 0.f;
+                            }
+                        } else {
+                            if (g.accumulate) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (e < nv) x[e] += cp[j4 * 4 + e];
+                            }
+                        }
+                        if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp + j4 * 4) = make_float4(x[0], x[1], x[2], x[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv) cp[j4 * 4 + e] = x[e];
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (lane == 0) {
+        // ================= MMA issuer (one thread) =================
+        constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR, MN_MAJOR);
+        constexpr uint32_t kLayout = MN_MAJOR ? kLayoutSW128Base32 : kLayoutSW128;
+        constexpr uint32_t kLbo = MN_MAJOR ? (uint32_t)(BK * 128) : 0u;         // MN-major: stride between 32-element MN atoms
+        constexpr uint32_t kSbo = MN_MAJOR ? 512u : 1024u;                      // MN: between 4-row k groups; K: between 8-row groups
+        constexpr uint32_t kStepBytes = MN_MAJOR ? 8u * 128u : 32u;             // advance of one UMMA_K = 8
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * Plan::kStage);
+            const uint32_t a_hi = st, a_lo = st + Plan::kATile;
+            const uint32_t b_hi = st + (TERMS == 3 ? 2 : 1) * Plan::kATile, b_lo = b_hi + Plan::kBTile;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+                const uint64_t da_hi = make_sdesc(a_hi + k * kStepBytes, kLbo, kSbo, kLayout);
+                const uint64_t db_hi = make_sdesc(b_hi + k * kStepBytes, kLbo, kSbo, kLayout);
+                if (TERMS == 3) {
+                    const uint64_t da_lo = make_sdesc(a_lo + k * kStepBytes, kLbo, kSbo, kLayout);
+                    const uint64_t db_lo = make_sdesc(b_lo + k * kStepBytes, kLbo, kSbo, kLayout);
+                    umma_tf32(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                    umma_tf32(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                    umma_tf32(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                } else {
+                    umma_tf32(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                }
+            }
+            umma_commit(&empty_bar[s]);        // stage s may be overwritten once these MMAs retire
+        }
+        if (nkb > 0) umma_commit(accum_bar);   // accumulator complete
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == kLoadWarps) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+static inline int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, bool MN_MAJOR, int TERMS, int EPI>
+static int launch(TcArgs& g, int slices, cudaStream_t st) {
+    using Plan = SmemPlan<BN, TERMS>;
+    g.tiles_n = (g.N + BN - 1) / BN;
+    const int tiles_m = (g.M + BM - 1) / BM;
+    DPPO_REQUIRE(tiles_m <= 65535, "tc_gemm: M=%d too large for one launch", g.M);
+    static bool configured = false;
+    if (!configured) {
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
+        configured = true;
+    }
+    dim3 grid(g.tiles_n * g.nets, tiles_m, slices);
+    ProfScope ps(KK_TC_GEMM, st);
+    tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI><<<grid, kThreads, Plan::kBytes, st>>>(g);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+static void fill_vec_flags(TcArgs& g) {
+    g.vecA = (g.lda % 4 == 0); g.vecB = (g.ldb % 4 == 0); g.vecC = (g.ldc % 4 == 0);
+    for (int i = 0; i < g.nets; ++i) { g.vecA &= aligned16(g.A[i]); g.vecB &= aligned16(g.B[i]); g.vecC &= aligned16(g.C[i]); }
+}
+
+template <int TERMS, bool MN_MAJOR, int EPI>
+static int dispatch_bn(TcArgs& g, int slices, cudaStream_t st) {
+    if (g.N > 128) return launch<256, MN_MAJOR, TERMS, EPI>(g, slices, st);
+    if (g.N > 64) return launch<128, MN_MAJOR, TERMS, EPI>(g, slices, st);
+    return launch<64, MN_MAJOR, TERMS, EPI>(g, slices, st);
+}
+
+}  // namespace tc
+
+// ---- colsum(dY) for the bias gradients of the tensor-core path: slab s of rows -> out[s*stride + n] -------
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ G, int rows, int N, int ld, int rows_per_slab,
+                                                     float* __restrict__ out, long long slab_stride, int accumulate) {
+    __shared__ double red[4][64];
+    const int col = threadIdx.x & 63, phase = threadIdx.x >> 6;
+    const int n = blockIdx.x * 64 + col;
+    const int r0 = blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
+    double acc = 0.0;
+    if (n < N)
+        for (int r = r0 + phase; r < r1; r += 4) acc += (double)__ldg(G + (size_t)r * ld + n);
+    red[phase][col] = acc;
+    __syncthreads();
+    if (phase == 0 && n < N) {
+        const float s = (float)(red[0][col] + red[1][col] + red[2][col] + red[3][col]);
+        float* o = out + (size_t)blockIdx.y * slab_stride + n;
+        *o = accumulate ? *o + s : s;
+    }
+}
+
+int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,
+              cudaStream_t st) {
+    if (slabs < 1) slabs = 1;
+    const int rps = (rows + slabs - 1) / slabs;
+    dim3 grid((N + 63) / 64, slabs);
+    ProfScope ps(KK_MISC, st);
+    colsum_kernel<<<grid, 256, 0, st>>>(G, rows, N, ld, rps > 0 ? rps : 1, out, slab_stride, accumulate);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- Wt[n][k] = W[k][n] for every dense layer of one net (K-major B operand of the forward product) -----
+struct TransposePlan { int n_layers; long long off[kMaxLayers + 1]; int in[kMaxLayers + 1], out[kMaxLayers + 1]; };
+__global__ void transpose_weights_kernel(TransposePlan p, const float* __restrict__ trunk0, const float* __restrict__ head0,
+                                         float* __restrict__ wt0, const float* __restrict__ trunk1,
+                                         const float* __restrict__ head1, float* __restrict__ wt1, long long total) {
+    const float* trunk = blockIdx.y ? trunk1 : trunk0;
+    const float* head = blockIdx.y ? head1 : head0;
+    float* wt = blockIdx.y ? wt1 : wt0;
+    if (trunk == nullptr) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int l = 0;
+        while (l + 1 < p.n_layers && i >= p.off[l + 1]) ++l;
+        const long long r = i - p.off[l];
+        if (r >= (long long)p.in[l] * p.out[l]) continue;      // bias slots are not transposed
+        const int n = (int)(r / p.in[l]), k = (int)(r % p.in[l]);
+        const float* src = (l == p.n_layers - 1) ? head : trunk + p.off[l];
+        wt[i] = src[(size_t)k * p.out[l] + n];
+    }
+}
+
+int tc_transpose_weights(const NetShape& s, const float* params_pi, const float* head_pi, float* wt_pi,
+                         const float* params_old, const float* head_old, float* wt_old, cudaStream_t st) {
+    TransposePlan p;
+    p.n_layers = s.L + 1;
+    for (int l = 0; l <= s.L; ++l) { p.off[l] = s.w_off[l]; p.in[l] = s.in_dim(l); p.out[l] = s.out_dim(l); }
+    dim3 grid((unsigned)((s.n_params + 255) / 256 > 592 ? 592 : (s.n_params + 255) / 256), 2);
+    ProfScope ps(KK_MISC, st);
+    transpose_weights_kernel<<<grid, 256, 0, st>>>(p, params_pi, head_pi, wt_pi, params_old, head_old, wt_old, s.n_params);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// C[M,N] = epi(A[M,K] . Bt[N,K]^T): both operands K-contiguous.  nets = 1 or 2 products sharing shapes.
+int tc_gemm_kk(int terms, int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0,
+               const float* B1, int ldb, float* C0, float* C1, int ldc, const float* bias0, const float* bias1,
+               int relu, const float* mask, int nets, cudaStream_t st) {
+    if (M == 0) return 0;
+    tc::TcArgs g{};
+    g.A[0] = A0; g.A[1] = A1; g.B[0] = B0; g.B[1] = B1; g.C[0] = C0; g.C[1] = C1; g.bias[0] = bias0; g.bias[1] = bias1;
+    g.mask = mask; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.nets = nets; g.relu = relu;
+    g.k_per_slice = ((K + tc::BK - 1) / tc::BK) * tc::BK;
+    tc::fill_vec_flags(g);
+    if (terms == 3) {
+        if (epi_nt) return tc::dispatch_bn<3, false, tc::EPI_NT>(g, 1, st);
+        return tc::dispatch_bn<3, false, tc::EPI_NN>(g, 1, st);
+    }
+    if (epi_nt) return tc::dispatch_bn<1, false, tc::EPI_NT>(g, 1, st);
+    return tc::dispatch_bn<1, false, tc::EPI_NN>(g, 1, st);
+}
+
+// C[s][M,N] (+)= A[k,M]^T . B[k,N] over k in slice s: both operands MN-contiguous (reduction over rows)
+int tc_gemm_tn_splitk(int terms, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                      int slices, long long slice_stride, int accumulate, cudaStream_t st) {
+    tc::TcArgs g{};
+    g.A[0] = A; g.B[0] = B; g.C[0] = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.nets = 1;
+    g.accumulate = accumulate; g.slice_stride = slice_stride;
+    if (slices < 1) slices = 1;
+    int kps = (K + slices - 1) / slices;
+    kps = ((kps + tc::BK - 1) / tc::BK) * tc::BK;
+    if (kps == 0) kps = tc::BK;
+    g.k_per_slice = kps;
+    tc::fill_vec_flags(g);
+    if (g.slice_stride % 4 != 0) g.vecC = 0;
+    if (terms == 3) return tc::dispatch_bn<3, true, tc::EPI_TN>(g, slices, st);
+    return tc::dispatch_bn<1, true, tc::EPI_TN>(g, slices, st);
+}
+
+}  // namespace dppo

@@ -3,7 +3,7 @@
 TAG=${1:-q}
 mkdir -p gpurun_out
 (timeout 600 python -m pytest tests -m gpu -q --timeout 500 ${2:+-k "$2"} 2>&1 | tail -40) > gpurun_out/tests_$TAG.log
-timeout 400 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 400 python bench.py --steps 30 --warmup 5 ${GEMM:+--gemm $GEMM} > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 tail -8 gpurun_out/tests_$TAG.log
 cat gpurun_out/bench_$TAG.json | python -c "
