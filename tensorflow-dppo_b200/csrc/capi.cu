@@ -57,6 +57,7 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
     DPPO_REQUIRE(cfg->obs_dim >= 1 && cfg->act_dim >= 1, "obs_dim=%d act_dim=%d must be >= 1", cfg->obs_dim, cfg->act_dim);
     DPPO_REQUIRE(cfg->n_hidden >= 0 && cfg->n_hidden <= kMaxLayers, "n_hidden=%d out of [0,%d]", cfg->n_hidden, kMaxLayers);
     s->obs = cfg->obs_dim; s->act = cfg->act_dim; s->L = cfg->n_hidden; s->P = 1 + 2 * cfg->act_dim;
+    s->Pld = (s->P + 3) & ~3;
     int64_t off = 0;
     int fan_in = cfg->obs_dim;
     for (int l = 0; l < s->L; ++l) {
@@ -112,16 +113,20 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     w.head_pi = (float*)take(head);
     w.head_old = (float*)take(head);
     if (cfg->gemm_mode != DPPO_GEMM_FP32_SIMT) {
-        w.wt_pi = (float*)take((size_t)s.n_params * sizeof(float));
-        w.wt_old = (float*)take((size_t)s.n_params * sizeof(float));
+        for (int l = 0; l <= s.L; ++l) {
+            const size_t fwd = (size_t)tc_image_floats(s.out_dim(l), s.in_dim(l)) * sizeof(float);
+            w.img_fwd_pi[l] = (float*)take(fwd);
+            w.img_fwd_old[l] = (float*)take(fwd);
+            w.img_dx_pi[l] = l > 0 ? (float*)take((size_t)tc_image_floats(s.in_dim(l), s.out_dim(l)) * sizeof(float)) : nullptr;
+        }
     }
     for (int l = 0; l < s.L; ++l) w.act_pi[l] = (float*)take(R * s.h[l] * sizeof(float));
     const size_t hm = (size_t)(s.hmax() > 0 ? s.hmax() : 1);
     w.scratch[0] = (float*)take(R * hm * sizeof(float));
     w.scratch[1] = (float*)take(R * hm * sizeof(float));
-    w.out_pi = (float*)take(R * s.P * sizeof(float));
-    w.out_old = (float*)take(R * s.P * sizeof(float));
-    w.d_out = (float*)take(R * s.P * sizeof(float));
+    w.out_pi = (float*)take(R * s.Pld * sizeof(float));
+    w.out_old = (float*)take(R * s.Pld * sizeof(float));
+    w.d_out = (float*)take(R * s.Pld * sizeof(float));
     w.partial = (float*)take((size_t)s.partial_floats * sizeof(float));
     const size_t tiles = (R + kLossTileRows - 1) / kLossTileRows + 64;
     w.loss_part = (double*)take(tiles * kLossSlots * sizeof(double));
@@ -143,7 +148,8 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
     const float* in0 = obs; const float* in1 = obs;
     if (c->cfg.gemm_mode == DPPO_GEMM_TF32X3) {
         // tensor cores: B operand K-major = transposed kernels, refreshed from the current parameters
-        if (int r = tc_transpose_weights(s, params_pi, w.head_pi, w.wt_pi, params_old, w.head_old, w.wt_old, st)) return r;
+        if (int r = tc_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
+                                   w.img_dx_pi, st)) return r;
         for (int l = 0; l <= s.L; ++l) {
             const bool head = (l == s.L);
             float* o0 = head ? w.out_pi : w.act_pi[l];
@@ -151,8 +157,8 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const int in = s.in_dim(l), out = s.out_dim(l);
             const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
-            if (int r = tc_gemm_kk(3, 0, rows, out, in, in0, in1, in, w.wt_pi + s.w_off[l], w.wt_old + s.w_off[l], in,
-                                   o0, o1, out, b0, b1, head ? 0 : 1, nullptr, nets, st)) return r;
+            if (int r = tc_gemm_kk_img(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
+                                       head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st)) return r;
             in0 = o0; in1 = o1;
         }
         return 0;
@@ -167,7 +173,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
         in0 = o0; in1 = o1;
     }
     const int H = s.in_dim(s.L);
-    return gemm_nn_dual(rows, s.P, H, in0, in1, H, w.head_pi, w.head_old, s.P, w.out_pi, w.out_old, s.P,
+    return gemm_nn_dual(rows, s.P, H, in0, in1, H, w.head_pi, w.head_old, s.P, w.out_pi, w.out_old, s.Pld,
                         w.head_pi + (size_t)H * s.P, w.head_old + (size_t)H * s.P, 0, nets, st);
 }
 
@@ -191,33 +197,35 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     // dW_l (+ db_l) into layer l's split-K partial region
     auto dense_dw = [&](int l, const float* x_in, const float* dY) -> int {
         const int in = s.in_dim(l), out = s.out_dim(l);
+        const int ldy = (l == s.L) ? s.Pld : out;
         float* p = w.partial + s.part_off[l];
         if (tcore) {
-            if (int r = tc_gemm_tn_splitk(3, in, out, rows, x_in, in, dY, out, p, out, s.slices[l], s.region[l],
+            if (int r = tc_gemm_tn_splitk(3, in, out, rows, x_in, in, dY, ldy, p, out, s.slices[l], s.region[l],
                                           accumulate, st)) return r;
-            return tc_colsum(dY, rows, out, out, s.slices[l], p + (size_t)in * out, s.region[l], accumulate, st);
+            return tc_colsum(dY, rows, out, ldy, s.slices[l], p + (size_t)in * out, s.region[l], accumulate, st);
         }
         tn.slice_stride = s.region[l]; tn.slices = s.slices[l]; tn.bias_out = p + (size_t)in * out;
-        return gemm_tn_splitk(in, out, rows, x_in, in, dY, out, p, out, tn, st);
+        return gemm_tn_splitk(in, out, rows, x_in, in, dY, ldy, p, out, tn, st);
     };
     // dX = (dY . W^T) * [h > 0]   (W is [n_out_of_this_product, k] row-major = K-major B operand)
-    auto dense_dx = [&](int M_, int N_, int K_, const float* dY, const float* W, float* dX, const float* mask) -> int {
-        if (tcore) return tc_gemm_kk(3, 1, M_, N_, K_, dY, nullptr, K_, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr,
-                                     0, mask, 1, st);
+    auto dense_dx = [&](int l_, int M_, int N_, int K_, const float* dY, int ldy, const float* W, float* dX,
+                        const float* mask) -> int {
+        if (tcore) return tc_gemm_kk_img(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_,
+                                         nullptr, nullptr, 0, mask, 1, st);
         GemmEpi nt; nt.mask = mask;
-        return gemm_nt(M_, N_, K_, dY, K_, W, K_, dX, N_, nt, st);
+        return gemm_nt(M_, N_, K_, dY, ldy, W, K_, dX, N_, nt, st);
     };
     if (int r = dense_dw(s.L, head_in, w.d_out)) return r;
     if (s.L == 0) return 0;
     // dh_L = (d_out . Wh^T) * [h_L > 0]
     int cur = 0;
-    if (int r = dense_dx(rows, H, s.P, w.d_out, w.head_pi, w.scratch[cur], w.act_pi[s.L - 1])) return r;
+    if (int r = dense_dx(s.L, rows, H, s.P, w.d_out, s.Pld, w.head_pi, w.scratch[cur], w.act_pi[s.L - 1])) return r;
     for (int l = s.L - 1; l >= 0; --l) {
         const float* dY = w.scratch[cur];
         const float* x_in = l ? w.act_pi[l - 1] : obs;
         if (int r = dense_dw(l, x_in, dY)) return r;
         if (l > 0) {
-            if (int r = dense_dx(rows, s.h[l - 1], s.h[l], dY, params_pi + s.w_off[l], w.scratch[cur ^ 1],
+            if (int r = dense_dx(l, rows, s.h[l - 1], s.h[l], dY, s.h[l], params_pi + s.w_off[l], w.scratch[cur ^ 1],
                                  w.act_pi[l - 1])) return r;
             cur ^= 1;
         }

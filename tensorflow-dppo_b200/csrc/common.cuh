@@ -41,6 +41,7 @@ constexpr int kPlanSMs = 148;               // B200: the split-K plan fills 2 CT
 // single GEMM.  Same total size as the public head block.
 struct NetShape {
     int obs, act, L, P;
+    int Pld;                         // row stride of the [rows, P] head buffers (P rounded up to 4: 16-B rows)
     int h[kMaxLayers];
     int64_t w_off[kMaxLayers + 1];   // trunk W_l offsets, [L] = packed head W
     int64_t b_off[kMaxLayers + 1];   // trunk b_l offsets, [L] = packed head b
@@ -62,8 +63,10 @@ struct Workspace {
     // all device pointers into the caller's workspace
     float* head_pi;      // packed head W|b of pi      [H_L*P + P]
     float* head_old;     // packed head W|b of oldpi
-    float* wt_pi;        // tensor-core path: transposed kernels Wt[out][in] of pi (internal layout offsets)
-    float* wt_old;       // ... of oldpi
+    // tensor-core path: per-layer weight images (B operand tiles as they sit in smem, hi|lo), see tc_pack_images
+    float* img_fwd_pi[kMaxLayers + 1];
+    float* img_fwd_old[kMaxLayers + 1];
+    float* img_dx_pi[kMaxLayers + 1];
     float* act_pi[kMaxLayers];   // post-ReLU activations of pi, layer l: [max_rows, h[l]]
     float* scratch[2];   // oldpi activations / dh ping-pong: [max_rows, hmax]
     float* out_pi;       // [max_rows, P]
@@ -139,6 +142,13 @@ int gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B,
 int tc_gemm_kk(int terms, int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0,
                const float* B1, int ldb, float* C0, float* C1, int ldc, const float* bias0, const float* bias1,
                int relu, const float* mask, int nets, cudaStream_t st);
+long long tc_image_floats(int N, int K);
+int tc_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
+                   const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
+                   cudaStream_t st);
+int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
+                   const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,
+                   const float* mask, int nets, cudaStream_t st);
 int tc_gemm_tn_splitk(int terms, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       int slices, long long slice_stride, int accumulate, cudaStream_t st);
 int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,
@@ -148,6 +158,7 @@ int tc_transpose_weights(const NetShape& s, const float* params_pi, const float*
 
 int launch_pack_heads(const NetShape& s, const float* params_pi, const float* params_old,
                       float* head_pi, float* head_old, cudaStream_t st);
+// out_pi / out_old / d_out are [rows, s.Pld] with P valid columns
 int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
                 const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st);

@@ -64,7 +64,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(kLossTileRows)
 ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_old,
                 const float* __restrict__ act, const float* __restrict__ adv,
-                const float* __restrict__ ret, int rows, int A, int tile0, float inv_B, float clip,
+                const float* __restrict__ ret, int rows, int A, int Pld, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* __restrict__ d_out,
                 double* __restrict__ loss_part) {
     extern __shared__ float smem[];
@@ -79,9 +79,12 @@ ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_
     const int tid = threadIdx.x;
 
     {   // coalesced tile loads
-        const float* gp = out_pi + (size_t)row0 * P;
-        const float* go = out_old + (size_t)row0 * P;
-        for (int i = tid; i < nrows * P; i += kLossTileRows) { s_pi[i] = __ldg(gp + i); s_old[i] = __ldg(go + i); }
+        const float* gp = out_pi + (size_t)row0 * Pld;   // global rows are Pld wide (16-B aligned), smem rows P wide
+        const float* go = out_old + (size_t)row0 * Pld;
+        for (int i = tid; i < nrows * Pld; i += kLossTileRows) {
+            const int r = i / Pld, cc = i - r * Pld;
+            if (cc < P) { s_pi[r * P + cc] = __ldg(gp + i); s_old[r * P + cc] = __ldg(go + i); }
+        }
         const float* ga = act + (size_t)row0 * A;
         for (int i = tid; i < nrows * A; i += kLossTileRows) s_act[i] = __ldg(ga + i);
     }
@@ -147,8 +150,11 @@ ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_
     }
     __syncthreads();
     {   // coalesced d_out store
-        float* gd = d_out + (size_t)row0 * P;
-        for (int i = tid; i < nrows * P; i += kLossTileRows) gd[i] = s_pi[i];
+        float* gd = d_out + (size_t)row0 * Pld;
+        for (int i = tid; i < nrows * Pld; i += kLossTileRows) {
+            const int r = i / Pld, cc = i - r * Pld;
+            gd[i] = cc < P ? s_pi[r * P + cc] : 0.f;
+        }
     }
     // block reduction of the batch sums
     const int warp = tid / 32, lane = tid % 32;
@@ -179,7 +185,7 @@ int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, co
     }
     const int grid = (rows + kLossTileRows - 1) / kLossTileRows;
     ProfScope ps(KK_LOSS, st);
-    ppo_loss_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, act, adv, ret, rows, s.act, tile0,
+    ppo_loss_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, act, adv, ret, rows, s.act, s.Pld, tile0,
                                                        inv_B, clip, entcoeff, vcoeff, d_out, loss_part);
     DPPO_LAUNCH_CHECK();
     return 0;
@@ -273,11 +279,12 @@ int launch_finalize(const NetShape& s, const float* partial, const double* loss_
 // ---------------------------------------------------------------------------------------------
 // out[rows,P] -> v[rows], pdflat[rows,2A]
 // ---------------------------------------------------------------------------------------------
-__global__ void split_heads_kernel(const float* __restrict__ out, long long total, int P,
+__global__ void split_heads_kernel(const float* __restrict__ out, long long total, int P, int Pld,
                                    float* __restrict__ v_out, float* __restrict__ pd_out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const long long r = i / P; const int c = (int)(i % P);
+        const long long r = i / Pld; const int c = (int)(i - r * Pld);
+        if (c >= P) continue;
         const float x = __ldg(out + i);
         if (c == 0) { if (v_out) v_out[r] = x; }
         else if (pd_out) pd_out[r * (P - 1) + (c - 1)] = x;
@@ -287,11 +294,11 @@ __global__ void split_heads_kernel(const float* __restrict__ out, long long tota
 int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
                        cudaStream_t st) {
     if (rows == 0) return 0;
-    const long long total = (long long)rows * s.P;
+    const long long total = (long long)rows * s.Pld;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     ProfScope ps(KK_MISC, st);
-    split_heads_kernel<<<grid, 256, 0, st>>>(out, total, s.P, v_out, pd_out);
+    split_heads_kernel<<<grid, 256, 0, st>>>(out, total, s.P, s.Pld, v_out, pd_out);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -342,7 +349,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
 }
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
-__global__ void sample_kernel(const float* __restrict__ out, int rows, int A, uint64_t seed, uint64_t offset,
+__global__ void sample_kernel(const float* __restrict__ out, int rows, int A, int Pld, uint64_t seed, uint64_t offset,
                               float* __restrict__ action, float* __restrict__ v_out) {
     const int P = 1 + 2 * A;
     const int quads = (A + 3) / 4;
@@ -360,7 +367,7 @@ __global__ void sample_kernel(const float* __restrict__ out, int rows, int A, ui
             sincosf(6.283185307179586f * u01(c[3]), &s1, &c1);
             z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
         }
-        const float* o = out + (size_t)r * P;
+        const float* o = out + (size_t)r * Pld;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int k = q * 4 + e;
@@ -433,7 +440,7 @@ int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, 
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     ProfScope ps(KK_MISC, st);
-    sample_kernel<<<grid, 256, 0, st>>>(out, rows, s.act, seed, offset, action, v_out);
+    sample_kernel<<<grid, 256, 0, st>>>(out, rows, s.act, s.Pld, seed, offset, action, v_out);
     DPPO_LAUNCH_CHECK();
     return 0;
 }

@@ -22,12 +22,14 @@ constexpr int BM = 128;          // UMMA M
 constexpr int BK = 32;           // 32 tf32 = 128 B = one swizzle row; 4 MMAs of K=8 per block
 constexpr int kLoadWarps = 8;
 constexpr int kLoadThreads = kLoadWarps * 32;
-constexpr int kThreads = kLoadThreads + 32;
+constexpr int kThreads = kLoadThreads + 64;   // + MMA warp + weight-image producer warp
+constexpr int kPrefetch = 3;                  // A k-blocks in flight per loader thread when B arrives by bulk copy
 
 enum { EPI_NN = 0, EPI_NT = 1, EPI_TN = 2 };
 
 struct TcArgs {
     const float* A[2]; const float* B[2]; float* C[2]; const float* bias[2];
+    const float* Bimg[2];      // B_IMAGE: weights pre-split and pre-swizzled as smem tile images (pack_images_kernel)
     const float* mask;
     int M, N, K;
     int lda, ldb, ldc;
@@ -46,6 +48,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -189,8 +199,9 @@ struct SmemPlan {
     static_assert(kStages >= 2, "need at least a double buffer");
 };
 
-template <int BN, bool MN_MAJOR, int TERMS, int EPI>
+template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
+    static_assert(!(B_IMAGE && MN_MAJOR), "weight images exist for the K-major products only");
     using Plan = SmemPlan<BN, TERMS>;
     constexpr int STAGES = Plan::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
     const int nkb = max(0, (k_end - k_begin + BK - 1) / BK);
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoadThreads); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoadThreads + (B_IMAGE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
@@ -228,6 +239,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
         // ================= operand movers =================
         const float* __restrict__ A = g.A[net];
         const float* __restrict__ B = g.B[net];
+        if (B_IMAGE) {
+            // only the activation operand goes through registers: kPrefetch k-blocks of loads stay in flight
+            float4 ra[kPrefetch][BM / 32];
+#pragma unroll
+            for (int j = 0; j < kPrefetch; ++j)
+                if (j < nkb) tile_load<BM, MN_MAJOR>(ra[j], A, g.lda, m0, g.M, k_begin + j * BK, k_end, g.vecA, tid);
+            for (int kb0 = 0; kb0 < nkb; kb0 += kPrefetch) {
+#pragma unroll
+                for (int j = 0; j < kPrefetch; ++j) {
+                    const int kb = kb0 + j;
+                    if (kb < nkb) {
+                        const int s = kb % STAGES;
+                        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                        uint8_t* st = smem + s * Plan::kStage;
+                        tile_store<BM, MN_MAJOR, TERMS>(ra[j], st, st + Plan::kATile, tid);
+                        fence_proxy_async();
+                        mbar_arrive(&full_bar[s]);
+                        if (kb + kPrefetch < nkb)
+                            tile_load<BM, MN_MAJOR>(ra[j], A, g.lda, m0, g.M, k_begin + (kb + kPrefetch) * BK, k_end, g.vecA, tid);
+                    }
+                }
+            }
+        } else {
         float4 ra[BM / 32], rb[BN / 32];
         if (nkb > 0) {
             tile_load<BM, MN_MAJOR>(ra, A, g.lda, m0, g.M, k_begin, k_end, g.vecA, tid);
@@ -258,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
                 for (int i = 0; i < BN / 32; ++i) rb[i] = nb[i];
             }
         }
+        }
 
         // ================= epilogue =================
         float* __restrict__ C = g.C[net];
@@ -269,15 +304,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
+        // TMEM -> registers (thread = accumulator row) -> per-warp smem staging -> coalesced row-wise global
+        // accesses (bias / ReLU-mask reads and the C store are full 128-B lines; a thread-per-row store would
+        // scatter 16-B pieces over 32 rows per instruction).  The operand stages are free once accum_bar fired.
         constexpr int kColsPerHalf = BN / 2 < 32 ? 32 : BN / 2;
+        constexpr int kStgLd = kColsPerHalf + 4;
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)warp * (32 * kStgLd);
+        const int col0 = half * kColsPerHalf;
 #pragma unroll 1
-        for (int cb = half * kColsPerHalf; cb < (half + 1) * kColsPerHalf && cb < BN; cb += 32) {
+        for (int cb = 0; cb < kColsPerHalf && col0 + cb < BN; cb += 32) {
             uint32_t v[32];
             if (nkb > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + cb), v);
                 if (TERMS == 3) {
                     uint32_t w2[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + cb), w2);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + col0 + cb), w2);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w2[j]));
                 }
@@ -285,49 +326,82 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            const int nb0 = n0 + cb;
-            if (m < g.M && nb0 < g.N) {          // predicated (no divergent `continue`: tcgen05.ld is warp-collective)
-                float* cp = C + (size_t)m * g.ldc + nb0;
-                const float* mp = (EPI == EPI_NT && g.mask) ? g.mask + (size_t)m * g.ldc + nb0 : nullptr;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const int n = nb0 + j4 * 4;
-                    const int nv = min(4, g.N - n);
-                    if (nv > 0) {
-                        float x[4];
+            for (int j4 = 0; j4 < 8; ++j4)
+                *reinterpret_cast<uint4*>(stg + lane * kStgLd + cb + j4 * 4) = make_uint4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        __syncwarp();
+        if (col0 < BN) {
+            constexpr int kLanesPerRow = kColsPerHalf / 4;
+            constexpr int kRowsPerIter = 32 / kLanesPerRow;
+            const int cl = (lane % kLanesPerRow) * 4;
+            const int n = n0 + col0 + cl;
+            const int nv = min(4, g.N - n);
+            float bv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (EPI == EPI_NN && bias) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[j4 * 4 + e]);
-                        if (EPI == EPI_NN) {
+                for (int e = 0; e < 4; ++e)
+                    if (e < nv) bv[e] = __ldg(bias + n + e);
+            }
+#pragma unroll 4
+            for (int it = 0; it < 32 / kRowsPerIter; ++it) {
+                const int r = it * kRowsPerIter + lane / kLanesPerRow;
+                const int m = m0 + q * 32 + r;
+                if (m < g.M && nv > 0) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+                    float x[4] = {t4.x, t4.y, t4.z, t4.w};
+                    float* cp = C + (size_t)m * g.ldc + n;
+                    if (EPI == EPI_NN) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (e < nv) {
-                                    const float y = x[e] + (bias ? __ldg(bias + n + e) : 0.f);
-                                    x[e] = g.relu ? fmaxf(y, 0.f) : y;
-                                }
-                        } else if (EPI == EPI_NT) {
-                            if (mp) {
+                        for (int e = 0; e < 4; ++e) {
+                            const float y = x[e] + bv[e];
+                            x[e] = g.relu ? fmaxf(y, 0.f) : y;
+                        }
+                    } else if (EPI == EPI_NT) {
+                        if (g.mask) {
+                            const float* mp = g.mask + (size_t)m * g.ldc + n;
+                            if (g.vecC && nv == 4) {
+                                const float4 mk = __ldg(reinterpret_cast<const float4*>(mp));
+                                x[0] = mk.x > 0.f ? x[0] : 0.f; x[1] = mk.y > 0.f ? x[1] : 0.f;
+                                x[2] = mk.z > 0.f ? x[2] : 0.f; x[3] = mk.w > 0.f ? x[3] : 0.f;
+                            } else {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    if (e < nv) x[e] = (__ldg(mp + j4 * 4 + e) > 0.f) ? x[e] : 0.f;
-                            }
-                        } else {
-                            if (g.accumulate) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (e < nv) x[e] += cp[j4 * 4 + e];
+                                    if (e < nv) x[e] = (__ldg(mp + e) > 0.f) ? x[e] : 0.f;
                             }
                         }
-                        if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp + j4 * 4) = make_float4(x[0], x[1], x[2], x[3]);
-                        else {
+                    } else {
+                        if (g.accumulate) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
-                                if (e < nv) cp[j4 * 4 + e] = x[e];
+                                if (e < nv) x[e] += cp[e];
                         }
+                    }
+                    if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (e < nv) cp[e] = x[e];
                     }
                 }
             }
         }
         tc_fence_before();
+    } else if (warp == kLoadWarps + 1) {
+        // ================= weight-image producer (one thread): bulk copies of ready-made B tiles =================
+        if (B_IMAGE && lane == 0) {
+            constexpr uint32_t kBytes = (TERMS == 3 ? 2 : 1) * Plan::kBTile;
+            const int kbs_total = (g.K + BK - 1) / BK;
+            const uint8_t* img = reinterpret_cast<const uint8_t*>(g.Bimg[net]) +
+                                 (size_t)(blockIdx.x % g.tiles_n) * kbs_total * (2 * Plan::kBTile);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                uint8_t* dst = smem + s * Plan::kStage + (TERMS == 3 ? 2 : 1) * Plan::kATile;
+                mbar_arrive_expect_tx(&full_bar[s], kBytes);
+                bulk_copy_g2s(dst, img + (size_t)(k_begin / BK + kb) * (2 * Plan::kBTile), kBytes, &full_bar[s]);
+            }
+        }
     } else if (lane == 0) {
         // ================= MMA issuer (one thread) =================
         constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR, MN_MAJOR);
@@ -370,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
 
 static inline int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, bool MN_MAJOR, int TERMS, int EPI>
+template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE>
 static int launch(TcArgs& g, int slices, cudaStream_t st) {
     using Plan = SmemPlan<BN, TERMS>;
     g.tiles_n = (g.N + BN - 1) / BN;
@@ -378,13 +452,13 @@ static int launch(TcArgs& g, int slices, cudaStream_t st) {
     DPPO_REQUIRE(tiles_m <= 65535, "tc_gemm: M=%d too large for one launch", g.M);
     static bool configured = false;
     if (!configured) {
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI>,
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
         configured = true;
     }
     dim3 grid(g.tiles_n * g.nets, tiles_m, slices);
     ProfScope ps(KK_TC_GEMM, st);
-    tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI><<<grid, kThreads, Plan::kBytes, st>>>(g);
+    tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE><<<grid, kThreads, Plan::kBytes, st>>>(g);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -394,11 +468,44 @@ static void fill_vec_flags(TcArgs& g) {
     for (int i = 0; i < g.nets; ++i) { g.vecA &= aligned16(g.A[i]); g.vecB &= aligned16(g.B[i]); g.vecC &= aligned16(g.C[i]); }
 }
 
-template <int TERMS, bool MN_MAJOR, int EPI>
+template <int TERMS, bool MN_MAJOR, int EPI, bool B_IMAGE = false>
 static int dispatch_bn(TcArgs& g, int slices, cudaStream_t st) {
-    if (g.N > 128) return launch<256, MN_MAJOR, TERMS, EPI>(g, slices, st);
-    if (g.N > 64) return launch<128, MN_MAJOR, TERMS, EPI>(g, slices, st);
-    return launch<64, MN_MAJOR, TERMS, EPI>(g, slices, st);
+    if (g.N > 128) return launch<256, MN_MAJOR, TERMS, EPI, B_IMAGE>(g, slices, st);
+    if (g.N > 64) return launch<128, MN_MAJOR, TERMS, EPI, B_IMAGE>(g, slices, st);
+    return launch<64, MN_MAJOR, TERMS, EPI, B_IMAGE>(g, slices, st);
+}
+
+// ---- weight images: B tiles exactly as they must sit in shared memory (K-major SWIZZLE_128B, hi then lo), so a
+// CTA fetches one (n-tile, k-block) with a single bulk copy instead of 8 warps of LDG/convert/STS ----
+struct ImgEntry { const float* src; float* dst; int N, K, ld, transposed, bn; };
+struct ImgPlan { int n; ImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
+
+__global__ void pack_images_kernel(ImgPlan p, long long total_units) {
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total_units; u += (long long)gridDim.x * blockDim.x) {
+        int i = 0;
+        while (u >= p.unit_end[i]) ++i;
+        const ImgEntry e = p.e[i];
+        long long r_ = u - (i ? p.unit_end[i - 1] : 0);
+        const int c = (int)(r_ & 7); r_ >>= 3;                 // 16-B chunk within the 128-B row
+        const int r = (int)(r_ % e.bn); r_ /= e.bn;           // row within the tile
+        const int kbs = (e.K + BK - 1) / BK;
+        const int kb = (int)(r_ % kbs), nt = (int)(r_ / kbs);
+        const int n = nt * e.bn + r, k0 = kb * BK + c * 4;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + q;
+            v[q] = (n < e.N && k < e.K) ? (e.transposed ? __ldg(e.src + (size_t)k * e.ld + n) : __ldg(e.src + (size_t)n * e.ld + k)) : 0.f;
+        }
+        uint4 h, l;
+        h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
+        l.x = to_tf32(v[0] - __uint_as_float(h.x)); l.y = to_tf32(v[1] - __uint_as_float(h.y));
+        l.z = to_tf32(v[2] - __uint_as_float(h.z)); l.w = to_tf32(v[3] - __uint_as_float(h.w));
+        uint8_t* tile = reinterpret_cast<uint8_t*>(e.dst) + ((size_t)nt * kbs + kb) * (size_t)(e.bn * 256);
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(tile + off) = h;
+        *reinterpret_cast<uint4*>(tile + (size_t)e.bn * 128 + off) = l;
+    }
 }
 
 }  // namespace tc
@@ -463,6 +570,60 @@ int tc_transpose_weights(const NetShape& s, const float* params_pi, const float*
     transpose_weights_kernel<<<grid, 256, 0, st>>>(p, params_pi, head_pi, wt_pi, params_old, head_old, wt_old, s.n_params);
     DPPO_LAUNCH_CHECK();
     return 0;
+}
+
+static inline int tc_bn_for(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
+// floats of one weight image: B is [N,K]
+long long tc_image_floats(int N, int K) {
+    const int bn = tc_bn_for(N);
+    return (long long)((N + bn - 1) / bn) * ((K + tc::BK - 1) / tc::BK) * bn * 64;     // bn*256 B per (n-tile, k-block)
+}
+
+// Build every weight image of one update: forward images of pi (and oldpi) from W_l^T, dX images of pi from W_l.
+// img_* are arrays of L+1 device pointers (nullptr = skip).
+int tc_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
+                   const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
+                   cudaStream_t st) {
+    tc::ImgPlan p; p.n = 0;
+    long long units = 0;
+    auto add = [&](const float* src, float* dst, int N, int K, int ld, int transposed) {
+        if (!src || !dst) return;
+        tc::ImgEntry& e = p.e[p.n];
+        e.src = src; e.dst = dst; e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = tc_bn_for(N);
+        units += (long long)((N + e.bn - 1) / e.bn) * ((K + tc::BK - 1) / tc::BK) * e.bn * 8;
+        p.unit_end[p.n++] = units;
+    };
+    for (int l = 0; l <= s.L; ++l) {
+        const int in = s.in_dim(l), out = s.out_dim(l);
+        const float* w_pi = (l == s.L) ? head_pi : params_pi + s.w_off[l];
+        const float* w_old = (l == s.L) ? head_old : (params_old ? params_old + s.w_off[l] : nullptr);
+        add(w_pi, img_fwd_pi[l], out, in, out, 1);                 // forward: B[n=out][k=in] = W[k][n]
+        add(params_old ? w_old : nullptr, img_fwd_old[l], out, in, out, 1);
+        if (l > 0) add(w_pi, img_dx_pi[l], in, out, out, 0);      // dX:      B[n=in][k=out] = W[n][k]
+    }
+    if (p.n == 0) return 0;
+    int grid = (int)((units + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_MISC, st);
+    tc::pack_images_kernel<<<grid, 256, 0, st>>>(p, units);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// C[M,N] = epi(A[M,K] . Bimg^T) with B given as weight images (see tc_pack_images)
+int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
+                   const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,
+                   const float* mask, int nets, cudaStream_t st) {
+    if (M == 0) return 0;
+    tc::TcArgs g{};
+    g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = img0; g.Bimg[1] = img1; g.C[0] = C0; g.C[1] = C1; g.bias[0] = bias0; g.bias[1] = bias1;
+    g.mask = mask; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = 4; g.ldc = ldc; g.nets = nets; g.relu = relu;
+    g.k_per_slice = ((K + tc::BK - 1) / tc::BK) * tc::BK;
+    g.B[0] = A0; g.B[1] = A1;          // unused in image mode; keeps fill_vec_flags well-defined
+    tc::fill_vec_flags(g);
+    if (epi_nt) return tc::dispatch_bn<3, false, tc::EPI_NT, true>(g, 1, st);
+    return tc::dispatch_bn<3, false, tc::EPI_NN, true>(g, 1, st);
 }
 
 // C[M,N] = epi(A[M,K] . Bt[N,K]^T): both operands K-contiguous.  nets = 1 or 2 products sharing shapes.
