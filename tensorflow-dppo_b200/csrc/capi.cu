@@ -521,6 +521,20 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
     CTX_GUARD(c);
     cudaStream_t st = (cudaStream_t)stream;
     GemmEpi e; e.bias = bias; e.relu = relu; e.mask = mask;
+    if (mode == 48 || mode == 49) {
+        // weight-image product (the path the update uses): Bt[N,K] is packed into a smem-tile image first.
+        // Test/microbenchmark hook only: the image scratch is allocated here, outside the caller's workspace.
+        static float* scratch = nullptr; static long long scratch_floats = 0;
+        const long long need = tc_image_floats(N, K);
+        if (need > scratch_floats) {
+            if (scratch) cudaFree(scratch);
+            DPPO_CHECK_CUDA(cudaMalloc((void**)&scratch, (size_t)need * sizeof(float)));
+            scratch_floats = need;
+        }
+        if (int r = tc_pack_one(B, scratch, N, K, K, 0, st)) return r;
+        return tc_gemm_kk_img(mode == 49, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, bias, nullptr, relu,
+                              mode == 49 ? mask : nullptr, 1, st);
+    }
     if (mode >= 16) {
         // tensor-core products: terms = 3 (modes 16..18) or 1 (modes 32..34).
         // 16/32: C = relu?(A[M,K].Bt[N,K]^T + bias); 17/33: same product, C *= (mask>0); 18/34: C = A[K,M]^T.B[K,N]

@@ -146,6 +146,7 @@ long long tc_image_floats(int N, int K);
 int tc_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
                    cudaStream_t st);
+int tc_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st);
 int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
                    const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,
                    const float* mask, int nets, cudaStream_t st);

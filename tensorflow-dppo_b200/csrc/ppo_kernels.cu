@@ -203,30 +203,52 @@ struct FinalizePlan {
     int slices[kMaxLayers + 1];
 };
 
-__global__ void finalize_kernel(const float* __restrict__ partial, FinalizePlan plan, long long n_params,
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, FinalizePlan plan, long long n_params,
                                 long long head_off, int H, int A, const double* __restrict__ loss_part, int n_tiles,
                                 float entcoeff, float vcoeff, float* __restrict__ grad_out,
                                 float* __restrict__ losses_out) {
     const int P = 1 + 2 * A;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += stride) {
-        int l = 0;
-        while (l + 1 < plan.n_regions && i >= plan.w_off[l + 1]) ++l;
-        const float* src = partial + plan.part_off[l] + (i - plan.w_off[l]);
+    // 4 lanes share one parameter: lane j of the quad sums slices j, j+4, ... (8 independent loads in flight each),
+    // then a fixed-order shuffle tree combines them -> deterministic, and enough memory parallelism to stream the
+    // partial buffer (slices x n_params floats) at HBM speed instead of one dependent load chain per thread.
+    const long long stride = (long long)gridDim.x * (blockDim.x / 4);
+    const int sub = threadIdx.x & 3;
+    for (long long i = (long long)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2); i < ((n_params + stride - 1) / stride) * stride;
+         i += stride) {
         float s = 0.f;
-        for (int k = 0; k < plan.slices[l]; ++k) s += __ldg(src + (size_t)k * plan.region[l]);
-        long long pub = i;
-        if (i >= head_off) {
-            const long long r = i - head_off;
-            if (r < (long long)H * P) {
-                const int k = (int)(r / P), c = (int)(r % P);
-                pub = head_off + (c == 0 ? k : (long long)H + 1 + (long long)k * 2 * A + (c - 1));
-            } else {
-                const int c = (int)(r - (long long)H * P);
-                pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + 2LL * A * H + (c - 1));
+        long long pub = 0;
+        const bool live = i < n_params;
+        if (live) {
+            int l = 0;
+            while (l + 1 < plan.n_regions && i >= plan.w_off[l + 1]) ++l;
+            const float* src = partial + plan.part_off[l] + (i - plan.w_off[l]);
+            const long long rg = plan.region[l];
+            const int ns = plan.slices[l];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+            int k = sub;
+            for (; k + 28 < ns; k += 32) {
+                a0 += __ldg(src + (size_t)(k + 0) * rg);  a1 += __ldg(src + (size_t)(k + 4) * rg);
+                a2 += __ldg(src + (size_t)(k + 8) * rg);  a3 += __ldg(src + (size_t)(k + 12) * rg);
+                a4 += __ldg(src + (size_t)(k + 16) * rg); a5 += __ldg(src + (size_t)(k + 20) * rg);
+                a6 += __ldg(src + (size_t)(k + 24) * rg); a7 += __ldg(src + (size_t)(k + 28) * rg);
+            }
+            for (; k < ns; k += 4) a0 += __ldg(src + (size_t)k * rg);
+            s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+            pub = i;
+            if (i >= head_off) {
+                const long long r = i - head_off;
+                if (r < (long long)H * P) {
+                    const int kk = (int)(r / P), c = (int)(r % P);
+                    pub = head_off + (c == 0 ? kk : (long long)H + 1 + (long long)kk * 2 * A + (c - 1));
+                } else {
+                    const int c = (int)(r - (long long)H * P);
+                    pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + 2LL * A * H + (c - 1));
+                }
             }
         }
-        grad_out[pub] = s;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (live && sub == 0) grad_out[pub] = s;
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         double acc[7];
@@ -266,7 +288,7 @@ int launch_finalize(const NetShape& s, const float* partial, const double* loss_
         plan.part_off[l] = s.part_off[l]; plan.slices[l] = s.slices[l];
     }
     const int H = s.in_dim(s.L);
-    int grid = (int)((s.n_params + 255) / 256);
+    int grid = (int)((s.n_params + 63) / 64);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
     ProfScope ps(KK_FINALIZE, st);
