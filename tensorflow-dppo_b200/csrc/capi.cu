@@ -200,6 +200,9 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
         const int ldy = (l == s.L) ? s.Pld : out;
         float* p = w.partial + s.part_off[l];
         if (tcore) {
+            if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
+                return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, s.slices[l],
+                                      s.region[l], accumulate, st);
             if (int r = tc_gemm_tn_splitk(3, in, out, rows, x_in, in, dY, ldy, p, out, s.slices[l], s.region[l],
                                           accumulate, st)) return r;
             return tc_colsum(dY, rows, out, ldy, s.slices[l], p + (size_t)in * out, s.region[l], accumulate, st);
@@ -543,6 +546,24 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
                                         nullptr, 1, st);
         if (sub == 1) return tc_gemm_kk(terms, 1, M, N, K, A, nullptr, K, B, nullptr, K, C, nullptr, N, nullptr, nullptr, 0,
                                         mask, 1, st);
+        if (sub == 3) {      // TMA-fed dW product with fused bias column sums
+            const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
+            int slices = (int)(c->shape.partial_floats / stride);
+            const int want = (K + 511) / 512;
+            if (slices > want) slices = want;
+            DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
+            DPPO_REQUIRE(tc_tn_tma_supported(A, M, B, N), "dppo_dbg_gemm: TMA path needs 16-byte aligned rows");
+            if (int r = tc_gemm_tn_tma(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride,
+                                       0, st)) return r;
+            ProfScope ps(KK_MISC, st);
+            reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
+            DPPO_LAUNCH_CHECK();
+            if (bias_out) {
+                reduce_slices_kernel<<<4, 256, 0, st>>>(c->ws.partial + (int64_t)M * N, slices, stride, N, bias_out);
+                DPPO_LAUNCH_CHECK();
+            }
+            return 0;
+        }
         if (sub == 2) {
             const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
             int slices = (int)(c->shape.partial_floats / stride);

@@ -152,6 +152,9 @@ int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float
                    const float* mask, int nets, cudaStream_t st);
 int tc_gemm_tn_splitk(int terms, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       int slices, long long slice_stride, int accumulate, cudaStream_t st);
+bool tc_tn_tma_supported(const float* A, int lda, const float* B, int ldb);
+int tc_gemm_tn_tma(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* bias_out,
+                   int slices, long long slice_stride, int accumulate, cudaStream_t st);
 int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,
               cudaStream_t st);
 int tc_transpose_weights(const NetShape& s, const float* params_pi, const float* head_pi, float* wt_pi,

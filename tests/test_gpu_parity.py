@@ -509,3 +509,15 @@ def test_loss_grad_vs_oracle_tensor_core(name, T, N, obs, hidden, A):
     # 1e-5 holds for the fp32 configs (H <= 256); the 4x1024 net (BASELINE configs[3], the bf16 config) reduces over
     # K=1024 per layer: 128 truncating TMEM adds per accumulator -> 1.5e-5 measured, bound stated here
     assert max(errs.values()) < (TOL if max(hidden, default=0) <= 256 else 3e-5), errs
+
+
+@pytest.mark.parametrize("M,N,Kr", [(128, 256, 32), (376, 256, 1000), (256, 36, 2048), (120, 64, 333), (256, 256, 4096),
+                                    (376, 256, 16), (64, 128, 7)])
+def test_tc_gemm_tn_tma(M, N, Kr):
+    """TMA-fed dW product (cp.async.bulk.tensor -> SWIZZLE_128B_ATOM_32B tiles, in-place hi/lo split, fused colsum)."""
+    eng = _engine(376, (256, 256), 17, 4096)
+    rng = np.random.default_rng(M + N + Kr)
+    X = rng.standard_normal((Kr, M)).astype(np.float32); G = rng.standard_normal((Kr, N)).astype(np.float32)
+    got, bo = eng.dbg_gemm(19, dev(X), dev(G), M, N, Kr, want_bias_out=True)
+    assert rel_err(got.cpu().numpy(), X.astype(np.float64).T @ G.astype(np.float64)) < 6e-6
+    assert rel_err(bo.cpu().numpy(), G.astype(np.float64).sum(0)) < 2e-6
