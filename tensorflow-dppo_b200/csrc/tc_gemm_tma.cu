@@ -18,12 +18,13 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace dppo {
 namespace tc {
 
 constexpr int TBK = 16;                       // rollout rows per stage
-constexpr int kTStages = 4;
 constexpr int kConvWarps = 8;
 constexpr int kConvThreads = kConvWarps * 32;
 constexpr int kTThreads = kConvThreads + 64;  // + MMA warp + TMA warp
@@ -43,8 +44,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
                  ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// BN = 256: one CTA per SM (TMEM full), 4 stages.  BN <= 128: sized so that TWO CTAs share an SM (256 TMEM columns and
+// ~100 KB of shared memory each): while one CTA drains its accumulator the other keeps the tensor pipe busy.
 template <int BN>
 struct TmaPlan {
+    static constexpr int kTStages = BN > 128 ? 4 : 3;
+    static constexpr int kMinBlocks = BN > 128 ? 1 : 2;
     static constexpr int kARaw = TBK * BM * 4;            // 8 KB: 4 feature atoms x 16 rows x 128 B
     static constexpr int kBRaw = TBK * BN * 4;
     static constexpr int kRaw = kARaw + kBRaw;            // hi (in place) region of a stage
@@ -56,9 +61,10 @@ struct TmaPlan {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kTThreads, 1)
+__global__ void __launch_bounds__(kTThreads, TmaPlan<BN>::kMinBlocks)
 tc_tn_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaArgs g) {
     using Plan = TmaPlan<BN>;
+    constexpr int kTStages = Plan::kTStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kBarOff = (Plan::kOperands > Plan::kStaging ? Plan::kOperands : Plan::kStaging);
@@ -141,28 +147,37 @@ tc_tn_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         constexpr int kChunksA = (BM / 32) * 8, kChunksB = (BN / 32) * 8;            // 32 and BN/4
         float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool want_bias = (g.bias_out != nullptr) && (blockIdx.y == 0);
-        auto convert = [&](uint8_t* base, int chunks_per_row, bool sum) {
-            const int cg = tid % chunks_per_row, atom = cg >> 3, lc = cg & 7;
-            const int rstep = kConvThreads / chunks_per_row;
+        // compile-time trip counts: all LDS.128 of a stage issue back to back, then the cvt/STS stream
+        auto convert = [&](uint8_t* base, auto cpr_tag, bool sum) {
+            constexpr int CPR = decltype(cpr_tag)::value;
+            constexpr int kStep = kConvThreads / CPR, kIt = TBK / kStep;
+            const int cg = tid % CPR, atom = cg >> 3, lc = cg & 7, kr0 = tid / CPR;
             uint8_t* ab = base + atom * (TBK * 128);
-            for (int kr = tid / chunks_per_row; kr < TBK; kr += rstep) {
-                const uint32_t off = (uint32_t)kr * 128u + (uint32_t)((((lc >> 1) ^ (kr & 3)) << 5) | ((lc & 1) << 4));
-                const float4 v = *reinterpret_cast<const float4*>(ab + off);
+            float4 v[kIt];
+            uint32_t off[kIt];
+#pragma unroll
+            for (int i = 0; i < kIt; ++i) {
+                const int kr = kr0 + i * kStep;
+                off[i] = (uint32_t)kr * 128u + (uint32_t)((((lc >> 1) ^ (kr & 3)) << 5) | ((lc & 1) << 4));
+                v[i] = *reinterpret_cast<const float4*>(ab + off[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < kIt; ++i) {
                 uint4 h, l;
-                h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-                l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
-                *reinterpret_cast<uint4*>(ab + off) = h;
-                *reinterpret_cast<uint4*>(ab + Plan::kRaw + off) = l;
-                if (sum) { csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w; }
+                h.x = to_tf32(v[i].x); h.y = to_tf32(v[i].y); h.z = to_tf32(v[i].z); h.w = to_tf32(v[i].w);
+                l.x = to_tf32(v[i].x - __uint_as_float(h.x)); l.y = to_tf32(v[i].y - __uint_as_float(h.y));
+                l.z = to_tf32(v[i].z - __uint_as_float(h.z)); l.w = to_tf32(v[i].w - __uint_as_float(h.w));
+                *reinterpret_cast<uint4*>(ab + off[i]) = h;
+                *reinterpret_cast<uint4*>(ab + Plan::kRaw + off[i]) = l;
+                if (sum) { csum.x += v[i].x; csum.y += v[i].y; csum.z += v[i].z; csum.w += v[i].w; }
             }
         };
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % kTStages;
             mbar_wait(&tma_full[s], (kb / kTStages) & 1);
             uint8_t* st = smem + s * Plan::kStage;
-            convert(st, kChunksA, false);
-            convert(st + Plan::kARaw, kChunksB, want_bias);
+            convert(st, std::integral_constant<int, kChunksA>{}, false);
+            convert(st + Plan::kARaw, std::integral_constant<int, kChunksB>{}, want_bias);
             fence_proxy_async();
             mbar_arrive(&conv_full[s]);
         }
@@ -338,7 +353,9 @@ int tc_gemm_tn_tma(int M, int N, int K, const float* A, int lda, const float* B,
     if (kps == 0) kps = tc::TBK;
     g.k_per_slice = kps;
     g.vecC = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (slice_stride % 4 == 0);
-    if (N > 128) return tc::launch_tma<256>(mA, mB, g, slices, st);
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("DPPO_TC_TN_WIDE"); wide = (e && e[0] == '1') ? 1 : 0; }
+    if (N > 128 && wide) return tc::launch_tma<256>(mA, mB, g, slices, st);
     if (N > 64) return tc::launch_tma<128>(mA, mB, g, slices, st);
     return tc::launch_tma<64>(mA, mB, g, slices, st);
 }
