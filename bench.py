@@ -228,12 +228,16 @@ def run_b200(args):
     state = {"t": 0}
 
     def step_device():
-        eng.gae(d["rew"], d["predv"], d["done"], gamma, lam, adv_out=adv, ret_out=ret)
-        eng.loss_grad(p_pi, p_old, d["obs"], d["act"], adv.view(-1), ret.view(-1), l_mul, grad_out=grad)
-        if world > 1:
-            eng.allreduce_avg(grad)
         state["t"] += 1
-        eng.adam_apply(p_pi, grad, m, v, state["t"], lr * l_mul)
+        if args.split_calls:       # the same update as five separate C-ABI calls
+            eng.gae(d["rew"], d["predv"], d["done"], gamma, lam, adv_out=adv, ret_out=ret)
+            eng.loss_grad(p_pi, p_old, d["obs"], d["act"], adv.view(-1), ret.view(-1), l_mul, grad_out=grad)
+            if world > 1:
+                eng.allreduce_avg(grad)
+            eng.adam_apply(p_pi, grad, m, v, state["t"], lr * l_mul)
+        else:                      # dppo_update: gae (side stream) + fwd + loss + bwd + allreduce + adam in one call
+            eng.update(p_pi, p_old, d["obs"], d["act"], d["rew"], d["predv"], d["done"], gamma, lam, l_mul,
+                       grad_out=grad, adam_m=m, adam_v=v, step=state["t"], lr=lr * l_mul)
 
     def step_host():
         losses, _ = eng.update_host(p_pi, p_old, host["obs"], host["act"], host["rew"], host["predv"], host["done"],
@@ -351,6 +355,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="humanoid-cfg3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-calls", action="store_true", help="time gae/loss_grad/allreduce/adam as separate calls")
     ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3"],
                     help="dense-layer arithmetic: fp32 FFMA, or tcgen05 kind::tf32 with the 3-term fp32-accurate split")
     args = ap.parse_args()

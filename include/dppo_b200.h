@@ -124,6 +124,16 @@ int dppo_sync_old(dppo_ctx* ctx, const float* params_pi, float* params_old, void
 int dppo_act(dppo_ctx* ctx, const float* params, const float* obs, int B, uint64_t seed,
              uint64_t offset, float* action_out, float* v_out, void* stream);
 
+/* one whole update on DEVICE-resident rollout buffers in a single call -- what one iteration of
+ * [sess.run(self.ppo.train, feed_dict) for _ in range(UPDATE_STEPS)] (Chief.py:64) does, plus the GAE of
+ * Worker.py:82-92: GAE (on a side stream, under the forward GEMMs) -> pi/oldpi forward -> loss -> backward ->
+ * allreduce when a communicator exists -> Adam when adam_m/adam_v are non-NULL (step = t after increment).
+ * grad_out as in dppo_loss_grad.  Asynchronous on `stream`. */
+int dppo_update(dppo_ctx* ctx, float* params_pi, const float* params_old, const float* obs, const float* act,
+                const float* rew, const float* predv, const float* done, int T, int N, double gamma, double lam,
+                int gae_mode, float l_mul, float* adam_m, float* adam_v, int step, float lr, float beta1,
+                float beta2, float eps, float* grad_out, void* stream);
+
 /* replaces the DiagGaussianPd methods as stand-alone graph ops (distributions.py:193-205) on a
  * [B,2A] flat parameter tensor: op 0 neglogp(arg=x[B,A]) -> out[B]; 1 entropy -> out[B];
  * 2 kl(arg=other flat[B,2A]) -> out[B]; 3 sample (Philox seed/offset) -> out[B,A]; 4 mode -> out[B,A]. */

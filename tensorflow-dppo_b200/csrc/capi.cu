@@ -180,10 +180,12 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
 // ---- fwd + loss + bwd over one block of rows; dW/db land in the split-K partial buffer --------
 static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
                           const float* act, const float* adv, const float* ret, int rows, int tile0,
-                          int B_total, float l_mul, int accumulate, cudaStream_t st) {
+                          int B_total, float l_mul, int accumulate, cudaStream_t st,
+                          cudaEvent_t adv_ready = nullptr) {
     const NetShape& s = c->shape;
     Workspace& w = c->ws;
     if (int r = forward_nets(c, params_pi, params_old, obs, rows, st)) return r;
+    if (adv_ready) DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, adv_ready, 0));   // adv/ret come from a side stream
     const float inv_B = 1.0f / (float)B_total;
     const float clip = c->cfg.clip_param * l_mul;                       // PPO.py:19
     if (int r = launch_loss(s, w.out_pi, w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
@@ -385,6 +387,35 @@ int dppo_loss_grad(dppo_ctx* c, const float* params_pi, const float* params_old,
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
     return launch_finalize(c->shape, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
                            losses_out, st);
+}
+
+int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const float* obs, const float* act,
+                const float* rew, const float* predv, const float* done, int T, int N, double gamma, double lam,
+                int gae_mode, float l_mul, float* adam_m, float* adam_v, int step, float lr, float beta1, float beta2,
+                float eps, float* grad_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params_pi && params_old && obs && act && rew && predv && done && grad_out, "dppo_update: null buffer");
+    DPPO_REQUIRE(gae_mode == DPPO_GAE_REFERENCE, "dppo_update: only DPPO_GAE_REFERENCE (last_v is not fed)");
+    const long long B64 = (long long)T * N;
+    DPPO_REQUIRE(T >= 1 && N >= 1 && B64 <= c->cfg.max_rows, "dppo_update: T*N=%lld exceeds max_rows=%d", B64, c->cfg.max_rows);
+    const int B = (int)B64;
+    cudaStream_t st = (cudaStream_t)stream, side = c->copy_stream;
+    // GAE depends only on rew/predv/done: it runs on a side stream underneath the forward GEMMs
+    DPPO_CHECK_CUDA(cudaEventRecord(c->done_ev, st));
+    DPPO_CHECK_CUDA(cudaStreamWaitEvent(side, c->done_ev, 0));
+    if (int r = launch_gae(rew, predv, done, nullptr, nullptr, T, N, gamma, lam, gae_mode, 1, c->ws.gae_adv, c->ws.gae_ret,
+                           side)) return r;
+    DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[0], side));
+    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, c->ws.gae_adv, c->ws.gae_ret, B, 0, B, l_mul, 0, st,
+                               c->chunk_ev[0])) return r;
+    const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
+    if (int r = launch_finalize(c->shape, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
+                                nullptr, st)) return r;
+    if (c->nccl_comm && c->world > 1)
+        if (int r = allreduce_avg(c, grad_out, c->shape.n_params + kLossSlots, st)) return r;
+    if (adam_m && adam_v)
+        return launch_adam(params_pi, grad_out, adam_m, adam_v, c->shape.n_params, step, lr, beta1, beta2, eps, st);
+    return 0;
 }
 
 int dppo_comm_unique_id(void* id_out) {

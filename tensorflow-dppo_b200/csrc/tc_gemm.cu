@@ -138,6 +138,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
     const int k_end = min(g.K, k_begin + g.k_per_slice);
     const int nkb = max(0, (k_end - k_begin + BK - 1) / BK);
 
+    // image mode: the first kPrefetch activation k-blocks are requested before the barrier/TMEM set-up, so their
+    // global latency overlaps the CTA prologue
+    float4 ra_img[B_IMAGE ? kPrefetch : 1][BM / 32];
+    if (B_IMAGE && warp < kLoadWarps) {
+#pragma unroll
+        for (int j = 0; j < kPrefetch; ++j)
+            if (j < nkb) tile_load<BM, MN_MAJOR>(ra_img[j], g.A[net], g.lda, m0, g.M, k_begin + j * BK, k_end, g.vecA, tid);
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoadThreads + (B_IMAGE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
@@ -159,10 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
         const float* __restrict__ B = g.B[net];
         if (B_IMAGE) {
             // only the activation operand goes through registers: kPrefetch k-blocks of loads stay in flight
-            float4 ra[kPrefetch][BM / 32];
-#pragma unroll
-            for (int j = 0; j < kPrefetch; ++j)
-                if (j < nkb) tile_load<BM, MN_MAJOR>(ra[j], A, g.lda, m0, g.M, k_begin + j * BK, k_end, g.vecA, tid);
+            float4 (&ra)[B_IMAGE ? kPrefetch : 1][BM / 32] = ra_img;
             for (int kb0 = 0; kb0 < nkb; kb0 += kPrefetch) {
 #pragma unroll
                 for (int j = 0; j < kPrefetch; ++j) {

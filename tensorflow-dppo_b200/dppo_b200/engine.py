@@ -166,6 +166,23 @@ class DppoEngine:
         self._check(self.lib.dppo_sync_old(self.ctx, self._dev(params_pi, self.n_params, "params_pi"),
                                            self._dev(params_old, self.n_params, "params_old"), self._stream()))
 
+    def update(self, params_pi, params_old, obs, act, rew, predv, done, gamma, lam, l_mul, grad_out=None,
+               adam_m=None, adam_v=None, step: int = 0, lr: float = 0.0, beta1=0.9, beta2=0.999, eps=1e-8,
+               gae_mode: int = L.GAE_REFERENCE):
+        """One whole update on device-resident buffers in one call: GAE (side stream) -> forward -> loss -> backward ->
+        allreduce (if a communicator exists) -> Adam (if adam_m/adam_v given).  Chief.py:64 + Worker.py:82-92."""
+        T, N = rew.shape
+        B = T * N
+        g = grad_out if grad_out is not None else self.new_grad_buffer()
+        self._check(self.lib.dppo_update(
+            self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
+            self._dev(obs, B * self.obs_dim, "obs"), self._dev(act, B * self.act_dim, "act"), self._dev(rew, B, "rew"),
+            self._dev(predv, B, "predv"), self._dev(done, B, "done"), T, N, float(gamma), float(lam), int(gae_mode),
+            float(l_mul), self._dev(adam_m, self.n_params, "adam_m") if adam_m is not None else None,
+            self._dev(adam_v, self.n_params, "adam_v") if adam_v is not None else None, int(step), float(lr),
+            beta1, beta2, eps, self._dev(g, self.grad_len, "grad_out"), self._stream()))
+        return g[self.n_params:], g
+
     # ------------------------------------------------------------------ host-buffer entry (e2e)
     def update_host(self, params_pi, params_old, obs_h, act_h, rew_h, predv_h, done_h, gamma, lam, l_mul,
                     grad_out=None, gae_mode: int = L.GAE_REFERENCE):

@@ -521,3 +521,32 @@ def test_tc_gemm_tn_tma(M, N, Kr):
     got, bo = eng.dbg_gemm(19, dev(X), dev(G), M, N, Kr, want_bias_out=True)
     assert rel_err(got.cpu().numpy(), X.astype(np.float64).T @ G.astype(np.float64)) < 6e-6
     assert rel_err(bo.cpu().numpy(), G.astype(np.float64).sum(0)) < 2e-6
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_update_single_call_equals_separate_calls(gemm_mode):
+    """dppo_update (GAE on a side stream under the forward GEMMs, then loss/backward/Adam) == the five separate calls."""
+    T, N, obs, hidden, A = 256, 64, 376, (256, 256), 17
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    eng = _engine(obs, hidden, A, T * N, gemm_mode=gemm_mode)
+    d = {k: dev(v) for k, v in buf.items()}
+    n = lay.n_params
+    # separate calls
+    p1 = dev(th_pi); m1 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")
+    adv, ret = eng.gae(d["rew"], d["predv"], d["done"], 0.99, 0.95)
+    _, g1 = eng.loss_grad(p1, dev(th_old), d["obs"], d["act"], adv.reshape(-1), ret.reshape(-1), 0.7)
+    g1 = g1.clone()
+    eng.adam_apply(p1, g1, m1, v1, 1, 2e-5 * 0.7)
+    # one call, twice (the second exercises the stream hand-over between consecutive updates)
+    p2 = dev(th_pi); m2 = torch.zeros(n, device="cuda"); v2 = torch.zeros(n, device="cuda")
+    _, g2 = eng.update(p2, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7,
+                       adam_m=m2, adam_v=v2, step=1, lr=2e-5 * 0.7)
+    g2 = g2.clone()
+    torch.cuda.synchronize()
+    assert torch.equal(g1, g2) and torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
+    eng.update(p2, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7,
+               adam_m=m2, adam_v=v2, step=2, lr=2e-5 * 0.7)
+    torch.cuda.synchronize()
+    assert torch.isfinite(p2).all() and not torch.equal(p1, p2)
