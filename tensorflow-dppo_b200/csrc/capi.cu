@@ -177,10 +177,28 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
                         w.head_pi + (size_t)H * s.P, w.head_old + (size_t)H * s.P, 0, nets, st);
 }
 
+// Split-K slices one update really needs: the plan (NetShape::slices) is sized for max_rows; a call over fewer rows
+// (minibatches, the row chunks of dppo_update_host) uses proportionally fewer, so the dW kernels launch fewer CTAs and
+// finalize_kernel streams fewer partials.  `rows` = the largest row block of the update (all its blocks share the count).
+static void active_slices(const dppo_ctx* c, int rows, int* active) {
+    const NetShape& s = c->shape;
+    for (int l = 0; l <= s.L; ++l) {
+        int a = s.slices[l];
+        if (c->cfg.gemm_mode == DPPO_GEMM_TF32X3) {
+            const int want = (rows + 511) / 512;            // <= 512 rows per TMEM accumulation chain
+            if (want < a) a = want;
+        } else {
+            const int want = (rows + 63) / 64;              // no point slicing below 64 rows per CTA
+            if (want < a) a = want;
+        }
+        active[l] = a < 1 ? 1 : a;
+    }
+}
+
 // ---- fwd + loss + bwd over one block of rows; dW/db land in the split-K partial buffer --------
 static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
                           const float* act, const float* adv, const float* ret, int rows, int tile0,
-                          int B_total, float l_mul, int accumulate, cudaStream_t st,
+                          int B_total, float l_mul, int accumulate, const int* active, cudaStream_t st,
                           cudaEvent_t adv_ready = nullptr) {
     const NetShape& s = c->shape;
     Workspace& w = c->ws;
@@ -203,13 +221,13 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
         float* p = w.partial + s.part_off[l];
         if (tcore) {
             if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
-                return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, s.slices[l],
+                return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l],
                                       s.region[l], accumulate, st);
-            if (int r = tc_gemm_tn_splitk(3, in, out, rows, x_in, in, dY, ldy, p, out, s.slices[l], s.region[l],
+            if (int r = tc_gemm_tn_splitk(3, in, out, rows, x_in, in, dY, ldy, p, out, active[l], s.region[l],
                                           accumulate, st)) return r;
-            return tc_colsum(dY, rows, out, ldy, s.slices[l], p + (size_t)in * out, s.region[l], accumulate, st);
+            return tc_colsum(dY, rows, out, ldy, active[l], p + (size_t)in * out, s.region[l], accumulate, st);
         }
-        tn.slice_stride = s.region[l]; tn.slices = s.slices[l]; tn.bias_out = p + (size_t)in * out;
+        tn.slice_stride = s.region[l]; tn.slices = active[l]; tn.bias_out = p + (size_t)in * out;
         return gemm_tn_splitk(in, out, rows, x_in, in, dY, ldy, p, out, tn, st);
     };
     // dX = (dY . W^T) * [h > 0]   (W is [n_out_of_this_product, k] row-major = K-major B operand)
@@ -383,9 +401,11 @@ int dppo_loss_grad(dppo_ctx* c, const float* params_pi, const float* params_old,
     DPPO_REQUIRE(params_pi && params_old && obs && act && adv && ret && grad_out, "dppo_loss_grad: null buffer");
     DPPO_REQUIRE(B >= 1 && B <= c->cfg.max_rows, "dppo_loss_grad: B=%d out of [1, max_rows=%d]", B, c->cfg.max_rows);
     cudaStream_t st = (cudaStream_t)stream;
-    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, adv, ret, B, 0, B, l_mul, 0, st)) return r;
+    int active[kMaxLayers + 1];
+    active_slices(c, B, active);
+    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, adv, ret, B, 0, B, l_mul, 0, active, st)) return r;
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    return launch_finalize(c->shape, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
+    return launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
                            losses_out, st);
 }
 
@@ -406,11 +426,13 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
     if (int r = launch_gae(rew, predv, done, nullptr, nullptr, T, N, gamma, lam, gae_mode, 1, c->ws.gae_adv, c->ws.gae_ret,
                            side)) return r;
     DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[0], side));
-    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, c->ws.gae_adv, c->ws.gae_ret, B, 0, B, l_mul, 0, st,
-                               c->chunk_ev[0])) return r;
+    int active[kMaxLayers + 1];
+    active_slices(c, B, active);
+    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, c->ws.gae_adv, c->ws.gae_ret, B, 0, B, l_mul, 0, active,
+                               st, c->chunk_ev[0])) return r;
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    if (int r = launch_finalize(c->shape, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
-                                nullptr, st)) return r;
+    if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
+                                grad_out, nullptr, st)) return r;
     if (c->nccl_comm && c->world > 1)
         if (int r = allreduce_avg(c, grad_out, c->shape.n_params + kLossSlots, st)) return r;
     if (adam_m && adam_v)
@@ -499,6 +521,8 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
                                         (size_t)rows * s.act * 4, cudaMemcpyHostToDevice, cp));
         DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[k + 1], cp));
     }
+    int active[kMaxLayers + 1];
+    active_slices(c, rows_per < B ? rows_per : B, active);
     DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[0], 0));
     if (int r = launch_gae(d_rew, d_pv, d_done, nullptr, nullptr, T, N, gamma, lam, gae_mode, 1, w.gae_adv,
                            w.gae_ret, st)) return r;
@@ -506,11 +530,11 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
         const int r0 = k * rows_per, rows = (B - r0 < rows_per) ? B - r0 : rows_per;
         DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[k + 1], 0));
         if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.act,
-                                   w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, st))
+                                   w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st))
             return r;
     }
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    if (int r = launch_finalize(s, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out, nullptr,
+    if (int r = launch_finalize(s, active, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out, nullptr,
                                 st)) return r;
     if (c->nccl_comm && c->world > 1)
         if (int r = allreduce_avg(c, grad_out, s.n_params + kLossSlots, st)) return r;

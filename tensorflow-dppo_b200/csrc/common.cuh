@@ -166,7 +166,8 @@ int launch_pack_heads(const NetShape& s, const float* params_pi, const float* pa
 int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
                 const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st);
-int launch_finalize(const NetShape& s, const float* partial, const double* loss_part, int n_loss_tiles,
+// active[l] = number of split-K slices the dW launches of this update actually wrote (<= s.slices[l])
+int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st);
 int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
                        cudaStream_t st);

@@ -279,13 +279,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     }
 }
 
-int launch_finalize(const NetShape& s, const float* partial, const double* loss_part, int n_loss_tiles,
+int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st) {
     FinalizePlan plan;
     plan.n_regions = s.L + 1;
     for (int l = 0; l <= s.L; ++l) {
         plan.w_off[l] = s.w_off[l]; plan.region[l] = s.region[l];
-        plan.part_off[l] = s.part_off[l]; plan.slices[l] = s.slices[l];
+        plan.part_off[l] = s.part_off[l]; plan.slices[l] = active ? active[l] : s.slices[l];
     }
     const int H = s.in_dim(s.L);
     int grid = (int)((s.n_params + 63) / 64);
