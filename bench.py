@@ -288,9 +288,17 @@ def run_b200(args):
     gemm_ms = sum(fam_ms.get(k, 0.0) for k in ("gemm_nn", "gemm_nt", "gemm_tn", "tc_gemm"))
     gemm_launches = sum(prof[k][0] for k in ("gemm_nn", "gemm_nt", "gemm_tn", "tc_gemm"))
     peaks = load_peaks()
+    traffic = None
+    try:        # measured DRAM bytes of the GEMM family for one step, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("workload") == args.workload and tj.get("gemm") == args.gemm:
+            traffic = tj["family_bytes_per_step"]
+    except (OSError, ValueError, KeyError):
+        pass
     F = flops_per_step(obs, hidden, act) * B
     achieved_tf = F * K / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     alg_bytes = bytes_per_step(obs, act) * B
+    alg_bytes_placeholder = alg_bytes
     hbm_gbs = alg_bytes * K / (ms_total * 1e-3) / 1e9
 
     # --- e2e pass: pinned host buffers through dppo_update_host ---------------------------------
@@ -321,7 +329,10 @@ def run_b200(args):
                 "kernel": ("tc_gemm_kernel (tcgen05 fwd / dX / dW)" if args.gemm == "tf32x3" else
                            "sgemm_kernel (fwd NN / dX NT / dW TN families)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
+                "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
+                "traffic_note": "DRAM bytes of all GEMM launches of one step (ncu capture under profiles/); algorithmic bytes "
+                                "of the whole update are %d -- the excess is fp32 activations (h1, h2, dh) round-tripping "
+                                "HBM between the per-layer kernels" % alg_bytes_placeholder,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "note": ("algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
                          + ("fp32-parity path: every algorithmic MAC is issued as 3 TF32 MMAs (half the bf16 rate each), so the "
@@ -348,6 +359,7 @@ def run_b200(args):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
