@@ -47,6 +47,10 @@ ProfScope::~ProfScope() {
     if (slot >= 0) cudaEventRecord(g_prof.ev1[slot], st);
 }
 
+bool peer_available(const dppo_ctx* ctx);
+float* peer_exchange_buffer(dppo_ctx* ctx);
+int peer_allreduce_adam(dppo_ctx* ctx, float* params, float* m, float* v, int step, float lr, float b1, float b2, float eps,
+                        float* grad_out, cudaStream_t st);
 int comm_unique_id(void* out);
 int comm_init(dppo_ctx* ctx, int rank, int world, const void* id_bytes);
 int comm_destroy(dppo_ctx* ctx);
@@ -431,6 +435,14 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
     if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, c->ws.gae_adv, c->ws.gae_ret, B, 0, B, l_mul, 0, active,
                                st, c->chunk_ev[0])) return r;
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
+    if (c->nccl_comm && c->world > 1 && peer_available(c)) {
+        // NVLink peer path: the rank's gradient goes straight into its exchange buffer; ONE kernel then averages over
+        // the ranks through peer loads and applies Adam (PPO.py:53,55-65)
+        if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
+                                    peer_exchange_buffer(c), nullptr, st)) return r;
+        return peer_allreduce_adam(c, params_pi, (adam_m && adam_v) ? adam_m : nullptr, adam_v, step, lr, beta1, beta2, eps,
+                                   grad_out, st);
+    }
     if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
                                 grad_out, nullptr, st)) return r;
     if (c->nccl_comm && c->world > 1)
@@ -534,10 +546,16 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
             return r;
     }
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    if (int r = launch_finalize(s, active, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out, nullptr,
-                                st)) return r;
-    if (c->nccl_comm && c->world > 1)
-        if (int r = allreduce_avg(c, grad_out, s.n_params + kLossSlots, st)) return r;
+    if (c->nccl_comm && c->world > 1 && peer_available(c)) {
+        if (int r = launch_finalize(s, active, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
+                                    peer_exchange_buffer(c), nullptr, st)) return r;
+        if (int r = peer_allreduce_adam(c, nullptr, nullptr, nullptr, 0, 0.f, 0.f, 0.f, 0.f, grad_out, st)) return r;
+    } else {
+        if (int r = launch_finalize(s, active, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
+                                    nullptr, st)) return r;
+        if (c->nccl_comm && c->world > 1)
+            if (int r = allreduce_avg(c, grad_out, s.n_params + kLossSlots, st)) return r;
+    }
     DPPO_CHECK_CUDA(cudaMemcpyAsync(c->losses_pinned, grad_out + s.n_params, kLossSlots * sizeof(float),
                                     cudaMemcpyDeviceToHost, st));
     DPPO_CHECK_CUDA(cudaStreamSynchronize(st));

@@ -92,6 +92,16 @@ struct dppo_ctx {
     // communicator (comm.cu)
     void* nccl_comm;
     int rank, world;
+    // NVLink peer-memory exchange (comm.cu): this rank's gradient exchange buffers (double-buffered), every
+    // rank's mapped copy of them, and the arrival flags
+    float* peer_self;            // [2][grad_len] owned by this rank (cudaMalloc + cudaIpc)
+    float** peer_bufs_dev;       // device array [world] of mapped base pointers (index rank == peer_self)
+    void* peer_mapped[16];       // host copy of the mapped pointers (for cudaIpcCloseMemHandle)
+    unsigned int* flags_self;    // [world] arrival epochs written by the peers, + [1] local go word
+    unsigned int** flags_dev;    // device array [world] of mapped flag arrays
+    void* flags_mapped[16];
+    unsigned int epoch;
+    int64_t peer_len;            // floats per exchange buffer
     // update_host plumbing
     cudaStream_t copy_stream;
     cudaEvent_t chunk_ev[64];

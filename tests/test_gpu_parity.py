@@ -425,6 +425,25 @@ def _multi_gpu_worker(rank, world, port, out_dir):
     torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f"g_{rank}.npy"), g.cpu().numpy())
     np.save(os.path.join(out_dir, f"p_{rank}.npy"), p_pi.cpu().numpy())
+    # whole update in one call: NVLink peer-memory allreduce fused with Adam (3 consecutive updates exercise the
+    # double-buffered exchange) vs the same update through ncclAllReduce + adam_kernel
+    n = lay.n_params
+    rb = {k: d(c["buf"][k][:, lo:hi]) for k in ("rew", "predv", "done")}
+    obs_r, act_r, old_r = d(c["buf"]["obs"][rows]), d(c["act"][rows]), d(c["theta_old"])
+    pa = d(c["theta_pi"]); ma = torch.zeros(n, device=f"cuda:{rank}"); va = torch.zeros_like(ma)
+    pb = d(c["theta_pi"]); mb = torch.zeros_like(ma); vb = torch.zeros_like(ma)
+    for step in (1, 2, 3):
+        _, ga = eng.update(pa, old_r, obs_r, act_r, rb["rew"], rb["predv"], rb["done"], 0.99, 0.95, 0.7,
+                           adam_m=ma, adam_v=va, step=step, lr=1e-3)
+        ga = ga.clone()
+        adv_b, ret_b = eng.gae(rb["rew"], rb["predv"], rb["done"], 0.99, 0.95)
+        _, gb = eng.loss_grad(pb, old_r, obs_r, act_r, adv_b.reshape(-1), ret_b.reshape(-1), 0.7)
+        eng.allreduce_avg(gb)
+        eng.adam_apply(pb, gb, mb, vb, step, 1e-3)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(ga.cpu().numpy(), gb.cpu().numpy(), rtol=2e-6, atol=2e-8)   # sum*1/W vs ncclAvg rounding
+        np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=1e-6)
+    np.save(os.path.join(out_dir, f"pa_{rank}.npy"), pa.cpu().numpy())
     dist.destroy_process_group()
 
 
@@ -452,8 +471,10 @@ def test_multi_gpu_allreduce_equals_tower_mean(tmp_path):
     ref = O.tower_mean(towers)
     gs = [np.load(tmp_path / f"g_{r}.npy") for r in range(world)]
     ps = [np.load(tmp_path / f"p_{r}.npy") for r in range(world)]
+    pas = [np.load(tmp_path / f"pa_{r}.npy") for r in range(world)]
     for r in range(1, world):
         np.testing.assert_array_equal(gs[0], gs[r]); np.testing.assert_array_equal(ps[0], ps[r])
+        np.testing.assert_array_equal(pas[0], pas[r])          # peer-memory path: bit-identical parameters on all ranks
     n = lay.n_params
     assert max(per_tensor_rel_err(gs[0][:n], ref[:n], lay).values()) < TOL
     np.testing.assert_allclose(gs[0][n:n + 4], ref[n:], rtol=TOL, atol=TOL)
