@@ -5,6 +5,7 @@
 //     -> allreduce (PPO.py:55-65) -> Adam (PPO.py:53).
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 
@@ -431,9 +432,18 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
                            side)) return r;
     DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[0], side));
     int active[kMaxLayers + 1];
-    active_slices(c, B, active);
-    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, c->ws.gae_adv, c->ws.gae_ret, B, 0, B, l_mul, 0, active,
-                               st, c->chunk_ev[0])) return r;
+    // Optional row chunking (DPPO_UPDATE_CHUNK_ROWS=n): every layer kernel then works on a block of rows whose
+    // activations stay L2-resident between the per-layer launches; dW partials accumulate across the blocks.
+    static int chunk_rows = -1;
+    if (chunk_rows < 0) { const char* e = getenv("DPPO_UPDATE_CHUNK_ROWS"); chunk_rows = e ? atoi(e) : 0; }
+    int rows_per = (chunk_rows >= kLossTileRows && chunk_rows < B) ? (chunk_rows / kLossTileRows) * kLossTileRows : B;
+    active_slices(c, rows_per, active);
+    for (int r0 = 0, k = 0; r0 < B; r0 += rows_per, ++k) {
+        const int rows = (B - r0 < rows_per) ? B - r0 : rows_per;
+        if (int r = loss_grad_rows(c, params_pi, params_old, obs + (size_t)r0 * c->shape.obs, act + (size_t)r0 * c->shape.act,
+                                   c->ws.gae_adv + r0, c->ws.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active,
+                                   st, k == 0 ? c->chunk_ev[0] : nullptr)) return r;
+    }
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
     if (c->nccl_comm && c->world > 1 && peer_available(c)) {
         // NVLink peer path: the rank's gradient goes straight into its exchange buffer; ONE kernel then averages over

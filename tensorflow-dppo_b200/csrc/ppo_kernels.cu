@@ -208,33 +208,35 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                                 float entcoeff, float vcoeff, float* __restrict__ grad_out,
                                 float* __restrict__ losses_out) {
     const int P = 1 + 2 * A;
-    // 4 lanes share one parameter: lane j of the quad sums slices j, j+4, ... (8 independent loads in flight each),
-    // then a fixed-order shuffle tree combines them -> deterministic, and enough memory parallelism to stream the
-    // partial buffer (slices x n_params floats) at HBM speed instead of one dependent load chain per thread.
-    const long long stride = (long long)gridDim.x * (blockDim.x / 4);
-    const int sub = threadIdx.x & 3;
-    for (long long i = (long long)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2); i < ((n_params + stride - 1) / stride) * stride;
-         i += stride) {
+    // A block owns 32 consecutive parameters.  Warp w streams slices w, w+8, ... of them: every load instruction
+    // is one full 128-byte line (32 lanes x consecutive parameters of ONE slice), 8 lines in flight per warp; the 8
+    // warps' sums are then combined in a fixed order through shared memory -> deterministic and DRAM-friendly.
+    __shared__ float red[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long i0 = (long long)blockIdx.x * 32; i0 < n_params; i0 += (long long)gridDim.x * 32) {
+        const long long i = i0 + lane;
         float s = 0.f;
-        long long pub = 0;
-        const bool live = i < n_params;
-        if (live) {
+        if (i < n_params) {
             int l = 0;
             while (l + 1 < plan.n_regions && i >= plan.w_off[l + 1]) ++l;
             const float* src = partial + plan.part_off[l] + (i - plan.w_off[l]);
             const long long rg = plan.region[l];
             const int ns = plan.slices[l];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
-            int k = sub;
-            for (; k + 28 < ns; k += 32) {
-                a0 += __ldg(src + (size_t)(k + 0) * rg);  a1 += __ldg(src + (size_t)(k + 4) * rg);
-                a2 += __ldg(src + (size_t)(k + 8) * rg);  a3 += __ldg(src + (size_t)(k + 12) * rg);
-                a4 += __ldg(src + (size_t)(k + 16) * rg); a5 += __ldg(src + (size_t)(k + 20) * rg);
-                a6 += __ldg(src + (size_t)(k + 24) * rg); a7 += __ldg(src + (size_t)(k + 28) * rg);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int k = warp;
+            for (; k + 24 < ns; k += 32) {
+                a0 += __ldg(src + (size_t)(k + 0) * rg);  a1 += __ldg(src + (size_t)(k + 8) * rg);
+                a2 += __ldg(src + (size_t)(k + 16) * rg); a3 += __ldg(src + (size_t)(k + 24) * rg);
             }
-            for (; k < ns; k += 4) a0 += __ldg(src + (size_t)k * rg);
-            s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-            pub = i;
+            for (; k < ns; k += 8) a0 += __ldg(src + (size_t)k * rg);
+            s = (a0 + a1) + (a2 + a3);
+        }
+        red[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0 && i < n_params) {
+            const float t = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
+                            ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+            long long pub = i;
             if (i >= head_off) {
                 const long long r = i - head_off;
                 if (r < (long long)H * P) {
@@ -245,10 +247,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                     pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + 2LL * A * H + (c - 1));
                 }
             }
+            grad_out[pub] = t;
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (live && sub == 0) grad_out[pub] = s;
+        __syncthreads();
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         double acc[7];
@@ -288,8 +289,8 @@ int launch_finalize(const NetShape& s, const int* active, const float* partial, 
         plan.part_off[l] = s.part_off[l]; plan.slices[l] = active ? active[l] : s.slices[l];
     }
     const int H = s.in_dim(s.L);
-    int grid = (int)((s.n_params + 63) / 64);
-    if (grid > 148 * 8) grid = 148 * 8;
+    int grid = (int)((s.n_params + 31) / 32);
+    if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
     ProfScope ps(KK_FINALIZE, st);
     finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.act, loss_part,
