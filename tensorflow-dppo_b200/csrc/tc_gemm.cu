@@ -112,13 +112,16 @@ template <int BN, int TERMS>
 struct SmemPlan {
     static constexpr int kATile = BM * 128, kBTile = BN * 128;
     static constexpr int kStage = TERMS == 3 ? 2 * (kATile + kBTile) : (kATile + kBTile);
-    static constexpr int kStages = (200 * 1024) / kStage >= 4 ? 4 : (200 * 1024) / kStage;
+    // BN = 64 (the 35-wide heads): thin products bound by activation streaming, not by MMA issue -> 2 stages and
+    // ~100 KB so that two CTAs share an SM and overlap each other's prologue / epilogue
+    static constexpr int kMinBlocks = BN <= 64 ? 2 : 1;
+    static constexpr int kStages = BN <= 64 ? 2 : ((200 * 1024) / kStage >= 4 ? 4 : (200 * 1024) / kStage);
     static constexpr int kBytes = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kStages >= 2, "need at least a double buffer");
 };
 
 template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const TcArgs g) {
+__global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_gemm_kernel(const TcArgs g) {
     static_assert(!(B_IMAGE && MN_MAJOR), "weight images exist for the K-major products only");
     using Plan = SmemPlan<BN, TERMS>;
     constexpr int STAGES = Plan::kStages;
