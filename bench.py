@@ -214,7 +214,7 @@ def run_b200(args):
     T, N, obs, act, hidden = WORKLOADS[args.workload]
     B = T * N
     gamma, lam, l_mul, lr = 0.99, 0.95, 0.7, 2e-5
-    eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode={"simt": 0, "tf32x3": 1}[args.gemm])
+    eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode={"simt": 0, "tf32x3": 1, "bf16": 2}[args.gemm])
     if world > 1:
         init_engine_comm(eng, rank, world)
     host = rollout_buffer(T, N, obs, act, seed=1234 + rank, pin=True)      # weak scaling: own buffer per rank
@@ -318,15 +318,16 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
                        "hidden": list(hidden), "rows_per_gpu": B, "parallelism": f"dp{world}",
-                       "gemm": {"simt": "fp32 SIMT FFMA", "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators"}[args.gemm],
+                       "gemm": {"simt": "fp32 SIMT FFMA", "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators",
+                                "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (NOT fp32-parity)"}[args.gemm],
                        "l2": f"inputs larger than L2: obs buffer {B * obs * 4 / 1e6:.0f} MB + activations "
                              f"{B * sum(hidden) * 4 * 2 / 1e6:.0f} MB stream through HBM every step (L2 126 MB)",
                        "step": "gae + pi/oldpi fwd + loss + bwd + allreduce(N>1) + adam"},
             "roofline": {
-                "kernel": ("tc_gemm_kernel (tcgen05 fwd / dX / dW)" if args.gemm == "tf32x3" else
+                "kernel": ("tc_gemm_kernel (tcgen05 fwd / dX / dW)" if args.gemm != "simt" else
                            "sgemm_kernel (fwd NN / dX NT / dW TN families)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
@@ -368,7 +369,7 @@ def main():
     ap.add_argument("--workload", default="humanoid-cfg3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split-calls", action="store_true", help="time gae/loss_grad/allreduce/adam as separate calls")
-    ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3"],
+    ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3", "bf16"],
                     help="dense-layer arithmetic: fp32 FFMA, or tcgen05 kind::tf32 with the 3-term fp32-accurate split")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -104,16 +104,28 @@ def init_params(lay: Layout, rng, trunk_std=0.01, head_std=0.01) -> np.ndarray:
 # --------------------------------------------------------------------------
 # MLP forward   (Model.py:11-15)
 # --------------------------------------------------------------------------
-def mlp_forward(theta, obs, lay: Layout, dtype=np.float64):
-    """Returns v[B], flat[B,2A], list of post-ReLU hidden activations."""
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16, returned in the input's float dtype (models the operand rounding of the
+    DPPO_GEMM_BF16 path: every matmul operand is rounded, products are exact, accumulation is wide)."""
+    import torch
+    a = np.asarray(x)
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(torch.bfloat16).to(torch.float32).numpy().astype(a.dtype)
+
+
+def _ident(x):
+    return x
+
+
+def mlp_forward(theta, obs, lay: Layout, dtype=np.float64, q=_ident):
+    """Returns v[B], flat[B,2A], list of post-ReLU hidden activations.  q = operand rounding of every matmul."""
     p = unflatten(np.asarray(theta, dtype), lay)
     h = np.asarray(obs, dtype)
     hs = []
     for l in range(len(lay.hidden)):
-        h = np.maximum(h @ p[f"W{l + 1}"] + p[f"b{l + 1}"], 0)   # Model.py:12 dense(relu)
+        h = np.maximum(q(h) @ q(p[f"W{l + 1}"]) + p[f"b{l + 1}"], 0)   # Model.py:12 dense(relu)
         hs.append(h)
-    v = (h @ p["Wv"] + p["bv"])[:, 0]                             # Model.py:13
-    flat = h @ p["Wp"] + p["bp"]                                  # Model.py:14
+    v = (q(h) @ q(p["Wv"]) + p["bv"])[:, 0]                       # Model.py:13
+    flat = q(h) @ q(p["Wp"]) + p["bp"]                            # Model.py:14
     return v, flat, hs
 
 
@@ -219,7 +231,7 @@ def ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret, l_mul, hp: HP
     return losses, d_out, aux
 
 
-def mlp_backward(theta, obs, hs, d_out, lay: Layout, dtype=np.float64):
+def mlp_backward(theta, obs, hs, d_out, lay: Layout, dtype=np.float64, q=_ident):
     """Dense backward: dW = h^T d, db = sum_b d, dh = d W^T * [h>0]; flat grad in layout order."""
     p = unflatten(np.asarray(theta, dtype), lay)
     g = np.zeros(lay.n_params, dtype)
@@ -228,34 +240,34 @@ def mlp_backward(theta, obs, hs, d_out, lay: Layout, dtype=np.float64):
     hL = hs[-1] if L else np.asarray(obs, dtype)
     d_v = d_out[:, :1]
     d_p = d_out[:, 1:]
-    gp["Wv"][...] = hL.T @ d_v
+    gp["Wv"][...] = q(hL).T @ q(d_v)
     gp["bv"][...] = d_v.sum(0)
-    gp["Wp"][...] = hL.T @ d_p
+    gp["Wp"][...] = q(hL).T @ q(d_p)
     gp["bp"][...] = d_p.sum(0)
-    dh = d_v @ p["Wv"].T + d_p @ p["Wp"].T
+    dh = q(d_v) @ q(p["Wv"]).T + q(d_p) @ q(p["Wp"]).T
     for l in range(L, 0, -1):
         dh = dh * (hs[l - 1] > 0)
         h_in = hs[l - 2] if l >= 2 else np.asarray(obs, dtype)
-        gp[f"W{l}"][...] = h_in.T @ dh
+        gp[f"W{l}"][...] = q(h_in).T @ q(dh)
         gp[f"b{l}"][...] = dh.sum(0)
         if l > 1:
-            dh = dh @ p[f"W{l}"].T
+            dh = q(dh) @ q(p[f"W{l}"]).T
     return g
 
 
 def ppo_loss_grad(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout,
-                  hp: HParams = HParams(), dtype=np.float64):
+                  hp: HParams = HParams(), dtype=np.float64, q=_ident):
     """One tower: pi fwd + oldpi fwd + loss + backward  (PPO.py:21-22,29-40,46).
 
     Returns (losses[4] = policy, value, entropy, total ; flat_grad ; aux dict).
     """
     obs = np.asarray(obs, dtype); act = np.asarray(act, dtype)
     adv = np.asarray(adv, dtype).reshape(-1); ret = np.asarray(ret, dtype).reshape(-1)
-    v, flat, hs = mlp_forward(theta_pi, obs, lay, dtype)
-    v_old, flat_old, _ = mlp_forward(theta_old, obs, lay, dtype)
+    v, flat, hs = mlp_forward(theta_pi, obs, lay, dtype, q)
+    v_old, flat_old, _ = mlp_forward(theta_old, obs, lay, dtype, q)
     losses, d_out, aux = ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret,
                                                dtype(l_mul), hp)
-    grad = mlp_backward(theta_pi, obs, hs, d_out.astype(dtype), lay, dtype)
+    grad = mlp_backward(theta_pi, obs, hs, d_out.astype(dtype), lay, dtype, q)
     aux.update(d_out=d_out, v=v, flat=flat, v_old=v_old, flat_old=flat_old, hs=hs)
     return losses, grad, aux
 

@@ -117,7 +117,11 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     Workspace w{};
     w.head_pi = (float*)take(head);
     w.head_old = (float*)take(head);
-    if (cfg->gemm_mode != DPPO_GEMM_FP32_SIMT) {
+    if (cfg->gemm_mode == DPPO_GEMM_BF16) {
+        w.wt_pi = (float*)take((size_t)s.n_params * sizeof(float));
+        w.wt_old = (float*)take((size_t)s.n_params * sizeof(float));
+    }
+    if (cfg->gemm_mode == DPPO_GEMM_TF32X3) {
         for (int l = 0; l <= s.L; ++l) {
             const size_t fwd = (size_t)tc_image_floats(s.out_dim(l), s.in_dim(l)) * sizeof(float);
             w.img_fwd_pi[l] = (float*)take(fwd);
@@ -151,6 +155,22 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
     const int nets = params_old ? 2 : 1;
     if (int r = launch_pack_heads(s, params_pi, params_old, w.head_pi, w.head_old, st)) return r;
     const float* in0 = obs; const float* in1 = obs;
+    if (c->cfg.gemm_mode == DPPO_GEMM_BF16) {
+        // bf16 tensor cores: B operand K-major = transposed kernels (fp32 in HBM, rounded to bf16 by the movers)
+        if (int r = tc_transpose_weights(s, params_pi, w.head_pi, w.wt_pi, params_old, w.head_old, w.wt_old, st)) return r;
+        for (int l = 0; l <= s.L; ++l) {
+            const bool head = (l == s.L);
+            float* o0 = head ? w.out_pi : w.act_pi[l];
+            float* o1 = head ? w.out_old : w.scratch[l & 1];
+            const int in = s.in_dim(l), out = s.out_dim(l);
+            const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
+            const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
+            if (int r = bf16_gemm_kk(0, rows, out, in, in0, in1, in, w.wt_pi + s.w_off[l], w.wt_old + s.w_off[l], in, o0, o1,
+                                     head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st)) return r;
+            in0 = o0; in1 = o1;
+        }
+        return 0;
+    }
     if (c->cfg.gemm_mode == DPPO_GEMM_TF32X3) {
         // tensor cores: B operand K-major = transposed kernels, refreshed from the current parameters
         if (int r = tc_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
@@ -219,11 +239,17 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const float* head_in = s.L ? w.act_pi[s.L - 1] : obs;
     // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
     const bool tcore = (c->cfg.gemm_mode == DPPO_GEMM_TF32X3);
+    const bool bf16 = (c->cfg.gemm_mode == DPPO_GEMM_BF16);
     // dW_l (+ db_l) into layer l's split-K partial region
     auto dense_dw = [&](int l, const float* x_in, const float* dY) -> int {
         const int in = s.in_dim(l), out = s.out_dim(l);
         const int ldy = (l == s.L) ? s.Pld : out;
         float* p = w.partial + s.part_off[l];
+        if (bf16) {
+            if (int r = bf16_gemm_tn_splitk(in, out, rows, x_in, in, dY, ldy, p, out, active[l], s.region[l], accumulate, st))
+                return r;
+            return tc_colsum(dY, rows, out, ldy, active[l], p + (size_t)in * out, s.region[l], accumulate, st);
+        }
         if (tcore) {
             if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
                 return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l],
@@ -240,6 +266,8 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
                         const float* mask) -> int {
         if (tcore) return tc_gemm_kk_img(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_,
                                          nullptr, nullptr, 0, mask, 1, st);
+        if (bf16) return bf16_gemm_kk(1, M_, N_, K_, dY, nullptr, ldy, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr, 0,
+                                      mask, 1, st);
         GemmEpi nt; nt.mask = mask;
         return gemm_nt(M_, N_, K_, dY, ldy, W, K_, dX, N_, nt, st);
     };
@@ -321,9 +349,9 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     NetShape s;
     if (int r = make_shape(cfg, &s)) return r;
     DPPO_REQUIRE(cfg->max_rows >= 1, "max_rows=%d must be >= 1", cfg->max_rows);
-    DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT || cfg->gemm_mode == DPPO_GEMM_TF32X3,
-                 "gemm_mode=%d is not built in this library version (DPPO_GEMM_FP32_SIMT=0, DPPO_GEMM_TF32X3=1)",
-                 cfg->gemm_mode);
+    DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT || cfg->gemm_mode == DPPO_GEMM_TF32X3 ||
+                     cfg->gemm_mode == DPPO_GEMM_BF16,
+                 "gemm_mode=%d unknown (DPPO_GEMM_FP32_SIMT=0, DPPO_GEMM_TF32X3=1, DPPO_GEMM_BF16=2)", cfg->gemm_mode);
     int ndev = 0;
     DPPO_CHECK_CUDA(cudaGetDeviceCount(&ndev));
     DPPO_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d CUDA devices)", cfg->device, ndev);
@@ -607,6 +635,20 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
     CTX_GUARD(c);
     cudaStream_t st = (cudaStream_t)stream;
     GemmEpi e; e.bias = bias; e.relu = relu; e.mask = mask;
+    if (mode >= 64 && mode <= 66) {
+        // bf16 tensor-core products: 64 C = relu?(A[M,K].Bt[N,K]^T + bias); 65 same product * (mask>0); 66 C = A[K,M]^T.B[K,N]
+        if (mode == 64) return bf16_gemm_kk(0, M, N, K, A, nullptr, K, B, nullptr, K, C, nullptr, N, bias, nullptr, relu, nullptr, 1, st);
+        if (mode == 65) return bf16_gemm_kk(1, M, N, K, A, nullptr, K, B, nullptr, K, C, nullptr, N, nullptr, nullptr, 0, mask, 1, st);
+        const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
+        int slices = (int)(c->shape.partial_floats / stride);
+        if (slices > 5) slices = 5;
+        DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
+        if (int r = bf16_gemm_tn_splitk(M, N, K, A, M, B, N, c->ws.partial, N, slices, stride, 0, st)) return r;
+        ProfScope ps(KK_MISC, st);
+        reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
+        DPPO_LAUNCH_CHECK();
+        return 0;
+    }
     if (mode == 48 || mode == 49) {
         // weight-image product (the path the update uses): Bt[N,K] is packed into a smem-tile image first.
         // Test/microbenchmark hook only: the image scratch is allocated here, outside the caller's workspace.

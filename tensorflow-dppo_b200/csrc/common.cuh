@@ -63,6 +63,8 @@ struct Workspace {
     // all device pointers into the caller's workspace
     float* head_pi;      // packed head W|b of pi      [H_L*P + P]
     float* head_old;     // packed head W|b of oldpi
+    float* wt_pi;        // bf16 path: transposed kernels Wt[out][in] of pi (internal layout offsets)
+    float* wt_old;       // ... of oldpi
     // tensor-core path: per-layer weight images (B operand tiles as they sit in smem, hi|lo), see tc_pack_images
     float* img_fwd_pi[kMaxLayers + 1];
     float* img_fwd_old[kMaxLayers + 1];
@@ -152,6 +154,11 @@ int gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B,
 int tc_gemm_kk(int terms, int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0,
                const float* B1, int ldb, float* C0, float* C1, int ldc, const float* bias0, const float* bias1,
                int relu, const float* mask, int nets, cudaStream_t st);
+int bf16_gemm_kk(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* B0, const float* B1,
+                 int ldb, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask,
+                 int nets, cudaStream_t st);
+int bf16_gemm_tn_splitk(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int slices,
+                        long long slice_stride, int accumulate, cudaStream_t st);
 long long tc_image_floats(int N, int K);
 int tc_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,

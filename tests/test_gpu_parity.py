@@ -571,3 +571,55 @@ def test_update_single_call_equals_separate_calls(gemm_mode):
                adam_m=m2, adam_v=v2, step=2, lr=2e-5 * 0.7)
     torch.cuda.synchronize()
     assert torch.isfinite(p2).all() and not torch.equal(p1, p2)
+
+
+# ------------------------------------------------------------------------------- bf16 tensor-core path (BASELINE configs[3])
+def _bf16(x):
+    return torch.as_tensor(x, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 256, 376), (777, 35, 256), (4096, 1024, 1024), (129, 200, 33)])
+def test_bf16_gemm_k_major(M, N, K):
+    """kind::f16 bf16 products, K-major operands: exact vs an fp64 product of the bf16-rounded operands (fp32 accumulate)."""
+    eng = _engine(376, (256, 256), 17, 4096)
+    rng = np.random.default_rng(M + 3 * N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32); Bt = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32); mask = rng.standard_normal((M, N)).astype(np.float32)
+    ref = _bf16(A) @ _bf16(Bt).T
+    got = eng.dbg_gemm(64, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(ref + bias, 0)) < 3e-6
+    got = eng.dbg_gemm(65, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    assert rel_err(got, ref * (mask > 0)) < 3e-6
+
+
+@pytest.mark.parametrize("M,N,Kr", [(128, 256, 32), (376, 256, 1000), (256, 35, 2048), (120, 64, 333), (1024, 1024, 512)])
+def test_bf16_gemm_mn_major(M, N, Kr):
+    eng = _engine(376, (1024, 1024), 17, 4096)
+    rng = np.random.default_rng(M + N + Kr)
+    X = rng.standard_normal((Kr, M)).astype(np.float32); G = rng.standard_normal((Kr, N)).astype(np.float32)
+    got = eng.dbg_gemm(66, dev(X), dev(G), M, N, Kr).cpu().numpy()
+    assert rel_err(got, _bf16(X).T @ _bf16(G)) < 3e-6
+
+
+@pytest.mark.parametrize("name,T,N,obs,hidden,A", [CASES[0], CASES[2], CASES[5]])
+def test_loss_grad_bf16_path(name, T, N, obs, hidden, A):
+    """DPPO_GEMM_BF16 tower vs the oracle run with the same operand rounding (every matmul operand rounded to bf16,
+    wide accumulation).  The few rows whose clip / ReLU branch sits within bf16-accumulation noise of a switch may
+    flip, so the bound is 2e-3 of each tensor's max magnitude; the distance to the un-rounded fp64 oracle (inherent to
+    8-bit mantissas: the PPO ratio is an exp of a difference of two rounded nets) is printed, not asserted."""
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]; B = T * N
+    eng = _engine(obs, hidden, A, B, gemm_mode=2)
+    losses, g = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(c["buf"]["obs"]), dev(c["act"]),
+                              dev(c["adv"]), dev(c["ret"]), c["l_mul"])
+    l_q, g_q, _ = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"], c["act"], c["adv"], c["ret"],
+                                  c["l_mul"], lay, q=O.bf16_round)
+    l_ref, g_ref, _ = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"], c["act"], c["adv"], c["ret"],
+                                      c["l_mul"], lay)
+    got = g.cpu().numpy()[:lay.n_params]
+    errs = per_tensor_rel_err(got, g_q, lay)
+    print(name, "bf16 vs bf16-rounding oracle", {k: f"{v:.2e}" for k, v in errs.items()})
+    print(name, "bf16 vs fp64 oracle (informative)", {k: f"{v:.2e}" for k, v in per_tensor_rel_err(got, g_ref, lay).items()})
+    np.testing.assert_allclose(losses.cpu().numpy()[:4], l_q, rtol=1e-4, atol=1e-4)
+    # 1024-row deep case: a single flipped ReLU/clip decision moves a gradient entry by ~1/sqrt(rows) = 3 %
+    assert max(errs.values()) < (2e-3 if B >= 8192 else 2e-2), errs

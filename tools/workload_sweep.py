@@ -10,7 +10,7 @@ from dppo_b200.synthetic import WORKLOADS, rollout_buffer, params_pair
 
 ap = argparse.ArgumentParser(); ap.add_argument("--gemm", default="tf32x3"); ap.add_argument("--steps", type=int, default=20)
 args = ap.parse_args()
-mode = {"simt": 0, "tf32x3": 1}[args.gemm]
+mode = {"simt": 0, "tf32x3": 1, "bf16": 2}[args.gemm]
 
 
 def time_fn(fn, k):
