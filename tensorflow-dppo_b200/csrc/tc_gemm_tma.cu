@@ -60,9 +60,18 @@ struct TmaPlan {
     static constexpr int kBytes = (kOperands > kStaging ? kOperands : kStaging) + 1024 + 512 + 4096;   // + align, barriers, colsum
 };
 
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// mapA3/mapB3 view the same matrices as [atom][row][32 features]: ONE box then brings all the full 32-feature atoms of a
+// tile (the 2-D maps handle a ragged last atom, which needs the column bound).  use3 bit 0 / 1: 3-D map valid for A / B.
 template <int BN>
 __global__ void __launch_bounds__(kTThreads, TmaPlan<BN>::kMinBlocks)
-tc_tn_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaArgs g) {
+tc_tn_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapA3, const __grid_constant__ CUtensorMap mapB3, const int use3,
+                 const TmaArgs g) {
     using Plan = TmaPlan<BN>;
     constexpr int kTStages = Plan::kTStages;
     extern __shared__ uint8_t smem_raw[];
@@ -106,11 +115,17 @@ tc_tn_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 uint8_t* st = smem + s * Plan::kStage;
                 mbar_arrive_expect_tx(&tma_full[s], Plan::kRaw);
                 const int row = k_begin + kb * TBK;
+                if ((use3 & 1) && m0 + BM <= (g.M / 32) * 32) tma_load_3d(st, &mapA3, 0, row, m0 / 32, &tma_full[s]);
+                else {
 #pragma unroll
-                for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * (TBK * 128), &mapA, m0 + j * 32, row, &tma_full[s]);
+                    for (int j = 0; j < BM / 32; ++j) tma_load_2d(st + j * (TBK * 128), &mapA, m0 + j * 32, row, &tma_full[s]);
+                }
+                if ((use3 & 2) && n0 + BN <= (g.N / 32) * 32) tma_load_3d(st + Plan::kARaw, &mapB3, 0, row, n0 / 32, &tma_full[s]);
+                else {
 #pragma unroll
-                for (int j = 0; j < BN / 32; ++j)
-                    tma_load_2d(st + Plan::kARaw + j * (TBK * 128), &mapB, n0 + j * 32, row, &tma_full[s]);
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_2d(st + Plan::kARaw + j * (TBK * 128), &mapB, n0 + j * 32, row, &tma_full[s]);
+                }
             }
         }
     } else if (warp == kConvWarps) {
@@ -315,17 +330,39 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
     return 0;
 }
 
+// 3-D view [atoms = cols/32][rows][32]: box {32, TBK, atoms_per_tile}; false when the driver rejects the strides
+static bool make_map3(CUtensorMap* map, const float* base, int rows, int cols, int ld, int atoms_per_tile) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc || cols / 32 < atoms_per_tile) return false;
+    const cuuint64_t dims[3] = {32u, (cuuint64_t)rows, (cuuint64_t)(cols / 32)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128u};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)TBK, (cuuint32_t)atoms_per_tile};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN>
-static int launch_tma(const CUtensorMap& mA, const CUtensorMap& mB, TmaArgs& g, int slices, cudaStream_t st) {
+static int launch_tma(const CUtensorMap& mA, const CUtensorMap& mB, const float* A, int lda, const float* B, int ldb,
+                      TmaArgs& g, int slices, cudaStream_t st) {
     using Plan = TmaPlan<BN>;
     static bool configured = false;
     if (!configured) {
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
         configured = true;
     }
+    static int want3 = -1;
+    if (want3 < 0) { const char* e = getenv("DPPO_TC_TMA_2D"); want3 = (e && e[0] == '1') ? 0 : 1; }
+    CUtensorMap mA3 = mA, mB3 = mB;
+    int use3 = 0;
+    if (want3) {
+        if (make_map3(&mA3, A, g.K, g.M, lda, BM / 32)) use3 |= 1; else mA3 = mA;
+        if (make_map3(&mB3, B, g.K, g.N, ldb, BN / 32)) use3 |= 2; else mB3 = mB;
+    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, slices);
     ProfScope ps(KK_TC_GEMM, st);
-    tc_tn_tma_kernel<BN><<<grid, kTThreads, Plan::kBytes, st>>>(mA, mB, g);
+    tc_tn_tma_kernel<BN><<<grid, kTThreads, Plan::kBytes, st>>>(mA, mB, mA3, mB3, use3, g);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -355,9 +392,9 @@ int tc_gemm_tn_tma(int M, int N, int K, const float* A, int lda, const float* B,
     g.vecC = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (slice_stride % 4 == 0);
     static int wide = -1;
     if (wide < 0) { const char* e = getenv("DPPO_TC_TN_WIDE"); wide = (e && e[0] == '1') ? 1 : 0; }
-    if (N > 128 && wide) return tc::launch_tma<256>(mA, mB, g, slices, st);
-    if (N > 64) return tc::launch_tma<128>(mA, mB, g, slices, st);
-    return tc::launch_tma<64>(mA, mB, g, slices, st);
+    if (N > 128 && wide) return tc::launch_tma<256>(mA, mB, A, lda, B, ldb, g, slices, st);
+    if (N > 64) return tc::launch_tma<128>(mA, mB, A, lda, B, ldb, g, slices, st);
+    return tc::launch_tma<64>(mA, mB, A, lda, B, ldb, g, slices, st);
 }
 
 }  // namespace dppo
