@@ -307,6 +307,15 @@ def run_b200(args):
         step_host()
     ms_e2e = timed(step_host, K)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
+    # the floor of that number: the same host bytes copied with nothing else going on
+    dst = {k: torch.empty_like(d[k]) for k in ("obs", "act", "rew", "predv", "done")}
+
+    def copy_only():
+        for k, t in dst.items():
+            t.copy_(host[k], non_blocking=True)
+    copy_only()
+    ms_copy = timed(copy_only, max(K // 4, 3)) / max(K // 4, 3)
+    del dst
     clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
@@ -347,6 +356,7 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(B * (obs + act + 3) * 4), "d2h_bytes_per_step": 32,
+                    "h2d_copy_only_ms": ms_copy, "frac_of_copy_floor": ms_copy / (ms_e2e / K),
                     "api": "DppoEngine.update_host -> dppo_update_host (pinned host rollout, 8-way chunked H2D "
                            "overlapped with fwd/loss/bwd) + adam_apply"},
             "gpu_launches": int(launches),

@@ -134,6 +134,28 @@ int dppo_update(dppo_ctx* ctx, float* params_pi, const float* params_old, const 
                 int gae_mode, float l_mul, float* adam_m, float* adam_v, int step, float lr, float beta1,
                 float beta2, float eps, float* grad_out, void* stream);
 
+/* ---- epoch / minibatch scheduler on the device ------------------------------------
+ * The reference trains on whole rollouts, UPDATE_STEPS times on the same feed (Chief.py:58-64); with
+ * n_epochs = UPDATE_STEPS, minibatch_rows = T*N, shuffle = 0 this call IS that loop (GAE once, then
+ * UPDATE_STEPS x [forward, loss, backward, tower mean, Adam], gradients at the current parameters).  With
+ * minibatch_rows < T*N every epoch is cut into ceil(T*N / minibatch_rows) minibatches (the last one may be short;
+ * every loss is the mean over the minibatch's own rows), contiguous row slices when shuffle = 0, rows drawn
+ * through the keyed permutation dppo_minibatch_perm(T*N, seed, epoch) when shuffle = 1 (gathered on the device,
+ * no host involvement, the whole call is asynchronous on `stream` and graph-capturable).
+ * Adam step numbers are step0, step0+1, ... (step0 = t after increment of the first minibatch).
+ * losses_out: device [n_epochs * n_minibatches, 8] (same 8 scalars as dppo_loss_grad) or NULL.
+ * grad_out [n_params + 8] holds the last minibatch's (all-reduced) gradient on return.
+ * With a communicator every rank must pass the same n_epochs/minibatch_rows/T/N (one exchange per minibatch). */
+int dppo_update_epochs(dppo_ctx* ctx, float* params_pi, const float* params_old, const float* obs, const float* act,
+                       const float* rew, const float* predv, const float* done, int T, int N, double gamma,
+                       double lam, int gae_mode, int n_epochs, int minibatch_rows, int shuffle, uint64_t seed,
+                       float l_mul, float* adam_m, float* adam_v, int step0, float lr, float beta1, float beta2,
+                       float eps, float* losses_out, float* grad_out, void* stream);
+
+/* perm_out[i] = position i of epoch `epoch`'s row permutation of [0, n): a keyed 4-round Feistel bijection with
+ * cycle walking (csrc/perm.cuh; restated in oracle/dppo_oracle.py:minibatch_perm).  Device int32[n]. */
+int dppo_minibatch_perm(dppo_ctx* ctx, int n, uint64_t seed, uint64_t epoch, int32_t* perm_out, void* stream);
+
 /* replaces the DiagGaussianPd methods as stand-alone graph ops (distributions.py:193-205) on a
  * [B,2A] flat parameter tensor: op 0 neglogp(arg=x[B,A]) -> out[B]; 1 entropy -> out[B];
  * 2 kl(arg=other flat[B,2A]) -> out[B]; 3 sample (Philox seed/offset) -> out[B,A]; 4 mode -> out[B,A]. */

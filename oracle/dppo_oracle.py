@@ -376,6 +376,80 @@ def adam_tf(theta, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.fl
     return theta, m, v
 
 
+# --------------------------------------------------------------------------
+# epoch / minibatch scheduler.  Not in the reference (Chief.py:58-64 feeds whole rollouts
+# UPDATE_STEPS times); restates this repo's csrc/perm.cuh so that the device scheduler has a bit-exact checker.
+# --------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def _perm_mix(x, key):
+    x = x ^ np.uint32(key)
+    x = x * np.uint32(0x9E3779B1); x = x ^ (x >> np.uint32(15))
+    x = x * np.uint32(0x85EBCA77); x = x ^ (x >> np.uint32(13))
+    x = x * np.uint32(0xC2B2AE3D); x = x ^ (x >> np.uint32(16))
+    return x
+
+
+def minibatch_perm(n: int, seed: int, epoch: int) -> np.ndarray:
+    """Keyed bijection of [0, n): 4-round (unbalanced) Feistel over max(2, ceil(log2 n)) bits + cycle walking."""
+    if n == 0:
+        return np.zeros(0, np.int64)
+    bits = 2
+    while bits < 31 and (1 << bits) < n:
+        bits += 1
+    s = _splitmix64((seed ^ ((epoch * 0xD1B54A32D192ED03) & _M64)) & _M64)
+    keys = []
+    for _ in range(4):
+        s = _splitmix64(s)
+        keys.append(s >> 32)
+    a0 = bits // 2; b0 = bits - a0
+    out = np.arange(n, dtype=np.uint32)
+    todo = np.ones(n, bool)
+    with np.errstate(over="ignore"):
+        while todo.any():
+            i = out[todo]
+            la, lb = a0, b0
+            L = i >> np.uint32(b0); R = i & np.uint32((1 << b0) - 1)
+            for r in range(4):
+                nl = R; nr = L ^ (_perm_mix(R, keys[r]) & np.uint32((1 << la) - 1))
+                L, R = nl, nr
+                la, lb = lb, la
+            i = (L << np.uint32(lb)) | R
+            out[todo] = i
+            todo[todo] = i >= n
+    return out.astype(np.int64)
+
+
+def update_epochs(theta_pi, theta_old, buf, gamma, lam, l_mul, lay: Layout, lr, n_epochs=1, minibatch_rows=0,
+                  shuffle=False, seed=0, step0=1, hp: HParams = HParams(), dtype=np.float64, q=_ident):
+    """GAE once (Worker.py:82-92), then epochs x minibatches of [loss_grad (PPO.py:21-46) -> Adam (PPO.py:20,53)];
+    n_epochs=UPDATE_STEPS with one whole-buffer minibatch is Chief.py:64.  Returns (theta, m, v, losses[k,4])."""
+    adv, ret = gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], gamma, lam)
+    adv = adv.reshape(-1); ret = ret.reshape(-1)
+    B = adv.size
+    mb = B if not minibatch_rows else min(minibatch_rows, B)
+    theta = np.asarray(theta_pi, np.float64).copy()
+    m = np.zeros_like(theta); v = np.zeros_like(theta)
+    step = step0; out = []
+    for e in range(n_epochs):
+        order = minibatch_perm(B, seed, e) if shuffle else np.arange(B)
+        for r0 in range(0, B, mb):
+            idx = order[r0:r0 + mb]
+            losses, g, _ = ppo_loss_grad(theta.astype(np.float32), theta_old, buf["obs"][idx], buf["act"][idx], adv[idx],
+                                         ret[idx], l_mul, lay, hp, dtype, q)
+            theta, m, v = adam_tf(theta.astype(np.float32), g.astype(np.float32), m, v, step, lr)
+            out.append(losses); step += 1
+    return theta, m, v, np.array(out)
+
+
 def lr_multiplier(schedule: str, cur_ep: int, epoch_max: int) -> float:
     """Worker.py:77-80."""
     if schedule == "constant":

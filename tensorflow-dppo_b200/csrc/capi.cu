@@ -289,6 +289,27 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     return 0;
 }
 
+// ---- tail of every update: split-K partials -> flat gradient (+8 loss scalars) -> tower mean over the ranks -> Adam ----
+static int reduce_and_apply(dppo_ctx* c, const int* active, int rows, float* params_pi, float* adam_m, float* adam_v,
+                            int step, float lr, float beta1, float beta2, float eps, float* grad_out, cudaStream_t st) {
+    const int tiles = (rows + kLossTileRows - 1) / kLossTileRows;
+    if (c->nccl_comm && c->world > 1 && peer_available(c)) {
+        // NVLink peer path: the rank's gradient goes straight into its exchange buffer; ONE kernel then averages over
+        // the ranks through peer loads and applies Adam (PPO.py:53,55-65)
+        if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
+                                    peer_exchange_buffer(c), nullptr, st)) return r;
+        return peer_allreduce_adam(c, params_pi, (adam_m && adam_v) ? adam_m : nullptr, adam_v, step, lr, beta1, beta2, eps,
+                                   grad_out, st);
+    }
+    if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
+                                grad_out, nullptr, st)) return r;
+    if (c->nccl_comm && c->world > 1)
+        if (int r = allreduce_avg(c, grad_out, c->shape.n_params + kLossSlots, st)) return r;
+    if (adam_m && adam_v)
+        return launch_adam(params_pi, grad_out, adam_m, adam_v, c->shape.n_params, step, lr, beta1, beta2, eps, st);
+    return 0;
+}
+
 __global__ void reduce_slices_kernel(const float* __restrict__ part, int n_slices, long long stride, long long n,
                                      float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -472,22 +493,67 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
                                    c->ws.gae_adv + r0, c->ws.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active,
                                    st, k == 0 ? c->chunk_ev[0] : nullptr)) return r;
     }
-    const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    if (c->nccl_comm && c->world > 1 && peer_available(c)) {
-        // NVLink peer path: the rank's gradient goes straight into its exchange buffer; ONE kernel then averages over
-        // the ranks through peer loads and applies Adam (PPO.py:53,55-65)
-        if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
-                                    peer_exchange_buffer(c), nullptr, st)) return r;
-        return peer_allreduce_adam(c, params_pi, (adam_m && adam_v) ? adam_m : nullptr, adam_v, step, lr, beta1, beta2, eps,
-                                   grad_out, st);
+    return reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st);
+}
+
+int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, const float* obs, const float* act,
+                       const float* rew, const float* predv, const float* done, int T, int N, double gamma, double lam,
+                       int gae_mode, int n_epochs, int minibatch_rows, int shuffle, uint64_t seed, float l_mul,
+                       float* adam_m, float* adam_v, int step0, float lr, float beta1, float beta2, float eps,
+                       float* losses_out, float* grad_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params_pi && params_old && obs && act && rew && predv && done && grad_out && adam_m && adam_v,
+                 "dppo_update_epochs: null buffer");
+    DPPO_REQUIRE(gae_mode == DPPO_GAE_REFERENCE, "dppo_update_epochs: only DPPO_GAE_REFERENCE (last_v is not fed)");
+    const long long B64 = (long long)T * N;
+    DPPO_REQUIRE(T >= 1 && N >= 1 && B64 <= c->cfg.max_rows, "dppo_update_epochs: T*N=%lld exceeds max_rows=%d", B64,
+                 c->cfg.max_rows);
+    const int B = (int)B64;
+    DPPO_REQUIRE(n_epochs >= 1 && minibatch_rows >= 1, "dppo_update_epochs: n_epochs=%d minibatch_rows=%d", n_epochs,
+                 minibatch_rows);
+    DPPO_REQUIRE(step0 >= 1, "dppo_update_epochs: step0=%d must be >= 1", step0);
+    const int mb = minibatch_rows < B ? minibatch_rows : B;
+    const int n_mb = (B + mb - 1) / mb;
+    const NetShape& s = c->shape;
+    Workspace& w = c->ws;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = launch_gae(rew, predv, done, nullptr, nullptr, T, N, gamma, lam, gae_mode, 1, w.gae_adv, w.gae_ret, st))
+        return r;
+    // gathered minibatch lives in the staging area (also used by dppo_update_host; one call at a time per context)
+    float* g_obs = w.stage;
+    float* g_act = g_obs + (size_t)mb * s.obs;
+    float* g_adv = g_act + (size_t)mb * s.act;
+    float* g_ret = g_adv + mb;
+    int active[kMaxLayers + 1];
+    active_slices(c, mb, active);
+    int step = step0, slot = 0;
+    for (int e = 0; e < n_epochs; ++e) {
+        const PermKey key = make_perm_key((uint32_t)B, seed, (uint64_t)e);
+        for (int k = 0; k < n_mb; ++k, ++step, ++slot) {
+            const int r0 = k * mb, rows = (B - r0 < mb) ? B - r0 : mb;
+            const float *x = obs + (size_t)r0 * s.obs, *a = act + (size_t)r0 * s.act, *ad = w.gae_adv + r0,
+                        *rt = w.gae_ret + r0;
+            if (shuffle) {
+                if (int r = launch_gather_rows(key, r0, rows, s.obs, s.act, obs, act, w.gae_adv, w.gae_ret, g_obs, g_act,
+                                               g_adv, g_ret, st)) return r;
+                x = g_obs; a = g_act; ad = g_adv; rt = g_ret;
+            }
+            if (int r = loss_grad_rows(c, params_pi, params_old, x, a, ad, rt, rows, 0, rows, l_mul, 0, active, st)) return r;
+            if (int r = reduce_and_apply(c, active, rows, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st))
+                return r;
+            if (losses_out)
+                DPPO_CHECK_CUDA(cudaMemcpyAsync(losses_out + (size_t)slot * kLossSlots, grad_out + s.n_params,
+                                                kLossSlots * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
     }
-    if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
-                                grad_out, nullptr, st)) return r;
-    if (c->nccl_comm && c->world > 1)
-        if (int r = allreduce_avg(c, grad_out, c->shape.n_params + kLossSlots, st)) return r;
-    if (adam_m && adam_v)
-        return launch_adam(params_pi, grad_out, adam_m, adam_v, c->shape.n_params, step, lr, beta1, beta2, eps, st);
     return 0;
+}
+
+int dppo_minibatch_perm(dppo_ctx* c, int n, uint64_t seed, uint64_t epoch, int32_t* perm_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(n >= 0 && (n == 0 || perm_out), "dppo_minibatch_perm: n=%d", n);
+    if (n == 0) return 0;
+    return launch_perm_fill(make_perm_key((uint32_t)n, seed, epoch), perm_out, (cudaStream_t)stream);
 }
 
 int dppo_comm_unique_id(void* id_out) {
@@ -561,10 +627,24 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
     int rows_per = (2 * kPlanSMs / col_tiles) * 128;
     if (rows_per < 4096) rows_per = 4096;
     while ((B + rows_per - 1) / rows_per > 32) rows_per *= 2;
-    int n_chunks = (B + rows_per - 1) / rows_per;
+    // chunk list: uniform chunks, then the tail tapers (1/2, 1/4, 1/4 of a chunk) so that the work left
+    // after the last byte arrives is a quarter chunk instead of a whole one
+    int chunk_r0[64], chunk_rows[64], n_chunks = 0;
+    {
+        int r0 = 0;
+        while (B - r0 > rows_per) { chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = rows_per; r0 += rows_per; }
+        int left = B - r0;
+        const int q = ((left / 4 + kLossTileRows - 1) / kLossTileRows) * kLossTileRows;
+        if (n_chunks > 0 && q >= 1024 && left - 2 * q > 0) {
+            const int parts[3] = {left - 2 * q, q, q};
+            for (int i = 0; i < 3; ++i) { chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = parts[i]; r0 += parts[i]; }
+        } else {
+            chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = left;
+        }
+    }
     DPPO_REQUIRE(n_chunks <= 63, "dppo_update_host: too many chunks");
     for (int k = 0; k < n_chunks; ++k) {
-        const int r0 = k * rows_per, rows = (B - r0 < rows_per) ? B - r0 : rows_per;
+        const int r0 = chunk_r0[k], rows = chunk_rows[k];
         DPPO_CHECK_CUDA(cudaMemcpyAsync(d_obs + (size_t)r0 * s.obs, obs_h + (size_t)r0 * s.obs,
                                         (size_t)rows * s.obs * 4, cudaMemcpyHostToDevice, cp));
         DPPO_CHECK_CUDA(cudaMemcpyAsync(d_act + (size_t)r0 * s.act, act_h + (size_t)r0 * s.act,
@@ -577,7 +657,7 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
     if (int r = launch_gae(d_rew, d_pv, d_done, nullptr, nullptr, T, N, gamma, lam, gae_mode, 1, w.gae_adv,
                            w.gae_ret, st)) return r;
     for (int k = 0; k < n_chunks; ++k) {
-        const int r0 = k * rows_per, rows = (B - r0 < rows_per) ? B - r0 : rows_per;
+        const int r0 = chunk_r0[k], rows = chunk_rows[k];
         DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[k + 1], 0));
         if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.act,
                                    w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st))

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include "../../include/dppo_b200.h"
+#include "perm.cuh"
 
 namespace dppo {
 
@@ -194,5 +195,9 @@ int launch_diag_gaussian(int op, const float* flat, const float* arg, int B, int
                          float* out, cudaStream_t st);
 int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,
                   float* action, float* v_out, cudaStream_t st);
+int launch_gather_rows(const PermKey& key, int first, int rows, int obs_dim, int act_dim, const float* obs,
+                       const float* act, const float* adv, const float* ret, float* obs_o, float* act_o, float* adv_o,
+                       float* ret_o, cudaStream_t st);
+int launch_perm_fill(const PermKey& key, int32_t* out, cudaStream_t st);
 
 }  // namespace dppo

@@ -357,6 +357,62 @@ int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Minibatch scheduler: row gather through the keyed permutation of perm.cuh.
+// Row j of the minibatch is source row perm(first + j); every warp moves one row (obs as float4 when obs % 4 == 0).
+// HBM-bound: 2 * 4 * (obs + A + 2) bytes per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(PermKey key, int first, int rows, int obs_dim, int act_dim,
+                                   const float* __restrict__ obs, const float* __restrict__ act,
+                                   const float* __restrict__ adv, const float* __restrict__ ret,
+                                   float* __restrict__ obs_o, float* __restrict__ act_o, float* __restrict__ adv_o,
+                                   float* __restrict__ ret_o) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < rows; j += warps) {
+        const size_t src = perm_index(key, (uint32_t)(first + j));
+        const float* so = obs + src * obs_dim;
+        float* dst = obs_o + (size_t)j * obs_dim;
+        if ((obs_dim & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(so);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int c = lane; c < (obs_dim >> 2); c += 32) d4[c] = __ldg(s4 + c);
+        } else {
+            for (int c = lane; c < obs_dim; c += 32) dst[c] = __ldg(so + c);
+        }
+        for (int c = lane; c < act_dim; c += 32) act_o[(size_t)j * act_dim + c] = __ldg(act + src * act_dim + c);
+        if (lane == 0) { adv_o[j] = __ldg(adv + src); ret_o[j] = __ldg(ret + src); }
+    }
+}
+
+int launch_gather_rows(const PermKey& key, int first, int rows, int obs_dim, int act_dim, const float* obs,
+                       const float* act, const float* adv, const float* ret, float* obs_o, float* act_o, float* adv_o,
+                       float* ret_o, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    int grid = (rows + 7) / 8;                  // 8 warps per CTA, one row per warp per pass
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_MISC, st);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(key, first, rows, obs_dim, act_dim, obs, act, adv, ret, obs_o, act_o, adv_o,
+                                             ret_o);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void perm_fill_kernel(PermKey key, int32_t* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < key.n; i += gridDim.x * blockDim.x)
+        out[i] = (int32_t)perm_index(key, i);
+}
+
+int launch_perm_fill(const PermKey& key, int32_t* out, cudaStream_t st) {
+    if (key.n == 0) return 0;
+    int grid = (int)((key.n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_MISC, st);
+    perm_fill_kernel<<<grid, 256, 0, st>>>(key, out);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // DiagGaussianPd.sample (distributions.py:204-205): a = mean + exp(logstd) * N(0,1)
 // Philox4x32-10 counter RNG (key = seed, counter = (offset, row, quad)), Box-Muller.
 // ---------------------------------------------------------------------------------------------

@@ -51,6 +51,10 @@ _PROTOS = {
                                    C.c_int, C.c_float, _p, _p, _p]),
     "dppo_update": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_float,
                               _p, _p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _p, _p]),
+    "dppo_update_epochs": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float, _p, _p, C.c_int, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, _p, _p, _p]),
+    "dppo_minibatch_perm": (C.c_int, [_p, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),
     "dppo_diag_gaussian": (C.c_int, [_p, C.c_int, _p, _p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),
     "dppo_profile_reset": (C.c_int, [C.c_int]),
     "dppo_profile_read": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int]),

@@ -183,6 +183,37 @@ class DppoEngine:
             beta1, beta2, eps, self._dev(g, self.grad_len, "grad_out"), self._stream()))
         return g[self.n_params:], g
 
+    # ------------------------------------------------------------------ epochs x minibatches on the device
+    def update_epochs(self, params_pi, params_old, obs, act, rew, predv, done, gamma, lam, l_mul, adam_m, adam_v,
+                      step0: int, lr: float, n_epochs: int = 1, minibatch_rows: int = 0, shuffle: bool = False,
+                      seed: int = 0, beta1=0.9, beta2=0.999, eps=1e-8, grad_out=None, losses_out=None,
+                      gae_mode: int = L.GAE_REFERENCE):
+        """GAE once, then n_epochs x ceil(T*N / minibatch_rows) x [forward, loss, backward, tower mean, Adam] with no host
+        involvement.  n_epochs=UPDATE_STEPS, minibatch_rows=0 (whole rollout buffer) is Chief.py:64's loop.
+        Returns (losses [n_epochs * n_minibatches, 8] device tensor, grad buffer of the last minibatch)."""
+        T, N = rew.shape
+        B = T * N
+        mb = B if minibatch_rows in (0, None) else min(int(minibatch_rows), B)
+        n_mb = (B + mb - 1) // mb
+        g = grad_out if grad_out is not None else self.new_grad_buffer()
+        if losses_out is None:
+            losses_out = torch.empty(n_epochs * n_mb, L.NUM_LOSS_SLOTS, dtype=torch.float32, device=g.device)
+        self._check(self.lib.dppo_update_epochs(
+            self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
+            self._dev(obs, B * self.obs_dim, "obs"), self._dev(act, B * self.act_dim, "act"), self._dev(rew, B, "rew"),
+            self._dev(predv, B, "predv"), self._dev(done, B, "done"), T, N, float(gamma), float(lam), int(gae_mode),
+            int(n_epochs), int(mb), int(bool(shuffle)), int(seed), float(l_mul),
+            self._dev(adam_m, self.n_params, "adam_m"), self._dev(adam_v, self.n_params, "adam_v"), int(step0), float(lr),
+            beta1, beta2, eps, self._dev(losses_out, n_epochs * n_mb * L.NUM_LOSS_SLOTS, "losses_out"),
+            self._dev(g, self.grad_len, "grad_out"), self._stream()))
+        return losses_out, g
+
+    def minibatch_perm(self, n: int, seed: int, epoch: int):
+        """Row permutation of [0, n) the scheduler uses for `epoch` (int32 device tensor)."""
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._check(self.lib.dppo_minibatch_perm(self.ctx, int(n), int(seed), int(epoch), out.data_ptr(), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ host-buffer entry (e2e)
     def update_host(self, params_pi, params_old, obs_h, act_h, rew_h, predv_h, done_h, gamma, lam, l_mul,
                     grad_out=None, gae_mode: int = L.GAE_REFERENCE):

@@ -106,3 +106,30 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in txt.replace("# oracle-free", ""), f"{fn} mentions the oracle"
+
+
+def test_minibatch_perm_header_matches_oracle(tmp_path):
+    """csrc/perm.cuh is plain C++ on the host side: compile it with g++ and compare the keyed
+    permutation with the oracle's numpy restatement, bit for bit (the device kernels inline the same header)."""
+    src = tmp_path / "perm_main.cpp"
+    src.write_text('''
+#include <cstdio>
+#include <cstdlib>
+#include "%s/tensorflow-dppo_b200/csrc/perm.cuh"
+int main(int argc, char** argv) {
+    const unsigned n = strtoul(argv[1], 0, 10);
+    const unsigned long long seed = strtoull(argv[2], 0, 10), epoch = strtoull(argv[3], 0, 10);
+    const dppo::PermKey k = dppo::make_perm_key(n, seed, epoch);
+    for (unsigned i = 0; i < n; ++i) printf("%%u\\n", dppo::perm_index(k, i));
+    return 0;
+}
+''' % ROOT)
+    exe = tmp_path / "perm_main"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), str(src)], check=True)
+    for n, seed, epoch in ((1, 0, 0), (2, 5, 1), (3, 5, 1), (7, 1234, 0), (1000, 1234, 3), (4096, 2**63 + 11, 2),
+                           (100003, 99, 7)):
+        out = subprocess.run([str(exe), str(n), str(seed), str(epoch)], capture_output=True, text=True, check=True).stdout
+        got = np.array(out.split(), dtype=np.int64)
+        ref = O.minibatch_perm(n, seed, epoch)
+        assert np.array_equal(got, ref), (n, seed, epoch)
+        assert np.array_equal(np.sort(ref), np.arange(n))

@@ -623,3 +623,101 @@ def test_loss_grad_bf16_path(name, T, N, obs, hidden, A):
     np.testing.assert_allclose(losses.cpu().numpy()[:4], l_q, rtol=1e-4, atol=1e-4)
     # 1024-row deep case: a single flipped ReLU/clip decision moves a gradient entry by ~1/sqrt(rows) = 3 %
     assert max(errs.values()) < (2e-3 if B >= 8192 else 2e-2), errs
+
+
+# ------------------------------------------------------------------------------- epoch / minibatch scheduler
+@pytest.mark.parametrize("n,seed,epoch", [(1, 0, 0), (2, 3, 1), (3, 3, 1), (1000, 1234, 0), (131072, 1234, 5),
+                                          (100003, 2**63 + 5, 9)])
+def test_minibatch_perm_bit_exact(n, seed, epoch):
+    eng = _engine(3, (16,), 1, 128)
+    got = eng.minibatch_perm(n, seed, epoch).cpu().numpy().astype(np.int64)
+    ref = O.minibatch_perm(n, seed, epoch)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(np.sort(got), np.arange(n))
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_update_epochs_whole_buffer_equals_update_steps_loop(gemm_mode):
+    """n_epochs = UPDATE_STEPS, one whole-buffer minibatch, no shuffle  ==  Chief.py:64's loop of single updates."""
+    T, N, obs, hidden, A = 256, 32, 376, (256, 256), 17
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    eng = _engine(obs, hidden, A, T * N, gemm_mode=gemm_mode)
+    d = {k: dev(v) for k, v in buf.items()}
+    n = lay.n_params
+    p1 = dev(th_pi); m1 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")
+    l1 = []
+    for t in (1, 2, 3, 4):
+        _, g1 = eng.update(p1, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7,
+                           adam_m=m1, adam_v=v1, step=t, lr=2e-5 * 0.7)
+        l1.append(g1[n:].clone())
+    p2 = dev(th_pi); m2 = torch.zeros(n, device="cuda"); v2 = torch.zeros(n, device="cuda")
+    l2, g2 = eng.update_epochs(p2, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7,
+                               m2, v2, step0=1, lr=2e-5 * 0.7, n_epochs=4)
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
+    assert torch.equal(torch.stack(l1), l2) and torch.equal(g1, g2)
+    assert not torch.equal(l2[0], l2[3])                 # the parameters did move between the epochs
+
+
+@pytest.mark.parametrize("gemm_mode,mb,shuffle", [(0, 2048, True), (1, 2048, True), (1, 2048, False), (1, 3000, True)])
+def test_update_epochs_minibatches_equal_manual_gather(gemm_mode, mb, shuffle):
+    """The device scheduler (keyed permutation + row gather + per-minibatch loss_grad/Adam) against the same
+    sequence driven from the host with torch indexing: bit-equal when every minibatch has the same row count."""
+    T, N, obs, hidden, A = 128, 64, 376, (256, 256), 17
+    B = T * N
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    eng = _engine(obs, hidden, A, B, gemm_mode=gemm_mode)
+    d = {k: dev(v) for k, v in buf.items()}
+    n = lay.n_params
+    adv, ret = eng.gae(d["rew"], d["predv"], d["done"], 0.99, 0.95)
+    adv = adv.reshape(-1).clone(); ret = ret.reshape(-1).clone()
+    p1 = dev(th_pi); m1 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")
+    step = 1; l1 = []
+    for e in range(2):
+        order = torch.as_tensor(O.minibatch_perm(B, 77, e) if shuffle else np.arange(B), device="cuda")
+        for r0 in range(0, B, mb):
+            idx = order[r0:r0 + mb]
+            _, g1 = eng.loss_grad(p1, dev(th_old), d["obs"][idx].contiguous(), d["act"][idx].contiguous(),
+                                  adv[idx].contiguous(), ret[idx].contiguous(), 0.7)
+            eng.adam_apply(p1, g1, m1, v1, step, 2e-5 * 0.7)
+            l1.append(g1[n:].clone()); step += 1
+    p2 = dev(th_pi); m2 = torch.zeros(n, device="cuda"); v2 = torch.zeros(n, device="cuda")
+    l2, _ = eng.update_epochs(p2, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7,
+                              m2, v2, step0=1, lr=2e-5 * 0.7, n_epochs=2, minibatch_rows=mb, shuffle=shuffle, seed=77)
+    torch.cuda.synchronize()
+    l1 = torch.stack(l1)
+    assert l2.shape == l1.shape == (2 * math.ceil(B / mb), 8)
+    if B % mb == 0:
+        assert torch.equal(l1, l2) and torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
+    else:       # the short last minibatch uses the full minibatches' split-K plan: same numbers to fp32 rounding
+        np.testing.assert_allclose(l2.cpu().numpy(), l1.cpu().numpy(), rtol=2e-5, atol=1e-6)
+        assert rel_err(m2.cpu().numpy(), m1.cpu().numpy()) < 1e-4
+
+
+def test_update_epochs_vs_oracle():
+    """Shuffled minibatch epochs against the numpy restatement: per-minibatch losses within 1e-5 while the parameters
+    move through 8 Adam steps (the fp32 update itself is compared where fp32 resolves it)."""
+    T, N, obs, hidden, A = 64, 16, 17, (64, 64), 6
+    B = T * N
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    eng = _engine(obs, hidden, A, B)
+    d = {k: dev(v) for k, v in buf.items()}
+    n = lay.n_params
+    lr = 1e-4
+    p = dev(th_pi); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    l, _ = eng.update_epochs(p, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7,
+                             m, v, step0=1, lr=lr, n_epochs=2, minibatch_rows=256, shuffle=True, seed=5)
+    th_ref, m_ref, v_ref, l_ref = O.update_epochs(th_pi, th_old, buf, 0.99, 0.95, 0.7, lay, lr, n_epochs=2,
+                                                  minibatch_rows=256, shuffle=True, seed=5)
+    lg = l.cpu().numpy()
+    assert lg.shape == (8, 8)
+    np.testing.assert_allclose(lg[:, :4], l_ref, rtol=3e-5, atol=3e-6)
+    assert rel_err(m.cpu().numpy(), m_ref) < 1e-4
+    upd = p.cpu().numpy().astype(np.float64) - th_pi
+    assert rel_err(upd, th_ref - th_pi) < 2e-2            # |update| ~ 8e-4 on O(0.1) parameters: fp32 ulp / update
