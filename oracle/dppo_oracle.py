@@ -58,9 +58,15 @@ class Layout:
     act_dim: int
     entries: Tuple[Tuple[str, Tuple[int, ...], int], ...] = field(default=())
     n_params: int = 0
+    pd: str = "gauss"          # "gauss": DiagGaussianPd, act_dim = A, policy head 2A wide (distributions.py:84-85)
+                               # "cat":   CategoricalPd,  act_dim = ncat, policy head ncat wide (distributions.py:53-54)
+
+    @property
+    def pd_width(self) -> int:
+        return 2 * self.act_dim if self.pd == "gauss" else self.act_dim
 
 
-def make_layout(obs_dim: int, hidden: Sequence[int], act_dim: int) -> Layout:
+def make_layout(obs_dim: int, hidden: Sequence[int], act_dim: int, pd: str = "gauss") -> Layout:
     entries = []
     off = 0
     fan_in = obs_dim
@@ -70,9 +76,11 @@ def make_layout(obs_dim: int, hidden: Sequence[int], act_dim: int) -> Layout:
         fan_in = h
     entries.append(("Wv", (fan_in, 1), off)); off += fan_in
     entries.append(("bv", (1,), off)); off += 1
-    entries.append(("Wp", (fan_in, 2 * act_dim), off)); off += fan_in * 2 * act_dim
-    entries.append(("bp", (2 * act_dim,), off)); off += 2 * act_dim
-    return Layout(obs_dim, tuple(hidden), act_dim, tuple(entries), off)
+    assert pd in ("gauss", "cat")
+    pw = 2 * act_dim if pd == "gauss" else act_dim                # Model.py:14 pdtype.param_shape()[0]
+    entries.append(("Wp", (fan_in, pw), off)); off += fan_in * pw
+    entries.append(("bp", (pw,), off)); off += pw
+    return Layout(obs_dim, tuple(hidden), act_dim, tuple(entries), off, pd)
 
 
 def unflatten(theta: np.ndarray, lay: Layout) -> dict:
@@ -171,6 +179,77 @@ def dg_mode(flat):
 
 
 # --------------------------------------------------------------------------
+# CategoricalPd  (distributions.py:124-159)
+# --------------------------------------------------------------------------
+def _cat_parts(logits):
+    a0 = logits - np.max(logits, axis=-1, keepdims=True)          # :141,149
+    ea0 = np.exp(a0)
+    z0 = np.sum(ea0, axis=-1, keepdims=True)
+    return a0, ea0, z0
+
+
+def cat_neglogp(logits, x):
+    """softmax_cross_entropy_with_logits(logits, one_hot(x))  (:131-138)."""
+    a0, _, z0 = _cat_parts(logits)
+    x = np.asarray(x).reshape(logits.shape[:-1]).astype(np.int64)
+    return np.log(z0[..., 0]) - np.take_along_axis(a0, x[..., None], axis=-1)[..., 0]
+
+
+def cat_logp(logits, x):
+    return -cat_neglogp(logits, x)                                # :25-26
+
+
+def cat_entropy(logits):
+    a0, ea0, z0 = _cat_parts(logits)
+    return np.sum(ea0 / z0 * (np.log(z0) - a0), axis=-1)          # :148-153
+
+
+def cat_kl(logits_p, logits_q):
+    a0, ea0, z0 = _cat_parts(logits_p)
+    a1, _, z1 = _cat_parts(logits_q)
+    return np.sum(ea0 / z0 * (a0 - np.log(z0) - a1 + np.log(z1)), axis=-1)   # :139-147
+
+
+def cat_mode(logits):
+    return np.argmax(logits, axis=-1)                             # :129-130
+
+
+def cat_sample(logits, u):
+    return np.argmax(logits - np.log(-np.log(u)), axis=-1)        # :154-156 (Gumbel max)
+
+
+def _ppo_losses_categorical(v, logits, v_old, logits_old, act, adv, ret, l_mul, hp):
+    B = v.shape[0]
+    c = hp.CLIP_PARAM * l_mul
+    x = np.asarray(act).reshape(B).astype(np.int64)
+    a0, ea0, z0 = _cat_parts(logits)
+    p = ea0 / z0
+    logp_all = a0 - np.log(z0)
+    ent = cat_entropy(logits)                                     # PPO.py:29
+    ratio = np.exp(cat_logp(logits, x) - cat_logp(logits_old, x))  # :31
+    surr1 = ratio * adv
+    surr2 = np.clip(ratio, 1.0 - c, 1.0 + c) * adv
+    policy_loss = -np.mean(np.minimum(surr1, surr2))
+    entropy_loss = (-hp.ENTCOEFF) * np.mean(ent)
+    vf1 = np.square(v - ret)
+    dv = v - v_old
+    vclip = v_old + np.clip(dv, -c, c)
+    vf2 = np.square(vclip - ret)
+    value_loss = hp.VCOEFF * np.mean(np.maximum(vf1, vf2))
+    total = policy_loss + entropy_loss + value_loss
+    g_logp = np.where(surr1 <= surr2, -adv / B, 0.0) * ratio
+    onehot = (x[:, None] == np.arange(logits.shape[-1])).astype(logits.dtype)
+    # d logp(a)/d logit_k = [k == a] - p_k ;  d H/d logit_k = -p_k (log p_k + H)
+    d_logits = g_logp[:, None] * (onehot - p) + (hp.ENTCOEFF / B) * p * (logp_all + ent[:, None])
+    in_clip = (dv >= -c) & (dv <= c)
+    d_v = (hp.VCOEFF / B) * np.where(vf1 >= vf2, 2.0 * (v - ret), 2.0 * (vclip - ret) * in_clip)
+    d_out = np.concatenate([d_v[:, None], d_logits], axis=1)
+    aux = dict(mean_kl=float(np.mean(cat_kl(logits_old, logits))), clip_frac=float(np.mean(surr1 > surr2)),
+               vclip_frac=float(np.mean((vf1 < vf2) & ~in_clip)), ratio=ratio)
+    return np.array([policy_loss, value_loss, entropy_loss, total]), d_out, aux
+
+
+# --------------------------------------------------------------------------
 # PPO loss + closed-form gradient  (PPO.py:19,29-40,46)
 # --------------------------------------------------------------------------
 @dataclass
@@ -184,12 +263,14 @@ class HParams:
     LEARNING_RATE: float = 2e-5
 
 
-def ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret, l_mul, hp: HParams):
-    """Loss values and d(total)/d[v, mean, logstd] per row (canonical per-sample mode).
+def ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret, l_mul, hp: HParams, pd: str = "gauss"):
+    """Loss values and d(total)/d[v, mean, logstd] (or d/d[v, logits] for pd="cat") per row (canonical per-sample mode).
 
     TF tie rules: minimum->first arg iff x<=y; maximum->first iff
     x>=y; clip_by_value passes gradient iff lo<=x<=hi.
     """
+    if pd == "cat":
+        return _ppo_losses_categorical(v, flat, v_old, flat_old, act, adv, ret, l_mul, hp)
     B = v.shape[0]
     A = act.shape[1]
     c = hp.CLIP_PARAM * l_mul                                     # PPO.py:19
@@ -261,12 +342,12 @@ def ppo_loss_grad(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout,
 
     Returns (losses[4] = policy, value, entropy, total ; flat_grad ; aux dict).
     """
-    obs = np.asarray(obs, dtype); act = np.asarray(act, dtype)
+    obs = np.asarray(obs, dtype); act = np.asarray(act, dtype if lay.pd == "gauss" else np.int64)
     adv = np.asarray(adv, dtype).reshape(-1); ret = np.asarray(ret, dtype).reshape(-1)
     v, flat, hs = mlp_forward(theta_pi, obs, lay, dtype, q)
     v_old, flat_old, _ = mlp_forward(theta_old, obs, lay, dtype, q)
     losses, d_out, aux = ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret,
-                                               dtype(l_mul), hp)
+                                               dtype(l_mul), hp, lay.pd)
     grad = mlp_backward(theta_pi, obs, hs, d_out.astype(dtype), lay, dtype, q)
     aux.update(d_out=d_out, v=v, flat=flat, v_old=v_old, flat_old=flat_old, hs=hs)
     return losses, grad, aux
@@ -462,12 +543,16 @@ def lr_multiplier(schedule: str, cur_ep: int, epoch_max: int) -> float:
 # --------------------------------------------------------------------------
 # synthetic frozen buffers; shared by tests, smoke and bench
 # --------------------------------------------------------------------------
-def make_buffer(T, N, obs_dim, act_dim, seed=1234):
+def make_buffer(T, N, obs_dim, act_dim, seed=1234, pd="gauss"):
+    """pd="cat": act is the reference's int32 [B,1] placeholder (PPO.py:26), classes uniform in [0, act_dim)."""
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
     B = T * N
     obs = torch.randn(B, obs_dim, generator=g, dtype=torch.float32).numpy()
-    act = torch.randn(B, act_dim, generator=g, dtype=torch.float32).numpy()
+    if pd == "cat":
+        act = torch.randint(0, act_dim, (B, 1), generator=g, dtype=torch.int32).numpy()
+    else:
+        act = torch.randn(B, act_dim, generator=g, dtype=torch.float32).numpy()
     rew = torch.randn(T, N, generator=g, dtype=torch.float32).numpy()
     done = (torch.rand(T, N, generator=g) < (1.0 / 200.0)).to(torch.float32).numpy()
     predv = torch.randn(T, N, generator=g, dtype=torch.float32).numpy()
@@ -591,7 +676,8 @@ def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, h
       * outside the clip and |vf1 - vf2| < margin  -> resample the return.
     Returns (act, ret, n_edited)."""
     rng = np.random.default_rng(seed)
-    act = np.array(act, np.float32, copy=True); ret = np.array(ret, np.float32, copy=True).reshape(-1)
+    cat = lay.pd == "cat"
+    act = np.array(act, np.int32 if cat else np.float32, copy=True); ret = np.array(ret, np.float32, copy=True).reshape(-1)
     v, flat, _ = mlp_forward(theta_pi, obs, lay)
     v_old, flat_old, _ = mlp_forward(theta_old, obs, lay)
     c = hp.CLIP_PARAM * l_mul
@@ -599,7 +685,8 @@ def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, h
     edited = 0
     for _ in range(50):
         a64 = act.astype(np.float64); r64 = ret.astype(np.float64)
-        ratio = np.exp(dg_logp(flat, a64) - dg_logp(flat_old, a64))
+        ratio = (np.exp(cat_logp(flat, act) - cat_logp(flat_old, act)) if cat else
+                 np.exp(dg_logp(flat, a64) - dg_logp(flat_old, a64)))
         bad_r = (np.abs(ratio - (1 - c)) < margin) | (np.abs(ratio - (1 + c)) < margin)
         edge = np.abs(np.abs(dv) - c) < margin
         vclip = v_old + np.clip(dv, -c, c)
@@ -611,7 +698,8 @@ def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, h
         if n == 0:
             break
         edited += n
-        act[bad_r] = rng.standard_normal((int(bad_r.sum()), act.shape[1])).astype(np.float32)
+        act[bad_r] = (rng.integers(0, lay.act_dim, (int(bad_r.sum()), 1)).astype(np.int32) if cat else
+                      rng.standard_normal((int(bad_r.sum()), act.shape[1])).astype(np.float32))
         sgn = np.where(dv[bad_edge] >= 0, 1.0, -1.0)
         ret[bad_edge] = (v_old[bad_edge] - sgn * (1.0 + np.abs(rng.standard_normal(int(bad_edge.sum()))))).astype(np.float32)
         ret[bad_v] = rng.standard_normal(int(bad_v.sum())).astype(np.float32)
@@ -621,11 +709,11 @@ def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, h
 
 
 def make_case(T, N, obs_dim, hidden, act_dim, seed=1234, l_mul=0.7, trunk_std=1.0, head_std=0.1, delta=0.02,
-              hp: HParams = HParams()):
+              hp: HParams = HParams(), pd="gauss"):
     """Frozen synthetic update case: buffer, GAE'd advantages/returns (oracle),
     pi != oldpi parameters, with branch-ambiguous rows removed.  Everything fp32."""
-    lay = make_layout(obs_dim, hidden, act_dim)
-    buf = make_buffer(T, N, obs_dim, act_dim, seed)
+    lay = make_layout(obs_dim, hidden, act_dim, pd)
+    buf = make_buffer(T, N, obs_dim, act_dim, seed, pd)
     th_pi, th_old = make_params_pair(lay, trunk_std, head_std, delta)
     adv, ret = gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], hp.GAMMA, hp.LAM)
     buf["obs"], n_obs = sanitize_obs(th_pi, buf["obs"], lay)

@@ -169,6 +169,52 @@ def make_distgauss(D):
           "kl", out["fix_kl"])
 
 
+# ---------------------------------------------------------------- CategoricalPd (distributions.py:124-159)
+def make_categorical(tf, U, D):
+    out = {}
+    # the reference self-check fixture (distributions.py:260)
+    p = np.array([-.2, .3, .5]); q = p + np.array([.1, -.05, .02])
+    pd, pdq = D.CategoricalPd(tf.as_tensor(p[None])), D.CategoricalPd(tf.as_tensor(q[None]))
+    out["fix_p"], out["fix_q"] = p, q
+    out["fix_entropy"] = pd.entropy(); out["fix_kl"] = pd.kl(pdq); out["fix_mode"] = pd.mode()
+    out["fix_neglogp"] = np.stack([pd.neglogp(np.array([k])) for k in range(3)])
+    rng = np.random.default_rng(13)
+    for n in (2, 6, 18):
+        fp = rng.standard_normal((64, n)) * 1.5
+        fq = fp + 0.2 * rng.standard_normal((64, n))
+        xs = rng.integers(0, n, size=64)
+        pd, pdq = D.CategoricalPd(tf.as_tensor(fp)), D.CategoricalPd(tf.as_tensor(fq))
+        pt = D.CategoricalPdType(n)
+        assert pt.param_shape() == [n] and pt.sample_shape() == []
+        out[f"n{n}_p"], out[f"n{n}_q"], out[f"n{n}_x"] = fp, fq, xs
+        out[f"n{n}_neglogp"] = pd.neglogp(xs); out[f"n{n}_logp"] = pd.logp(xs)
+        out[f"n{n}_entropy"] = pd.entropy(); out[f"n{n}_kl"] = pd.kl(pdq)
+        out[f"n{n}_mode"] = pd.mode()
+    # PPO.py:29-40 over CategoricalPd heads: a is the reference's own int32 [B,1] placeholder (PPO.py:26)
+    src = ref_lines("PPO.py", 29, 40)
+    for tag, n, B, l_mul in (("a", 2, 64, 0.7), ("b", 6, 96, 1.0), ("c", 18, 50, 0.35)):
+        flat = rng.standard_normal((B, 1, n))
+        flat_old = flat + 0.2 * rng.standard_normal((B, 1, n))
+        a = rng.integers(0, n, size=(B, 1))
+        adv = rng.standard_normal((B, 1)); etr = rng.standard_normal((B, 1))
+        v = rng.standard_normal((B, 1)); v_old = v + 0.3 * rng.standard_normal((B, 1))
+        self = types.SimpleNamespace(a=a, adv=adv, etr=etr, pipredv=v)
+        ns = dict(tf=tf, U=U, np=np, self=self, piPD=D.CategoricalPd(tf.as_tensor(flat)),
+                  oldpiPD=D.CategoricalPd(tf.as_tensor(flat_old)), oldpredv=v_old,
+                  CLIP_PARAM=0.2 * l_mul, ENTCOEFF=0.01, VCOEFF=0.5)
+        exec(src, ns)
+        out[f"loss_{tag}_flat"], out[f"loss_{tag}_flat_old"] = flat[:, 0], flat_old[:, 0]
+        out[f"loss_{tag}_act"], out[f"loss_{tag}_adv"], out[f"loss_{tag}_etr"] = a[:, 0], adv[:, 0], etr[:, 0]
+        out[f"loss_{tag}_v"], out[f"loss_{tag}_v_old"] = v[:, 0], v_old[:, 0]
+        out[f"loss_{tag}_l_mul"] = np.array(l_mul)
+        out[f"loss_{tag}_ratio"] = np.asarray(ns["ratio"])[:, 0]
+        out[f"loss_{tag}_losses"] = np.array([self.policyLoss, self.valueLoss, self.entropyLoss, self.total_loss],
+                                             np.float64)
+    np.savez_compressed(os.path.join(OUT, "categorical_ref.npz"), **{k: np.asarray(v_) for k, v_ in out.items()})
+    print("categorical_ref.npz: entropy", out["fix_entropy"], "neglogp", out["fix_neglogp"].ravel(), "kl", out["fix_kl"],
+          "losses(a)", out["loss_a_losses"])
+
+
 # ---------------------------------------------------------------- Model.FC
 def make_model_fc(tf, M, spaces):
     out = {}
@@ -227,3 +273,4 @@ if __name__ == "__main__":
     make_distgauss(D)
     make_model_fc(tf, M, spaces)
     make_ppo_loss(tf, U, D)
+    make_categorical(tf, U, D)

@@ -23,6 +23,17 @@ class _Var(np.ndarray):
     pass
 
 
+class Tensor(np.ndarray):
+    """ndarray with the static-shape accessor CategoricalPd.neglogp uses (distributions.py:135)."""
+    def get_shape(self):
+        shp = self.shape
+        return types.SimpleNamespace(as_list=lambda: list(shp))
+
+
+def as_tensor(x, dtype=None):
+    return np.asarray(x, dtype).view(Tensor)
+
+
 _state = types.SimpleNamespace(scope=[], variables=[])
 
 
@@ -91,9 +102,33 @@ def random_normal(shape_, dtype=None):
     return _rng.standard_normal(tuple(int(s) for s in shape_))
 
 
+def reduce_max(x, axis=None, keep_dims=False):
+    if isinstance(axis, (list, tuple)):
+        axis = tuple(axis)
+    return np.max(x, axis=axis, keepdims=keep_dims)
+
+
+def argmax(x, axis=None): return np.argmax(x, axis=axis)
+
+
+def one_hot(x, depth):
+    return (np.asarray(x)[..., None] == np.arange(depth)).astype(np.float64)
+
+
+def random_uniform(shape_, dtype=None):
+    return _rng.random(tuple(int(s) for s in shape_))
+
+
 class _nn:
     @staticmethod
     def relu(x): return np.maximum(x, 0)
+
+    @staticmethod
+    def softmax_cross_entropy_with_logits(logits=None, labels=None):
+        """TF op semantics (restated): -sum(labels * log_softmax(logits)) over the last axis, max-shifted."""
+        z = logits - np.max(logits, axis=-1, keepdims=True)
+        lsm = z - np.log(np.sum(np.exp(z), axis=-1, keepdims=True))
+        return -np.sum(labels * lsm, axis=-1)
 
 
 nn = _nn

@@ -204,3 +204,81 @@ def test_lr_multiplier():
     assert O.lr_multiplier("constant", 10, 500) == 1.0
     assert O.lr_multiplier("linear", 125, 500) == 0.75
     assert O.lr_multiplier("linear", 900, 500) == 0
+
+
+# ------------------------------------------------------------------ CategoricalPd (distributions.py:124-159) -- SURVEY 8 f4
+def test_categorical_matches_reference_class(golden_dir):
+    g = _npz(golden_dir, "categorical_ref.npz")
+    p, q = g["fix_p"][None], g["fix_q"][None]
+    np.testing.assert_allclose(O.cat_entropy(p), g["fix_entropy"], rtol=1e-13)
+    np.testing.assert_allclose(O.cat_kl(p, q), g["fix_kl"], rtol=1e-10)
+    assert O.cat_mode(p)[0] == g["fix_mode"][0] == 2
+    for k in range(3):
+        np.testing.assert_allclose(O.cat_neglogp(p, np.array([k])), g["fix_neglogp"][k], rtol=1e-13)
+    for n in (2, 6, 18):
+        fp, fq, x = g[f"n{n}_p"], g[f"n{n}_q"], g[f"n{n}_x"]
+        np.testing.assert_allclose(O.cat_neglogp(fp, x), g[f"n{n}_neglogp"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(O.cat_logp(fp, x), g[f"n{n}_logp"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(O.cat_entropy(fp), g[f"n{n}_entropy"], rtol=1e-12)
+        np.testing.assert_allclose(O.cat_kl(fp, fq), g[f"n{n}_kl"], rtol=1e-10, atol=1e-15)
+        assert np.array_equal(O.cat_mode(fp), g[f"n{n}_mode"])
+
+
+def test_categorical_monte_carlo_identities():
+    """The reference's own self-check (distributions.py:260,269-295) on its categorical fixture, 3 sigma."""
+    rng = np.random.default_rng(0)
+    pdparam = np.array([-.2, .3, .5]); Nn = 100000
+    M = np.repeat(pdparam[None], Nn, 0)
+    X = O.cat_sample(M, rng.random(M.shape))
+    ll = O.cat_logp(M, X)
+    assert abs(O.cat_entropy(M).mean() + ll.mean()) < 3 * ll.std() / math.sqrt(Nn)
+    q = pdparam + rng.standard_normal(3) * 0.1
+    M2 = np.repeat(q[None], Nn, 0)
+    ll2 = O.cat_logp(M2, X)
+    assert abs(O.cat_kl(M, M2).mean() - (-O.cat_entropy(M).mean() - ll2.mean())) < 3 * ll2.std() / math.sqrt(Nn)
+
+
+def test_categorical_ppo_loss_matches_reference_lines(golden_dir):
+    g = _npz(golden_dir, "categorical_ref.npz")
+    for tag in "abc":
+        k = f"loss_{tag}_"
+        losses, d_out, aux = O.ppo_losses_from_heads(g[k + "v"], g[k + "flat"], g[k + "v_old"], g[k + "flat_old"],
+                                                     g[k + "act"], g[k + "adv"], g[k + "etr"], float(g[k + "l_mul"]),
+                                                     O.HParams(), pd="cat")
+        np.testing.assert_allclose(losses, g[k + "losses"], rtol=1e-12)
+        np.testing.assert_allclose(aux["ratio"], g[k + "ratio"], rtol=1e-12)
+        assert d_out.shape == (len(g[k + "v"]), 1 + g[k + "flat"].shape[1])
+
+
+@pytest.mark.parametrize("obs_dim,hidden,ncat,B", [(4, (16,), 2, 200), (17, (32, 24), 6, 300), (5, (), 3, 64)])
+def test_categorical_closed_form_grad_equals_autograd(obs_dim, hidden, ncat, B):
+    lay = O.make_layout(obs_dim, hidden, ncat, pd="cat")
+    assert lay.pd_width == ncat
+    th_pi, th_old = O.make_params_pair(lay, 1.0, 0.5, 0.05)
+    rng = np.random.default_rng(1)
+    obs = rng.standard_normal((B, obs_dim)); act = rng.integers(0, ncat, (B, 1))
+    adv = rng.standard_normal(B); ret = rng.standard_normal(B)
+    hp = O.HParams()
+    losses, grad, aux = O.ppo_loss_grad(th_pi, th_old, obs, act, adv, ret, 0.7, lay, hp)
+
+    def net(th):
+        h = torch.tensor(obs)
+        p = {name: th[off:off + int(np.prod(shape))].view(*shape) for name, shape, off in lay.entries}
+        for l in range(len(lay.hidden)):
+            h = torch.relu(h @ p[f"W{l + 1}"] + p[f"b{l + 1}"])
+        return (h @ p["Wv"] + p["bv"])[:, 0], h @ p["Wp"] + p["bp"]
+    t = torch.tensor(th_pi, dtype=torch.float64, requires_grad=True)
+    v, lg = net(t)
+    with torch.no_grad():
+        vo, lo = net(torch.tensor(th_old, dtype=torch.float64))
+    a = torch.tensor(act[:, 0]); advt, rt = torch.tensor(adv), torch.tensor(ret)
+    lsm, lsm_o = torch.log_softmax(lg, -1), torch.log_softmax(lo, -1)
+    ratio = torch.exp(lsm.gather(1, a[:, None])[:, 0] - lsm_o.gather(1, a[:, None])[:, 0])
+    c = hp.CLIP_PARAM * 0.7
+    pl = -torch.minimum(ratio * advt, torch.clamp(ratio, 1 - c, 1 + c) * advt).mean()
+    el = -hp.ENTCOEFF * (-(lsm.exp() * lsm).sum(-1)).mean()
+    vl = hp.VCOEFF * torch.maximum((v - rt) ** 2, (vo + torch.clamp(v - vo, -c, c) - rt) ** 2).mean()
+    (pl + el + vl).backward()
+    np.testing.assert_allclose(losses, [pl.item(), vl.item(), el.item(), (pl + el + vl).item()], rtol=1e-12)
+    np.testing.assert_allclose(grad, t.grad.numpy(), rtol=1e-9, atol=1e-14)
+    assert 0.02 < aux["clip_frac"] < 0.98
