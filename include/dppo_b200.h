@@ -57,7 +57,18 @@ typedef struct dppo_config {
     float   entcoeff;                   /* parameter_dict['ENTCOEFF']   (main.py:15, PPO.py:11)    */
     float   vcoeff;                     /* parameter_dict['VCOEFF']     (main.py:16, PPO.py:12)    */
     float   clip_param;                 /* parameter_dict['CLIP_PARAM'] (main.py:17, PPO.py:10,19) */
+    int32_t pd_type;                    /* DPPO_PD_*: what make_pdtype(env.action_space) returns    */
+                                        /* (distributions.py:231-243)                               */
 } dppo_config;
+
+/* Policy distribution of the pi/oldpi heads (Model.py:9,14-15):
+ *   DPPO_PD_DIAG_GAUSSIAN  spaces.Box      -> DiagGaussianPd; act_dim = A, policy head 2A wide (mean | logstd),
+ *                          actions are fp32 [B, A];
+ *   DPPO_PD_CATEGORICAL    spaces.Discrete -> CategoricalPd (distributions.py:124-159); act_dim = ncat, policy head
+ *                          ncat wide (logits), actions are int32 [B, 1] -- the reference's own `a` placeholder
+ *                          (PPO.py:26) -- passed through the same `act` / `action_out` pointers (4-byte elements). */
+#define DPPO_PD_DIAG_GAUSSIAN 0
+#define DPPO_PD_CATEGORICAL   1
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* dppo_last_error(void);
@@ -133,6 +144,13 @@ int dppo_update(dppo_ctx* ctx, float* params_pi, const float* params_old, const 
                 const float* rew, const float* predv, const float* done, int T, int N, double gamma, double lam,
                 int gae_mode, float l_mul, float* adam_m, float* adam_v, int step, float lr, float beta1,
                 float beta2, float eps, float* grad_out, void* stream);
+
+/* replaces the CategoricalPd methods as stand-alone graph ops (distributions.py:124-159) on a [B,ncat] logits tensor:
+ * op 0 neglogp(arg = int32 x[B]) -> out[B] (out-of-range x gives 0, as tf.one_hot does); 1 entropy -> out[B];
+ * 2 kl(arg = other logits [B,ncat]) -> out[B]; 3 sample (Gumbel-max, Philox seed/offset) -> int32 out[B];
+ * 4 mode (argmax, first maximum) -> int32 out[B]. */
+int dppo_categorical(dppo_ctx* ctx, int op, const float* logits, const void* arg, int B, int ncat,
+                     uint64_t seed, uint64_t offset, void* out, void* stream);
 
 /* ---- epoch / minibatch scheduler on the device ------------------------------------
  * The reference trains on whole rollouts, UPDATE_STEPS times on the same feed (Chief.py:58-64); with

@@ -61,7 +61,13 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
     DPPO_REQUIRE(cfg != nullptr, "null config");
     DPPO_REQUIRE(cfg->obs_dim >= 1 && cfg->act_dim >= 1, "obs_dim=%d act_dim=%d must be >= 1", cfg->obs_dim, cfg->act_dim);
     DPPO_REQUIRE(cfg->n_hidden >= 0 && cfg->n_hidden <= kMaxLayers, "n_hidden=%d out of [0,%d]", cfg->n_hidden, kMaxLayers);
-    s->obs = cfg->obs_dim; s->act = cfg->act_dim; s->L = cfg->n_hidden; s->P = 1 + 2 * cfg->act_dim;
+    DPPO_REQUIRE(cfg->pd_type == DPPO_PD_DIAG_GAUSSIAN || cfg->pd_type == DPPO_PD_CATEGORICAL,
+                 "pd_type=%d unknown (DPPO_PD_DIAG_GAUSSIAN=0, DPPO_PD_CATEGORICAL=1)", cfg->pd_type);
+    s->obs = cfg->obs_dim; s->act = cfg->act_dim; s->L = cfg->n_hidden;
+    s->pd = cfg->pd_type;
+    s->pdw = (s->pd == DPPO_PD_CATEGORICAL) ? cfg->act_dim : 2 * cfg->act_dim;      // pdtype.param_shape()[0], Model.py:14
+    s->acols = (s->pd == DPPO_PD_CATEGORICAL) ? 1 : cfg->act_dim;
+    s->P = 1 + s->pdw;
     s->Pld = (s->P + 3) & ~3;
     int64_t off = 0;
     int fan_in = cfg->obs_dim;
@@ -141,7 +147,7 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     w.loss_part = (double*)take(tiles * kLossSlots * sizeof(double));
     w.gae_adv = (float*)take(R * sizeof(float));
     w.gae_ret = (float*)take(R * sizeof(float));
-    w.stage_floats = R * ((size_t)s.obs + s.act + 3);
+    w.stage_floats = R * ((size_t)s.obs + s.acols + 3);
     w.stage = (float*)take(w.stage_floats * sizeof(float));
     if (ws) *ws = w;
     return off;
@@ -348,7 +354,7 @@ int dppo_param_offsets(const dppo_config* cfg, int64_t* offsets, int capacity) {
     offsets[2 * s.L + 0] = head;                         // Wv [H,1]
     offsets[2 * s.L + 1] = head + H;                     // bv [1]
     offsets[2 * s.L + 2] = head + H + 1;                 // Wp [H,2A]
-    offsets[2 * s.L + 3] = head + H + 1 + 2 * s.act * H; // bp [2A]
+    offsets[2 * s.L + 3] = head + H + 1 + (int64_t)s.pdw * H; // bp [2A | ncat]
     return n;
 }
 
@@ -489,7 +495,7 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
     active_slices(c, rows_per, active);
     for (int r0 = 0, k = 0; r0 < B; r0 += rows_per, ++k) {
         const int rows = (B - r0 < rows_per) ? B - r0 : rows_per;
-        if (int r = loss_grad_rows(c, params_pi, params_old, obs + (size_t)r0 * c->shape.obs, act + (size_t)r0 * c->shape.act,
+        if (int r = loss_grad_rows(c, params_pi, params_old, obs + (size_t)r0 * c->shape.obs, act + (size_t)r0 * c->shape.acols,
                                    c->ws.gae_adv + r0, c->ws.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active,
                                    st, k == 0 ? c->chunk_ev[0] : nullptr)) return r;
     }
@@ -522,7 +528,7 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
     // gathered minibatch lives in the staging area (also used by dppo_update_host; one call at a time per context)
     float* g_obs = w.stage;
     float* g_act = g_obs + (size_t)mb * s.obs;
-    float* g_adv = g_act + (size_t)mb * s.act;
+    float* g_adv = g_act + (size_t)mb * s.acols;
     float* g_ret = g_adv + mb;
     int active[kMaxLayers + 1];
     active_slices(c, mb, active);
@@ -531,10 +537,10 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
         const PermKey key = make_perm_key((uint32_t)B, seed, (uint64_t)e);
         for (int k = 0; k < n_mb; ++k, ++step, ++slot) {
             const int r0 = k * mb, rows = (B - r0 < mb) ? B - r0 : mb;
-            const float *x = obs + (size_t)r0 * s.obs, *a = act + (size_t)r0 * s.act, *ad = w.gae_adv + r0,
+            const float *x = obs + (size_t)r0 * s.obs, *a = act + (size_t)r0 * s.acols, *ad = w.gae_adv + r0,
                         *rt = w.gae_ret + r0;
             if (shuffle) {
-                if (int r = launch_gather_rows(key, r0, rows, s.obs, s.act, obs, act, w.gae_adv, w.gae_ret, g_obs, g_act,
+                if (int r = launch_gather_rows(key, r0, rows, s.obs, s.acols, obs, act, w.gae_adv, w.gae_ret, g_obs, g_act,
                                                g_adv, g_ret, st)) return r;
                 x = g_obs; a = g_act; ad = g_adv; rt = g_ret;
             }
@@ -608,7 +614,7 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
     cudaStream_t st = (cudaStream_t)stream, cp = c->copy_stream;
     float* d_obs = w.stage;
     float* d_act = d_obs + (size_t)B * s.obs;
-    float* d_rew = d_act + (size_t)B * s.act;
+    float* d_rew = d_act + (size_t)B * s.acols;
     float* d_pv = d_rew + B;
     float* d_done = d_pv + B;
 
@@ -647,8 +653,8 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
         const int r0 = chunk_r0[k], rows = chunk_rows[k];
         DPPO_CHECK_CUDA(cudaMemcpyAsync(d_obs + (size_t)r0 * s.obs, obs_h + (size_t)r0 * s.obs,
                                         (size_t)rows * s.obs * 4, cudaMemcpyHostToDevice, cp));
-        DPPO_CHECK_CUDA(cudaMemcpyAsync(d_act + (size_t)r0 * s.act, act_h + (size_t)r0 * s.act,
-                                        (size_t)rows * s.act * 4, cudaMemcpyHostToDevice, cp));
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(d_act + (size_t)r0 * s.acols, act_h + (size_t)r0 * s.acols,
+                                        (size_t)rows * s.acols * 4, cudaMemcpyHostToDevice, cp));
         DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[k + 1], cp));
     }
     int active[kMaxLayers + 1];
@@ -659,7 +665,7 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
     for (int k = 0; k < n_chunks; ++k) {
         const int r0 = chunk_r0[k], rows = chunk_rows[k];
         DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[k + 1], 0));
-        if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.act,
+        if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.acols,
                                    w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st))
             return r;
     }
@@ -686,6 +692,13 @@ int dppo_diag_gaussian(dppo_ctx* c, int op, const float* flat, const float* arg,
     CTX_GUARD(c);
     DPPO_REQUIRE(B >= 0 && A >= 1, "dppo_diag_gaussian: B=%d A=%d", B, A);
     return launch_diag_gaussian(op, flat, arg, B, A, seed, offset, out, (cudaStream_t)stream);
+}
+
+int dppo_categorical(dppo_ctx* c, int op, const float* logits, const void* arg, int B, int ncat, uint64_t seed,
+                     uint64_t offset, void* out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(B >= 0 && ncat >= 1, "dppo_categorical: B=%d ncat=%d", B, ncat);
+    return launch_categorical(op, logits, arg, B, ncat, seed, offset, out, (cudaStream_t)stream);
 }
 
 int dppo_profile_reset(int enable_timing) {

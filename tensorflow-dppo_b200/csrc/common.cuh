@@ -42,6 +42,9 @@ constexpr int kPlanSMs = 148;               // B200: the split-K plan fills 2 CT
 // single GEMM.  Same total size as the public head block.
 struct NetShape {
     int obs, act, L, P;
+    int pd;                          // DPPO_PD_*
+    int pdw;                         // policy-head width: 2A (mean | logstd) or ncat (logits); P = 1 + pdw
+    int acols;                       // 4-byte columns of an action row: A (fp32) or 1 (int32 class index)
     int Pld;                         // row stride of the [rows, P] head buffers (P rounded up to 4: 16-B rows)
     int h[kMaxLayers];
     int64_t w_off[kMaxLayers + 1];   // trunk W_l offsets, [L] = packed head W
@@ -181,6 +184,8 @@ int tc_transpose_weights(const NetShape& s, const float* params_pi, const float*
 int launch_pack_heads(const NetShape& s, const float* params_pi, const float* params_old,
                       float* head_pi, float* head_old, cudaStream_t st);
 // out_pi / out_old / d_out are [rows, s.Pld] with P valid columns
+int launch_categorical(int op, const float* logits, const void* arg, int B, int ncat, uint64_t seed, uint64_t offset,
+                       void* out, cudaStream_t st);
 int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
                 const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st);

@@ -13,9 +13,9 @@ namespace dppo {
 // (Model.py:13-14 creates two dense layers on the same input; one GEMM serves both.)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_heads_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
-                                  float* __restrict__ h0, float* __restrict__ h1, int H, int A,
+                                  float* __restrict__ h0, float* __restrict__ h1, int H, int W,
                                   long long head_off) {
-    const int P = 1 + 2 * A;
+    const int P = 1 + W;                     // W = policy-head width (2A or ncat)
     const int total = H * P + P;
     const float* src = (blockIdx.y == 0 ? p0 : p1);
     float* dst = (blockIdx.y == 0 ? h0 : h1);
@@ -25,10 +25,10 @@ __global__ void pack_heads_kernel(const float* __restrict__ p0, const float* __r
         float v;
         if (i < H * P) {
             const int k = i / P, c = i % P;
-            v = (c == 0) ? src[k] : src[H + 1 + k * 2 * A + (c - 1)];
+            v = (c == 0) ? src[k] : src[H + 1 + k * W + (c - 1)];
         } else {
             const int c = i - H * P;
-            v = (c == 0) ? src[H] : src[H + 1 + 2 * A * H + (c - 1)];
+            v = (c == 0) ? src[H] : src[H + 1 + W * H + (c - 1)];
         }
         dst[i] = v;
     }
@@ -40,7 +40,7 @@ int launch_pack_heads(const NetShape& s, const float* params_pi, const float* pa
     const int total = H * s.P + s.P;
     dim3 grid((total + 255) / 256, 2);
     ProfScope ps(KK_MISC, st);
-    pack_heads_kernel<<<grid, 256, 0, st>>>(params_pi, params_old, head_pi, head_old, H, s.act,
+    pack_heads_kernel<<<grid, 256, 0, st>>>(params_pi, params_old, head_pi, head_old, H, s.pdw,
                                             (long long)s.w_off[s.L]);
     DPPO_LAUNCH_CHECK();
     return 0;
@@ -172,10 +172,133 @@ ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_
     }
 }
 
+// Same tile scheme for CategoricalPd heads (distributions.py:124-159): the row's [v | logits(ncat)] for pi and oldpi,
+// one int32 class index per row.  logp = log_softmax(logits)[a] (:131-138; an out-of-range a gives a zero one_hot row,
+// hence logp = 0 and no policy gradient, as TF's op does), entropy :148-153, KL(old || new) :139-147 as a diagnostic.
+//   d total / d logit_k = g_logp * ([k == a] - p_k) + (ENTCOEFF / B) * p_k * (log p_k + H)
+__global__ void __launch_bounds__(kLossTileRows)
+ppo_loss_cat_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_old,
+                    const int* __restrict__ act, const float* __restrict__ adv,
+                    const float* __restrict__ ret, int rows, int ncat, int Pld, int tile0, float inv_B, float clip,
+                    float entcoeff, float vcoeff, float* __restrict__ d_out,
+                    double* __restrict__ loss_part) {
+    extern __shared__ float smem[];
+    const int P = 1 + ncat;
+    const int Ps = P | 1;                            // odd smem row stride: the row-strided per-thread reads stay conflict free
+    float* s_pi = smem;                              // [R][Ps]  (becomes d_out)
+    float* s_old = s_pi + kLossTileRows * Ps;        // [R][Ps]
+    __shared__ double s_red[kLossTileRows / 32][kLossSlots];
+
+    const int row0 = blockIdx.x * kLossTileRows;
+    const int nrows = min(kLossTileRows, rows - row0);
+    const int tid = threadIdx.x;
+    {
+        const float* gp = out_pi + (size_t)row0 * Pld;
+        const float* go = out_old + (size_t)row0 * Pld;
+        for (int i = tid; i < nrows * Pld; i += kLossTileRows) {
+            const int r = i / Pld, cc = i - r * Pld;
+            if (cc < P) { s_pi[r * Ps + cc] = __ldg(gp + i); s_old[r * Ps + cc] = __ldg(go + i); }
+        }
+    }
+    __syncthreads();
+
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (tid < nrows) {
+        float* o = s_pi + tid * Ps;
+        const float* q = s_old + tid * Ps;
+        const int a = __ldg(act + row0 + tid);
+        const bool valid = (a >= 0) && (a < ncat);
+        const float advb = __ldg(adv + row0 + tid);
+        const float R = __ldg(ret + row0 + tid);
+
+        float m = o[1], mo = q[1];
+        for (int k = 1; k < ncat; ++k) { m = fmaxf(m, o[1 + k]); mo = fmaxf(mo, q[1 + k]); }
+        float z = 0.f, zo = 0.f;
+        for (int k = 0; k < ncat; ++k) { z += expf(o[1 + k] - m); zo += expf(q[1 + k] - mo); }
+        const float lz = logf(z), lzo = logf(zo), inv_z = 1.f / z, inv_zo = 1.f / zo;
+        float ent = 0.f, kl = 0.f;
+        for (int k = 0; k < ncat; ++k) {
+            const float a0 = o[1 + k] - m, a1 = q[1 + k] - mo;
+            ent += expf(a0) * inv_z * (lz - a0);                          // :148-153
+            kl += expf(a1) * inv_zo * (a1 - lzo - a0 + lz);               // :139-147, self = oldpi
+        }
+        const float logp = valid ? (o[1 + a] - m) - lz : 0.f;
+        const float logpo = valid ? (q[1 + a] - mo) - lzo : 0.f;
+        const float ratio = expf(logp - logpo);                          // PPO.py:31
+        const float surr1 = ratio * advb;
+        const float rc = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+        const float surr2 = rc * advb;
+        const bool first = (surr1 <= surr2);
+        const float g_logp = (first && valid) ? (-advb * inv_B) * ratio : 0.f;
+
+        const float v = o[0], vo = q[0];
+        const float dv = v - vo;
+        const float vclip = vo + fminf(fmaxf(dv, -clip), clip);
+        const float e1 = (v - R) * (v - R);
+        const float e2 = (vclip - R) * (vclip - R);
+        const bool vfirst = (e1 >= e2);
+        const bool inclip = (dv >= -clip) && (dv <= clip);
+        const float g_v = vcoeff * inv_B * (vfirst ? 2.f * (v - R) : (inclip ? 2.f * (vclip - R) : 0.f));
+
+        acc[0] = -(double)fminf(surr1, surr2);
+        acc[1] = (double)fmaxf(e1, e2);
+        acc[2] = (double)ent;
+        acc[3] = (double)kl;
+        acc[4] = first ? 0.0 : 1.0;
+        acc[5] = (!vfirst && !inclip) ? 1.0 : 0.0;
+        acc[6] = 1.0;
+
+        const float ent_g = entcoeff * inv_B;
+        for (int k = 0; k < ncat; ++k) {
+            const float a0 = o[1 + k] - m;
+            const float pk = expf(a0) * inv_z;
+            o[1 + k] = g_logp * ((k == a ? 1.f : 0.f) - pk) + ent_g * pk * ((a0 - lz) + ent);
+        }
+        o[0] = g_v;
+    }
+    __syncthreads();
+    {
+        float* gd = d_out + (size_t)row0 * Pld;
+        for (int i = tid; i < nrows * Pld; i += kLossTileRows) {
+            const int r = i / Pld, cc = i - r * Pld;
+            gd[i] = cc < P ? s_pi[r * Ps + cc] : 0.f;
+        }
+    }
+    const int warp = tid / 32, lane = tid % 32;
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+        const double w = warp_sum(acc[s]);
+        if (lane == 0) s_red[warp][s] = w;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLossTileRows / 32; ++w) t += s_red[w][tid];
+        loss_part[(size_t)(tile0 + blockIdx.x) * kLossSlots + tid] = t;
+    }
+}
+
 int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
                 const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st) {
     if (rows == 0) return 0;
+    const int grid = (rows + kLossTileRows - 1) / kLossTileRows;
+    if (s.pd == DPPO_PD_CATEGORICAL) {
+        const size_t smem = (size_t)kLossTileRows * 2 * (s.P | 1) * sizeof(float);
+        DPPO_REQUIRE(smem <= 200 * 1024, "loss kernel: ncat=%d needs %zu B of shared memory", s.act, smem);
+        static size_t configured_cat = 0;
+        if (smem > 48 * 1024 && smem > configured_cat) {
+            DPPO_CHECK_CUDA(cudaFuncSetAttribute(ppo_loss_cat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured_cat = smem;
+        }
+        ProfScope ps(KK_LOSS, st);
+        ppo_loss_cat_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, reinterpret_cast<const int*>(act), adv, ret,
+                                                               rows, s.act, s.Pld, tile0, inv_B, clip, entcoeff, vcoeff,
+                                                               d_out, loss_part);
+        DPPO_LAUNCH_CHECK();
+        return 0;
+    }
     const size_t smem = (size_t)kLossTileRows * (2 * s.P + s.act) * sizeof(float);
     DPPO_REQUIRE(smem <= 200 * 1024, "loss kernel: act_dim=%d needs %zu B of shared memory", s.act, smem);
     static size_t configured = 0;
@@ -183,7 +306,6 @@ int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, co
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(ppo_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = (rows + kLossTileRows - 1) / kLossTileRows;
     ProfScope ps(KK_LOSS, st);
     ppo_loss_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, act, adv, ret, rows, s.act, s.Pld, tile0,
                                                        inv_B, clip, entcoeff, vcoeff, d_out, loss_part);
@@ -204,10 +326,10 @@ struct FinalizePlan {
 };
 
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, FinalizePlan plan, long long n_params,
-                                long long head_off, int H, int A, const double* __restrict__ loss_part, int n_tiles,
+                                long long head_off, int H, int W, const double* __restrict__ loss_part, int n_tiles,
                                 float entcoeff, float vcoeff, float* __restrict__ grad_out,
                                 float* __restrict__ losses_out) {
-    const int P = 1 + 2 * A;
+    const int P = 1 + W;                     // W = policy-head width (2A or ncat)
     // A block owns 32 consecutive parameters.  Warp w streams slices w, w+8, ... of them: every load instruction
     // is one full 128-byte line (32 lanes x consecutive parameters of ONE slice), 8 lines in flight per warp; the 8
     // warps' sums are then combined in a fixed order through shared memory -> deterministic and DRAM-friendly.
@@ -241,10 +363,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                 const long long r = i - head_off;
                 if (r < (long long)H * P) {
                     const int kk = (int)(r / P), c = (int)(r % P);
-                    pub = head_off + (c == 0 ? kk : (long long)H + 1 + (long long)kk * 2 * A + (c - 1));
+                    pub = head_off + (c == 0 ? kk : (long long)H + 1 + (long long)kk * W + (c - 1));
                 } else {
                     const int c = (int)(r - (long long)H * P);
-                    pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + 2LL * A * H + (c - 1));
+                    pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + (long long)W * H + (c - 1));
                 }
             }
             grad_out[pub] = t;
@@ -293,7 +415,7 @@ int launch_finalize(const NetShape& s, const int* active, const float* partial, 
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
     ProfScope ps(KK_FINALIZE, st);
-    finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.act, loss_part,
+    finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.pdw, loss_part,
                                           n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out);
     DPPO_LAUNCH_CHECK();
     return 0;
@@ -512,9 +634,89 @@ int launch_diag_gaussian(int op, const float* flat, const float* arg, int B, int
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// CategoricalPd (distributions.py:124-159): sample = argmax(logits - log(-log(u))) (:154-156, Gumbel max; one Philox
+// call yields 4 uniforms = 4 classes), mode = argmax (:129-130, first maximum).  One thread per row.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int gumbel_argmax(const float* __restrict__ lg, int ncat, int r, uint64_t seed, uint64_t offset) {
+    float best = -INFINITY; int arg = 0;
+    for (int q4 = 0; q4 < (ncat + 3) / 4; ++q4) {
+        uint32_t c[4] = {(uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)r, (uint32_t)q4};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        for (int e = 0; e < 4; ++e) {
+            const int k = q4 * 4 + e;
+            if (k < ncat) {
+                const float g = lg[k] - logf(-logf(u01(c[e])));
+                if (g > best) { best = g; arg = k; }
+            }
+        }
+    }
+    return arg;
+}
+
+__global__ void sample_cat_kernel(const float* __restrict__ out, int rows, int ncat, int Pld, uint64_t seed, uint64_t offset,
+                                  int* __restrict__ action, float* __restrict__ v_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* o = out + (size_t)r * Pld;
+    action[r] = gumbel_argmax(o + 1, ncat, r, seed, offset);
+    if (v_out) v_out[r] = o[0];
+}
+
+__global__ void categorical_kernel(int op, const float* __restrict__ logits, const void* __restrict__ arg, int B, int ncat,
+                                   uint64_t seed, uint64_t offset, void* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const float* f = logits + (size_t)r * ncat;
+    if (op == 3) { reinterpret_cast<int*>(out)[r] = gumbel_argmax(f, ncat, r, seed, offset); return; }
+    float m = f[0]; int am = 0;
+    for (int k = 1; k < ncat; ++k) if (f[k] > m) { m = f[k]; am = k; }
+    if (op == 4) { reinterpret_cast<int*>(out)[r] = am; return; }
+    float z = 0.f;
+    for (int k = 0; k < ncat; ++k) z += expf(f[k] - m);
+    const float lz = logf(z);
+    float* o = reinterpret_cast<float*>(out);
+    if (op == 0) {            // :131-138
+        const int x = reinterpret_cast<const int*>(arg)[r];
+        o[r] = (x >= 0 && x < ncat) ? lz - (f[x] - m) : 0.f;
+    } else if (op == 1) {     // :148-153
+        float e = 0.f;
+        for (int k = 0; k < ncat; ++k) { const float a0 = f[k] - m; e += expf(a0) / z * (lz - a0); }
+        o[r] = e;
+    } else {                  // :139-147   KL(self || other)
+        const float* q = reinterpret_cast<const float*>(arg) + (size_t)r * ncat;
+        float mq = q[0];
+        for (int k = 1; k < ncat; ++k) mq = fmaxf(mq, q[k]);
+        float zq = 0.f;
+        for (int k = 0; k < ncat; ++k) zq += expf(q[k] - mq);
+        const float lzq = logf(zq);
+        float kl = 0.f;
+        for (int k = 0; k < ncat; ++k) { const float a0 = f[k] - m, a1 = q[k] - mq; kl += expf(a0) / z * (a0 - lz - a1 + lzq); }
+        o[r] = kl;
+    }
+}
+
+int launch_categorical(int op, const float* logits, const void* arg, int B, int ncat, uint64_t seed, uint64_t offset,
+                       void* out, cudaStream_t st) {
+    DPPO_REQUIRE(op >= 0 && op <= 4, "dppo_categorical: bad op %d", op);
+    DPPO_REQUIRE(logits && out && (arg || (op != 0 && op != 2)), "dppo_categorical: null buffer");
+    if (B == 0) return 0;
+    ProfScope ps(KK_MISC, st);
+    categorical_kernel<<<(B + 127) / 128, 128, 0, st>>>(op, logits, arg, B, ncat, seed, offset, out);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,
                   float* action, float* v_out, cudaStream_t st) {
     if (rows == 0) return 0;
+    if (s.pd == DPPO_PD_CATEGORICAL) {
+        ProfScope ps(KK_MISC, st);
+        sample_cat_kernel<<<(rows + 127) / 128, 128, 0, st>>>(out, rows, s.act, s.Pld, seed, offset,
+                                                             reinterpret_cast<int*>(action), v_out);
+        DPPO_LAUNCH_CHECK();
+        return 0;
+    }
     const long long total = (long long)rows * ((s.act + 3) / 4);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;

@@ -10,6 +10,7 @@ NUM_LOSS_SLOTS = 8
 NCCL_UNIQUE_ID_BYTES = 128
 GAE_REFERENCE, GAE_STANDARD = 0, 1
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_BF16 = 0, 1, 2
+PD_DIAG_GAUSSIAN, PD_CATEGORICAL = 0, 1
 
 
 class LibraryMissing(RuntimeError):
@@ -21,6 +22,7 @@ class DppoConfig(C.Structure):
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("n_hidden", C.c_int32),
         ("hidden", C.c_int32 * MAX_HIDDEN), ("max_rows", C.c_int32), ("device", C.c_int32),
         ("gemm_mode", C.c_int32), ("entcoeff", C.c_float), ("vcoeff", C.c_float), ("clip_param", C.c_float),
+        ("pd_type", C.c_int32),
     ]
 
 
@@ -51,6 +53,7 @@ _PROTOS = {
                                    C.c_int, C.c_float, _p, _p, _p]),
     "dppo_update": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_float,
                               _p, _p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _p, _p]),
+    "dppo_categorical": (C.c_int, [_p, C.c_int, _p, _p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),
     "dppo_update_epochs": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_float, _p, _p, C.c_int, C.c_float,
                                      C.c_float, C.c_float, C.c_float, _p, _p, _p]),

@@ -23,14 +23,19 @@ class DppoEngine:
 
     def __init__(self, obs_dim: int, act_dim: int, hidden: Sequence[int], max_rows: int, device: int = 0,
                  entcoeff: float = 0.01, vcoeff: float = 0.5, clip_param: float = 0.2,
-                 gemm_mode: int = L.GEMM_FP32_SIMT):
+                 gemm_mode: int = L.GEMM_FP32_SIMT, pd_type: int = L.PD_DIAG_GAUSSIAN):
+        """pd_type = L.PD_CATEGORICAL: act_dim is the number of classes, actions are int32 [B, 1] (PPO.py:26)."""
         self.lib = L.load_library()
         if not torch.cuda.is_available():
             raise RuntimeError("DppoEngine needs a CUDA device (sm_100a); there is no CPU path")
         if len(hidden) > L.MAX_HIDDEN:
             raise ValueError(f"at most {L.MAX_HIDDEN} hidden layers")
-        self.layout = ParamLayout(obs_dim, hidden, act_dim)
+        self.is_categorical = int(pd_type) == L.PD_CATEGORICAL
+        self.pd_width = act_dim if self.is_categorical else 2 * act_dim
+        self.act_cols = 1 if self.is_categorical else act_dim
+        self.layout = ParamLayout(obs_dim, hidden, act_dim, self.pd_width)
         cfg = L.DppoConfig()
+        cfg.pd_type = int(pd_type)
         cfg.obs_dim, cfg.act_dim, cfg.n_hidden = obs_dim, act_dim, len(hidden)
         for i, h in enumerate(hidden):
             cfg.hidden[i] = int(h)
@@ -69,6 +74,17 @@ class DppoEngine:
             raise ValueError(f"{name}: expected {numel} elements, got {t.numel()}")
         return t.data_ptr()
 
+    def _act(self, t: torch.Tensor, rows: int, name: str = "act"):
+        """action tensor: fp32 [rows, A] (DiagGaussianPd) or int32 [rows, 1] (CategoricalPd, PPO.py:26)"""
+        want = torch.int32 if self.is_categorical else torch.float32
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == want and t.is_contiguous()):
+            raise TypeError(f"{name}: expected a contiguous {want} CUDA tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name}: on {t.device}, engine is on {self.device}")
+        if t.numel() != rows * self.act_cols:
+            raise ValueError(f"{name}: expected {rows * self.act_cols} elements, got {t.numel()}")
+        return t.data_ptr()
+
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx.value:
             self.lib.dppo_destroy(self.ctx)
@@ -102,7 +118,7 @@ class DppoEngine:
         """(v[B], pdflat[B,2A]) = Model.FC forward.  Model.py:11-15."""
         B = obs.shape[0]
         v = torch.empty(B, dtype=torch.float32, device=self.device)
-        pd = torch.empty(B, 2 * self.act_dim, dtype=torch.float32, device=self.device)
+        pd = torch.empty(B, self.pd_width, dtype=torch.float32, device=self.device)
         self._check(self.lib.dppo_forward(self.ctx, self._dev(params, self.n_params, "params"),
                                           self._dev(obs, B * self.obs_dim, "obs"), B, v.data_ptr(), pd.data_ptr(),
                                           self._stream()))
@@ -111,7 +127,8 @@ class DppoEngine:
     def act(self, params, obs, seed: int, offset: int):
         """(action[B,A], v[B]) = piPD.sample(), pipredv.  PPO.py:23, Worker.py:146."""
         B = obs.shape[0]
-        a = torch.empty(B, self.act_dim, dtype=torch.float32, device=self.device)
+        a = (torch.empty(B, 1, dtype=torch.int32, device=self.device) if self.is_categorical else
+             torch.empty(B, self.act_dim, dtype=torch.float32, device=self.device))
         v = torch.empty(B, dtype=torch.float32, device=self.device)
         self._check(self.lib.dppo_act(self.ctx, self._dev(params, self.n_params, "params"),
                                       self._dev(obs, B * self.obs_dim, "obs"), B, int(seed), int(offset),
@@ -125,7 +142,7 @@ class DppoEngine:
         g = grad_out if grad_out is not None else self.new_grad_buffer()
         self._check(self.lib.dppo_loss_grad(
             self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
-            self._dev(obs, B * self.obs_dim, "obs"), self._dev(act, B * self.act_dim, "act"),
+            self._dev(obs, B * self.obs_dim, "obs"), self._act(act, B),
             self._dev(adv, B, "adv"), self._dev(ret, B, "ret"), B, float(l_mul),
             self._dev(losses_out, L.NUM_LOSS_SLOTS, "losses_out") if losses_out is not None else None,
             self._dev(g, self.grad_len, "grad_out"), self._stream()))
@@ -176,7 +193,7 @@ class DppoEngine:
         g = grad_out if grad_out is not None else self.new_grad_buffer()
         self._check(self.lib.dppo_update(
             self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
-            self._dev(obs, B * self.obs_dim, "obs"), self._dev(act, B * self.act_dim, "act"), self._dev(rew, B, "rew"),
+            self._dev(obs, B * self.obs_dim, "obs"), self._act(act, B), self._dev(rew, B, "rew"),
             self._dev(predv, B, "predv"), self._dev(done, B, "done"), T, N, float(gamma), float(lam), int(gae_mode),
             float(l_mul), self._dev(adam_m, self.n_params, "adam_m") if adam_m is not None else None,
             self._dev(adam_v, self.n_params, "adam_v") if adam_v is not None else None, int(step), float(lr),
@@ -200,7 +217,7 @@ class DppoEngine:
             losses_out = torch.empty(n_epochs * n_mb, L.NUM_LOSS_SLOTS, dtype=torch.float32, device=g.device)
         self._check(self.lib.dppo_update_epochs(
             self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
-            self._dev(obs, B * self.obs_dim, "obs"), self._dev(act, B * self.act_dim, "act"), self._dev(rew, B, "rew"),
+            self._dev(obs, B * self.obs_dim, "obs"), self._act(act, B), self._dev(rew, B, "rew"),
             self._dev(predv, B, "predv"), self._dev(done, B, "done"), T, N, float(gamma), float(lam), int(gae_mode),
             int(n_epochs), int(mb), int(bool(shuffle)), int(seed), float(l_mul),
             self._dev(adam_m, self.n_params, "adam_m"), self._dev(adam_v, self.n_params, "adam_v"), int(step0), float(lr),
@@ -221,10 +238,11 @@ class DppoEngine:
         chunked H2D overlapped with GAE + loss_grad (+ allreduce), losses read back.  Synchronises."""
         T, N = rew_h.shape
         B = T * N
-        for name, t, n in (("obs_h", obs_h, B * self.obs_dim), ("act_h", act_h, B * self.act_dim),
+        for name, t, n in (("obs_h", obs_h, B * self.obs_dim), ("act_h", act_h, B * self.act_cols),
                            ("rew_h", rew_h, B), ("predv_h", predv_h, B), ("done_h", done_h, B)):
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
-                raise TypeError(f"{name}: expected a contiguous float32 host tensor with {n} elements")
+            want = torch.int32 if (self.is_categorical and name == "act_h") else torch.float32
+            if t.is_cuda or t.dtype != want or not t.is_contiguous() or t.numel() != n:
+                raise TypeError(f"{name}: expected a contiguous {want} host tensor with {n} elements")
             if not t.is_pinned():
                 raise TypeError(f"{name}: host buffers must be pinned (torch.Tensor.pin_memory())")
         g = grad_out if grad_out is not None else self.new_grad_buffer()
@@ -235,6 +253,24 @@ class DppoEngine:
             float(gamma), float(lam), int(gae_mode), float(l_mul), losses, self._dev(g, self.grad_len, "grad_out"),
             self._stream()))
         return list(losses), g
+
+    # ------------------------------------------------------------------ CategoricalPd methods
+    def categorical(self, op: str, logits, arg=None, seed: int = 0, offset: int = 0):
+        """distributions.py:124-159 on a [B,ncat] logits tensor: neglogp(arg=int32 x[B]) / entropy / kl(arg=other logits)
+        -> fp32 [B]; sample / mode -> int32 [B]."""
+        B, n = logits.shape
+        code = self.PD_OPS[op]
+        out = torch.empty(B, dtype=torch.int32 if code >= 3 else torch.float32, device=self.device)
+        a = None
+        if code == 0:
+            if not (arg.is_cuda and arg.dtype == torch.int32 and arg.is_contiguous() and arg.numel() == B):
+                raise TypeError("categorical neglogp: x must be a contiguous int32 CUDA tensor with B elements")
+            a = arg.data_ptr()
+        elif code == 2:
+            a = self._dev(arg, B * n, "other")
+        self._check(self.lib.dppo_categorical(self.ctx, code, self._dev(logits, B * n, "logits"), a, B, n, int(seed),
+                                              int(offset), out.data_ptr(), self._stream()))
+        return out
 
     # ------------------------------------------------------------------ DiagGaussianPd methods
     PD_OPS = {"neglogp": 0, "entropy": 1, "kl": 2, "sample": 3, "mode": 4}

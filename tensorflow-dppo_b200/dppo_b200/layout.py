@@ -24,8 +24,10 @@ class ParamEntry:
 
 
 class ParamLayout:
-    def __init__(self, obs_dim: int, hidden: Sequence[int], act_dim: int):
+    def __init__(self, obs_dim: int, hidden: Sequence[int], act_dim: int, pd_width: int = None):
+        """pd_width = pdtype.param_shape()[0] (Model.py:14): 2*act_dim for DiagGaussianPd (default), ncat for CategoricalPd."""
         self.obs_dim, self.hidden, self.act_dim = int(obs_dim), tuple(int(h) for h in hidden), int(act_dim)
+        pw = self.pd_width = 2 * self.act_dim if pd_width is None else int(pd_width)
         entries: List[ParamEntry] = []
         off, fan_in = 0, self.obs_dim
         for l, h in enumerate(self.hidden):
@@ -34,8 +36,8 @@ class ParamLayout:
             fan_in = h
         entries.append(ParamEntry("Wv", (fan_in, 1), off)); off += fan_in          # Model.py:13
         entries.append(ParamEntry("bv", (1,), off)); off += 1
-        entries.append(ParamEntry("Wp", (fan_in, 2 * self.act_dim), off)); off += fan_in * 2 * self.act_dim  # :14
-        entries.append(ParamEntry("bp", (2 * self.act_dim,), off)); off += 2 * self.act_dim
+        entries.append(ParamEntry("Wp", (fan_in, pw), off)); off += fan_in * pw                         # :14
+        entries.append(ParamEntry("bp", (pw,), off)); off += pw
         self.entries = entries
         self.n_params = off
 

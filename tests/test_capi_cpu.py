@@ -133,3 +133,17 @@ int main(int argc, char** argv) {
         ref = O.minibatch_perm(n, seed, epoch)
         assert np.array_equal(got, ref), (n, seed, epoch)
         assert np.array_equal(np.sort(ref), np.arange(n))
+
+
+@pytest.mark.parametrize("obs,hidden,ncat", [(4, (16,), 2), (128, (256, 256), 18), (5, (), 3)])
+def test_param_layout_categorical_matches_oracle(lib, obs, hidden, ncat):
+    """pd_type = DPPO_PD_CATEGORICAL: the policy head is ncat wide (distributions.py:53-54, Model.py:14)."""
+    c = _cfg(obs, hidden, ncat)
+    c.pd_type = 1
+    lay = O.make_layout(obs, hidden, ncat, pd="cat")
+    assert lib.dppo_param_count(C.byref(c)) == lay.n_params
+    offs = (C.c_int64 * 32)()
+    k = lib.dppo_param_offsets(C.byref(c), offs, 32)
+    assert list(offs[:k]) == [e[2] for e in lay.entries]
+    c.pd_type = 5
+    assert lib.dppo_param_count(C.byref(c)) < 0 and b"pd_type" in lib.dppo_last_error()

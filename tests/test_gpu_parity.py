@@ -721,3 +721,136 @@ def test_update_epochs_vs_oracle():
     assert rel_err(m.cpu().numpy(), m_ref) < 1e-4
     upd = p.cpu().numpy().astype(np.float64) - th_pi
     assert rel_err(upd, th_ref - th_pi) < 2e-2            # |update| ~ 8e-4 on O(0.1) parameters: fp32 ulp / update
+
+
+# ------------------------------------------------------------------------------- CategoricalPd path (distributions.py:124-159)
+def _cat_engine(obs, hidden, ncat, max_rows, **kw):
+    from dppo_b200 import _lib as L
+    return _engine(obs, hidden, ncat, max_rows, pd_type=L.PD_CATEGORICAL, **kw)
+
+
+def idev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.int32).cuda()
+
+
+def test_categorical_methods_golden(golden_dir):
+    """dppo_categorical ops against the reference class executed from source (tests/golden/categorical_ref.npz)."""
+    g = np.load(os.path.join(golden_dir, "categorical_ref.npz"))
+    eng = _cat_engine(3, (), 3, 64)
+    p, q = dev(g["fix_p"][None]), dev(g["fix_q"][None])
+    assert abs(float(eng.categorical("entropy", p)[0]) - float(g["fix_entropy"][0])) < 2e-6
+    assert abs(float(eng.categorical("kl", p, q)[0]) - float(g["fix_kl"][0])) < 1e-6
+    assert int(eng.categorical("mode", p)[0]) == int(g["fix_mode"][0])
+    for k in range(3):
+        assert abs(float(eng.categorical("neglogp", p, idev([k]))[0]) - float(g["fix_neglogp"][k][0])) < 2e-6
+    assert float(eng.categorical("neglogp", p, idev([7]))[0]) == 0.0        # tf.one_hot of an out-of-range class is all zeros
+    for n in (2, 6, 18):
+        fp, fq, x = dev(g[f"n{n}_p"]), dev(g[f"n{n}_q"]), idev(g[f"n{n}_x"])
+        np.testing.assert_allclose(eng.categorical("neglogp", fp, x).cpu().numpy(), g[f"n{n}_neglogp"], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(eng.categorical("entropy", fp).cpu().numpy(), g[f"n{n}_entropy"], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(eng.categorical("kl", fp, fq).cpu().numpy(), g[f"n{n}_kl"], rtol=1e-4, atol=2e-6)
+        assert np.array_equal(eng.categorical("mode", fp).cpu().numpy(), g[f"n{n}_mode"])
+
+
+def test_categorical_sampling_monte_carlo_identities():
+    """The reference's self-check on its categorical fixture (distributions.py:260,269-295): Gumbel-max samples,
+    entropy == -E[logp] and KL == -H - E_p[log q], 3 sigma; plus class frequencies == softmax."""
+    pdparam = np.array([-.2, .3, .5]); Nn = 100000
+    eng = _cat_engine(3, (), 3, Nn)
+    M = dev(np.repeat(pdparam[None], Nn, 0))
+    X = eng.categorical("sample", M, seed=42, offset=0)
+    X2 = eng.categorical("sample", M, seed=42, offset=0); X3 = eng.categorical("sample", M, seed=42, offset=1)
+    assert torch.equal(X, X2) and not torch.equal(X, X3)
+    Xn = X.cpu().numpy(); Mn = np.repeat(pdparam[None], Nn, 0)
+    ll = O.cat_logp(Mn, Xn)
+    assert abs(O.cat_entropy(Mn).mean() + ll.mean()) < 3 * ll.std() / math.sqrt(Nn)
+    q = pdparam + np.random.default_rng(0).standard_normal(3) * 0.1
+    M2 = np.repeat(q[None], Nn, 0)
+    ll2 = O.cat_logp(M2, Xn)
+    kl_dev = float(eng.categorical("kl", M, dev(M2)).mean())
+    assert abs(kl_dev - (-O.cat_entropy(Mn).mean() - ll2.mean())) < 3 * ll2.std() / math.sqrt(Nn) + 1e-6
+    sm = np.exp(pdparam) / np.exp(pdparam).sum()
+    freq = np.bincount(Xn, minlength=3) / Nn
+    assert np.all(np.abs(freq - sm) < 4 * np.sqrt(sm * (1 - sm) / Nn))
+
+
+def test_categorical_loss_matches_reference_ppo_lines_golden(golden_dir):
+    """PPO.py:29-40 executed from the reference source over CategoricalPd heads and the reference's own int32 [B,1]
+    action placeholder (PPO.py:26), fed through identity heads."""
+    g = np.load(os.path.join(golden_dir, "categorical_ref.npz"))
+    for tag in "abc":
+        k = f"loss_{tag}_"
+        flat, flat_old = g[k + "flat"], g[k + "flat_old"]
+        B, n = flat.shape
+        P = 1 + n
+        obs = np.concatenate([g[k + "v"][:, None], flat, g[k + "v_old"][:, None], flat_old], 1).astype(np.float32)
+        lay = O.make_layout(2 * P, (), n, pd="cat")
+        th = []
+        for base in (0, P):
+            t = np.zeros(lay.n_params, np.float32); p = O.unflatten(t, lay)
+            p["Wv"][base, 0] = 1.0
+            for j in range(n):
+                p["Wp"][base + 1 + j, j] = 1.0
+            th.append(t)
+        eng = _cat_engine(2 * P, (), n, B)
+        losses, _ = eng.loss_grad(dev(th[0]), dev(th[1]), dev(obs), idev(g[k + "act"][:, None]), dev(g[k + "adv"]),
+                                  dev(g[k + "etr"]), float(g[k + "l_mul"]))
+        np.testing.assert_allclose(losses.cpu().numpy()[:4], g[k + "losses"], rtol=2e-5, atol=2e-6)
+
+
+CAT_CASES = [("cartpole", 200, 4, 4, (16,), 2), ("atari-ram-ish", 128, 32, 128, (256, 256), 18),
+             ("odd", 37, 5, 11, (24, 40), 5), ("no-hidden", 64, 4, 5, (), 3)]
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+@pytest.mark.parametrize("name,T,N,obs,hidden,ncat", CAT_CASES)
+def test_categorical_loss_grad_vs_oracle(name, T, N, obs, hidden, ncat, gemm_mode):
+    c = O.make_case(T, N, obs, hidden, ncat, pd="cat", head_std=0.5, delta=0.1)
+    lay = c["lay"]; B = T * N
+    eng = _cat_engine(obs, hidden, ncat, B, gemm_mode=gemm_mode)
+    losses, g = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(c["buf"]["obs"]), idev(c["act"]),
+                              dev(c["adv"]), dev(c["ret"]), c["l_mul"])
+    l_ref, g_ref, aux = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"], c["act"], c["adv"], c["ret"],
+                                        c["l_mul"], lay)
+    got_l = losses.cpu().numpy(); got_g = g.cpu().numpy()[:lay.n_params]
+    np.testing.assert_allclose(got_l[:4], l_ref, rtol=TOL, atol=TOL)
+    assert abs(got_l[4] - aux["mean_kl"]) < 1e-5 * max(1, aux["mean_kl"]) + 1e-7
+    assert abs(got_l[5] - aux["clip_frac"]) < 1e-9 + 1.0 / B and got_l[7] == B
+    errs = per_tensor_rel_err(got_g, g_ref, lay)
+    print(name, "per-tensor rel err", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < (TOL if gemm_mode == 0 else 2e-5), errs
+    assert aux["clip_frac"] > 0.01
+
+
+def test_categorical_act_and_update_epochs():
+    """dppo_act draws int32 classes (Gumbel max over the policy logits); the whole scheduler path runs on int32 actions
+    (gather moves 4-byte words) and matches the host-driven sequence bit for bit."""
+    T, N, obs, hidden, ncat = 64, 32, 8, (64, 64), 6
+    B = T * N
+    lay = O.make_layout(obs, hidden, ncat, pd="cat")
+    th_pi, th_old = O.make_params_pair(lay, 1.0, 0.5, 0.05)
+    buf = O.make_buffer(T, N, obs, ncat, pd="cat")
+    eng = _cat_engine(obs, hidden, ncat, B)
+    a, v = eng.act(dev(th_pi), dev(buf["obs"]), seed=3, offset=0)
+    assert a.dtype == torch.int32 and a.shape == (B, 1) and int(a.min()) >= 0 and int(a.max()) < ncat
+    v_ref, logits_ref, _ = O.mlp_forward(th_pi, buf["obs"], lay)
+    assert rel_err(v.cpu().numpy(), v_ref) < TOL
+    sm = np.exp(logits_ref - logits_ref.max(-1, keepdims=True)); sm /= sm.sum(-1, keepdims=True)
+    freq = np.bincount(a.cpu().numpy()[:, 0], minlength=ncat) / B
+    assert np.all(np.abs(freq - sm.mean(0)) < 5 * np.sqrt(0.25 / B))
+    d = {k: (idev(x) if k == "act" else dev(x)) for k, x in buf.items()}
+    n = lay.n_params
+    adv, ret = eng.gae(d["rew"], d["predv"], d["done"], 0.99, 0.95)
+    adv = adv.reshape(-1).clone(); ret = ret.reshape(-1).clone()
+    p1 = dev(th_pi); m1 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")
+    order = torch.as_tensor(O.minibatch_perm(B, 9, 0), device="cuda")
+    for k, r0 in enumerate(range(0, B, 512)):
+        idx = order[r0:r0 + 512]
+        _, g1 = eng.loss_grad(p1, dev(th_old), d["obs"][idx].contiguous(), d["act"][idx].contiguous(),
+                              adv[idx].contiguous(), ret[idx].contiguous(), 0.7)
+        eng.adam_apply(p1, g1, m1, v1, k + 1, 1e-4)
+    p2 = dev(th_pi); m2 = torch.zeros(n, device="cuda"); v2 = torch.zeros(n, device="cuda")
+    eng.update_epochs(p2, dev(th_old), d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7, m2, v2,
+                      step0=1, lr=1e-4, n_epochs=1, minibatch_rows=512, shuffle=True, seed=9)
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2) and torch.equal(m1, m2)
