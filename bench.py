@@ -307,6 +307,17 @@ def run_b200(args):
         step_host()
     ms_e2e = timed(step_host, K)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
+    # --- the reference's UPDATE_STEPS=4 loop (main.py:24, Chief.py:64) as ONE call: GAE once, 4 x [fwd, loss, bwd, mean, Adam]
+    reset_state()
+    us4_losses = torch.empty(4, 8, device=dev)
+
+    def step_epochs4():
+        eng.update_epochs(p_pi, p_old, d["obs"], d["act"], d["rew"], d["predv"], d["done"], gamma, lam, l_mul, m, v,
+                          step0=state["t"] + 1, lr=lr * l_mul, n_epochs=4, grad_out=grad, losses_out=us4_losses)
+        state["t"] += 4
+    step_epochs4()
+    k4 = max(K // 4, 3)
+    ms_us4 = timed(step_epochs4, k4) / k4
     # the floor of that number: the same host bytes copied with nothing else going on
     dst = {k: torch.empty_like(d[k]) for k in ("obs", "act", "rew", "predv", "done")}
 
@@ -359,6 +370,9 @@ def run_b200(args):
                     "h2d_copy_only_ms": ms_copy, "frac_of_copy_floor": ms_copy / (ms_e2e / K),
                     "api": "DppoEngine.update_host -> dppo_update_host (pinned host rollout, 8-way chunked H2D "
                            "overlapped with fwd/loss/bwd) + adam_apply"},
+            "update_steps4": {"ms_per_rollout_batch": ms_us4, "value": world * B / (ms_us4 * 1e-3), "unit": UNIT,
+                              "note": "Chief.py:64 loop, UPDATE_STEPS=4 (main.py:24) through dppo_update_epochs: env-steps "
+                                      "consumed per second when every rollout batch is trained on 4 times"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -42,8 +42,10 @@ class Model(object):
         s = state if s is None else s
         obs_dim = int(s.shape[-1])
         pdtype = make_pdtype(action_space)
-        act_dim = pdtype.param_shape()[0] // 2
-        layout = ParamLayout(obs_dim, self.hidden, act_dim)
+        pd_width = pdtype.param_shape()[0]                      # Model.py:14
+        discrete = hasattr(action_space, "n")
+        act_dim = pd_width if discrete else pd_width // 2
+        layout = ParamLayout(obs_dim, self.hidden, act_dim, pd_width)
         initializer = U.normc_initializer(0.01)                 # Model.py:10
         theta = np.zeros(layout.n_params, np.float32)
         for e in layout.entries:

@@ -2,7 +2,8 @@
 for the one family the DPPO update path uses: the diagonal Gaussian selected by make_pdtype for
 Box action spaces (distributions.py:231-235).
 
-Same class and method names (Pd / PdType / DiagGaussianPd / DiagGaussianPdType / make_pdtype).
+Same class and method names (Pd / PdType / DiagGaussianPd / DiagGaussianPdType / CategoricalPd /
+CategoricalPdType / make_pdtype).
 The reference methods build TensorFlow graph ops; here a DiagGaussianPd wraps a [B,2A] device
 tensor and every method is one launch of the sm_100a kernel behind dppo_diag_gaussian().  Inside
 the training step these formulas are not called one by one: they are fused into the loss kernel.
@@ -88,11 +89,54 @@ class DiagGaussianPd(Pd):
         return cls(flat, engine)
 
 
+class CategoricalPdType(PdType):
+    """distributions.py:48-58."""
+    def __init__(self, ncat):
+        self.ncat = ncat
+    def pdclass(self):
+        return CategoricalPd
+    def param_shape(self):
+        return [self.ncat]
+    def sample_shape(self):
+        return []
+    def sample_dtype(self):
+        import torch
+        return torch.int32
+
+
+class CategoricalPd(Pd):
+    """distributions.py:124-159 over a [B,ncat] float32 CUDA logits tensor; x / samples / mode are int32 [B]."""
+    def __init__(self, logits, engine=None):
+        if engine is None:
+            raise RuntimeError("CategoricalPd needs the DppoEngine that owns the device (no CPU path)")
+        self.logits = logits
+        self.engine = engine
+        self.seed = 0
+    def flatparam(self):
+        return self.logits
+    def mode(self):
+        return self.engine.categorical("mode", self.logits)
+    def neglogp(self, x):
+        return self.engine.categorical("neglogp", self.logits, x)
+    def kl(self, other):
+        assert isinstance(other, CategoricalPd)
+        return self.engine.categorical("kl", self.logits, other.logits)
+    def entropy(self):
+        return self.engine.categorical("entropy", self.logits)
+    def sample(self):
+        return self.engine.categorical("sample", self.logits, seed=self.seed, offset=next(_counter))
+    @classmethod
+    def fromflat(cls, flat, engine=None):
+        return cls(flat, engine)
+
+
 def make_pdtype(ac_space):
-    """distributions.py:231-243.  Box -> DiagGaussianPdType; the discrete families of the reference
-    (Categorical / MultiCategorical / Bernoulli) are outside the accelerated path."""
+    """distributions.py:231-243.  Box -> DiagGaussianPdType, Discrete -> CategoricalPdType; the MultiCategorical /
+    Bernoulli families of the reference are outside the accelerated path."""
+    if hasattr(ac_space, "n"):
+        return CategoricalPdType(ac_space.n)
     shape = getattr(ac_space, "shape", None)
-    if shape is not None and not hasattr(ac_space, "n"):
+    if shape is not None:
         assert len(shape) == 1
         return DiagGaussianPdType(shape[0])
-    raise NotImplementedError("only Box action spaces (DiagGaussianPd) are built; see DESIGN.md, out of scope")
+    raise NotImplementedError("only Box (DiagGaussianPd) and Discrete (CategoricalPd) action spaces are built")

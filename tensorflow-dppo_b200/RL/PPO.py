@@ -24,19 +24,19 @@ from RL.session import Placeholder, Fetch
 _ENGINES = {}
 
 
-def _get_backend(parameter_dict, obs_dim, act_dim, hidden):
+def _get_backend(parameter_dict, obs_dim, act_dim, hidden, discrete=False):
     """One engine per process / GPU, shared by every PPO object (they shared one tf.Session, main.py:31)."""
     backend = parameter_dict.get('BACKEND')
     if backend is not None:
         return backend
     rows = int(parameter_dict['MAX_EPOCH_STEPS']) * int(parameter_dict.get('NUM_ENVS', 1)) \
         * int(parameter_dict['NUM_WORKERS'])
-    key = (obs_dim, act_dim, tuple(hidden), rows, parameter_dict.get('DEVICE_INDEX', 0))
+    key = (obs_dim, act_dim, tuple(hidden), rows, parameter_dict.get('DEVICE_INDEX', 0), bool(discrete))
     if key not in _ENGINES:
         from dppo_b200 import DppoEngine                   # raises if the CUDA library is missing
         _ENGINES[key] = DppoEngine(obs_dim, act_dim, hidden, max(rows, 128), device=key[4],
                                    entcoeff=parameter_dict['ENTCOEFF'], vcoeff=parameter_dict['VCOEFF'],
-                                   clip_param=parameter_dict['CLIP_PARAM'])
+                                   clip_param=parameter_dict['CLIP_PARAM'], pd_type=1 if discrete else 0)
     return _ENGINES[key]
 
 
@@ -54,8 +54,10 @@ class PPO(object):
         observation_space = env.observation_space
         action_space = env.action_space
         self.obs_dim = observation_space.shape[0]
-        self.act_dim = action_space.shape[0]
-        self.backend = _get_backend(parameter_dict, self.obs_dim, self.act_dim, hidden)
+        self.discrete = hasattr(action_space, 'n')                       # spaces.Discrete -> CategoricalPd
+        self.act_dim = action_space.n if self.discrete else action_space.shape[0]
+        self.act_cols = 1 if self.discrete else self.act_dim             # PPO.py:26: a is int32 [None, 1]
+        self.backend = _get_backend(parameter_dict, self.obs_dim, self.act_dim, hidden, self.discrete)
         self.device = getattr(self.backend, 'device', 'cuda')
         model = Model(hidden)
         self.s = Placeholder(scope + '/s', [None, self.obs_dim])
@@ -69,7 +71,7 @@ class PPO(object):
         self._draws = 0
 
         if scope != "Chief":
-            self.a = Placeholder(scope + '/a', [None, self.act_dim])
+            self.a = Placeholder(scope + '/a', [None, self.act_cols])
             self.adv = Placeholder(scope + '/adv', [None, 1])
             self.etr = Placeholder(scope + '/etr', [None, 1])
             self.action = self.act = self.a                              # Worker.py:106, Chief.py:60
@@ -101,7 +103,10 @@ class PPO(object):
 
     def _feeds(self, feed_dict):
         s = self._dev(feed_dict[self.s], self.obs_dim)
-        a = self._dev(feed_dict[self.a], self.act_dim)
+        if self.discrete:
+            a = torch.as_tensor(np.asarray(feed_dict[self.a]).astype(np.int32)).reshape(-1, 1).to(self.device).contiguous()
+        else:
+            a = self._dev(feed_dict[self.a], self.act_dim)
         adv = self._dev(feed_dict[self.adv]).reshape(-1)
         etr = self._dev(feed_dict[self.etr]).reshape(-1)
         return s, a, adv, etr
@@ -128,7 +133,7 @@ class PPO(object):
             s = self._dev(feed_dict[self.s], self.obs_dim)
             self._draws += 1
             a, v = be.act(self.pipara.flat, s, self._seed, self._draws)
-            vals['ca'] = a.cpu().numpy()[:, None, :]             # [B,1,A]  (Model.py:11 rank-3 convention)
+            vals['ca'] = a.cpu().numpy()[:, None, :]             # [B,1,A] (or [B,1,1] class index)  (Model.py:11 rank-3 convention)
             vals['pipredv'] = v.cpu().numpy()[:, None, None]     # [B,1,1]
         if 'sync_pis' in kinds:
             be.sync_old(self.pipara.flat, self.oldpipara.flat)   # PPO.py:47

@@ -35,6 +35,7 @@ class Worker(object):
         self.ENV_SAMPLE_ITERATIONS = parameter_dict.get('ENV_SAMPLE_ITERATIONS')   # read, never used (D5)
         self.LOG_FILE_PATH = parameter_dict['LOG_FILE_PATH']
         self.VERBOSE = parameter_dict.get('VERBOSE', True)
+        self._explore_rng = np.random.default_rng(abs(hash(scope)) % (2 ** 31))
 
     def work(self, PUSH_EVENT, UPDATE_EVENT, log_writer, iterations=None):
         """Worker.py:29-138.  `iterations=k` returns after k rollouts (synchronous driver)."""
@@ -42,7 +43,7 @@ class Worker(object):
         while not self.COORD.should_stop():
             N, T = self.NUM_ENVS, self.MAX_EPOCH_STEPS
             buffer_s = np.empty((T, N, self.ppo.obs_dim), np.float32)
-            buffer_a = np.empty((T, N, self.ppo.act_dim), np.float32)
+            buffer_a = np.empty((T, N, self.ppo.act_cols), np.int32 if self.ppo.discrete else np.float32)
             buffer_r = np.empty((T, N), np.float32)
             buffer_predv = np.empty((T, N), np.float32)
             buffer_done = np.empty((T, N), np.float32)
@@ -108,7 +109,15 @@ class Worker(object):
 
     def act(self, s):
         """Worker.py:140-153 for a batch of N states.  The epsilon-greedy override there is
-        discrete-only (`action_space.n`) and is dropped for Box spaces."""
+        discrete-only (`action_space.n`): applied per env for Discrete spaces, dropped for Box spaces."""
         action, pred_v = self.sess.run([self.ppo.ca, self.ppo.pipredv], {self.ppo.s: s})
         self.returnAction = action[:, 0, :]
+        if self.ppo.discrete:
+            if self.CUR_EP >= self.AC_EXP_EPOCH:                             # Worker.py:141-144
+                cur_exp_rate = self.MIN_AC_EXP_RATE
+            else:
+                cur_exp_rate = self.MAX_AC_EXP_RATE + self.CUR_EP * (self.MIN_AC_EXP_RATE - self.MAX_AC_EXP_RATE) / self.AC_EXP_EPOCH
+            explore = self._explore_rng.random(len(self.returnAction)) < cur_exp_rate          # Worker.py:149-150
+            rand = self._explore_rng.integers(0, self.env.action_space.n, len(self.returnAction))
+            self.returnAction = np.where(explore[:, None], rand[:, None], self.returnAction).astype(np.int32)
         return self.returnAction, pred_v[:, 0, 0]

@@ -12,6 +12,48 @@ class Box:
         self.low, self.high, self.shape = low, high, tuple(shape)
 
 
+class Discrete:
+    """gym.spaces.Discrete surface used by make_pdtype (distributions.py:236-237) and Worker.act (Worker.py:150)."""
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+
+
+class CartPoleVec:
+    """N classic cart-poles (the committed default game, main.py:13 'CartPole-v0'): obs = [x, xdot, th, thdot],
+    two discrete actions (push left / right), reward 1 per step, episode ends when the pole falls, the cart leaves
+    the track, or after 200 steps."""
+    gravity, masscart, masspole, length, force_mag, tau, horizon = 9.8, 1.0, 0.1, 0.5, 10.0, 0.02, 200
+    th_limit, x_limit = 12 * 2 * np.pi / 360, 2.4
+
+    def __init__(self, num_envs=1, seed=0):
+        self.n = num_envs
+        self.rng = np.random.default_rng(seed)
+        self.observation_space = Box(-np.inf, np.inf, (4,))
+        self.action_space = Discrete(2)
+        self.state = np.zeros((self.n, 4)); self.t = np.zeros(self.n, np.int64)
+
+    def reset(self, mask=None):
+        m = np.ones(self.n, bool) if mask is None else mask
+        self.state[m] = self.rng.uniform(-0.05, 0.05, (int(m.sum()), 4))
+        self.t[m] = 0
+        return self.state.astype(np.float32)
+
+    def step(self, action):
+        a = np.asarray(action).reshape(self.n).astype(np.int64)
+        x, xd, th, thd = self.state.T
+        force = np.where(a == 1, self.force_mag, -self.force_mag)
+        total_mass = self.masscart + self.masspole; pml = self.masspole * self.length
+        temp = (force + pml * thd ** 2 * np.sin(th)) / total_mass
+        thacc = (self.gravity * np.sin(th) - np.cos(th) * temp) / (
+            self.length * (4.0 / 3.0 - self.masspole * np.cos(th) ** 2 / total_mass))
+        xacc = temp - pml * thacc * np.cos(th) / total_mass
+        self.state = np.stack([x + self.tau * xd, xd + self.tau * xacc, th + self.tau * thd, thd + self.tau * thacc], 1)
+        self.t += 1
+        done = (np.abs(self.state[:, 0]) > self.x_limit) | (np.abs(self.state[:, 2]) > self.th_limit) | (self.t >= self.horizon)
+        return self.state.astype(np.float32), np.ones(self.n, np.float32), done, {}
+
+
 class PendulumVec:
     """N classic torque-limited pendulums (obs = [cos th, sin th, thdot], 1-D action, 200-step episodes)."""
     max_speed, max_torque, dt, g, m, l, horizon = 8.0, 2.0, 0.05, 10.0, 1.0, 1.0, 200
@@ -78,6 +120,8 @@ def make(game, num_envs=1, seed=0):
     """gym.make stand-in (Worker.py:10, Chief.py:10)."""
     if game.startswith("Pendulum"):
         return PendulumVec(num_envs, seed)
+    if game.startswith("CartPole"):
+        return CartPoleVec(num_envs, seed)
     for k, (o, a) in _SHAPES.items():
         if game.startswith(k):
             return SyntheticVec(o, a, num_envs, seed)

@@ -19,7 +19,7 @@ from RL.session import Session, Coordinator, FileWriter   # noqa: E402
 
 def build_parameter_dict(**overrides):
     parameter_dict = {
-        'GAME': 'Pendulum-v0',                     # reference default: 'CartPole-v0' (discrete; out of scope)
+        'GAME': 'Pendulum-v0',                     # reference default: 'CartPole-v0' (main.py:13; also runs: Discrete -> CategoricalPd)
         'LEARNING_RATE': 2e-5,
         'ENTCOEFF': 0.01,
         'VCOEFF': 0.5,

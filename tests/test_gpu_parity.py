@@ -854,3 +854,34 @@ def test_categorical_act_and_update_epochs():
                       step0=1, lr=1e-4, n_epochs=1, minibatch_rows=512, shuffle=True, seed=9)
     torch.cuda.synchronize()
     assert torch.equal(p1, p2) and torch.equal(m1, m2)
+
+
+# ------------------------------------------------------------------------------- the reference-named API on the real engine
+@pytest.mark.parametrize("game,obs,pdw,discrete", [("Pendulum-v0", 3, 2, False), ("CartPole-v0", 4, 2, True)])
+def test_reference_api_runs_on_engine(game, obs, pdw, discrete):
+    """main.py / Chief / Worker / PPO (reference names) driving the CUDA engine end to end: 2 chief updates of
+    UPDATE_STEPS=2, Box and Discrete action spaces; the worker-side loss fetch equals the oracle on the same feed."""
+    import main as dppo_main
+    # 200 steps: a Pendulum episode is 200 long and the reference pushes a batch only once an episode has ended (Worker.py:121,135)
+    pd = dppo_main.build_parameter_dict(GAME=game, NUM_WORKERS=2, NUM_ENVS=4, MAX_EPOCH_STEPS=200, VERBOSE=False,
+                                        UPDATE_STEPS=2, EPOCH_MAX=3, LOG_FILE_PATH="/tmp/dppo_test_logs")
+    chief, workers = dppo_main.run(pd, max_updates=2)
+    n = chief.ppo.pipara.flat.numel()
+    assert n == obs * 16 + 16 + 16 + 1 + 16 * pdw + pdw
+    assert chief.ppo._t == 4 and torch.isfinite(chief.ppo.pipara.flat).all()
+    for wk in workers:
+        assert torch.equal(wk.ppo.pipara.flat, chief.ppo.pipara.flat) and wk.ppo.discrete == discrete
+    # one more loss evaluation through the placeholders, checked against the oracle
+    w = workers[0].ppo
+    rng = np.random.default_rng(0)
+    B = 256
+    s = rng.standard_normal((B, obs)).astype(np.float32)
+    a = rng.integers(0, 2, (B, 1)).astype(np.int32) if discrete else rng.standard_normal((B, 1)).astype(np.float32)
+    adv = rng.standard_normal((B, 1)).astype(np.float32); etr = rng.standard_normal((B, 1)).astype(np.float32)
+    w.pipara.flat.add_(0.01 * torch.randn(n, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+    feed = {w.s: s, w.a: a, w.adv: adv, w.etr: etr, w.l_mul: 0.5}
+    from RL.session import Session
+    got = Session().run([w.policyLoss, w.valueLoss, w.entropyLoss, w.total_loss], feed)
+    lay = O.make_layout(obs, (16,), 2 if discrete else 1, pd="cat" if discrete else "gauss")
+    ref, _, _ = O.ppo_loss_grad(w.pipara.flat.cpu().numpy(), w.oldpipara.flat.cpu().numpy(), s, a, adv, etr, 0.5, lay)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)

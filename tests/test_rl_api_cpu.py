@@ -13,8 +13,8 @@ class OracleBackend:
     device = "cpu"
     world = 1
 
-    def __init__(self, obs, act, hidden):
-        self.lay = O.make_layout(obs, hidden, act)
+    def __init__(self, obs, act, hidden, pd="gauss"):
+        self.lay = O.make_layout(obs, hidden, act, pd)
         self.hp = O.HParams()
         self.calls = []
 
@@ -26,6 +26,10 @@ class OracleBackend:
     def act(self, params, obs, seed, offset):
         self.calls.append("act")
         v, flat, _ = O.mlp_forward(params.numpy(), obs.numpy(), self.lay)
+        if self.lay.pd == "cat":
+            u = np.random.default_rng(seed + offset).random(flat.shape)
+            return (torch.from_numpy(O.cat_sample(flat, u).astype(np.int32)[:, None]),
+                    torch.from_numpy(v.astype(np.float32)))
         eps = np.random.default_rng(seed + offset).standard_normal((obs.shape[0], self.lay.act_dim))
         return torch.from_numpy(O.dg_sample(flat, eps).astype(np.float32)), torch.from_numpy(v.astype(np.float32))
 
@@ -94,3 +98,30 @@ def test_reference_api_surface_and_two_updates():
     _, _, para = Model().FC("x", state=w.s, action_space=workers[0].env.action_space, device="cpu")
     W1 = list(para)[0].numpy()
     np.testing.assert_allclose(np.sqrt((W1 ** 2).sum(0)), 0.01, rtol=1e-5)       # normc(0.01), Model.py:10
+
+
+def test_cartpole_default_game_discrete_actions():
+    """The reference's committed default (main.py:13 'CartPole-v0'): Discrete(2) -> CategoricalPd (distributions.py:236-237),
+    int32 [B,1] action placeholder (PPO.py:26), epsilon-greedy exploration in Worker.act (Worker.py:141-152)."""
+    import main as dppo_main
+    from RL.Others.distributions import make_pdtype, CategoricalPdType, CategoricalPd
+    be = OracleBackend(4, 2, (16,), pd="cat")
+    pd = dppo_main.build_parameter_dict(GAME='CartPole-v0', BACKEND=be, NUM_WORKERS=2, NUM_ENVS=2, MAX_EPOCH_STEPS=100,
+                                        VERBOSE=False, UPDATE_STEPS=2, EPOCH_MAX=3)
+    chief, workers = dppo_main.run(pd, max_updates=2)
+    w = workers[0]
+    assert w.ppo.discrete and w.ppo.act_dim == 2 and w.ppo.act_cols == 1 and w.ppo.a.shape == [None, 1]
+    # Model.py:14: the policy head is param_shape()[0] = ncat wide -> [W1 [4,16], b1, Wv, bv, Wp [16,2], bp [2]]
+    assert [tuple(p.shape) for p in chief.ppo.pipara] == [(4, 16), (16,), (16, 1), (1,), (16, 2), (2,)]
+    assert be.calls.count("adam") == 4
+    batch = None
+    for wk in workers:
+        assert torch.equal(wk.ppo.pipara.flat, chief.ppo.pipara.flat)
+    a, v = w.act(w.env.reset())
+    assert a.dtype == np.int32 and a.shape == (2, 1) and set(np.unique(a)) <= {0, 1}
+    pt = make_pdtype(w.env.action_space)
+    assert isinstance(pt, CategoricalPdType) and pt.param_shape() == [2] and pt.sample_shape() == []
+    assert pt.pdclass() is CategoricalPd
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        CategoricalPd(torch.zeros(4, 2))
+    assert np.isfinite(chief.ppo.last_losses.numpy()).all()
