@@ -44,16 +44,19 @@ struct TcArgs {
 };
 
 // ---- tile movers -----------------------------------------------------------------------------------
-// One operand tile is R (128 or BN) x BK fp32 = R*128 B.  Each loader thread owns R/32 16-B chunks.
-template <int R, bool MN_MAJOR>
-__device__ __forceinline__ void tile_load(float4 (&reg)[R / 32], const float* __restrict__ P, int ld, int r0, int rdim,
+// One operand tile is R (128 or BN) x KB fp32 = R*KB*4 B (KB = 32: 128-B rows, SWIZZLE_128B; KB = 16: 64-B rows,
+// SWIZZLE_64B, K-major only).  Each loader thread owns R*KB/1024 16-B chunks.
+template <int R, bool MN_MAJOR, int KB = BK>
+__device__ __forceinline__ void tile_load(float4 (&reg)[R * KB / 1024], const float* __restrict__ P, int ld, int r0, int rdim,
                                           int k0, int kend, int vec, int tid) {
+    static_assert(KB == 32 || (KB == 16 && !MN_MAJOR), "16-wide k-blocks exist for the K-major layout only");
+    constexpr int kCpr = KB / 4;               // 16-B chunks per tile row
 #pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
+    for (int i = 0; i < R * KB / 1024; ++i) {
         const int q = tid + i * kLoadThreads;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!MN_MAJOR) {                       // element (r,k) at P[r*ld + k]
-            const int r = r0 + (q >> 3), k = k0 + (q & 7) * 4;
+            const int r = r0 + q / kCpr, k = k0 + (q % kCpr) * 4;
             if (r < rdim && k < kend) {
                 const float* p = P + (size_t)r * ld + k;
                 if (vec && k + 3 < kend) v = __ldg(reinterpret_cast<const float4*>(p));
@@ -81,15 +84,17 @@ __device__ __forceinline__ void tile_load(float4 (&reg)[R / 32], const float* __
     }
 }
 
-template <int R, bool MN_MAJOR, int TERMS>
-__device__ __forceinline__ void tile_store(const float4 (&reg)[R / 32], uint8_t* hi, uint8_t* lo, int tid) {
+template <int R, bool MN_MAJOR, int TERMS, int KB = BK>
+__device__ __forceinline__ void tile_store(const float4 (&reg)[R * KB / 1024], uint8_t* hi, uint8_t* lo, int tid) {
+    constexpr int kCpr = KB / 4;
 #pragma unroll
-    for (int i = 0; i < R / 32; ++i) {
+    for (int i = 0; i < R * KB / 1024; ++i) {
         const int q = tid + i * kLoadThreads;
         uint32_t off;
         if (!MN_MAJOR) {
-            const int r = q >> 3, c = q & 7;
-            off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+            const int r = q / kCpr, c = q % kCpr;
+            off = (KB == 32) ? (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4)            // SWIZZLE_128B: chunk ^= row % 8
+                             : (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);     // SWIZZLE_64B:  chunk ^= (row / 2) % 4
         } else {
             const int kr = q / (R / 4), cc = q % (R / 4);
             const int atom = cc >> 3, c = cc & 7;
@@ -108,22 +113,27 @@ __device__ __forceinline__ void tile_store(const float4 (&reg)[R / 32], uint8_t*
     }
 }
 
-template <int BN, int TERMS>
+template <int BN, int TERMS, int KB = BK>
 struct SmemPlan {
-    static constexpr int kATile = BM * 128, kBTile = BN * 128;
+    static constexpr int kATile = BM * KB * 4, kBTile = BN * KB * 4;
     static constexpr int kStage = TERMS == 3 ? 2 * (kATile + kBTile) : (kATile + kBTile);
-    // BN = 64 (the 35-wide heads): thin products bound by activation streaming, not by MMA issue -> 2 stages and
-    // ~100 KB so that two CTAs share an SM and overlap each other's prologue / epilogue
-    static constexpr int kMinBlocks = BN <= 64 ? 2 : 1;
-    static constexpr int kStages = BN <= 64 ? 2 : ((200 * 1024) / kStage >= 4 ? 4 : (200 * 1024) / kStage);
+    // Two CTAs per SM whenever they fit: one CTA's prologue / epilogue (TMEM drain, mask loads, C stores) then runs under
+    // the other's MMA main loop instead of leaving the tensor pipe idle.
+    //   BN = 64 (the 35-wide heads), 128-B rows: 2 stages x 48 KB;
+    //   BN = 128 with 64-B rows (KB = 16):       3 stages x 32 KB, 2 x 256 TMEM columns.
+    static constexpr int kMinBlocks = (BN <= 64 || KB == 16) ? 2 : 1;
+    static constexpr int kStages = KB == 16 ? 3 : (BN <= 64 ? 2 : ((200 * 1024) / kStage >= 4 ? 4 : (200 * 1024) / kStage));
     static constexpr int kBytes = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kStages >= 2, "need at least a double buffer");
+    static_assert(KB == 32 || (BN <= 128 && kBytes <= 112 * 1024), "KB = 16 tiles are meant for two CTAs per SM");
 };
 
-template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE>
-__global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_gemm_kernel(const TcArgs g) {
+template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE, int KB = BK>
+__global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks) tc_gemm_kernel(const TcArgs g) {
     static_assert(!(B_IMAGE && MN_MAJOR), "weight images exist for the K-major products only");
-    using Plan = SmemPlan<BN, TERMS>;
+    static_assert(KB == 32 || (B_IMAGE && !MN_MAJOR), "KB = 16 is built for the image-fed K-major products");
+    using Plan = SmemPlan<BN, TERMS, KB>;
+    constexpr int kRegA = BM * KB / 1024;
     constexpr int STAGES = Plan::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -139,15 +149,15 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_
     const int slice = blockIdx.z;
     const int k_begin = slice * g.k_per_slice;
     const int k_end = min(g.K, k_begin + g.k_per_slice);
-    const int nkb = max(0, (k_end - k_begin + BK - 1) / BK);
+    const int nkb = max(0, (k_end - k_begin + KB - 1) / KB);
 
     // image mode: the first kPrefetch activation k-blocks are requested before the barrier/TMEM set-up, so their
     // global latency overlaps the CTA prologue
-    float4 ra_img[B_IMAGE ? kPrefetch : 1][BM / 32];
+    float4 ra_img[B_IMAGE ? kPrefetch : 1][kRegA];
     if (B_IMAGE && warp < kLoadWarps) {
 #pragma unroll
         for (int j = 0; j < kPrefetch; ++j)
-            if (j < nkb) tile_load<BM, MN_MAJOR>(ra_img[j], g.A[net], g.lda, m0, g.M, k_begin + j * BK, k_end, g.vecA, tid);
+            if (j < nkb) tile_load<BM, MN_MAJOR, KB>(ra_img[j], g.A[net], g.lda, m0, g.M, k_begin + j * KB, k_end, g.vecA, tid);
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoadThreads + (B_IMAGE ? 1 : 0)); mbar_init(&empty_bar[s], 1); }
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_
         const float* __restrict__ B = g.B[net];
         if (B_IMAGE) {
             // only the activation operand goes through registers: kPrefetch k-blocks of loads stay in flight
-            float4 (&ra)[B_IMAGE ? kPrefetch : 1][BM / 32] = ra_img;
+            float4 (&ra)[B_IMAGE ? kPrefetch : 1][kRegA] = ra_img;
             for (int kb0 = 0; kb0 < nkb; kb0 += kPrefetch) {
 #pragma unroll
                 for (int j = 0; j < kPrefetch; ++j) {
@@ -179,15 +189,15 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_
                         const int s = kb % STAGES;
                         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
                         uint8_t* st = smem + s * Plan::kStage;
-                        tile_store<BM, MN_MAJOR, TERMS>(ra[j], st, st + Plan::kATile, tid);
+                        tile_store<BM, MN_MAJOR, TERMS, KB>(ra[j], st, st + Plan::kATile, tid);
                         fence_proxy_async();
                         mbar_arrive(&full_bar[s]);
                         if (kb + kPrefetch < nkb)
-                            tile_load<BM, MN_MAJOR>(ra[j], A, g.lda, m0, g.M, k_begin + (kb + kPrefetch) * BK, k_end, g.vecA, tid);
+                            tile_load<BM, MN_MAJOR, KB>(ra[j], A, g.lda, m0, g.M, k_begin + (kb + kPrefetch) * KB, k_end, g.vecA, tid);
                     }
                 }
             }
-        } else {
+        } else if (KB == 32) {
         float4 ra[BM / 32], rb[BN / 32];
         if (nkb > 0) {
             tile_load<BM, MN_MAJOR>(ra, A, g.lda, m0, g.M, k_begin, k_end, g.vecA, tid);
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_
         // ================= weight-image producer (one thread): bulk copies of ready-made B tiles =================
         if (B_IMAGE && lane == 0) {
             constexpr uint32_t kBytes = (TERMS == 3 ? 2 : 1) * Plan::kBTile;
-            const int kbs_total = (g.K + BK - 1) / BK;
+            const int kbs_total = (g.K + KB - 1) / KB;
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g.Bimg[net]) +
                                  (size_t)(blockIdx.y % kImgReplicas) * g.img_replica_bytes +
                                  (size_t)(blockIdx.x % g.tiles_n) * kbs_total * (2 * Plan::kBTile);
@@ -338,15 +348,15 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_
                 mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
                 uint8_t* dst = smem + s * Plan::kStage + (TERMS == 3 ? 2 : 1) * Plan::kATile;
                 mbar_arrive_expect_tx(&full_bar[s], kBytes);
-                bulk_copy_g2s(dst, img + (size_t)(k_begin / BK + kb) * (2 * Plan::kBTile), kBytes, &full_bar[s]);
+                bulk_copy_g2s(dst, img + (size_t)(k_begin / KB + kb) * (2 * Plan::kBTile), kBytes, &full_bar[s]);
             }
         }
     } else if (lane == 0) {
         // ================= MMA issuer (one thread) =================
         constexpr uint32_t idesc = make_idesc(BN, MN_MAJOR, MN_MAJOR);
-        constexpr uint32_t kLayout = MN_MAJOR ? kLayoutSW128Base32 : kLayoutSW128;
+        constexpr uint32_t kLayout = MN_MAJOR ? kLayoutSW128Base32 : (KB == 32 ? kLayoutSW128 : kLayoutSW64);
         constexpr uint32_t kLbo = MN_MAJOR ? (uint32_t)(BK * 128) : 0u;         // MN-major: stride between 32-element MN atoms
-        constexpr uint32_t kSbo = MN_MAJOR ? 512u : 1024u;                      // MN: between 4-row k groups; K: between 8-row groups
+        constexpr uint32_t kSbo = MN_MAJOR ? 512u : (KB == 32 ? 1024u : 512u);  // MN: between 4-row k groups; K: between 8-row groups
         constexpr uint32_t kStepBytes = MN_MAJOR ? 8u * 128u : 32u;             // advance of one UMMA_K = 8
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
@@ -356,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS>::kMinBlocks) tc_
             const uint32_t a_hi = st, a_lo = st + Plan::kATile;
             const uint32_t b_hi = st + (TERMS == 3 ? 2 : 1) * Plan::kATile, b_lo = b_hi + Plan::kBTile;
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
+            for (int k = 0; k < KB / 8; ++k) {
                 const uint64_t da_hi = make_sdesc(a_hi + k * kStepBytes, kLbo, kSbo, kLayout);
                 const uint64_t db_hi = make_sdesc(b_hi + k * kStepBytes, kLbo, kSbo, kLayout);
                 if (TERMS == 3) {
@@ -615,21 +625,21 @@ static int launch_persistent(TcArgs& g, cudaStream_t st) {
 
 static inline int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE>
+template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE, int KB = BK>
 static int launch(TcArgs& g, int slices, cudaStream_t st) {
-    using Plan = SmemPlan<BN, TERMS>;
+    using Plan = SmemPlan<BN, TERMS, KB>;
     g.tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + BM - 1) / BM;
     DPPO_REQUIRE(tiles_m <= 65535, "tc_gemm: M=%d too large for one launch", g.M);
     static bool configured = false;
     if (!configured) {
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE>,
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE, KB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
         configured = true;
     }
     dim3 grid(g.tiles_n * g.nets, tiles_m, slices);
     ProfScope ps(KK_TC_GEMM, st);
-    tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE><<<grid, kThreads, Plan::kBytes, st>>>(g);
+    tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE, KB><<<grid, kThreads, Plan::kBytes, st>>>(g);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -648,7 +658,7 @@ static int dispatch_bn(TcArgs& g, int slices, cudaStream_t st) {
 
 // ---- weight images: B tiles exactly as they must sit in shared memory (K-major SWIZZLE_128B, hi then lo), so a
 // CTA fetches one (n-tile, k-block) with a single bulk copy instead of 8 warps of LDG/convert/STS ----
-struct ImgEntry { const float* src; float* dst; int N, K, ld, transposed, bn; };
+struct ImgEntry { const float* src; float* dst; int N, K, ld, transposed, bn, bk; };
 struct ImgPlan { int n; ImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
 
 __global__ void pack_images_kernel(ImgPlan p, long long total_units) {
@@ -657,11 +667,12 @@ __global__ void pack_images_kernel(ImgPlan p, long long total_units) {
         while (u >= p.unit_end[i]) ++i;
         const ImgEntry e = p.e[i];
         long long r_ = u - (i ? p.unit_end[i - 1] : 0);
-        const int c = (int)(r_ & 7); r_ >>= 3;                 // 16-B chunk within the 128-B row
+        const int cpr = e.bk / 4;                              // 16-B chunks per tile row (128-B or 64-B rows)
+        const int c = (int)(r_ % cpr); r_ /= cpr;
         const int r = (int)(r_ % e.bn); r_ /= e.bn;           // row within the tile
-        const int kbs = (e.K + BK - 1) / BK;
+        const int kbs = (e.K + e.bk - 1) / e.bk;
         const int kb = (int)(r_ % kbs), nt = (int)(r_ / kbs);
-        const int n = nt * e.bn + r, k0 = kb * BK + c * 4;
+        const int n = nt * e.bn + r, k0 = kb * e.bk + c * 4;
         float v[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -673,13 +684,15 @@ __global__ void pack_images_kernel(ImgPlan p, long long total_units) {
         l.x = to_tf32(v[0] - __uint_as_float(h.x)); l.y = to_tf32(v[1] - __uint_as_float(h.y));
         l.z = to_tf32(v[2] - __uint_as_float(h.z)); l.w = to_tf32(v[3] - __uint_as_float(h.w));
         const size_t ntiles = (size_t)((e.N + e.bn - 1) / e.bn);
-        const size_t replica_bytes = ntiles * kbs * (size_t)(e.bn * 256);
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+        const size_t plane = (size_t)e.bn * e.bk * 4;          // bytes of the hi (or lo) tile
+        const size_t replica_bytes = ntiles * kbs * 2 * plane;
+        const uint32_t off = (e.bk == 32) ? (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4)
+                                          : (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 #pragma unroll
         for (int rep = 0; rep < kImgReplicas; ++rep) {
-            uint8_t* tile = reinterpret_cast<uint8_t*>(e.dst) + rep * replica_bytes + ((size_t)nt * kbs + kb) * (size_t)(e.bn * 256);
+            uint8_t* tile = reinterpret_cast<uint8_t*>(e.dst) + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * plane;
             *reinterpret_cast<uint4*>(tile + off) = h;
-            *reinterpret_cast<uint4*>(tile + (size_t)e.bn * 128 + off) = l;
+            *reinterpret_cast<uint4*>(tile + plane + off) = l;
         }
     }
 }
@@ -754,12 +767,22 @@ static inline bool tc_use_persistent() {
     if (v < 0) { const char* e = getenv("DPPO_TC_PERSISTENT"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
-static inline int tc_bn_for(int n) { return n > 64 ? ((n > 128 && !tc_use_persistent()) ? 256 : 128) : 64; }
+// DPPO_TC_BK16=1: 64-B operand rows (k-blocks of 16) + 128-wide tiles -> two co-resident CTAs per SM for every product
+// wider than 64 columns.  Measured SLOWER than the default 256-wide single-CTA tiles at cfg3 (1.45 vs 1.31 ms/update):
+// halving the tile width doubles the activation movers' LDG/convert/STS work per MMA and that, not the idle tensor pipe
+// during the epilogue, is then the limiter ("what did not work").  Kept as an opt-in experiment.
+static inline bool tc_use_bk16() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DPPO_TC_BK16"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1 && !tc_use_persistent();
+}
+static inline int tc_bk_for(int n) { return (n > 64 && tc_use_bk16()) ? 16 : tc::BK; }
+static inline int tc_bn_for(int n) { return n > 64 ? ((n > 128 && !tc_use_persistent() && !tc_use_bk16()) ? 256 : 128) : 64; }
 
 // floats of one weight image: B is [N,K]
 static long long tc_image_replica_floats(int N, int K) {
-    const int bn = tc_bn_for(N);
-    return (long long)((N + bn - 1) / bn) * ((K + tc::BK - 1) / tc::BK) * bn * 64;     // bn*256 B per (n-tile, k-block)
+    const int bn = tc_bn_for(N), bk = tc_bk_for(N);
+    return (long long)((N + bn - 1) / bn) * ((K + bk - 1) / bk) * bn * bk * 2;          // hi + lo tile per (n-tile, k-block)
 }
 long long tc_image_floats(int N, int K) { return tc::kImgReplicas * tc_image_replica_floats(N, K); }
 
@@ -774,7 +797,8 @@ int tc_pack_images(const NetShape& s, const float* params_pi, const float* head_
         if (!src || !dst) return;
         tc::ImgEntry& e = p.e[p.n];
         e.src = src; e.dst = dst; e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = tc_bn_for(N);
-        units += (long long)((N + e.bn - 1) / e.bn) * ((K + tc::BK - 1) / tc::BK) * e.bn * 8;
+        e.bk = tc_bk_for(N);
+        units += (long long)((N + e.bn - 1) / e.bn) * ((K + e.bk - 1) / e.bk) * e.bn * (e.bk / 4);
         p.unit_end[p.n++] = units;
     };
     for (int l = 0; l <= s.L; ++l) {
@@ -799,7 +823,8 @@ int tc_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
     tc::ImgPlan p; p.n = 1;
     tc::ImgEntry& e = p.e[0];
     e.src = src; e.dst = dst; e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = tc_bn_for(N);
-    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + tc::BK - 1) / tc::BK) * e.bn * 8;
+    e.bk = tc_bk_for(N);
+    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + e.bk - 1) / e.bk) * e.bn * (e.bk / 4);
     p.unit_end[0] = units;
     int grid = (int)((units + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
@@ -824,6 +849,10 @@ int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float
     if (N > 64 && tc_use_persistent()) {         // experimental: 128-wide persistent tiles, overlapped epilogue
         if (epi_nt) return tc::launch_persistent<tc::EPI_NT>(g, st);
         return tc::launch_persistent<tc::EPI_NN>(g, st);
+    }
+    if (N > 64 && tc_use_bk16()) {               // 128-wide tiles, 64-B operand rows, two CTAs per SM
+        if (epi_nt) return tc::launch<128, false, 3, tc::EPI_NT, true, 16>(g, 1, st);
+        return tc::launch<128, false, 3, tc::EPI_NN, true, 16>(g, 1, st);
     }
     if (epi_nt) return tc::dispatch_bn<3, false, tc::EPI_NT, true>(g, 1, st);
     return tc::dispatch_bn<3, false, tc::EPI_NN, true>(g, 1, st);

@@ -92,6 +92,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
 }
 constexpr uint32_t kLayoutSW128 = 2;          // K-major, 16-B swizzle granule, 8-row atoms
 constexpr uint32_t kLayoutSW128Base32 = 1;    // MN-major fp32/tf32, 32-B granule, 4-row atoms
+constexpr uint32_t kLayoutSW64 = 4;           // K-major, 64-B rows: 16-B chunk ^= (row / 2) % 4, 8-row (512 B) atoms
 
 
 }  // namespace tc
