@@ -444,6 +444,21 @@ def _multi_gpu_worker(rank, world, port, out_dir):
         np.testing.assert_allclose(ga.cpu().numpy(), gb.cpu().numpy(), rtol=2e-6, atol=2e-8)   # sum*1/W vs ncclAvg rounding
         np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), rtol=0, atol=1e-6)
     np.save(os.path.join(out_dir, f"pa_{rank}.npy"), pa.cpu().numpy())
+    # the device scheduler across ranks: 2 epochs x shuffled minibatches, one exchange per minibatch, == three more
+    # single updates when the minibatch is the whole shard and nothing is shuffled
+    pc = pa.clone(); mc = ma.clone(); vc = va.clone()
+    for step in (4, 5):
+        eng.update(pa, old_r, obs_r, act_r, rb["rew"], rb["predv"], rb["done"], 0.99, 0.95, 0.7, adam_m=ma, adam_v=va,
+                   step=step, lr=1e-3)
+    eng.update_epochs(pc, old_r, obs_r, act_r, rb["rew"], rb["predv"], rb["done"], 0.99, 0.95, 0.7, mc, vc, step0=4, lr=1e-3,
+                      n_epochs=2)
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pc) and torch.equal(ma, mc)
+    le, _ = eng.update_epochs(pc, old_r, obs_r, act_r, rb["rew"], rb["predv"], rb["done"], 0.99, 0.95, 0.7, mc, vc, step0=6,
+                              lr=1e-3, n_epochs=2, minibatch_rows=max(len(rows) // 4, 1), shuffle=True, seed=11)
+    torch.cuda.synchronize()
+    assert le.shape[0] == 8 and torch.isfinite(le).all() and torch.isfinite(pc).all()
+    np.save(os.path.join(out_dir, f"pc_{rank}.npy"), pc.cpu().numpy())
     dist.destroy_process_group()
 
 
@@ -475,6 +490,7 @@ def test_multi_gpu_allreduce_equals_tower_mean(tmp_path):
     for r in range(1, world):
         np.testing.assert_array_equal(gs[0], gs[r]); np.testing.assert_array_equal(ps[0], ps[r])
         np.testing.assert_array_equal(pas[0], pas[r])          # peer-memory path: bit-identical parameters on all ranks
+        np.testing.assert_array_equal(np.load(tmp_path / "pc_0.npy"), np.load(tmp_path / f"pc_{r}.npy"))   # after the scheduler
     n = lay.n_params
     assert max(per_tensor_rel_err(gs[0][:n], ref[:n], lay).values()) < TOL
     np.testing.assert_allclose(gs[0][n:n + 4], ref[n:], rtol=TOL, atol=TOL)
