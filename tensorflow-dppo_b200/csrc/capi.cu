@@ -742,6 +742,34 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         DPPO_LAUNCH_CHECK();
         return 0;
     }
+    if (mode >= 80 && mode <= 83) {
+        // planes path (tc_gemm_pl.cu): A is split into hi/lo planes first, Bt[N,K] packed into 128-wide images.
+        // 80: C = relu?(A.Bt^T + bias);  81: C = (A.Bt^T) * (mask > 0);  82/83: same, but the result is returned as
+        // hi + lo of the planes the kernel wrote (what the next consumer would read).
+        // Test/microbenchmark hook only: scratch is allocated here, outside the caller's workspace.
+        static float* img = nullptr; static long long img_floats = 0;
+        static float* planes = nullptr; static long long plane_floats = 0;
+        static float* oplanes = nullptr; static long long oplane_floats = 0;
+        DPPO_REQUIRE(K % 4 == 0 && N % 4 == 0, "dppo_dbg_gemm planes modes need K %% 4 == 0 and N %% 4 == 0");
+        const long long need = tc_pl_image_floats(N, K), pneed = 2ll * M * K, oneed = 2ll * M * N;
+        if (need > img_floats) { if (img) cudaFree(img); DPPO_CHECK_CUDA(cudaMalloc((void**)&img, (size_t)need * 4)); img_floats = need; }
+        if (pneed > plane_floats) { if (planes) cudaFree(planes); DPPO_CHECK_CUDA(cudaMalloc((void**)&planes, (size_t)pneed * 4)); plane_floats = pneed; }
+        if (oneed > oplane_floats) { if (oplanes) cudaFree(oplanes); DPPO_CHECK_CUDA(cudaMalloc((void**)&oplanes, (size_t)oneed * 4)); oplane_floats = oneed; }
+        float* hi = planes; float* lo = planes + (size_t)M * K;
+        if (int r = tc_split_planes(A, (long long)M * K, hi, lo, st)) return r;
+        if (int r = tc_pack_one_ex(B, img, N, K, K, 0, 128, 32, st)) return r;
+        const bool want_planes = mode >= 82;
+        float* ohi = want_planes ? oplanes : nullptr; float* olo = want_planes ? oplanes + (size_t)M * N : nullptr;
+        const int nt = (mode & 1);
+        if (int r = tc_pl_gemm(nt, M, N, K, hi, lo, nullptr, nullptr, K, img, nullptr, want_planes ? nullptr : C, nullptr, ohi, olo,
+                               nullptr, nullptr, N, nt ? nullptr : bias, nullptr, nt ? 0 : relu, nt ? mask : nullptr, 1, st)) return r;
+        if (want_planes) {
+            ProfScope ps(KK_MISC, st);
+            reduce_slices_kernel<<<256, 256, 0, st>>>(oplanes, 2, (long long)M * N, (long long)M * N, C);
+            DPPO_LAUNCH_CHECK();
+        }
+        return 0;
+    }
     if (mode == 48 || mode == 49) {
         // weight-image product (the path the update uses): Bt[N,K] is packed into a smem-tile image first.
         // Test/microbenchmark hook only: the image scratch is allocated here, outside the caller's workspace.

@@ -834,6 +834,21 @@ int tc_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
     return 0;
 }
 
+// one image with an explicit tile geometry (bn rows per n-tile, bk = 32 or 16 floats per k-block)
+int tc_pack_one_ex(const float* src, float* dst, int N, int K, int ld, int transposed, int bn, int bk, cudaStream_t st) {
+    tc::ImgPlan p; p.n = 1;
+    tc::ImgEntry& e = p.e[0];
+    e.src = src; e.dst = dst; e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = bn; e.bk = bk;
+    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + e.bk - 1) / e.bk) * e.bn * (e.bk / 4);
+    p.unit_end[0] = units;
+    int grid = (int)((units + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_MISC, st);
+    tc::pack_images_kernel<<<grid, 256, 0, st>>>(p, units);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
 // C[M,N] = epi(A[M,K] . Bimg^T) with B given as weight images (see tc_pack_images)
 int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
                    const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,

@@ -15,6 +15,13 @@ shapes = [  # (mode, M, N, K, label)
     (48, 131072, 35, 256, "img  fwd head"),
     (49, 131072, 256, 35, "img  dX head"),
     (49, 131072, 256, 256, "img  dX L2"),
+    (80, 18944, 256, 4096, "pl   one wave, long K"),
+    (80, 131072, 256, 376, "pl   fwd L1"),
+    (80, 131072, 256, 256, "pl   fwd L2"),
+    (82, 131072, 256, 256, "pl   fwd L2 -> planes"),
+    (81, 131072, 256, 256, "pl   dX L2"),
+    (83, 131072, 256, 256, "pl   dX L2 -> planes"),
+    (81, 131072, 256, 36, "pl   dX head"),
     (16, 18944, 256, 4096, "reg  one wave, long K"),
     (16, 131072, 256, 256, "reg  fwd L2"),
     (18, 376, 256, 131072, "tn   dW1"),
@@ -29,17 +36,18 @@ for mode, M, N, K, label in shapes:
         A = torch.randn(M, K, device="cuda"); B = torch.randn(K, N, device="cuda")
     else:
         A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
-    mask = torch.randn(M, N, device="cuda") if mode in (49,) else None
-    bias = torch.randn(N, device="cuda") if mode in (48, 16, 0) else None
+    mask = torch.randn(M, N, device="cuda") if mode in (49, 81, 83) else None
+    bias = torch.randn(N, device="cuda") if mode in (48, 16, 0, 80, 82) else None
+    relu = mode in (48, 16, 0, 80, 82)
     for _ in range(3):
-        eng.dbg_gemm(mode, A, B, M, N, K, bias=bias, mask=mask, relu=mode in (48, 16, 0))
+        eng.dbg_gemm(mode, A, B, M, N, K, bias=bias, mask=mask, relu=relu)
     torch.cuda.synchronize()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     reps = 10
-    e0.record()
+    eng.profile_reset(True)                      # CUDA events around every library launch: GEMM kernels only, no packing
     for _ in range(reps):
-        eng.dbg_gemm(mode, A, B, M, N, K, bias=bias, mask=mask, relu=mode in (48, 16, 0))
-    e1.record(); torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / reps
+        eng.dbg_gemm(mode, A, B, M, N, K, bias=bias, mask=mask, relu=relu)
+    prof = eng.profile_read(); eng.profile_reset(False)
+    fam = "tc_gemm" if mode >= 16 else {0: "gemm_nn", 1: "gemm_nt", 2: "gemm_tn"}[mode]
+    us = prof[fam][1] * 1e3 / reps
     fl = 2.0 * M * N * K
     print(f"{label:26s} M={M:7d} N={N:4d} K={K:7d}  {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s (algorithmic)")
