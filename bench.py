@@ -212,6 +212,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     T, N, obs, act, hidden = WORKLOADS[args.workload]
+    if args.scaling == "strong":            # total work fixed: the workload's N rollouts are split over the ranks
+        assert N % world == 0, f"--scaling strong needs N={N} divisible by {world} ranks"
+        N //= world
     B = T * N
     gamma, lam, l_mul, lr = 0.99, 0.95, 0.7, 2e-5
     eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode={"simt": 0, "tf32x3": 1, "bf16": 2}[args.gemm])
@@ -337,7 +340,7 @@ def run_b200(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
                        "hidden": list(hidden), "rows_per_gpu": B, "parallelism": f"dp{world}",
@@ -393,6 +396,9 @@ def main():
     ap.add_argument("--workload", default="humanoid-cfg3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split-calls", action="store_true", help="time gae/loss_grad/allreduce/adam as separate calls")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the reference's semantics: every replica owns a full workload buffer) or strong "
+                         "(the workload's N rollouts are divided over the ranks)")
     ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3", "bf16"],
                     help="dense-layer arithmetic: fp32 FFMA, or tcgen05 kind::tf32 with the 3-term fp32-accurate split")
     args = ap.parse_args()

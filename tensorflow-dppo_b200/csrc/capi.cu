@@ -230,14 +230,16 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
 static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
                           const float* act, const float* adv, const float* ret, int rows, int tile0,
                           int B_total, float l_mul, int accumulate, const int* active, cudaStream_t st,
-                          cudaEvent_t adv_ready = nullptr) {
+                          cudaEvent_t adv_ready = nullptr, const float* old_rows = nullptr) {
     const NetShape& s = c->shape;
     Workspace& w = c->ws;
-    if (int r = forward_nets(c, params_pi, params_old, obs, rows, st)) return r;
+    // old_rows: the oldpi head outputs [rows, Pld] of exactly these rows, computed earlier (oldpi is frozen while the
+    // chief trains, so epochs after the first need not re-evaluate it); nullptr -> evaluate both nets here
+    if (int r = forward_nets(c, params_pi, old_rows ? nullptr : params_old, obs, rows, st)) return r;
     if (adv_ready) DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, adv_ready, 0));   // adv/ret come from a side stream
     const float inv_B = 1.0f / (float)B_total;
     const float clip = c->cfg.clip_param * l_mul;                       // PPO.py:19
-    if (int r = launch_loss(s, w.out_pi, w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
+    if (int r = launch_loss(s, w.out_pi, old_rows ? old_rows : w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
                             c->cfg.vcoeff, w.d_out, w.loss_part, st)) return r;
 
     GemmEpi tn; tn.accumulate = accumulate;
@@ -532,6 +534,17 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
     float* g_ret = g_adv + mb;
     int active[kMaxLayers + 1];
     active_slices(c, mb, active);
+    // oldpi does not change during the call (sync_pis happens in the worker, PPO.py:47 / Worker.py:42): evaluate its heads
+    // ONCE over the whole buffer and reuse the rows in every minibatch of every epoch.  The reference re-evaluates oldpi
+    // in-graph on every sess.run (PPO.py:22) and gets the same numbers.  DPPO_NO_OLD_CACHE=1 restores the recomputation.
+    static int no_cache = -1;
+    if (no_cache < 0) { const char* e = getenv("DPPO_NO_OLD_CACHE"); no_cache = (e && e[0] == '1') ? 1 : 0; }
+    const bool cache_old = !no_cache && (long long)n_epochs * n_mb > 1 && (!shuffle || s.hmax() >= s.Pld);
+    if (cache_old) {
+        if (int r = forward_nets(c, params_old, nullptr, obs, B, st)) return r;          // oldpi through the "pi" slot
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(w.out_old, w.out_pi, (size_t)B * s.Pld * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    float* g_old = w.scratch[1];         // gathered oldpi rows of a shuffled minibatch (free until the backward pass)
     int step = step0, slot = 0;
     for (int e = 0; e < n_epochs; ++e) {
         const PermKey key = make_perm_key((uint32_t)B, seed, (uint64_t)e);
@@ -539,12 +552,15 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
             const int r0 = k * mb, rows = (B - r0 < mb) ? B - r0 : mb;
             const float *x = obs + (size_t)r0 * s.obs, *a = act + (size_t)r0 * s.acols, *ad = w.gae_adv + r0,
                         *rt = w.gae_ret + r0;
+            const float* old_rows = cache_old ? w.out_old + (size_t)r0 * s.Pld : nullptr;
             if (shuffle) {
                 if (int r = launch_gather_rows(key, r0, rows, s.obs, s.acols, obs, act, w.gae_adv, w.gae_ret, g_obs, g_act,
-                                               g_adv, g_ret, st)) return r;
+                                               g_adv, g_ret, cache_old ? w.out_old : nullptr, g_old, s.Pld, st)) return r;
                 x = g_obs; a = g_act; ad = g_adv; rt = g_ret;
+                if (cache_old) old_rows = g_old;
             }
-            if (int r = loss_grad_rows(c, params_pi, params_old, x, a, ad, rt, rows, 0, rows, l_mul, 0, active, st)) return r;
+            if (int r = loss_grad_rows(c, params_pi, params_old, x, a, ad, rt, rows, 0, rows, l_mul, 0, active, st, nullptr,
+                                       old_rows)) return r;
             if (int r = reduce_and_apply(c, active, rows, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st))
                 return r;
             if (losses_out)

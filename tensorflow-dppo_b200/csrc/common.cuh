@@ -211,7 +211,7 @@ int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, 
                   float* action, float* v_out, cudaStream_t st);
 int launch_gather_rows(const PermKey& key, int first, int rows, int obs_dim, int act_dim, const float* obs,
                        const float* act, const float* adv, const float* ret, float* obs_o, float* act_o, float* adv_o,
-                       float* ret_o, cudaStream_t st);
+                       float* ret_o, const float* old_src, float* old_dst, int pld, cudaStream_t st);
 int launch_perm_fill(const PermKey& key, int32_t* out, cudaStream_t st);
 
 }  // namespace dppo

@@ -487,7 +487,8 @@ __global__ void gather_rows_kernel(PermKey key, int first, int rows, int obs_dim
                                    const float* __restrict__ obs, const float* __restrict__ act,
                                    const float* __restrict__ adv, const float* __restrict__ ret,
                                    float* __restrict__ obs_o, float* __restrict__ act_o, float* __restrict__ adv_o,
-                                   float* __restrict__ ret_o) {
+                                   float* __restrict__ ret_o, const float* __restrict__ old_src, float* __restrict__ old_dst,
+                                   int pld) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < rows; j += warps) {
@@ -503,18 +504,23 @@ __global__ void gather_rows_kernel(PermKey key, int first, int rows, int obs_dim
         }
         for (int c = lane; c < act_dim; c += 32) act_o[(size_t)j * act_dim + c] = __ldg(act + src * act_dim + c);
         if (lane == 0) { adv_o[j] = __ldg(adv + src); ret_o[j] = __ldg(ret + src); }
+        if (old_src) {                              // cached oldpi head outputs [.., pld] (pld % 4 == 0, 16-B aligned rows)
+            const float4* s4 = reinterpret_cast<const float4*>(old_src + src * pld);
+            float4* d4 = reinterpret_cast<float4*>(old_dst + (size_t)j * pld);
+            for (int c = lane; c < (pld >> 2); c += 32) d4[c] = __ldg(s4 + c);
+        }
     }
 }
 
 int launch_gather_rows(const PermKey& key, int first, int rows, int obs_dim, int act_dim, const float* obs,
                        const float* act, const float* adv, const float* ret, float* obs_o, float* act_o, float* adv_o,
-                       float* ret_o, cudaStream_t st) {
+                       float* ret_o, const float* old_src, float* old_dst, int pld, cudaStream_t st) {
     if (rows <= 0) return 0;
     int grid = (rows + 7) / 8;                  // 8 warps per CTA, one row per warp per pass
     if (grid > 148 * 8) grid = 148 * 8;
     ProfScope ps(KK_MISC, st);
     gather_rows_kernel<<<grid, 256, 0, st>>>(key, first, rows, obs_dim, act_dim, obs, act, adv, ret, obs_o, act_o, adv_o,
-                                             ret_o);
+                                             ret_o, old_src, old_dst, pld);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
