@@ -235,18 +235,82 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
         if (EPI == EPI_TN) C += (size_t)slice * g.slice_stride;
         const float* __restrict__ bias = g.bias[net];
         const int q = warp & 3, half = warp >> 2;
-        const int m = m0 + q * 32 + lane;
-        if (nkb > 0) {
-            mbar_wait(accum_bar, 0);
-            tc_fence_after();
-        }
         // TMEM -> registers (thread = accumulator row) -> per-warp smem staging -> coalesced row-wise global
         // accesses (bias / ReLU-mask reads and the C store are full 128-B lines; a thread-per-row store would
         // scatter 16-B pieces over 32 rows per instruction).  The operand stages are free once accum_bar fired.
         constexpr int kColsPerHalf = BN / 2 < 32 ? 32 : BN / 2;
         constexpr int kStgLd = kColsPerHalf + 4;
+        constexpr int kLanesPerRow = kColsPerHalf / 4;
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;
+        constexpr int kIters = 32 / kRowsPerIter;
+        constexpr int kBatch = kIters < 8 ? kIters : 8;       // rows whose mask / partial loads are in flight together
+        constexpr int kNB = kIters / kBatch;
+        // single-CTA-per-SM variants have registers to spare: the first batch of ReLU-mask (dX) / partial (dW +=) rows is
+        // requested BEFORE waiting for the accumulator and batch b+1 while batch b is written, so that their global
+        // latency hides under the MMA tail and the stores instead of standing between them
+        constexpr bool kEarlyAux = (EPI != EPI_NN) && (Plan::kMinBlocks == 1);
         float* stg = reinterpret_cast<float*>(smem) + (size_t)warp * (32 * kStgLd);
         const int col0 = half * kColsPerHalf;
+        const int cl = (lane % kLanesPerRow) * 4;
+        const int n = n0 + col0 + cl;
+        const int nv = min(4, g.N - n);
+        auto load_batch = [&](int it0, float4 (&aux)[kBatch]) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int r = (it0 + u) * kRowsPerIter + lane / kLanesPerRow;
+                const int m = m0 + q * 32 + r;
+                aux[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                const float* src = (EPI == EPI_NT) ? g.mask : (g.accumulate ? C : nullptr);
+                if (EPI == EPI_TN && !g.accumulate) aux[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src && m < g.M && nv > 0) {
+                    const float* sp = src + (size_t)m * g.ldc + n;
+                    if (g.vecC && nv == 4) aux[u] = __ldg(reinterpret_cast<const float4*>(sp));
+                    else {
+                        aux[u].x = sp[0];
+                        if (nv > 1) aux[u].y = sp[1];
+                        if (nv > 2) aux[u].z = sp[2];
+                        if (nv > 3) aux[u].w = sp[3];
+                    }
+                }
+            }
+        };
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        auto write_batch = [&](int it0, const float4 (&aux)[kBatch]) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int r = (it0 + u) * kRowsPerIter + lane / kLanesPerRow;
+                const int m = m0 + q * 32 + r;
+                if (m < g.M && nv > 0) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
+                    float x[4] = {t4.x, t4.y, t4.z, t4.w};
+                    float* cp = C + (size_t)m * g.ldc + n;
+                    if (EPI == EPI_NN) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float y = x[e] + bv[e];
+                            x[e] = g.relu ? fmaxf(y, 0.f) : y;
+                        }
+                    } else if (EPI == EPI_NT) {
+                        x[0] = aux[u].x > 0.f ? x[0] : 0.f; x[1] = aux[u].y > 0.f ? x[1] : 0.f;
+                        x[2] = aux[u].z > 0.f ? x[2] : 0.f; x[3] = aux[u].w > 0.f ? x[3] : 0.f;
+                    } else {
+                        x[0] += aux[u].x; x[1] += aux[u].y; x[2] += aux[u].z; x[3] += aux[u].w;
+                    }
+                    if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (e < nv) cp[e] = x[e];
+                    }
+                }
+            }
+        };
+        float4 aux_a[kBatch], aux_b[kBatch];
+        if (kEarlyAux && col0 < BN) load_batch(0, aux_a);
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
 #pragma unroll 1
         for (int cb = 0; cb < kColsPerHalf && col0 + cb < BN; cb += 32) {
             uint32_t v[32];
@@ -268,69 +332,19 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
         }
         __syncwarp();
         if (col0 < BN) {
-            constexpr int kLanesPerRow = kColsPerHalf / 4;
-            constexpr int kRowsPerIter = 32 / kLanesPerRow;
-            const int cl = (lane % kLanesPerRow) * 4;
-            const int n = n0 + col0 + cl;
-            const int nv = min(4, g.N - n);
-            float bv[4] = {0.f, 0.f, 0.f, 0.f};
             if (EPI == EPI_NN && bias) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if (e < nv) bv[e] = __ldg(bias + n + e);
             }
-            constexpr int kIters = 32 / kRowsPerIter;
-            constexpr int kBatch = kIters < 8 ? kIters : 8;       // rows whose mask / partial loads are in flight together
+            if (EPI != EPI_NN && !kEarlyAux) load_batch(0, aux_a);
 #pragma unroll 1
-            for (int it0 = 0; it0 < kIters; it0 += kBatch) {
-                float4 aux[kBatch];
-                if (EPI != EPI_NN) {
-#pragma unroll
-                    for (int u = 0; u < kBatch; ++u) {
-                        const int r = (it0 + u) * kRowsPerIter + lane / kLanesPerRow;
-                        const int m = m0 + q * 32 + r;
-                        aux[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-                        const float* src = (EPI == EPI_NT) ? g.mask : (g.accumulate ? C : nullptr);
-                        if (EPI == EPI_TN && !g.accumulate) aux[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (src && m < g.M && nv > 0) {
-                            const float* sp = src + (size_t)m * g.ldc + n;
-                            if (g.vecC && nv == 4) aux[u] = __ldg(reinterpret_cast<const float4*>(sp));
-                            else {
-                                aux[u].x = sp[0];
-                                if (nv > 1) aux[u].y = sp[1];
-                                if (nv > 2) aux[u].z = sp[2];
-                                if (nv > 3) aux[u].w = sp[3];
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) {
-                    const int r = (it0 + u) * kRowsPerIter + lane / kLanesPerRow;
-                    const int m = m0 + q * 32 + r;
-                    if (m < g.M && nv > 0) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
-                        float x[4] = {t4.x, t4.y, t4.z, t4.w};
-                        float* cp = C + (size_t)m * g.ldc + n;
-                        if (EPI == EPI_NN) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float y = x[e] + bv[e];
-                                x[e] = g.relu ? fmaxf(y, 0.f) : y;
-                            }
-                        } else if (EPI == EPI_NT) {
-                            x[0] = aux[u].x > 0.f ? x[0] : 0.f; x[1] = aux[u].y > 0.f ? x[1] : 0.f;
-                            x[2] = aux[u].z > 0.f ? x[2] : 0.f; x[3] = aux[u].w > 0.f ? x[3] : 0.f;
-                        } else {
-                            x[0] += aux[u].x; x[1] += aux[u].y; x[2] += aux[u].z; x[3] += aux[u].w;
-                        }
-                        if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
-                        else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (e < nv) cp[e] = x[e];
-                        }
-                    }
+            for (int bidx = 0; bidx < kNB; bidx += 2) {
+                if (EPI != EPI_NN && bidx + 1 < kNB) load_batch((bidx + 1) * kBatch, aux_b);
+                write_batch(bidx * kBatch, aux_a);
+                if (bidx + 1 < kNB) {
+                    if (EPI != EPI_NN && bidx + 2 < kNB) load_batch((bidx + 2) * kBatch, aux_a);
+                    write_batch((bidx + 1) * kBatch, aux_b);
                 }
             }
         }
