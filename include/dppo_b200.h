@@ -182,12 +182,14 @@ int dppo_diag_gaussian(dppo_ctx* ctx, int op, const float* flat, const float* ar
 
 /* the whole update from HOST buffers (what Chief._train feeds through feed_dict,
  * Chief.py:54-64): pinned host rollout -> chunked H2D overlapped with GAE + loss_grad ->
- * (allreduce if a communicator exists) -> losses back to host.  Synchronises `stream`.
- * params_pi/params_old/grad_out are device pointers; everything *_h is host memory. */
-int dppo_update_host(dppo_ctx* ctx, const float* params_pi, const float* params_old,
+ * (allreduce if a communicator exists) -> Adam when adam_m/adam_v are non-NULL (PPO.py:53; step = t after
+ * increment, as dppo_update) -> losses back to host.  Synchronises `stream`.
+ * params_pi, params_old, adam_m, adam_v and grad_out are device pointers; every ..._h argument is host memory. */
+int dppo_update_host(dppo_ctx* ctx, float* params_pi, const float* params_old,
                      const float* obs_h, const float* act_h, const float* rew_h,
                      const float* predv_h, const float* done_h, int T, int N,
                      double gamma, double lam, int gae_mode, float l_mul,
+                     float* adam_m, float* adam_v, int step, float lr, float beta1, float beta2, float eps,
                      float* losses_out_h, float* grad_out, void* stream);
 
 /* ---- launch accounting -------------------------------------------------------------------------

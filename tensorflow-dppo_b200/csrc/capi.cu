@@ -613,10 +613,10 @@ int dppo_sync_old(dppo_ctx* c, const float* params_pi, float* params_old, void* 
     return 0;
 }
 
-int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs_h,
+int dppo_update_host(dppo_ctx* c, float* params_pi, const float* params_old, const float* obs_h,
                      const float* act_h, const float* rew_h, const float* predv_h, const float* done_h, int T,
-                     int N, double gamma, double lam, int gae_mode, float l_mul, float* losses_out_h,
-                     float* grad_out, void* stream) {
+                     int N, double gamma, double lam, int gae_mode, float l_mul, float* adam_m, float* adam_v, int step,
+                     float lr, float beta1, float beta2, float eps, float* losses_out_h, float* grad_out, void* stream) {
     CTX_GUARD(c);
     DPPO_REQUIRE(params_pi && params_old && obs_h && act_h && rew_h && predv_h && done_h && grad_out,
                  "dppo_update_host: null buffer");
@@ -685,17 +685,7 @@ int dppo_update_host(dppo_ctx* c, const float* params_pi, const float* params_ol
                                    w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st))
             return r;
     }
-    const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
-    if (c->nccl_comm && c->world > 1 && peer_available(c)) {
-        if (int r = launch_finalize(s, active, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
-                                    peer_exchange_buffer(c), nullptr, st)) return r;
-        if (int r = peer_allreduce_adam(c, nullptr, nullptr, nullptr, 0, 0.f, 0.f, 0.f, 0.f, grad_out, st)) return r;
-    } else {
-        if (int r = launch_finalize(s, active, w.partial, w.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
-                                    nullptr, st)) return r;
-        if (c->nccl_comm && c->world > 1)
-            if (int r = allreduce_avg(c, grad_out, s.n_params + kLossSlots, st)) return r;
-    }
+    if (int r = reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st)) return r;
     DPPO_CHECK_CUDA(cudaMemcpyAsync(c->losses_pinned, grad_out + s.n_params, kLossSlots * sizeof(float),
                                     cudaMemcpyDeviceToHost, st));
     DPPO_CHECK_CUDA(cudaStreamSynchronize(st));

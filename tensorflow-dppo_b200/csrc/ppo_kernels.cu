@@ -78,15 +78,26 @@ ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_
     const int nrows = min(kLossTileRows, rows - row0);
     const int tid = threadIdx.x;
 
-    {   // coalesced tile loads
-        const float* gp = out_pi + (size_t)row0 * Pld;   // global rows are Pld wide (16-B aligned), smem rows P wide
-        const float* go = out_old + (size_t)row0 * Pld;
-        for (int i = tid; i < nrows * Pld; i += kLossTileRows) {
-            const int r = i / Pld, cc = i - r * Pld;
-            if (cc < P) { s_pi[r * P + cc] = __ldg(gp + i); s_old[r * P + cc] = __ldg(go + i); }
+    {   // coalesced 16-B tile loads: global rows are Pld wide (Pld % 4 == 0, 16-B aligned), smem rows P wide
+        const float4* gp = reinterpret_cast<const float4*>(out_pi + (size_t)row0 * Pld);
+        const float4* go = reinterpret_cast<const float4*>(out_old + (size_t)row0 * Pld);
+        const int pld4 = Pld >> 2;
+        for (int i = tid; i < nrows * pld4; i += kLossTileRows) {
+            const int r = i / pld4, c0 = (i - r * pld4) * 4;
+            const float4 a4 = __ldg(gp + i), b4 = __ldg(go + i);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c0 + e < P) { s_pi[r * P + c0 + e] = av[e]; s_old[r * P + c0 + e] = bv[e]; }
         }
         const float* ga = act + (size_t)row0 * A;
-        for (int i = tid; i < nrows * A; i += kLossTileRows) s_act[i] = __ldg(ga + i);
+        const int na = nrows * A;
+        if (((na & 3) == 0) && ((reinterpret_cast<uintptr_t>(ga) & 15) == 0)) {
+            const float4* ga4 = reinterpret_cast<const float4*>(ga);
+            for (int i = tid; i < (na >> 2); i += kLossTileRows) reinterpret_cast<float4*>(s_act)[i] = __ldg(ga4 + i);
+        } else {
+            for (int i = tid; i < na; i += kLossTileRows) s_act[i] = __ldg(ga + i);
+        }
     }
     __syncthreads();
 
@@ -149,11 +160,15 @@ ppo_loss_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_
         o[0] = g_v;
     }
     __syncthreads();
-    {   // coalesced d_out store
-        float* gd = d_out + (size_t)row0 * Pld;
-        for (int i = tid; i < nrows * Pld; i += kLossTileRows) {
-            const int r = i / Pld, cc = i - r * Pld;
-            gd[i] = cc < P ? s_pi[r * P + cc] : 0.f;
+    {   // coalesced 16-B d_out store (pad columns get zeros)
+        float4* gd = reinterpret_cast<float4*>(d_out + (size_t)row0 * Pld);
+        const int pld4 = Pld >> 2;
+        for (int i = tid; i < nrows * pld4; i += kLossTileRows) {
+            const int r = i / pld4, c0 = (i - r * pld4) * 4;
+            float o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] = (c0 + e < P) ? s_pi[r * P + c0 + e] : 0.f;
+            gd[i] = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
     }
     // block reduction of the batch sums

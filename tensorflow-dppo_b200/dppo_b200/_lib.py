@@ -49,8 +49,8 @@ _PROTOS = {
                                   C.c_float, _p]),
     "dppo_sync_old": (C.c_int, [_p, _p, _p, _p]),
     "dppo_act": (C.c_int, [_p, _p, _p, C.c_int, C.c_uint64, C.c_uint64, _p, _p, _p]),
-    "dppo_update_host": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double,
-                                   C.c_int, C.c_float, _p, _p, _p]),
+    "dppo_update_host": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   C.c_float, _p, _p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _p, _p, _p]),
     "dppo_update": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_float,
                               _p, _p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _p, _p]),
     "dppo_categorical": (C.c_int, [_p, C.c_int, _p, _p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),

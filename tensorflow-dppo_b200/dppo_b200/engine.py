@@ -233,9 +233,11 @@ class DppoEngine:
 
     # ------------------------------------------------------------------ host-buffer entry (e2e)
     def update_host(self, params_pi, params_old, obs_h, act_h, rew_h, predv_h, done_h, gamma, lam, l_mul,
-                    grad_out=None, gae_mode: int = L.GAE_REFERENCE):
+                    grad_out=None, gae_mode: int = L.GAE_REFERENCE, adam_m=None, adam_v=None, step: int = 0,
+                    lr: float = 0.0, beta1=0.9, beta2=0.999, eps=1e-8):
         """Whole update from pinned HOST buffers (what Chief._train feeds, Chief.py:54-64):
-        chunked H2D overlapped with GAE + loss_grad (+ allreduce), losses read back.  Synchronises."""
+        chunked H2D overlapped with GAE + loss_grad (+ allreduce) (+ Adam when adam_m/adam_v are given), losses read
+        back.  Synchronises."""
         T, N = rew_h.shape
         B = T * N
         for name, t, n in (("obs_h", obs_h, B * self.obs_dim), ("act_h", act_h, B * self.act_cols),
@@ -250,8 +252,10 @@ class DppoEngine:
         self._check(self.lib.dppo_update_host(
             self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"),
             obs_h.data_ptr(), act_h.data_ptr(), rew_h.data_ptr(), predv_h.data_ptr(), done_h.data_ptr(), T, N,
-            float(gamma), float(lam), int(gae_mode), float(l_mul), losses, self._dev(g, self.grad_len, "grad_out"),
-            self._stream()))
+            float(gamma), float(lam), int(gae_mode), float(l_mul),
+            self._dev(adam_m, self.n_params, "adam_m") if adam_m is not None else None,
+            self._dev(adam_v, self.n_params, "adam_v") if adam_v is not None else None, int(step), float(lr),
+            beta1, beta2, eps, losses, self._dev(g, self.grad_len, "grad_out"), self._stream()))
         return list(losses), g
 
     # ------------------------------------------------------------------ CategoricalPd methods

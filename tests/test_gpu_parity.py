@@ -358,6 +358,13 @@ def test_update_host_equals_device_path():
     n = lay.n_params
     assert max(per_tensor_rel_err(g_h.cpu().numpy()[:n], g_dev.cpu().numpy()[:n], lay).values()) < TOL
     np.testing.assert_allclose(np.array(l_h), g_dev.cpu().numpy()[n:], rtol=1e-6, atol=1e-7)
+    # with the optimiser inside the call: same parameters as adam_apply on the returned gradient
+    p1 = d_pi.clone(); m1 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")
+    eng.adam_apply(p1, g_h, m1, v1, 1, 1e-4)
+    p2 = d_pi.clone(); m2 = torch.zeros(n, device="cuda"); v2 = torch.zeros(n, device="cuda")
+    _, g2 = eng.update_host(p2, d_old, pin["obs"], pin["act"], pin["rew"], pin["predv"], pin["done"], 0.99, 0.95, 0.7,
+                            adam_m=m2, adam_v=v2, step=1, lr=1e-4)
+    assert torch.equal(g2[:n], g_h[:n]) and torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
 
 
 def test_errors_are_loud():
