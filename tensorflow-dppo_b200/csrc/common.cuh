@@ -127,6 +127,29 @@ struct ProfScope {
     ~ProfScope();
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember per device ordinal what has been configured,
+// so that one process driving several GPUs (one dppo_ctx each) configures every one of them.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if ((mask >> d) & 1ull) return false;
+        mask |= 1ull << d;
+        return true;
+    }
+};
+struct PerDeviceMax {
+    size_t cur[64] = {};
+    bool need(size_t bytes) {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (bytes <= cur[d]) return false;
+        cur[d] = bytes;
+        return true;
+    }
+};
+
 // ---- kernels' host launchers (one per .cu) ----
 int launch_gae(const float* rew, const float* predv, const float* done, const float* last_v,
                const float* last_done, int T, int N, double gamma, double lam, int mode,

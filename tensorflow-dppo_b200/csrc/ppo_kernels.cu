@@ -302,11 +302,9 @@ int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, co
     if (s.pd == DPPO_PD_CATEGORICAL) {
         const size_t smem = (size_t)kLossTileRows * 2 * (s.P | 1) * sizeof(float);
         DPPO_REQUIRE(smem <= 200 * 1024, "loss kernel: ncat=%d needs %zu B of shared memory", s.act, smem);
-        static size_t configured_cat = 0;
-        if (smem > 48 * 1024 && smem > configured_cat) {
+        static PerDeviceMax configured_cat;
+        if (smem > 48 * 1024 && configured_cat.need(smem))
             DPPO_CHECK_CUDA(cudaFuncSetAttribute(ppo_loss_cat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured_cat = smem;
-        }
         ProfScope ps(KK_LOSS, st);
         ppo_loss_cat_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, reinterpret_cast<const int*>(act), adv, ret,
                                                                rows, s.act, s.Pld, tile0, inv_B, clip, entcoeff, vcoeff,
@@ -316,11 +314,9 @@ int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, co
     }
     const size_t smem = (size_t)kLossTileRows * (2 * s.P + s.act) * sizeof(float);
     DPPO_REQUIRE(smem <= 200 * 1024, "loss kernel: act_dim=%d needs %zu B of shared memory", s.act, smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDeviceMax configured;
+    if (smem > 48 * 1024 && configured.need(smem))
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(ppo_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     ProfScope ps(KK_LOSS, st);
     ppo_loss_kernel<<<grid, kLossTileRows, smem, st>>>(out_pi, out_old, act, adv, ret, rows, s.act, s.Pld, tile0,
                                                        inv_B, clip, entcoeff, vcoeff, d_out, loss_part);

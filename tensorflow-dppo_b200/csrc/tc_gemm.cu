@@ -624,11 +624,10 @@ static int launch_persistent(TcArgs& g, cudaStream_t st) {
     const int tiles_m = (g.M + BM - 1) / BM;
     const long long total = (long long)tiles_m * g.tiles_n * g.nets;
     DPPO_REQUIRE(total < (1ll << 30), "tc_gemm: too many tiles");
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              kPSmemBytes));
-        configured = true;
     }
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);
@@ -645,11 +644,10 @@ static int launch(TcArgs& g, int slices, cudaStream_t st) {
     g.tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + BM - 1) / BM;
     DPPO_REQUIRE(tiles_m <= 65535, "tc_gemm: M=%d too large for one launch", g.M);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, MN_MAJOR, TERMS, EPI, B_IMAGE, KB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
-        configured = true;
     }
     dim3 grid(g.tiles_n * g.nets, tiles_m, slices);
     ProfScope ps(KK_TC_GEMM, st);

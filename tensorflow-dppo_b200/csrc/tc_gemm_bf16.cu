@@ -266,10 +266,9 @@ static int launch(Args& g, int slices, cudaStream_t st) {
     g.tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + BM - 1) / BM;
     DPPO_REQUIRE(tiles_m <= 65535, "bf16 gemm: M=%d too large for one launch", g.M);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(bf16_gemm_kernel<BN, MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
-        configured = true;
     }
     dim3 grid(g.tiles_n * g.nets, tiles_m, slices);
     ProfScope ps(KK_TC_GEMM, st);

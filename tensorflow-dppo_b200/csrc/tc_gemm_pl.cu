@@ -1,18 +1,20 @@
+// EXPERIMENT (not on the update path; dppo_dbg_gemm modes 80-83, tests/test_gpu_parity.py::test_tc_planes_gemm):
 // TMA-fed K-major products on pre-split operand PLANES (sm_100a, tcgen05 kind::tf32, 3-term fp32-accurate split).
 //
 // tc_gemm.cu moves the activation operand global -> registers -> RN hi/lo split -> swizzled st.shared with 8 SIMT warps
-// per CTA; that conversion, not the tensor pipe, bounds every tile shape narrower than 256 columns ("what did
-// not work").  Here the activation arrives as two fp32 planes (hi = RN-tf32(x), lo = RN-tf32(x - hi)) that the PRODUCING
-// kernel's epilogue wrote, so a single thread feeds the operand stages with cp.async.bulk.tensor (SWIZZLE_128B boxes
-// {32 k, 128 rows}) next to the weight-image bulk copy and no thread touches the data between HBM and the MMA.
-//
-// With the movers gone the CTA is persistent (grid = #SMs) over 128x128 tiles, TMEM holds TWO accumulator sets
-// (main + correction, 2 x 256 columns) and four epilogue warps drain set i while the MMA thread fills set i^1:
-// prologue, epilogue and output stores run under the next tile's main loop.
+// per CTA.  The question this kernel answers: is that conversion what limits the tiles narrower than 256 columns?  Here
+// the activation arrives as two fp32 planes (hi = RN-tf32(x), lo = RN-tf32(x - hi)) that a PRODUCING epilogue wrote, so
+// one thread feeds the operand stages with cp.async.bulk.tensor (SWIZZLE_128B boxes {32 k, 128 rows}) next to the
+// weight-image bulk copy and no thread touches the data between HBM and the MMA; the CTA is persistent (grid = #SMs)
+// over 128x128 tiles, TMEM holds TWO accumulator sets (main + correction, 2 x 256 columns) and four epilogue warps
+// drain set i while the MMA thread fills set i^1.
 //   warp 0   : producer (one thread): per k-block 2 TMA boxes (A hi, A lo) + 1 bulk copy (B image hi|lo), 3 stages x 64 KB
 //   warp 1   : TMEM owner + MMA issuer (one thread): 12 MMAs per k-block, tcgen05.commit frees the stage
 //   warps 2-5: epilogue: tcgen05.ld -> smem staging (32-column slices) -> bias/ReLU | ReLU-mask -> coalesced stores of the
 //              fp32 result and/or its hi/lo planes for the next consumer
+// MEASURED ANSWER: no.  Long-K steady state 160 TFLOP/s (algorithmic) vs 244 for the 256-wide mover kernel; forward L2
+// 111 us = 111 us.  A kind::tf32 MMA covers K = 8 per instruction with a fixed ~30-cycle cost that a 128x128x8
+// instruction amortises far worse than a 128x256x8 one, so 256-wide tiles stay the product path.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
@@ -344,11 +346,10 @@ int tc_pl_gemm(int epi_nt, int M, int N, int K, const float* Ahi0, const float* 
     const int tiles_m = (M + tc::BM - 1) / tc::BM;
     const long long total = (long long)tiles_m * g.tiles_n * nets;
     DPPO_REQUIRE(total < (1ll << 30), "tc_pl_gemm: too many tiles");
-    static bool configured[2] = {false, false};
-    if (!configured[epi_nt ? 1 : 0]) {
+    static PerDeviceOnce configured[2];
+    if (configured[epi_nt ? 1 : 0].need()) {
         if (epi_nt) DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc::tc_pl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kLSmemBytes));
         else DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc::tc_pl_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kLSmemBytes));
-        configured[epi_nt ? 1 : 0] = true;
     }
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);

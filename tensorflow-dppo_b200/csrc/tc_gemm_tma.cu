@@ -347,10 +347,9 @@ template <int BN>
 static int launch_tma(const CUtensorMap& mA, const CUtensorMap& mB, const float* A, int lda, const float* B, int ldb,
                       TmaArgs& g, int slices, cudaStream_t st) {
     using Plan = TmaPlan<BN>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_tn_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes));
-        configured = true;
     }
     static int want3 = -1;
     if (want3 < 0) { const char* e = getenv("DPPO_TC_TMA_2D"); want3 = (e && e[0] == '1') ? 0 : 1; }
