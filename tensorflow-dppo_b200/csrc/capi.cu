@@ -136,6 +136,8 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
         }
     }
     for (int l = 0; l < s.L; ++l) w.act_pi[l] = (float*)take(R * s.h[l] * sizeof(float));
+    if (cfg->gemm_mode == DPPO_GEMM_TF32X3)
+        for (int l = 0; l < s.L; ++l) w.act_bits[l] = (uint32_t*)take((size_t)tc_bits_words((long long)R, s.h[l]) * sizeof(uint32_t));
     const size_t hm = (size_t)(s.hmax() > 0 ? s.hmax() : 1);
     w.scratch[0] = (float*)take(R * hm * sizeof(float));
     w.scratch[1] = (float*)take(R * hm * sizeof(float));
@@ -189,7 +191,8 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
             if (int r = tc_gemm_kk_img(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
-                                       head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st)) return r;
+                                       head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st,
+                                       head ? nullptr : w.act_bits[l], nullptr)) return r;
             in0 = o0; in1 = o1;
         }
         return 0;
@@ -270,10 +273,11 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
         return gemm_tn_splitk(in, out, rows, x_in, in, dY, ldy, p, out, tn, st);
     };
     // dX = (dY . W^T) * [h > 0]   (W is [n_out_of_this_product, k] row-major = K-major B operand)
+    // mask = activations of hidden layer l_ - 1 (N_ wide); the tensor-core path reads their sign bitmap instead
     auto dense_dx = [&](int l_, int M_, int N_, int K_, const float* dY, int ldy, const float* W, float* dX,
                         const float* mask) -> int {
         if (tcore) return tc_gemm_kk_img(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_,
-                                         nullptr, nullptr, 0, mask, 1, st);
+                                         nullptr, nullptr, 0, mask, 1, st, nullptr, w.act_bits[l_ - 1]);
         if (bf16) return bf16_gemm_kk(1, M_, N_, K_, dY, nullptr, ldy, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr, 0,
                                       mask, 1, st);
         GemmEpi nt; nt.mask = mask;

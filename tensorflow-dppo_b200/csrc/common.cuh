@@ -74,6 +74,7 @@ struct Workspace {
     float* img_fwd_old[kMaxLayers + 1];
     float* img_dx_pi[kMaxLayers + 1];
     float* act_pi[kMaxLayers];   // post-ReLU activations of pi, layer l: [max_rows, h[l]]
+    uint32_t* act_bits[kMaxLayers];  // tensor-core path: their sign bitmaps (the dX ReLU mask; layout private to tc_gemm.cu)
     float* scratch[2];   // oldpi activations / dh ping-pong: [max_rows, hmax]
     float* out_pi;       // [max_rows, P]
     float* out_old;      // [max_rows, P]
@@ -200,9 +201,12 @@ int tc_pl_gemm(int epi_nt, int M, int N, int K, const float* Ahi0, const float* 
                int lda, const float* img0, const float* img1, float* C0, float* C1, float* Chi0, float* Clo0, float* Chi1,
                float* Clo1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
                cudaStream_t st);
+bool tc_bits_supported();
 int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
                    const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,
-                   const float* mask, int nets, cudaStream_t st);
+                   const float* mask, int nets, cudaStream_t st, uint32_t* bits_out0 = nullptr,
+                   const uint32_t* bits_in = nullptr);
+long long tc_bits_words(long long rows, int N);
 int tc_gemm_tn_splitk(int terms, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                       int slices, long long slice_stride, int accumulate, cudaStream_t st);
 bool tc_tn_tma_supported(const float* A, int lda, const float* B, int ldb);

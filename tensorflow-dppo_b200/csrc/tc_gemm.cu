@@ -33,6 +33,12 @@ struct TcArgs {
     const float* A[2]; const float* B[2]; float* C[2]; const float* bias[2];
     const float* Bimg[2];      // B_IMAGE: weights pre-split and pre-swizzled as smem tile images (pack_images_kernel)
     const float* mask;
+    // ReLU sign bitmap of an activation matrix (4 MB instead of the 134 MB fp32 tile at cfg3): the forward epilogue
+    // writes it next to h, the dX epilogue of the same width reads it as its mask.  The layout is private to the two
+    // epilogues, which share the thread -> (row, column) mapping: one word per (CTA tile, column half, lane quarter,
+    // row batch, lane) = 8 rows x 4 columns, bit u*4 + e  ->  every warp access is one coalesced 128-B line.
+    uint32_t* bits_out[2];
+    const uint32_t* bits_in;
     int M, N, K;
     int lda, ldb, ldc;
     int tiles_n, nets;
@@ -254,6 +260,8 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
         const int cl = (lane % kLanesPerRow) * 4;
         const int n = n0 + col0 + cl;
         const int nv = min(4, g.N - n);
+        static_assert(kBatch == 8, "sign-bitmap words hold 8 rows x 4 columns");
+        const size_t bits_base = ((size_t)(blockIdx.y * g.tiles_n + (blockIdx.x % g.tiles_n)) * 8 + (size_t)(half * 4 + q)) * (kNB * 32) + lane;
         auto load_batch = [&](int it0, float4 (&aux)[kBatch]) {
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
@@ -262,7 +270,9 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
                 aux[u] = make_float4(1.f, 1.f, 1.f, 1.f);
                 const float* src = (EPI == EPI_NT) ? g.mask : (g.accumulate ? C : nullptr);
                 if (EPI == EPI_TN && !g.accumulate) aux[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src && m < g.M && nv > 0) {
+                if (EPI == EPI_NT && g.bits_in) {            // one raw word per batch (decoded at use: no dependent op here)
+                    if (u == 0) aux[0].x = __uint_as_float(__ldg(g.bits_in + bits_base + (size_t)(it0 / kBatch) * 32));
+                } else if (src && m < g.M && nv > 0) {
                     const float* sp = src + (size_t)m * g.ldc + n;
                     if (g.vecC && nv == 4) aux[u] = __ldg(reinterpret_cast<const float4*>(sp));
                     else {
@@ -275,11 +285,14 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
             }
         };
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t* __restrict__ bits_out = (EPI == EPI_NN) ? g.bits_out[net] : nullptr;
         auto write_batch = [&](int it0, const float4 (&aux)[kBatch]) {
+            uint32_t wbits = (EPI == EPI_NT) ? __float_as_uint(aux[0].x) : 0u;
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int r = (it0 + u) * kRowsPerIter + lane / kLanesPerRow;
                 const int m = m0 + q * 32 + r;
+                uint32_t nib = 0u;
                 if (m < g.M && nv > 0) {
                     const float4 t4 = *reinterpret_cast<const float4*>(stg + r * kStgLd + cl);
                     float x[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -290,9 +303,20 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
                             const float y = x[e] + bv[e];
                             x[e] = g.relu ? fmaxf(y, 0.f) : y;
                         }
+                        if (bits_out) {                      // warp-uniform: only the pi net's hidden layers keep a sign bitmap
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv && x[e] > 0.f) nib |= 1u << e;
+                        }
                     } else if (EPI == EPI_NT) {
-                        x[0] = aux[u].x > 0.f ? x[0] : 0.f; x[1] = aux[u].y > 0.f ? x[1] : 0.f;
-                        x[2] = aux[u].z > 0.f ? x[2] : 0.f; x[3] = aux[u].w > 0.f ? x[3] : 0.f;
+                        if (g.bits_in) {
+                            const uint32_t b4 = wbits >> (4 * u);
+                            x[0] = (b4 & 1u) ? x[0] : 0.f; x[1] = (b4 & 2u) ? x[1] : 0.f;
+                            x[2] = (b4 & 4u) ? x[2] : 0.f; x[3] = (b4 & 8u) ? x[3] : 0.f;
+                        } else {
+                            x[0] = aux[u].x > 0.f ? x[0] : 0.f; x[1] = aux[u].y > 0.f ? x[1] : 0.f;
+                            x[2] = aux[u].z > 0.f ? x[2] : 0.f; x[3] = aux[u].w > 0.f ? x[3] : 0.f;
+                        }
                     } else {
                         x[0] += aux[u].x; x[1] += aux[u].y; x[2] += aux[u].z; x[3] += aux[u].w;
                     }
@@ -303,7 +327,9 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
                             if (e < nv) cp[e] = x[e];
                     }
                 }
+                if (EPI == EPI_NN) wbits |= nib << (4 * u);
             }
+            if (EPI == EPI_NN && bits_out) bits_out[bits_base + (size_t)(it0 / kBatch) * 32] = wbits;
         };
         float4 aux_a[kBatch], aux_b[kBatch];
         if (kEarlyAux && col0 < BN) load_batch(0, aux_a);
@@ -862,11 +888,20 @@ int tc_pack_one_ex(const float* src, float* dst, int N, int K, int ld, int trans
 }
 
 // C[M,N] = epi(A[M,K] . Bimg^T) with B given as weight images (see tc_pack_images)
+// the default 256/64-wide tc_gemm_kernel writes / reads the ReLU sign bitmap; the opt-in experimental tilings do not
+bool tc_bits_supported() { return !tc_use_persistent() && !tc_use_bk16(); }
+// 32-bit words of the sign bitmap of a [rows, N] activation matrix (whole 128 x BN tiles)
+long long tc_bits_words(long long rows, int N) {
+    const int bn = tc_bn_for(N);
+    return ((rows + tc::BM - 1) / tc::BM) * ((N + bn - 1) / bn) * (long long)(tc::BM * bn / 32);
+}
+
 int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
                    const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,
-                   const float* mask, int nets, cudaStream_t st) {
+                   const float* mask, int nets, cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in) {
     if (M == 0) return 0;
     tc::TcArgs g{};
+    if (tc_bits_supported()) { g.bits_out[0] = bits_out0; g.bits_in = bits_in; }
     g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = img0; g.Bimg[1] = img1; g.C[0] = C0; g.C[1] = C1; g.bias[0] = bias0; g.bias[1] = bias1;
     g.mask = mask; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = 4; g.ldc = ldc; g.nets = nets; g.relu = relu;
     g.k_per_slice = ((K + tc::BK - 1) / tc::BK) * tc::BK;
