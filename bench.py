@@ -181,7 +181,7 @@ def run_reference(args):
     T, N, obs, act, hidden = WORKLOADS[args.workload]
     steps = min(args.steps, 10)
     val, cores, desc, ms = cpu_reference_run(args.workload, steps, min(args.warmup, 2))
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -190,7 +190,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------------------------
@@ -301,7 +301,6 @@ def run_b200(args):
     F = flops_per_step(obs, hidden, act) * B
     achieved_tf = F * K / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     alg_bytes = bytes_per_step(obs, act) * B
-    alg_bytes_placeholder = alg_bytes
     hbm_gbs = alg_bytes * K / (ms_total * 1e-3) / 1e9
 
     # --- e2e pass: pinned host buffers through dppo_update_host ---------------------------------
@@ -356,7 +355,7 @@ def run_b200(args):
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
                 "traffic_note": "DRAM bytes of all GEMM launches of one step (ncu capture under profiles/); algorithmic bytes "
                                 "of the whole update are %d -- the excess is fp32 activations (h1, h2, dh) round-tripping "
-                                "HBM between the per-layer kernels" % alg_bytes_placeholder,
+                                "HBM between the per-layer kernels" % alg_bytes,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "note": ("algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
                          + ("fp32-parity path: every algorithmic MAC is issued as 3 TF32 MMAs (half the bf16 rate each), so the "
@@ -381,13 +380,34 @@ def run_b200(args):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its "NCCL version ..." banner with
+    printf on fd 1 during communicator creation): keep a private duplicate of the real stdout for the JSON line and point
+    fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
