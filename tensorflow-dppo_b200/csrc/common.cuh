@@ -202,6 +202,10 @@ int tc_pl_gemm(int epi_nt, int M, int N, int K, const float* Ahi0, const float* 
                float* Clo1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
                cudaStream_t st);
 bool tc_bits_supported();
+// A kind::tf32 MMA reads only the upper 19 bits of an fp32 operand (verified on sm_100a: the parity tests pass with raw
+// tiles), i.e. it sees trunc(x).  The activation split can therefore be hi = x as it is (no conversion, and for the
+// TMA-fed dW kernel no rewrite of the tile at all) and lo = RN-tf32(x - trunc(x)).  DPPO_TC_RAWHI=0 restores hi = RN-tf32(x).
+bool tc_raw_hi();
 int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0,
                    const float* img1, float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu,
                    const float* mask, int nets, cudaStream_t st, uint32_t* bits_out0 = nullptr,

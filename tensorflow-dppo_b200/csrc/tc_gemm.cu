@@ -46,6 +46,7 @@ struct TcArgs {
     int k_per_slice;
     long long slice_stride;
     int vecA, vecB, vecC;
+    int raw_hi;                     // image mode: activation hi operand = the raw fp32 value (see tc_raw_hi)
     long long img_replica_bytes;    // B_IMAGE: byte distance between replicas of the weight image
 };
 
@@ -91,7 +92,8 @@ __device__ __forceinline__ void tile_load(float4 (&reg)[R * KB / 1024], const fl
 }
 
 template <int R, bool MN_MAJOR, int TERMS, int KB = BK>
-__device__ __forceinline__ void tile_store(const float4 (&reg)[R * KB / 1024], uint8_t* hi, uint8_t* lo, int tid) {
+__device__ __forceinline__ void tile_store(const float4 (&reg)[R * KB / 1024], uint8_t* hi, uint8_t* lo, int tid,
+                                           bool raw_hi = false) {
     constexpr int kCpr = KB / 4;
 #pragma unroll
     for (int i = 0; i < R * KB / 1024; ++i) {
@@ -108,8 +110,15 @@ __device__ __forceinline__ void tile_store(const float4 (&reg)[R * KB / 1024], u
         }
         const float4 v = reg[i];
         uint4 h;
-        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-        *reinterpret_cast<uint4*>(hi + off) = h;
+        if (TERMS == 3 && raw_hi) {
+            // the MMA ignores the low 13 mantissa bits: store x itself as the hi operand, split off x - trunc(x) as lo
+            *reinterpret_cast<float4*>(hi + off) = v;
+            h.x = __float_as_uint(v.x) & 0xFFFFE000u; h.y = __float_as_uint(v.y) & 0xFFFFE000u;
+            h.z = __float_as_uint(v.z) & 0xFFFFE000u; h.w = __float_as_uint(v.w) & 0xFFFFE000u;
+        } else {
+            h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+            *reinterpret_cast<uint4*>(hi + off) = h;
+        }
         if (TERMS == 3) {
             uint4 l;
             l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
                         const int s = kb % STAGES;
                         mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
                         uint8_t* st = smem + s * Plan::kStage;
-                        tile_store<BM, MN_MAJOR, TERMS, KB>(ra[j], st, st + Plan::kATile, tid);
+                        tile_store<BM, MN_MAJOR, TERMS, KB>(ra[j], st, st + Plan::kATile, tid, g.raw_hi != 0);
                         fence_proxy_async();
                         mbar_arrive(&full_bar[s]);
                         if (kb + kPrefetch < nkb)
@@ -890,6 +899,11 @@ int tc_pack_one_ex(const float* src, float* dst, int N, int K, int ld, int trans
 // C[M,N] = epi(A[M,K] . Bimg^T) with B given as weight images (see tc_pack_images)
 // the default 256/64-wide tc_gemm_kernel writes / reads the ReLU sign bitmap; the opt-in experimental tilings do not
 bool tc_bits_supported() { return !tc_use_persistent() && !tc_use_bk16(); }
+bool tc_raw_hi() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DPPO_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 // 32-bit words of the sign bitmap of a [rows, N] activation matrix (whole 128 x BN tiles)
 long long tc_bits_words(long long rows, int N) {
     const int bn = tc_bn_for(N);
@@ -902,6 +916,7 @@ int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float
     if (M == 0) return 0;
     tc::TcArgs g{};
     if (tc_bits_supported()) { g.bits_out[0] = bits_out0; g.bits_in = bits_in; }
+    g.raw_hi = tc_raw_hi() ? 1 : 0;
     g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = img0; g.Bimg[1] = img1; g.C[0] = C0; g.C[1] = C1; g.bias[0] = bias0; g.bias[1] = bias1;
     g.mask = mask; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = 4; g.ldc = ldc; g.nets = nets; g.relu = relu;
     g.k_per_slice = ((K + tc::BK - 1) / tc::BK) * tc::BK;

@@ -37,6 +37,7 @@ struct TmaArgs {
     long long slice_stride;
     int accumulate;
     int vecC;
+    int raw_hi;                   // leave the raw fp32 tile in place as the hi operand (a tf32 MMA ignores the low 13 bits)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -179,10 +180,15 @@ tc_tn_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int i = 0; i < kIt; ++i) {
                 uint4 h, l;
-                h.x = to_tf32(v[i].x); h.y = to_tf32(v[i].y); h.z = to_tf32(v[i].z); h.w = to_tf32(v[i].w);
+                if (g.raw_hi) {       // hi = the value with its low 13 mantissa bits cleared = what a tf32 MMA reads from raw fp32
+                    h.x = __float_as_uint(v[i].x) & 0xFFFFE000u; h.y = __float_as_uint(v[i].y) & 0xFFFFE000u;
+                    h.z = __float_as_uint(v[i].z) & 0xFFFFE000u; h.w = __float_as_uint(v[i].w) & 0xFFFFE000u;
+                } else {
+                    h.x = to_tf32(v[i].x); h.y = to_tf32(v[i].y); h.z = to_tf32(v[i].z); h.w = to_tf32(v[i].w);
+                }
                 l.x = to_tf32(v[i].x - __uint_as_float(h.x)); l.y = to_tf32(v[i].y - __uint_as_float(h.y));
                 l.z = to_tf32(v[i].z - __uint_as_float(h.z)); l.w = to_tf32(v[i].w - __uint_as_float(h.w));
-                *reinterpret_cast<uint4*>(ab + off[i]) = h;
+                if (!g.raw_hi) *reinterpret_cast<uint4*>(ab + off[i]) = h;
                 *reinterpret_cast<uint4*>(ab + Plan::kRaw + off[i]) = l;
                 if (sum) { csum.x += v[i].x; csum.y += v[i].y; csum.z += v[i].z; csum.w += v[i].w; }
             }
@@ -389,6 +395,7 @@ int tc_gemm_tn_tma(int M, int N, int K, const float* A, int lda, const float* B,
     if (kps == 0) kps = tc::TBK;
     g.k_per_slice = kps;
     g.vecC = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (slice_stride % 4 == 0);
+    g.raw_hi = tc_raw_hi() ? 1 : 0;
     static int wide = -1;
     if (wide < 0) { const char* e = getenv("DPPO_TC_TN_WIDE"); wide = (e && e[0] == '1') ? 1 : 0; }
     if (N > 128 && wide) return tc::launch_tma<256>(mA, mB, A, lda, B, ldb, g, slices, st);
