@@ -355,14 +355,20 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
             const float* src = partial + plan.part_off[l] + (i - plan.w_off[l]);
             const long long rg = plan.region[l];
             const int ns = plan.slices[l];
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
             int k = warp;
+            for (; k + 56 < ns; k += 64) {           // 8 independent 128-B lines in flight per warp
+                a0 += __ldg(src + (size_t)(k + 0) * rg);  a1 += __ldg(src + (size_t)(k + 8) * rg);
+                a2 += __ldg(src + (size_t)(k + 16) * rg); a3 += __ldg(src + (size_t)(k + 24) * rg);
+                a4 += __ldg(src + (size_t)(k + 32) * rg); a5 += __ldg(src + (size_t)(k + 40) * rg);
+                a6 += __ldg(src + (size_t)(k + 48) * rg); a7 += __ldg(src + (size_t)(k + 56) * rg);
+            }
             for (; k + 24 < ns; k += 32) {
                 a0 += __ldg(src + (size_t)(k + 0) * rg);  a1 += __ldg(src + (size_t)(k + 8) * rg);
                 a2 += __ldg(src + (size_t)(k + 16) * rg); a3 += __ldg(src + (size_t)(k + 24) * rg);
             }
             for (; k < ns; k += 8) a0 += __ldg(src + (size_t)k * rg);
-            s = (a0 + a1) + (a2 + a3);
+            s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
         }
         red[warp][lane] = s;
         __syncthreads();
