@@ -91,9 +91,10 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
         if (cfg->gemm_mode == DPPO_GEMM_TF32X3) {
             // tensor-core accumulators truncate on every add: bound the rows one CTA reduces (<= 512, i.e. 64
             // MMA steps); the cross-slice sum in finalize_kernel is round-to-nearest fp32
+            // (+25 % head-room: active_slices() may round the count up to whole waves of the dW grid)
             sl = (cfg->max_rows + 511) / 512;
-            if (sl < 1) sl = 1;
-            if (sl > 512) sl = 512;
+            sl = sl + sl / 4 + 1;
+            if (sl > 640) sl = 640;
         } else {
             if (sl < 1) sl = 1;
             if (sl > kMaxSplitK) sl = kMaxSplitK;
@@ -219,7 +220,19 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
     for (int l = 0; l <= s.L; ++l) {
         int a = s.slices[l];
         if (c->cfg.gemm_mode == DPPO_GEMM_TF32X3) {
-            const int want = (rows + 511) / 512;            // <= 512 rows per TMEM accumulation chain
+            int want = (rows + 511) / 512;                  // <= 512 rows per TMEM accumulation chain
+            // whole waves: the dW grid is tiles x slices CTAs on 2 x 148 slots (two CTAs per SM).  Round the slice count
+            // up to the next count that fills its last wave when that costs <= 25 % more slices (cfg3: 256 -> 296, the
+            // 6-tile layer-1 grid goes from 5.2 to 6.0 waves of 12 % shorter CTAs), then drop slices left without rows.
+            const int in = s.in_dim(l), out = s.out_dim(l);
+            const int tiles = ((in + 127) / 128) * ((out + (out > 64 ? 127 : 63)) / (out > 64 ? 128 : 64));
+            int g = 2 * kPlanSMs, t = tiles;
+            while (t) { const int r = g % t; g = t; t = r; }            // gcd(slots, tiles)
+            const int W = 2 * kPlanSMs / g;
+            const int up = ((want + W - 1) / W) * W;
+            if (up * 4 <= want * 5) want = up;
+            const int kps = (((rows + want - 1) / want + 15) / 16) * 16;
+            want = (rows + kps - 1) / kps;
             if (want < a) a = want;
         } else {
             const int want = (rows + 63) / 64;              // no point slicing below 64 rows per CTA
