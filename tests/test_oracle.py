@@ -282,3 +282,34 @@ def test_categorical_closed_form_grad_equals_autograd(obs_dim, hidden, ncat, B):
     np.testing.assert_allclose(losses, [pl.item(), vl.item(), el.item(), (pl + el + vl).item()], rtol=1e-12)
     np.testing.assert_allclose(grad, t.grad.numpy(), rtol=1e-9, atol=1e-14)
     assert 0.02 < aux["clip_frac"] < 0.98
+
+
+# ------------------------------------------------------------------ epoch / minibatch scheduler restatement
+def test_minibatch_perm_is_a_bijection_property():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 5000), seed=st.integers(0, 2**64 - 1), epoch=st.integers(0, 1000))
+    def check(n, seed, epoch):
+        p = O.minibatch_perm(n, seed, epoch)
+        assert p.shape == (n,) and np.array_equal(np.sort(p), np.arange(n))
+    check()
+    a, b = O.minibatch_perm(4096, 1, 0), O.minibatch_perm(4096, 1, 1)
+    assert (a != b).mean() > 0.99 and abs(np.corrcoef(a, np.arange(4096))[0, 1]) < 0.05
+
+
+def test_update_epochs_whole_buffer_is_the_update_steps_loop():
+    """n_epochs = UPDATE_STEPS, one whole-buffer minibatch, no shuffle == Chief.py:64: UPDATE_STEPS x [loss_grad, Adam]."""
+    T, N, obs, hidden, A = 32, 4, 5, (8,), 2
+    lay = O.make_layout(obs, hidden, A)
+    th_pi, th_old = O.make_params_pair(lay)
+    buf = O.make_buffer(T, N, obs, A)
+    th, m, v, losses = O.update_epochs(th_pi, th_old, buf, 0.99, 0.95, 0.7, lay, 1e-3, n_epochs=3)
+    adv, ret = O.gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], 0.99, 0.95)
+    t2 = th_pi.astype(np.float64); m2 = np.zeros_like(t2); v2 = np.zeros_like(t2)
+    for step in (1, 2, 3):
+        l, g, _ = O.ppo_loss_grad(t2.astype(np.float32), th_old, buf["obs"], buf["act"], adv.reshape(-1), ret.reshape(-1), 0.7, lay)
+        t2, m2, v2 = O.adam_tf(t2.astype(np.float32), g.astype(np.float32), m2, v2, step, 1e-3)
+        np.testing.assert_allclose(losses[step - 1], l, rtol=1e-12)
+    np.testing.assert_array_equal(th, t2)
+    assert losses.shape == (3, 4) and not np.allclose(losses[0], losses[2])
