@@ -163,6 +163,8 @@ int dppo_categorical(dppo_ctx* ctx, int op, const float* logits, const void* arg
  * Adam step numbers are step0, step0+1, ... (step0 = t after increment of the first minibatch).
  * losses_out: device [n_epochs * n_minibatches, 8] (same 8 scalars as dppo_loss_grad) or NULL.
  * grad_out [n_params + 8] holds the last minibatch's (all-reduced) gradient on return.
+ * oldpi is frozen during the call (sync_pis happens in the worker, PPO.py:47): its head outputs are evaluated once
+ * and the rows reused by every minibatch -- the same numbers the reference's in-graph re-evaluation (PPO.py:22) gives.
  * With a communicator every rank must pass the same n_epochs/minibatch_rows/T/N (one exchange per minibatch). */
 int dppo_update_epochs(dppo_ctx* ctx, float* params_pi, const float* params_old, const float* obs, const float* act,
                        const float* rew, const float* predv, const float* done, int T, int N, double gamma,
