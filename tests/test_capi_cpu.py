@@ -147,3 +147,11 @@ def test_param_layout_categorical_matches_oracle(lib, obs, hidden, ncat):
     assert list(offs[:k]) == [e[2] for e in lay.entries]
     c.pd_type = 5
     assert lib.dppo_param_count(C.byref(c)) < 0 and b"pd_type" in lib.dppo_last_error()
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/dppo_b200.h must compile as C99 (no C++-isms, no torch types)."""
+    hdr = os.path.join(ROOT, "include", "dppo_b200.h")
+    subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", hdr], check=True)
+    txt = open(hdr).read()
+    assert "torch" not in txt.lower() and "at::" not in txt and "std::" not in txt
