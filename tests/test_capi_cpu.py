@@ -155,3 +155,35 @@ def test_header_is_plain_c():
     subprocess.run(["gcc", "-x", "c", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", hdr], check=True)
     txt = open(hdr).read()
     assert "torch" not in txt.lower() and "at::" not in txt and "std::" not in txt
+
+
+def test_c_program_links_and_calls_the_abi(lib, tmp_path):
+    """A plain C consumer (what a cgo/JNI/FFI binding compiles down to): link libdppo_b200.so, call the host-only entry
+    points, check the layout numbers and the error path -- no Python, no torch in the process."""
+    from dppo_b200 import _lib
+    src = tmp_path / "consumer.c"
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "dppo_b200.h"
+int main(void) {
+    dppo_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.obs_dim = 376; cfg.act_dim = 17; cfg.n_hidden = 2; cfg.hidden[0] = 256; cfg.hidden[1] = 256;
+    cfg.max_rows = 131072; cfg.gemm_mode = DPPO_GEMM_TF32X3; cfg.pd_type = DPPO_PD_DIAG_GAUSSIAN;
+    cfg.entcoeff = 0.01f; cfg.vcoeff = 0.5f; cfg.clip_param = 0.2f;
+    printf("%d %lld %lld %zu\\n", dppo_version(), (long long)dppo_param_count(&cfg), (long long)dppo_grad_buffer_len(&cfg),
+           dppo_workspace_bytes(&cfg));
+    cfg.pd_type = 9;
+    printf("%lld|%s\\n", (long long)dppo_param_count(&cfg), dppo_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-ldppo_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    ver, n, glen, ws = out[0].split()
+    assert int(ver) >= 100 and int(n) == 171299 and int(glen) == 171307 and int(ws) > 500 * (1 << 20)
+    assert out[1].startswith("-1|") and "pd_type" in out[1]
