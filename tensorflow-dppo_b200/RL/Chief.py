@@ -1,85 +1,81 @@
 # -*- coding: utf-8 -*-
-"""Chief of the reference (/root/reference/Chief.py): waits for rollouts, averages the towers'
-gradients, applies Adam, broadcasts the weights.  Same constructor and methods (`check`, `_train`,
-`_update_local_workers_weight`, `_get_data_size`, `_logs_writer`, `act`).  One Chief object lives
-on every rank (there is no chief rank: every rank applies the same all-reduced update)."""
-from collections import deque
-import sys
+"""The reference's `Chief` (/root/reference/Chief.py) on the sm_100a engine: collect the workers' rollouts, train the
+chief parameters on them UPDATE_STEPS times, hand the new weights back.
 
+Public surface kept: `Chief(scope, parameter_dict, SESS, MEMORY_DICT, COORD, workers)`, `check`, `_train`,
+`_update_local_workers_weight`, `_get_data_size`, `_logs_writer`, `act`.  One Chief object lives on every rank -- there is
+no chief rank: every rank applies the same all-reduced update."""
 import numpy as np
 
 from RL import envs
 from RL.PPO import PPO
 
+# positions inside one pushed batch (Worker.py:94-136): states, actions, advantages, returns, lr multiplier, logs
+_S, _A, _ADV, _RET, _LMUL, _LOGS = range(6)
+# positions inside the logs list (Worker.py:123-133)
+_LOG_MAX_RETURN, _LOG_EPOCH = 2, 8
+
 
 class Chief(object):
     def __init__(self, scope, parameter_dict, SESS, MEMORY_DICT, COORD, workers):
-        env = envs.make(parameter_dict['GAME'], 1)
-        self.ppo = PPO(scope, parameter_dict, env, workers)
-        self.sess = SESS
-        self.MEMORY_DICT = MEMORY_DICT
-        self.workers = workers
-        self.UPDATE_STEPS = parameter_dict['UPDATE_STEPS']
-        self.COORD = COORD
-        self.NUM_WORKERS = parameter_dict['NUM_WORKERS']
-        self.EPOCH_MAX = parameter_dict['EPOCH_MAX']
+        self.sess, self.COORD, self.MEMORY_DICT, self.workers = SESS, COORD, MEMORY_DICT, workers
+        for key in ('UPDATE_STEPS', 'NUM_WORKERS', 'EPOCH_MAX'):
+            setattr(self, key, parameter_dict[key])
+        self.ppo = PPO(scope, parameter_dict, envs.make(parameter_dict['GAME'], 1), workers)
 
+    # ---------------------------------------------------------------------------------------------------------
     def check(self, PUSH_EVENT, UPDATE_EVENT, once=False):
-        """Chief.py:19-28.  `once=True` runs a single pass (one process per GPU drives the loop
-        synchronously instead of parking the chief in a thread)."""
+        """Chief.py:19-28: on every UPDATE_EVENT, if each worker has pushed at least one batch, stop the workers from
+        pushing, train, redistribute the weights and let them continue.  `once=True` handles a single event (one process
+        per GPU drives the loop synchronously instead of parking the chief in a thread)."""
         while not self.COORD.should_stop():
             UPDATE_EVENT.wait()
-            min_data_size, _ = self._get_data_size()
-            if min_data_size >= 1:
+            fewest, _ = self._get_data_size()
+            if fewest > 0:
                 PUSH_EVENT.clear()
-                self._train()
-                self._update_local_workers_weight()
-                PUSH_EVENT.set()
+                try:
+                    self._train()
+                    self._update_local_workers_weight()
+                finally:
+                    PUSH_EVENT.set()
             UPDATE_EVENT.clear()
             if once:
-                break
+                return
+
+    def _drain(self):
+        """Every queued batch of every worker, round-robin over the deques (Chief.py:33-48)."""
+        batches = []
+        while any(self.MEMORY_DICT.values()):
+            batches.extend(list(q.popleft()) for q in self.MEMORY_DICT.values() if q)
+        return batches
 
     def _train(self):
-        data_stack = []
-        _, max_data_size = self._get_data_size()
-        while max_data_size > 0:                                   # Chief.py:33-48: drain every deque
-            for key, value in self.MEMORY_DICT.items():
-                if len(value) > 0:
-                    data_stack.append(list(value.popleft()))
-            _, max_data_size = self._get_data_size()
-        data_stack.sort(key=lambda x: x[5][2], reverse=True)       # Chief.py:51: best max-episode-return first
-
-        feed_dict = {}
-        l_mul = data_stack[0][4]
-        feed_dict[self.ppo.l_mul] = l_mul
-        for i in range(self.NUM_WORKERS):                          # Chief.py:58-63: tower i <- i-th best rollout
-            feed_dict[self.workers[i].ppo.s] = data_stack[i][0]
-            feed_dict[self.workers[i].ppo.act] = data_stack[i][1]
-            feed_dict[self.workers[i].ppo.adv] = data_stack[i][2]
-            feed_dict[self.workers[i].ppo.str] = data_stack[i][3]
-            feed_dict[self.workers[i].ppo.l_mul] = l_mul
-        [self.sess.run(self.ppo.train, feed_dict=feed_dict) for _ in range(self.UPDATE_STEPS)]
-        self._logs_writer(data_stack)
+        ranked = sorted(self._drain(), key=lambda b: b[_LOGS][_LOG_MAX_RETURN], reverse=True)   # Chief.py:51
+        l_mul = ranked[0][_LMUL]
+        feed = {self.ppo.l_mul: l_mul}
+        for worker, batch in zip(self.workers[:self.NUM_WORKERS], ranked):     # tower i <- i-th best rollout, Chief.py:58-63
+            tower = worker.ppo
+            feed.update({tower.s: batch[_S], tower.act: batch[_A], tower.adv: batch[_ADV], tower.str: batch[_RET],
+                         tower.l_mul: l_mul})
+        for _ in range(self.UPDATE_STEPS):                                       # Chief.py:64
+            self.sess.run(self.ppo.train, feed_dict=feed)
+        self._logs_writer(ranked)
 
     def _update_local_workers_weight(self):
-        for worker in self.workers:                                # Chief.py:67-70
-            worker.ppo.pipara.assign(self.ppo.pipara)
+        """Chief.py:67-70: every worker's pi <- the chief's pi."""
+        for w in self.workers:
+            w.ppo.pipara.assign(self.ppo.pipara)
 
     def _get_data_size(self):
-        min_data_size = sys.maxsize
-        max_data_size = -1
-        for key, value in self.MEMORY_DICT.items():
-            min_data_size = min(min_data_size, len(value))
-            max_data_size = max(max_data_size, len(value))
-        return min_data_size, max_data_size
+        """(fewest, most) batches queued by any worker (Chief.py:72-78)."""
+        sizes = [len(q) for q in self.MEMORY_DICT.values()]
+        return (min(sizes), max(sizes)) if sizes else (0, -1)
 
     def _logs_writer(self, data_stack):
-        logs = [item[5] for item in data_stack]
-        localsteps = logs[0][8]
-        if localsteps >= self.EPOCH_MAX:                           # Chief.py:86 hard-codes 500
+        """Stop condition of Chief.py:80-87; the reference hard-codes 500 epochs there, EPOCH_MAX here."""
+        if data_stack[0][_LOGS][_LOG_EPOCH] >= self.EPOCH_MAX:
             self.COORD.request_stop()
 
     def act(self, s):
-        s = np.array([s])
-        action = self.sess.run(self.ppo.ca, {self.ppo.s: s})
-        return action[0][0]
+        """Chief.py:89-92: the action for ONE state."""
+        return self.sess.run(self.ppo.ca, {self.ppo.s: np.asarray(s)[None]})[0][0]
