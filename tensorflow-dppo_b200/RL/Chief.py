@@ -9,6 +9,7 @@ import numpy as np
 
 from RL import envs
 from RL.PPO import PPO
+from dppo_b200.dist import all_ranks_true
 
 # positions inside one pushed batch (Worker.py:94-136): states, actions, advantages, returns, lr multiplier, logs
 _S, _A, _ADV, _RET, _LMUL, _LOGS = range(6)
@@ -31,7 +32,9 @@ class Chief(object):
         while not self.COORD.should_stop():
             UPDATE_EVENT.wait()
             fewest, _ = self._get_data_size()
-            if fewest > 0:
+            # one Chief per rank: _train contains the cross-rank gradient exchange, so every rank must take the same
+            # branch -- train only when EVERY rank has a batch from each of its workers (collective AND)
+            if all_ranks_true(fewest > 0):
                 PUSH_EVENT.clear()
                 try:
                     self._train()

@@ -15,11 +15,14 @@ valueLoss, total_loss, summary_op, gradient, sync_pis`; chief-only `train`; para
 The spellings Worker.py / Chief.py use for the placeholders (`action`, `advantage`,
 `estimatedReturn`, `act`, `str` -- SURVEY D4) are kept as aliases.
 """
+import os
+
 import numpy as np
 import torch
 
 from RL.Model import Model
 from RL.session import Placeholder, Fetch
+from dppo_b200.dist import stable_seed
 
 _ENGINES = {}
 
@@ -67,7 +70,7 @@ class PPO(object):
                                         device=self.device)
         self.pipredv = Fetch(self, 'pipredv')
         self.ca = Fetch(self, 'ca')
-        self._seed = abs(hash(scope)) % (2 ** 31)
+        self._seed = stable_seed(scope, parameter_dict.get('SEED', 0), os.environ.get('RANK', 0))
         self._draws = 0
 
         if scope != "Chief":
@@ -120,6 +123,13 @@ class PPO(object):
         return tower_grads
 
     def _run(self, kinds, feed_dict):
+        lock = getattr(self.backend, 'lock', None)
+        if lock is None:
+            return self._run_locked(kinds, feed_dict)
+        with lock:                       # all PPO objects of a process share ONE engine / workspace
+            return self._run_locked(kinds, feed_dict)
+
+    def _run_locked(self, kinds, feed_dict):
         vals = {}
         be = self.backend
         if any(k in self._LOSS_KINDS for k in kinds):

@@ -6,11 +6,14 @@ Public surface kept: `Worker(scope, parameter_dict, SESS, MEMORY_DICT, COORD)`, 
 reference sets (`env`, `ppo`, `name`, `CUR_EP`, `cur_lr`, `returnAction`, the upper-case hyper-parameters).
 What the target design changes: one replica steps NUM_ENVS environments at once (the engine's [T, N] buffer, one
 column per rollout) and the GAE of Worker.py:82-92 is ONE launch of the CUDA scan (dppo_gae) over all N rollouts."""
+import os
+
 import numpy as np
 import torch
 
 from RL import envs
 from RL.PPO import PPO
+from dppo_b200.dist import stable_seed
 
 # hyper-parameters copied from parameter_dict under their own names (Worker.py:16-27)
 _COPIED_KEYS = ('EPOCH_MAX', 'MAX_EPOCH_STEPS', 'MAX_AC_EXP_RATE', 'MIN_AC_EXP_RATE', 'SCHEDULE', 'GAMMA', 'LAM',
@@ -26,7 +29,8 @@ class Worker(object):
         self.ENV_SAMPLE_ITERATIONS = parameter_dict.get('ENV_SAMPLE_ITERATIONS')      # read, never used
         self.NUM_ENVS = int(parameter_dict.get('NUM_ENVS', 1))
         self.VERBOSE = parameter_dict.get('VERBOSE', True)
-        seed = abs(hash(scope))
+        # stable across processes (str hash() is salted), distinct per rank: ranks must not replay each other's rollouts
+        seed = stable_seed(scope, parameter_dict.get('SEED', 0), os.environ.get('RANK', 0))
         self.env = envs.make(parameter_dict['GAME'], self.NUM_ENVS, seed=seed % 65536)
         self.ppo = PPO(scope, parameter_dict, self.env)
         self.CUR_EP, self.cur_lr, self.returnAction = 0, 1.0, None

@@ -673,9 +673,12 @@ int dppo_update_host(dppo_ctx* c, float* params_pi, const float* params_old, con
         int r0 = 0;
         while (B - r0 > rows_per) { chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = rows_per; r0 += rows_per; }
         int left = B - r0;
+        // every chunk but the last must be a whole number of loss tiles (loss_part is indexed by r0 / kLossTileRows):
+        // only the final chunk may be ragged
         const int q = ((left / 4 + kLossTileRows - 1) / kLossTileRows) * kLossTileRows;
-        if (n_chunks > 0 && q >= 1024 && left - 2 * q > 0) {
-            const int parts[3] = {left - 2 * q, q, q};
+        const int first = ((left - 2 * q + kLossTileRows - 1) / kLossTileRows) * kLossTileRows;
+        if (n_chunks > 0 && q >= 1024 && first > 0 && left - first - q > 0) {
+            const int parts[3] = {first, q, left - first - q};
             for (int i = 0; i < 3; ++i) { chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = parts[i]; r0 += parts[i]; }
         } else {
             chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = left;

@@ -45,3 +45,25 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def all_ranks_true(flag: bool, device=None, group=None) -> bool:
+    """Collective AND of a per-rank decision.  Chief.check (Chief.py:19-28) trains only when every worker queued a
+    batch; across ranks that decision must be unanimous, because _train contains the gradient exchange: a rank that
+    skipped it while the others entered would hang the job (and the parameters would diverge)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(flag)
+    if device is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
+def stable_seed(*parts) -> int:
+    """Process-independent 31-bit seed from strings / ints (python's hash() of a str is salted per process)."""
+    import zlib
+    h = 0
+    for p in parts:
+        h = zlib.crc32(str(p).encode("utf-8"), h)
+    return h & 0x7FFFFFFF

@@ -56,6 +56,10 @@ class DppoEngine:
         self._check(self.lib.dppo_create(C.byref(cfg), self.workspace.data_ptr(), nbytes, C.byref(ctx)))
         self.ctx = ctx
         self.world = 1
+        # a dppo_ctx is not thread-safe (one workspace, one side stream): callers that share an engine between
+        # threads (the reference's Worker.work / Chief.check threads funnel into one session) hold this lock per call
+        import threading
+        self.lock = threading.RLock()
 
     # ------------------------------------------------------------------ helpers
     def _check(self, rc):
