@@ -88,7 +88,7 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
         const int bn = out > 64 ? 128 : 64;
         const int tiles = ((in + 127) / 128) * ((out + bn - 1) / bn);
         int sl = (2 * kPlanSMs) / tiles;
-        if (cfg->gemm_mode == DPPO_GEMM_TF32X3) {
+        if (tc_mode(cfg->gemm_mode)) {
             // tensor-core accumulators truncate on every add: bound the rows one CTA reduces (<= 512, i.e. 64
             // MMA steps); the cross-slice sum in finalize_kernel is round-to-nearest fp32
             // (+25 % head-room: active_slices() may round the count up to whole waves of the dW grid)
@@ -139,6 +139,15 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     for (int l = 0; l < s.L; ++l) w.act_pi[l] = (float*)take(R * s.h[l] * sizeof(float));
     if (cfg->gemm_mode == DPPO_GEMM_TF32X3)
         for (int l = 0; l < s.L; ++l) w.act_bits[l] = (uint32_t*)take((size_t)tc_bits_words((long long)R, s.h[l]) * sizeof(uint32_t));
+    if (cfg->gemm_mode == DPPO_GEMM_FP16X2) {
+        for (int l = 0; l <= s.L; ++l) {
+            const size_t fwd = (size_t)th_image_floats(s.out_dim(l), s.in_dim(l)) * sizeof(float);
+            w.img_fwd_pi[l] = (float*)take(fwd);
+            w.img_fwd_old[l] = (float*)take(fwd);
+            w.img_dx_pi[l] = l > 0 ? (float*)take((size_t)th_image_floats(s.in_dim(l), s.out_dim(l)) * sizeof(float)) : nullptr;
+        }
+        for (int l = 0; l < s.L; ++l) w.act_bits[l] = (uint32_t*)take((size_t)th_bits_words((long long)R, s.h[l]) * sizeof(uint32_t));
+    }
     const size_t hm = (size_t)(s.hmax() > 0 ? s.hmax() : 1);
     w.scratch[0] = (float*)take(R * hm * sizeof(float));
     w.scratch[1] = (float*)take(R * hm * sizeof(float));
@@ -176,6 +185,24 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
             if (int r = bf16_gemm_kk(0, rows, out, in, in0, in1, in, w.wt_pi + s.w_off[l], w.wt_old + s.w_off[l], in, o0, o1,
                                      head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st)) return r;
+            in0 = o0; in1 = o1;
+        }
+        return 0;
+    }
+    if (c->cfg.gemm_mode == DPPO_GEMM_FP16X2) {
+        // persistent fp16-split kernels: weight images (fp16 hi | lo tiles) refreshed from the current parameters
+        if (int r = th_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
+                                   w.img_dx_pi, st)) return r;
+        for (int l = 0; l <= s.L; ++l) {
+            const bool head = (l == s.L);
+            float* o0 = head ? w.out_pi : w.act_pi[l];
+            float* o1 = head ? w.out_old : w.scratch[l & 1];
+            const int in = s.in_dim(l), out = s.out_dim(l);
+            const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
+            const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
+            if (int r = th_gemm(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
+                                head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, 1.0f, st,
+                                head ? nullptr : w.act_bits[l], nullptr)) return r;
             in0 = o0; in1 = o1;
         }
         return 0;
@@ -219,7 +246,7 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
     const NetShape& s = c->shape;
     for (int l = 0; l <= s.L; ++l) {
         int a = s.slices[l];
-        if (c->cfg.gemm_mode == DPPO_GEMM_TF32X3) {
+        if (tc_mode(c->cfg.gemm_mode)) {
             int want = (rows + 511) / 512;                  // <= 512 rows per TMEM accumulation chain
             // whole waves: the dW grid is tiles x slices CTAs on 2 x 148 slots (two CTAs per SM).  Round the slice count
             // up to the next count that fills its last wave when that costs <= 25 % more slices (cfg3: 256 -> 296, the
@@ -262,7 +289,11 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const int H = s.in_dim(s.L);
     const float* head_in = s.L ? w.act_pi[s.L - 1] : obs;
     // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
-    const bool tcore = (c->cfg.gemm_mode == DPPO_GEMM_TF32X3);
+    const bool tcore = tc_mode(c->cfg.gemm_mode);
+    const bool fp16x2 = (c->cfg.gemm_mode == DPPO_GEMM_FP16X2);
+    // the dX operands are 1/B-scaled gradients: bring them to O(1) for the fp16 split (exact power of two, divided out in
+    // the epilogue)
+    const float dx_scale = exp2f(floorf(log2f((float)(B_total > 1 ? B_total : 1))));
     const bool bf16 = (c->cfg.gemm_mode == DPPO_GEMM_BF16);
     // dW_l (+ db_l) into layer l's split-K partial region
     auto dense_dw = [&](int l, const float* x_in, const float* dY) -> int {
@@ -289,6 +320,8 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     // mask = activations of hidden layer l_ - 1 (N_ wide); the tensor-core path reads their sign bitmap instead
     auto dense_dx = [&](int l_, int M_, int N_, int K_, const float* dY, int ldy, const float* W, float* dX,
                         const float* mask) -> int {
+        if (fp16x2) return th_gemm(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_, nullptr, nullptr,
+                                   0, mask, 1, dx_scale, st, nullptr, w.act_bits[l_ - 1]);
         if (tcore) return tc_gemm_kk_img(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_,
                                          nullptr, nullptr, 0, mask, 1, st, nullptr, w.act_bits[l_ - 1]);
         if (bf16) return bf16_gemm_kk(1, M_, N_, K_, dY, nullptr, ldy, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr, 0,
@@ -396,8 +429,9 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     if (int r = make_shape(cfg, &s)) return r;
     DPPO_REQUIRE(cfg->max_rows >= 1, "max_rows=%d must be >= 1", cfg->max_rows);
     DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT || cfg->gemm_mode == DPPO_GEMM_TF32X3 ||
-                     cfg->gemm_mode == DPPO_GEMM_BF16,
-                 "gemm_mode=%d unknown (DPPO_GEMM_FP32_SIMT=0, DPPO_GEMM_TF32X3=1, DPPO_GEMM_BF16=2)", cfg->gemm_mode);
+                     cfg->gemm_mode == DPPO_GEMM_BF16 || cfg->gemm_mode == DPPO_GEMM_FP16X2,
+                 "gemm_mode=%d unknown (DPPO_GEMM_FP32_SIMT=0, DPPO_GEMM_TF32X3=1, DPPO_GEMM_BF16=2, DPPO_GEMM_FP16X2=3)",
+                 cfg->gemm_mode);
     int ndev = 0;
     DPPO_CHECK_CUDA(cudaGetDeviceCount(&ndev));
     DPPO_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d CUDA devices)", cfg->device, ndev);
@@ -795,6 +829,21 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
             DPPO_LAUNCH_CHECK();
         }
         return 0;
+    }
+    if (mode == 96 || mode == 97 || mode == 98) {
+        // persistent fp16-split product (tc_gemm_h.cu): Bt[N,K] is packed into an fp16 hi|lo tile image first (scratch from
+        // the caller's workspace).  96: C = relu?(A.Bt^T + bias); 97: C = (A.Bt^T) * (mask > 0), A pre-scaled by 2^17;
+        // 98: as 96, and bias_out receives the kernel's clock64 time line (bias_out must hold 128 int64)
+        const long long need = th_image_floats(N, K);
+        float* scratch = nullptr;
+        if (c->shape.partial_floats >= need) scratch = c->ws.partial;
+        else if ((long long)c->ws.stage_floats >= need) scratch = c->ws.stage;
+        DPPO_REQUIRE(scratch != nullptr, "dppo_dbg_gemm: the workspace has no %lld-float scratch for the weight image", need);
+        if (int r = th_pack_one(B, scratch, N, K, K, 0, st)) return r;
+        if (mode == 97)
+            return th_gemm(1, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, nullptr, nullptr, 0, mask, 1, 131072.0f, st);
+        return th_gemm(0, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, bias, nullptr, relu, nullptr, 1, 1.0f, st,
+                       nullptr, nullptr, mode == 98 ? reinterpret_cast<long long*>(bias_out) : nullptr);
     }
     if (mode == 48 || mode == 49) {
         // weight-image product (the path the update uses): Bt[N,K] is packed into a smem-tile image first.

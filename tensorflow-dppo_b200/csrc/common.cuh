@@ -216,6 +216,19 @@ int tc_gemm_tn_splitk(int terms, int M, int N, int K, const float* A, int lda, c
 bool tc_tn_tma_supported(const float* A, int lda, const float* B, int ldb);
 int tc_gemm_tn_tma(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float* bias_out,
                    int slices, long long slice_stride, int accumulate, cudaStream_t st);
+// persistent fp16-split tensor-core products (tc_gemm_h.cu, DPPO_GEMM_FP16X2)
+long long th_image_floats(int N, int K);
+long long th_bits_words(long long rows, int N);
+int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
+                   const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
+                   cudaStream_t st);
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st);
+int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
+            float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
+            float a_scale, cudaStream_t st, uint32_t* bits_out0 = nullptr, const uint32_t* bits_in = nullptr,
+            long long* timeline = nullptr);
+// tensor-core gemm modes whose dW runs on the tf32 TMA kernel with the 512-row accumulation bound
+inline bool tc_mode(int gemm_mode) { return gemm_mode == DPPO_GEMM_TF32X3 || gemm_mode == DPPO_GEMM_FP16X2; }
 int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,
               cudaStream_t st);
 int tc_transpose_weights(const NetShape& s, const float* params_pi, const float* head_pi, float* wt_pi,

@@ -1,0 +1,535 @@
+// Persistent tensor-core dense layers on 16-bit operands: tcgen05.mma kind::f16, fp32 accumulation in TMEM (sm_100a).
+//
+// DPPO_GEMM_FP16X2: the forward (NN) and dX (NT) products of /root/reference/Model.py:12-14 and of the auto-diff of
+// PPO.py:46 at fp32 accuracy on the HALF-precision tensor pipe (twice the tf32 rate, half the shared-memory bytes):
+//        x = hi + lo / 2^11,   hi = RN-fp16(x),  lo = RN-fp16((x - hi) * 2^11)          (11 + 11 significand bits,
+//        A.B ~= A_hi.B_hi + (A_lo.B_hi + A_hi.B_lo) / 2^11                                the same 22 as the tf32 split)
+// The 2^11 pre-scale keeps `lo` inside fp16's normal range, and the correction products live in their own TMEM
+// accumulator anyway (the tensor core truncates on every fp32 add: DESIGN.md, precision), so the scale costs nothing.
+// Operands whose magnitude is far from 1 (the 1/B-scaled gradients of the dX products) are multiplied by a power of two
+// (`a_scale`) on their way into shared memory and the result is scaled back in the epilogue.  fp16 range: |x * a_scale|
+// must stay below 65504 (observations / activations / weights of a working policy are; DESIGN.md states the bound).
+//
+// What is new against tc_gemm.cu, whose one-tile-per-CTA kernels leave the tensor pipe idle during every prologue and
+// epilogue (45 % of their time at cfg3):
+//   * persistent CTAs (grid = #SMs) walk output tiles; the operand rings run straight across tile boundaries;
+//   * the epilogue has its own 8 warps and drains TMEM -> registers -> a swizzled shared-memory staging buffer in two
+//     128-column phases, releases TMEM as soon as the last column is read, and only then streams the second phase to
+//     HBM: the next tile's MMAs overlap the write-out (all 512 TMEM columns are one 128x256 tile's main + correction
+//     accumulators, so TMEM itself cannot be double-buffered);
+//   * separate rings for the activation operand (2 slots, filled by 8 mover warps: LDG fp32 -> fp16 hi/lo -> swizzled
+//     st.shared, 3 k-blocks in flight in registers) and for the weight operand (4 slots, ONE cp.async.bulk of a ready-made
+//     tile image per k-block), so the weight stream can run 3 k-blocks ahead;
+//   * ReLU sign bitmaps are plain row-major bit matrices (1 bit / activation), written by the forward epilogue and read by
+//     the dX epilogue of the same width.
+// Warps: 0-7 movers | 8 TMEM owner + MMA issuer (one thread) | 9 weight-image producer (one thread) | 10-17 epilogue.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace dppo {
+namespace th {
+
+using namespace tc;
+
+constexpr int kMoverWarps = 8;
+constexpr int kMoverThreads = kMoverWarps * 32;
+constexpr int kMmaWarp = kMoverWarps;
+constexpr int kProdWarp = kMoverWarps + 1;
+constexpr int kEpiWarp0 = kMoverWarps + 2;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;      // 576
+constexpr int kKB = 32;                                      // reduction elements per k-block: 32 fp16 = one 64-B swizzle row
+constexpr int kASlots = 2, kBSlots = 4;
+constexpr int kPrefetch = 3;                                 // activation k-blocks in flight per mover thread
+constexpr int kImgReplicas = 8;                              // copies of every weight image (spreads the hot L2 lines)
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+
+enum { EPI_NN = 0, EPI_NT = 1 };
+
+struct HArgs {
+    const float* A[2]; const uint8_t* Bimg[2]; float* C[2]; const float* bias[2];
+    const float* mask;                 // NT: fp32 mask [M,N] (row stride ldc), C *= (mask > 0); used when bits_in == nullptr
+    const uint32_t* bits_in;           // NT: ReLU sign bitmap [M, bits_wpr]
+    uint32_t* bits_out[2];             // NN: sign bitmap of the result (nullable per net)
+    int M, N, K, lda, ldc;
+    int tiles_n, nets, relu, vecA, vecC, bits_wpr;
+    float a_scale, out_scale;          // powers of two: operand pre-scale and its inverse
+    long long img_replica_bytes;
+    long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_timeline.py)
+};
+
+template <int BN>
+struct HPlan {
+    static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
+    static constexpr int kASlot = 2 * kAHalf;
+    static constexpr int kBHalf = BN * 64;
+    static constexpr int kBSlot = 2 * kBHalf;
+    static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
+    static constexpr int kPhases = BN / kPhaseCols;
+    static constexpr int kStaging = BM * kPhaseCols * 4;
+    static constexpr int kBOff = kASlots * kASlot;
+    static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
+    static constexpr int kBarOff = kStgOff + kStaging;
+    static constexpr int kBytes = kBarOff + 256 + 1024;
+    static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
+};
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = f32, A = B = fp16 (format 0), both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// two fp32 -> packed fp16 hi pair and packed fp16 lo pair (lo pre-scaled by 2^11)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---- activation movers: one k-block = 128 rows x 32 elements = 512 units of 8 elements, two per thread ----------------
+struct MoverRegs { float4 v[2][2]; };
+
+__device__ __forceinline__ void mover_load(MoverRegs& r, const float* __restrict__ A, int lda, int m0, int M, int k0, int K,
+                                           int vec, int tid) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (tid >> 2) + j * 64, c = tid & 3;
+        const int m = m0 + row, k = k0 + c * 8;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (m < M && k < K) {
+            const float* p = A + (size_t)m * lda + k;
+            if (vec && k + 7 < K) {
+                a = __ldg(reinterpret_cast<const float4*>(p));
+                b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            } else {
+                float t[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] = (k + e < K) ? __ldg(p + e) : 0.f;
+                a = make_float4(t[0], t[1], t[2], t[3]); b = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        }
+        r.v[j][0] = a; r.v[j][1] = b;
+    }
+}
+
+__device__ __forceinline__ void mover_store(const MoverRegs& r, uint8_t* hi_tile, uint8_t* lo_tile, float s, int tid) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (tid >> 2) + j * 64, c = tid & 3;
+        const uint32_t off = (uint32_t)row * 64u + (uint32_t)((c ^ ((row >> 1) & 3)) << 4);     // SWIZZLE_64B
+        const float4 a = r.v[j][0], b = r.v[j][1];
+        uint4 h, l;
+        split2(a.x * s, a.y * s, h.x, l.x); split2(a.z * s, a.w * s, h.y, l.y);
+        split2(b.x * s, b.y * s, h.z, l.z); split2(b.z * s, b.w * s, h.w, l.w);
+        *reinterpret_cast<uint4*>(hi_tile + off) = h;
+        *reinterpret_cast<uint4*>(lo_tile + off) = l;
+    }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int total_tiles) {
+    using P = HPlan<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + P::kBOff;
+    uint8_t* stg = smem + P::kStgOff;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + P::kBarOff);
+    uint64_t* empty_a = full_a + kASlots;
+    uint64_t* full_b = empty_a + kASlots;
+    uint64_t* empty_b = full_b + kBSlots;
+    uint64_t* acc_full = empty_b + kBSlots;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (g.K + kKB - 1) / kKB;
+    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per_cta;
+    const int t_end = min(total_tiles, t_begin + per_cta);
+    const int my_tiles = max(0, t_end - t_begin);
+    const long long total_it = (long long)my_tiles * nkb;
+
+    if (tid == 0) {
+        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], kMoverThreads); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < kBSlots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
+        fence_barrier_init();
+    }
+    constexpr uint32_t kTmemCols = 2 * BN;          // [0,BN) main (hi.hi), [BN,2BN) correction (lo.hi + hi.lo, scaled 2^11)
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t -> (m-tile, net, n-tile): the two nets of one row block are neighbours, the second finds the rows in L2
+    auto decode = [&](int t, int& mt, int& net, int& nt) {
+        nt = t % g.tiles_n; t /= g.tiles_n;
+        net = t % g.nets; mt = t / g.nets;
+    };
+
+    if (warp < kMoverWarps) {
+        // ================= activation movers =================
+        MoverRegs ra[kPrefetch];
+        auto issue = [&](MoverRegs& r, long long it) {
+            int mt, net, nt;
+            decode(t_begin + (int)(it / nkb), mt, net, nt);
+            mover_load(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * kKB, g.K, g.vecA, tid);
+        };
+#pragma unroll
+        for (int j = 0; j < kPrefetch; ++j)
+            if (j < total_it) issue(ra[j], j);
+        const float s = g.a_scale;
+        for (long long it0 = 0; it0 < total_it; it0 += kPrefetch) {
+#pragma unroll
+            for (int j = 0; j < kPrefetch; ++j) {
+                const long long it = it0 + j;
+                if (it < total_it) {
+                    const int sa = (int)(it % kASlots);
+                    mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
+                    uint8_t* slot = a_ring + sa * P::kASlot;
+                    mover_store(ra[j], slot, slot + P::kAHalf, s, tid);
+                    fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
+                    mbar_arrive(&full_a[sa]);
+                    if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
+                }
+            }
+        }
+    } else if (warp == kProdWarp) {
+        // ================= weight-image producer (one thread) =================
+        if (lane == 0) {
+            for (long long it = 0; it < total_it; ++it) {
+                int mt, net, nt;
+                decode(t_begin + (int)(it / nkb), mt, net, nt);
+                const int kb = (int)(it % nkb);
+                const int sb = (int)(it % kBSlots);
+                mbar_wait(&empty_b[sb], (uint32_t)(((it / kBSlots) & 1) ^ 1));
+                const uint8_t* img = g.Bimg[net] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
+                                     ((size_t)nt * nkb + (size_t)kb) * P::kBSlot;
+                mbar_arrive_expect_tx(&full_b[sb], (uint32_t)P::kBSlot);
+                bulk_copy_g2s(b_ring + sb * P::kBSlot, img, (uint32_t)P::kBSlot, &full_b[sb]);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BN);
+            const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+            long long it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));          // the epilogue has read tile i-1 out of TMEM
+                tc_fence_after();
+                if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 0] = clock64();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int sa = (int)(it % kASlots), sb = (int)(it % kBSlots);
+                    mbar_wait(&full_a[sa], (uint32_t)((it / kASlots) & 1));
+                    mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
+                    tc_fence_after();
+                    const uint32_t a_hi = a_base + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
+                    const uint32_t b_hi = b_base + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
+#pragma unroll
+                    for (int k = 0; k < kKB / 16; ++k) {
+                        const uint64_t da_hi = make_sdesc(a_hi + k * 32, 0, 512, kLayoutSW64);
+                        const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
+                        const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
+                        const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
+                        umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                        umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                        umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_a[sa]);         // the slots may be refilled once these MMAs retire
+                    umma_commit(&empty_b[sb]);
+                }
+                umma_commit(acc_full);                 // accumulators of tile i complete
+                if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 1] = clock64();
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ================= epilogue warps =================
+        constexpr int PC = P::kPhaseCols;
+        constexpr int kRowBytes = PC * 4;
+        constexpr int kDrainCols = PC / 2;                        // columns each of the two warps of a lane quarter drains
+        constexpr int kLanesPerRow = PC / 4;                      // float4 lanes covering one staged row
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;
+        constexpr int kIters = (BM / kEpiWarps) / kRowsPerIter;   // 16 rows per warp
+        const int ew = warp - kEpiWarp0;
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int ch = ew >> 2;
+        const int lr = lane / kLanesPerRow, cl = lane % kLanesPerRow;
+        const float oscale = g.out_scale;
+        for (int i = 0; i < my_tiles; ++i) {
+            int mt, net, nt;
+            decode(t_begin + i, mt, net, nt);
+            float* __restrict__ C = g.C[net];
+            const float* __restrict__ bias = g.bias[net];
+            uint32_t* __restrict__ bits_out = (EPI == EPI_NN) ? g.bits_out[net] : nullptr;
+            mbar_wait(acc_full, (uint32_t)(i & 1));
+            tc_fence_after();
+            if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 2] = clock64();
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int p = 0; p < P::kPhases; ++p) {
+                epi_bar();                                         // the staging buffer has been written out
+                // ---- drain: thread = accumulator row; main + correction / 2^11, scaled back, to the staging tile ----
+                const int r = q * 32 + lane;
+#pragma unroll 1
+                for (int cb = 0; cb < kDrainCols; cb += 32) {
+                    const int col = p * PC + ch * kDrainCols + cb;
+                    uint32_t v[32], w2[32];
+                    tmem_ld32(acc + (uint32_t)col, v);
+                    tmem_ld32(acc + (uint32_t)(BN + col), w2);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 o;
+                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0])) * oscale;
+                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1])) * oscale;
+                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2])) * oscale;
+                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3])) * oscale;
+                        const int c = (ch * kDrainCols + cb) / 4 + j4;               // 16-B chunk of the staged row
+                        const int pc = (c & ~7) | ((c ^ r) & 7);                      // XOR swizzle: conflict-free both ways
+                        *reinterpret_cast<float4*>(stg + r * kRowBytes + pc * 16) = o;
+                    }
+                }
+                if (p == P::kPhases - 1) {                         // every column of this tile is out of TMEM
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 3] = clock64();
+                }
+                // NT: the mask words of this warp's rows are requested before the barrier
+                uint32_t mw[kIters];
+                if (EPI == EPI_NT && g.bits_in) {
+#pragma unroll
+                    for (int it = 0; it < kIters; ++it) {
+                        const int m = mt * BM + ew * 16 + it * kRowsPerIter + lr;
+                        const int n = nt * BN + p * PC + cl * 4;
+                        mw[it] = (m < g.M && n < g.N) ? __ldg(g.bits_in + (size_t)m * g.bits_wpr + (n >> 5)) : 0u;
+                    }
+                }
+                epi_bar();                                         // staging complete
+                // ---- write-out: one staged row (or two) per warp instruction, coalesced ----
+                const int n = nt * BN + p * PC + cl * 4;
+                const int nv = min(4, g.N - n);
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (EPI == EPI_NN && bias) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < nv) bv[e] = __ldg(bias + n + e);
+                }
+#pragma unroll
+                for (int it = 0; it < kIters; ++it) {
+                    const int rr = ew * 16 + it * kRowsPerIter + lr;
+                    const int m = mt * BM + rr;
+                    const int pc = (cl & ~7) | ((cl ^ rr) & 7);
+                    const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * kRowBytes + pc * 16);
+                    float x[4] = {t4.x, t4.y, t4.z, t4.w};
+                    uint32_t nib = 0u;
+                    const bool ok = (m < g.M) && (nv > 0);
+                    if (EPI == EPI_NN) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float y = x[e] + bv[e];
+                            x[e] = g.relu ? fmaxf(y, 0.f) : y;
+                            if (ok && e < nv && x[e] > 0.f) nib |= 1u << e;
+                        }
+                        if (bits_out) {                            // warp-uniform
+                            uint32_t w = nib << (4 * (lane & 7));
+                            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                            if ((lane & 7) == 0 && m < g.M && n < g.N) bits_out[(size_t)m * g.bits_wpr + (n >> 5)] = w;
+                        }
+                    } else {
+                        if (g.bits_in) {
+                            const uint32_t b4 = mw[it] >> (4 * (lane & 7));
+                            x[0] = (b4 & 1u) ? x[0] : 0.f; x[1] = (b4 & 2u) ? x[1] : 0.f;
+                            x[2] = (b4 & 4u) ? x[2] : 0.f; x[3] = (b4 & 8u) ? x[3] : 0.f;
+                        } else if (g.mask && ok) {
+                            const float* mp = g.mask + (size_t)m * g.ldc + n;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv) x[e] = (__ldg(mp + e) > 0.f) ? x[e] : 0.f;
+                        }
+                    }
+                    if (ok) {
+                        float* cp = C + (size_t)m * g.ldc + n;
+                        if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv) cp[e] = x[e];
+                        }
+                    }
+                }
+            }
+            if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 4] = clock64();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---- weight images: per (n-tile, k-block) the fp16 hi tile then the lo tile, K-major SWIZZLE_64B, exactly as the MMA
+// reads them from shared memory -> one cp.async.bulk per k-block ----
+struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn; };
+struct HImgPlan { int n; HImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
+
+__global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total_units; u += (long long)gridDim.x * blockDim.x) {
+        int i = 0;
+        while (u >= p.unit_end[i]) ++i;
+        const HImgEntry e = p.e[i];
+        long long r_ = u - (i ? p.unit_end[i - 1] : 0);
+        const int c = (int)(r_ % 4); r_ /= 4;                  // 16-B chunk (8 fp16) of the 64-B row
+        const int r = (int)(r_ % e.bn); r_ /= e.bn;           // row within the tile
+        const int kbs = (e.K + kKB - 1) / kKB;
+        const int kb = (int)(r_ % kbs), nt = (int)(r_ / kbs);
+        const int n = nt * e.bn + r, k0 = kb * kKB + c * 8;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = k0 + q;
+            v[q] = (n < e.N && k < e.K) ? (e.transposed ? __ldg(e.src + (size_t)k * e.ld + n) : __ldg(e.src + (size_t)n * e.ld + k)) : 0.f;
+        }
+        uint4 h, l;
+        split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
+        const size_t ntiles = (size_t)((e.N + e.bn - 1) / e.bn);
+        const size_t half = (size_t)e.bn * 64;
+        const size_t replica_bytes = ntiles * kbs * 2 * half;
+        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+#pragma unroll
+        for (int rep = 0; rep < kImgReplicas; ++rep) {
+            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * half;
+            *reinterpret_cast<uint4*>(tile + off) = h;
+            *reinterpret_cast<uint4*>(tile + half + off) = l;
+        }
+    }
+}
+
+static inline int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, int EPI>
+static int launch_h(HArgs& g, cudaStream_t st) {
+    using P = HPlan<BN>;
+    g.tiles_n = (g.N + BN - 1) / BN;
+    const int tiles_m = (g.M + BM - 1) / BM;
+    const long long total = (long long)tiles_m * g.tiles_n * g.nets;
+    DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
+    static PerDeviceOnce configured;
+    if (configured.need())
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
+    ProfScope ps(KK_TC_GEMM, st);
+    h_gemm_kernel<BN, EPI><<<grid, kThreads, P::kBytes, st>>>(g, (int)total);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace th
+
+static inline int th_bn_for(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
+// bytes of one replica of the weight image of B[N,K]
+static long long th_image_replica_bytes(int N, int K) {
+    const int bn = th_bn_for(N);
+    return (long long)((N + bn - 1) / bn) * ((K + th::kKB - 1) / th::kKB) * bn * 64 * 2;
+}
+long long th_image_floats(int N, int K) { return th::kImgReplicas * th_image_replica_bytes(N, K) / 4; }
+long long th_bits_words(long long rows, int N) { return rows * ((N + 31) / 32); }
+
+// Every weight image of one update: forward images of pi (and oldpi) from W_l^T, dX images of pi from W_l
+// (img_* are arrays of L+1 device pointers; nullptr = skip).
+int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
+                   const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
+                   cudaStream_t st) {
+    th::HImgPlan p; p.n = 0;
+    long long units = 0;
+    auto add = [&](const float* src, float* dst, int N, int K, int ld, int transposed) {
+        if (!src || !dst) return;
+        th::HImgEntry& e = p.e[p.n];
+        e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed;
+        e.bn = th_bn_for(N);
+        units += (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
+        p.unit_end[p.n++] = units;
+    };
+    for (int l = 0; l <= s.L; ++l) {
+        const int in = s.in_dim(l), out = s.out_dim(l);
+        const float* w_pi = (l == s.L) ? head_pi : params_pi + s.w_off[l];
+        const float* w_old = (l == s.L) ? head_old : (params_old ? params_old + s.w_off[l] : nullptr);
+        add(w_pi, img_fwd_pi[l], out, in, out, 1);                 // forward: B[n=out][k=in] = W[k][n]
+        add(params_old ? w_old : nullptr, img_fwd_old[l], out, in, out, 1);
+        if (l > 0) add(w_pi, img_dx_pi[l], in, out, out, 0);      // dX:      B[n=in][k=out] = W[n][k]
+    }
+    if (p.n == 0) return 0;
+    int grid = (int)((units + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_MISC, st);
+    th::pack_images_h_kernel<<<grid, 256, 0, st>>>(p, units);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// one image from a [N,K] (transposed = 0) or [K,N] (transposed = 1) matrix with row stride ld
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st) {
+    th::HImgPlan p; p.n = 1;
+    th::HImgEntry& e = p.e[0];
+    e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N);
+    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
+    p.unit_end[0] = units;
+    int grid = (int)((units + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    ProfScope ps(KK_MISC, st);
+    th::pack_images_h_kernel<<<grid, 256, 0, st>>>(p, units);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// C[M,N] = epi(A[M,K] . B^T) with B given as fp16 hi/lo weight images (th_pack_images).  nets = 1 or 2 products sharing
+// shapes.  epi_nt = 0: C = relu?(acc + bias), optional sign bitmap of C to bits_out0 (net 0 only);
+// epi_nt = 1: C = acc * mask, mask = bits_in (sign bitmap) or the fp32 matrix `mask`.
+// a_scale: power of two applied to A on its way into shared memory (and divided out of the result).
+int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
+            float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
+            float a_scale, cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline) {
+    if (M == 0) return 0;
+    th::HArgs g{};
+    g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = reinterpret_cast<const uint8_t*>(img0); g.Bimg[1] = reinterpret_cast<const uint8_t*>(img1);
+    g.C[0] = C0; g.C[1] = C1; g.bias[0] = bias0; g.bias[1] = bias1; g.mask = mask; g.bits_in = bits_in;
+    g.bits_out[0] = bits_out0; g.bits_out[1] = nullptr;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldc = ldc; g.nets = nets; g.relu = relu;
+    g.bits_wpr = (N + 31) / 32;
+    g.a_scale = a_scale; g.out_scale = 1.0f / a_scale;
+    g.img_replica_bytes = th_image_replica_bytes(N, K);
+    g.timeline = timeline;
+    g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
+    g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
+    const int bn = th_bn_for(N);
+    if (epi_nt) {
+        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, st);
+        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, st);
+        return th::launch_h<64, th::EPI_NT>(g, st);
+    }
+    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, st);
+    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, st);
+    return th::launch_h<64, th::EPI_NN>(g, st);
+}
+
+}  // namespace dppo

@@ -9,7 +9,7 @@ MAX_HIDDEN = 8
 NUM_LOSS_SLOTS = 8
 NCCL_UNIQUE_ID_BYTES = 128
 GAE_REFERENCE, GAE_STANDARD = 0, 1
-GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_BF16 = 0, 1, 2
+GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_BF16, GEMM_FP16X2 = 0, 1, 2, 3
 PD_DIAG_GAUSSIAN, PD_CATEGORICAL = 0, 1
 
 

@@ -308,9 +308,10 @@ class DppoEngine:
         return {name: (int(cnt[i]), float(ms[i])) for i, name in enumerate(L.PROFILE_KINDS)}
 
     # ------------------------------------------------------------------ unit-test hook
-    def dbg_gemm(self, mode, A, B, M, N, K, bias=None, mask=None, relu=False, want_bias_out=False):
+    def dbg_gemm(self, mode, A, B, M, N, K, bias=None, mask=None, relu=False, want_bias_out=False, aux_out=None):
+        """aux_out: a caller-provided tensor passed in the bias_out slot (mode 98: int64[128] kernel time line)."""
         Cm = torch.empty(M, N, dtype=torch.float32, device=self.device)
-        bo = torch.empty(N, dtype=torch.float32, device=self.device) if want_bias_out else None
+        bo = torch.empty(N, dtype=torch.float32, device=self.device) if want_bias_out else aux_out
         self._check(self.lib.dppo_dbg_gemm(self.ctx, mode, M, N, K, self._dev(A, None, "A"), self._dev(B, None, "B"),
                                            Cm.data_ptr(), bias.data_ptr() if bias is not None else None,
                                            mask.data_ptr() if mask is not None else None, int(relu),

@@ -929,3 +929,40 @@ def test_tc_planes_gemm(M, N, K):
     assert rel_err(got, np.maximum(ref + bias, 0)) < 6e-6, "NN epilogue, planes out"   # hi + lo loses < 2^-22
     got = eng.dbg_gemm(83, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
     assert rel_err(got, ref * (mask > 0)) < 6e-6, "NT epilogue, planes out"
+
+
+# ------------------------------------------------------------------------------- persistent fp16-split kernels (gemm_mode 3)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (256, 256, 64), (1000, 256, 376), (777, 35, 256), (130, 128, 100),
+                                   (4096, 256, 256), (20000, 256, 376), (129, 200, 33), (300, 64, 17), (5000, 1024, 1024)])
+def test_h_gemm_fp16_split(M, N, K):
+    """tc_gemm_h.cu through dppo_dbg_gemm: persistent tcgen05 kind::f16 product with the 2-term fp16 split vs an fp64
+    product, forward epilogue (bias + ReLU) and dX epilogue (fp32 mask, operand pre-scaled by 2^17)."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    eng = _engine(376, (256, 256), 17, max(M, 4096), gemm_mode=1)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = (rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = A.astype(np.float64) @ Bt.astype(np.float64).T + bias
+    got = eng.dbg_gemm(96, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(ref, 0)) < 2e-6
+    mask = rng.standard_normal((M, N)).astype(np.float32)
+    G = (A / 131072.0).astype(np.float32)                 # 1/B-scaled gradients, as the dX products see them
+    ref2 = (G.astype(np.float64) @ Bt.astype(np.float64).T) * (mask > 0)
+    got2 = eng.dbg_gemm(97, dev(G), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    assert rel_err(got2, ref2) < 2e-6
+
+
+@pytest.mark.parametrize("name,T,N,obs,hidden,A", CASES)
+def test_loss_grad_vs_oracle_fp16x2(name, T, N, obs, hidden, A):
+    """The whole tower on the persistent fp16-split kernels (forward, dX; dW on the TMA-fed tf32 kernel), 1e-5 bar."""
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]; B = T * N
+    eng = _engine(obs, hidden, A, B, gemm_mode=3)
+    losses, g = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(c["buf"]["obs"]), dev(c["act"]),
+                              dev(c["adv"]), dev(c["ret"]), c["l_mul"])
+    l_ref, g_ref, aux = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], c["buf"]["obs"], c["act"], c["adv"], c["ret"],
+                                        c["l_mul"], lay)
+    np.testing.assert_allclose(losses.cpu().numpy()[:4], l_ref, rtol=TOL, atol=TOL)
+    errs = per_tensor_rel_err(g.cpu().numpy()[:lay.n_params], g_ref, lay)
+    print(name, "fp16x2 per-tensor rel err", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < (3e-5 if max(hidden or (0,)) >= 1024 else TOL), errs
