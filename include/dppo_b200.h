@@ -34,6 +34,7 @@ extern "C" {
 #define DPPO_MAX_HIDDEN 8
 #define DPPO_NUM_LOSS_SLOTS 8          /* policy, value, entropy, total, mean_kl, clip_frac, vclip_frac, rows */
 #define DPPO_NCCL_UNIQUE_ID_BYTES 128
+#define DPPO_PEER_HANDLE_BYTES 128     /* two cudaIpcMemHandle_t: exchange buffer, arrival flags */
 
 /* GAE modes (Worker.py:82-92) */
 #define DPPO_GAE_REFERENCE 0   /* mask 1-done[t+1]; bootstrap predv[T-1]*(1-done[T-1]) -- as written */
@@ -121,6 +122,14 @@ int dppo_comm_unique_id(void* id_out_128_bytes);
 int dppo_comm_init(dppo_ctx* ctx, int rank, int world, const void* id_128_bytes);
 int dppo_comm_destroy(dppo_ctx* ctx);
 int dppo_allreduce_avg(dppo_ctx* ctx, float* buf, int64_t n, void* stream);
+/* The same tower mean without NCCL, for hosts that bring their own bootstrap: the fused peer-memory exchange of
+ * dppo_update / dppo_update_host / dppo_update_epochs (one kernel: arrive/wait over NVLink, mean in rank order, Adam --
+ * PPO.py:53,55-65) only needs every rank's two cudaIpc handles.  export allocates this rank's exchange buffers and writes
+ * DPPO_PEER_HANDLE_BYTES to handle_out; the host gathers the blobs of all ranks in rank order by any means (file, pipe,
+ * MPI, a socket) and passes the world * DPPO_PEER_HANDLE_BYTES bytes to import.  Ranks may share one device
+ * (two processes on one GPU), which is how the exchange kernel is tested on a single-GPU box.  2 <= world <= 16. */
+int dppo_comm_peer_export(dppo_ctx* ctx, int rank, int world, void* handle_out);
+int dppo_comm_peer_import(dppo_ctx* ctx, const void* all_handles);
 
 /* replaces Optimizer.apply_gradients (PPO.py:20,53): tf.train.AdamOptimizer step in TF-1.x
  * form, lr = LEARNING_RATE*l_mul, step = t after increment (1-based). */

@@ -708,6 +708,50 @@ def sanitize_rows(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, h
     return act, ret, edited
 
 
+def sanitize_for_update(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout, hp: HParams = HParams(),
+                        margin=1e-4, relu_margin=2e-5, seed=97):
+    """Branch-robust inputs for the WHOLE-UPDATE entry points (dppo_update / dppo_update_host), which compute
+    adv / ret themselves from rew / predv / done: those two are therefore fixed here and only the synthetic obs / act
+    rows are edited.  A row is resampled until it is (i) not within relu_margin of a ReLU switch of pi
+    (sanitize_obs), (ii) not within margin of a ratio-clip switch (new action row), (iii) not within margin of a
+    value-clip / max switch (new observation row: predv is an independent input of the synthetic buffer, so v and
+    v_old move and the GAE outputs do not).  Same criteria as sanitize_rows.  Returns (obs, act, n_edited)."""
+    rng = np.random.default_rng(seed)
+    obs = np.array(obs, np.float32, copy=True)
+    act = np.array(act, np.float32, copy=True)
+    ret = np.asarray(ret, np.float64).reshape(-1)
+    c = hp.CLIP_PARAM * l_mul
+    p = unflatten(np.asarray(theta_pi, np.float64), lay)
+    rows = np.arange(obs.shape[0]); edited = 0
+    for _ in range(200):
+        o = obs[rows].astype(np.float64)
+        h = o; bad_relu = np.zeros(len(rows), bool)
+        for l in range(len(lay.hidden)):
+            z = h @ p[f"W{l + 1}"] + p[f"b{l + 1}"]
+            bad_relu |= (np.abs(z) < relu_margin).any(axis=1)
+            h = np.maximum(z, 0)
+        v, flat, _ = mlp_forward(theta_pi, obs[rows], lay)
+        v_old, flat_old, _ = mlp_forward(theta_old, obs[rows], lay)
+        a64 = act[rows].astype(np.float64); r64 = ret[rows]
+        ratio = np.exp(dg_logp(flat, a64) - dg_logp(flat_old, a64))
+        bad_r = (np.abs(ratio - (1 - c)) < margin) | (np.abs(ratio - (1 + c)) < margin)
+        dv = v - v_old
+        edge = np.abs(np.abs(dv) - c) < margin
+        vclip = v_old + np.clip(dv, -c, c)
+        vf1 = np.square(v - r64); vf2 = np.square(vclip - r64)
+        on_far_side = np.sign(dv) * (v_old - r64) > 0.5
+        bad_v = (edge & ~on_far_side) | ((np.abs(dv) > c) & ~edge & (np.abs(vf1 - vf2) < margin * (1 + vf1)))
+        bad_obs = bad_relu | bad_v
+        bad = bad_obs | bad_r
+        if not bad.any():
+            return obs, act, edited
+        edited += int(bad.sum())
+        obs[rows[bad_obs]] = rng.standard_normal((int(bad_obs.sum()), obs.shape[1])).astype(np.float32)
+        act[rows[bad_r]] = rng.standard_normal((int(bad_r.sum()), act.shape[1])).astype(np.float32)
+        rows = rows[bad]
+    raise RuntimeError("sanitize_for_update did not converge")
+
+
 def make_case(T, N, obs_dim, hidden, act_dim, seed=1234, l_mul=0.7, trunk_std=1.0, head_std=0.1, delta=0.02,
               hp: HParams = HParams(), pd="gauss"):
     """Frozen synthetic update case: buffer, GAE'd advantages/returns (oracle),

@@ -55,6 +55,8 @@ int peer_allreduce_adam(dppo_ctx* ctx, float* params, float* m, float* v, int st
 int comm_unique_id(void* out);
 int comm_init(dppo_ctx* ctx, int rank, int world, const void* id_bytes);
 int comm_destroy(dppo_ctx* ctx);
+int comm_peer_export(dppo_ctx* ctx, int rank, int world, void* handle_out);
+int comm_peer_import(dppo_ctx* ctx, const void* all_handles);
 int allreduce_avg(dppo_ctx* ctx, float* buf, int64_t n, cudaStream_t st);
 
 int make_shape(const dppo_config* cfg, NetShape* s) {
@@ -351,7 +353,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
 static int reduce_and_apply(dppo_ctx* c, const int* active, int rows, float* params_pi, float* adam_m, float* adam_v,
                             int step, float lr, float beta1, float beta2, float eps, float* grad_out, cudaStream_t st) {
     const int tiles = (rows + kLossTileRows - 1) / kLossTileRows;
-    if (c->nccl_comm && c->world > 1 && peer_available(c)) {
+    if (c->world > 1 && peer_available(c)) {
         // NVLink peer path: the rank's gradient goes straight into its exchange buffer; ONE kernel then averages over
         // the ranks through peer loads and applies Adam (PPO.py:53,55-65)
         if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
@@ -637,6 +639,16 @@ int dppo_comm_init(dppo_ctx* c, int rank, int world, const void* id) {
     CTX_GUARD(c);
     DPPO_REQUIRE(id != nullptr, "dppo_comm_init: null id");
     return comm_init(c, rank, world, id);
+}
+int dppo_comm_peer_export(dppo_ctx* c, int rank, int world, void* handle_out) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(handle_out != nullptr, "dppo_comm_peer_export: null buffer");
+    return comm_peer_export(c, rank, world, handle_out);
+}
+int dppo_comm_peer_import(dppo_ctx* c, const void* all_handles) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(all_handles != nullptr, "dppo_comm_peer_import: null buffer");
+    return comm_peer_import(c, all_handles);
 }
 int dppo_comm_destroy(dppo_ctx* c) {
     DPPO_REQUIRE(c != nullptr, "null dppo_ctx");

@@ -90,28 +90,26 @@ static int peer_teardown(dppo_ctx* ctx) {
     return 0;
 }
 
-static int peer_setup(dppo_ctx* ctx) {
-    const int W = ctx->world, R = ctx->rank;
+struct PeerHandles { cudaIpcMemHandle_t buf, flags; };
+static_assert(sizeof(PeerHandles) == DPPO_PEER_HANDLE_BYTES, "DPPO_PEER_HANDLE_BYTES must match the two IPC handles");
+
+// step 1: this rank's exchange buffers + their IPC handles
+static int peer_alloc(dppo_ctx* ctx, PeerHandles* mine) {
+    const int W = ctx->world;
     ctx->peer_len = ((ctx->shape.n_params + kLossSlots + 3) / 4) * 4;
     DPPO_CHECK_CUDA(cudaMalloc((void**)&ctx->peer_self, (size_t)2 * ctx->peer_len * sizeof(float)));
     DPPO_CHECK_CUDA(cudaMalloc((void**)&ctx->flags_self, (size_t)(W + 1) * sizeof(unsigned int)));
     DPPO_CHECK_CUDA(cudaMemset(ctx->flags_self, 0, (size_t)(W + 1) * sizeof(unsigned int)));
     DPPO_CHECK_CUDA(cudaMemset(ctx->peer_self, 0, (size_t)2 * ctx->peer_len * sizeof(float)));
-    // exchange the IPC handles with the communicator we already have
-    struct Handles { cudaIpcMemHandle_t buf, flags; };
-    Handles mine;
-    DPPO_CHECK_CUDA(cudaIpcGetMemHandle(&mine.buf, ctx->peer_self));
-    DPPO_CHECK_CUDA(cudaIpcGetMemHandle(&mine.flags, ctx->flags_self));
-    Handles* d_all = nullptr;
-    DPPO_CHECK_CUDA(cudaMalloc((void**)&d_all, sizeof(Handles) * W));
-    DPPO_CHECK_CUDA(cudaMemcpy(d_all + R, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
-    cudaStream_t s0 = 0;
-    const int rc = g_nccl.AllGather(d_all + R, d_all, sizeof(Handles), /*ncclInt8*/ 0, (nccl_comm_t)ctx->nccl_comm, s0);
-    if (rc != 0) { cudaFree(d_all); DPPO_REQUIRE(false, "ncclAllGather of IPC handles: %s", g_nccl.GetErrorString(rc)); }
-    Handles all[16];
-    DPPO_CHECK_CUDA(cudaStreamSynchronize(s0));
-    DPPO_CHECK_CUDA(cudaMemcpy(all, d_all, sizeof(Handles) * W, cudaMemcpyDeviceToHost));
-    cudaFree(d_all);
+    DPPO_CHECK_CUDA(cudaDeviceSynchronize());          // the zeroed flags must be in memory before a peer maps them
+    DPPO_CHECK_CUDA(cudaIpcGetMemHandle(&mine->buf, ctx->peer_self));
+    DPPO_CHECK_CUDA(cudaIpcGetMemHandle(&mine->flags, ctx->flags_self));
+    return 0;
+}
+
+// step 2: map every peer's buffers (all[] in rank order; all[rank] is this rank's own entry and is not opened)
+static int peer_map(dppo_ctx* ctx, const PeerHandles* all) {
+    const int W = ctx->world, R = ctx->rank;
     float* bufs[16]; unsigned int* flags[16];
     for (int p = 0; p < W; ++p) {
         if (p == R) { bufs[p] = ctx->peer_self; flags[p] = ctx->flags_self; continue; }
@@ -124,6 +122,43 @@ static int peer_setup(dppo_ctx* ctx) {
     DPPO_CHECK_CUDA(cudaMemcpy(ctx->peer_bufs_dev, bufs, sizeof(float*) * W, cudaMemcpyHostToDevice));
     DPPO_CHECK_CUDA(cudaMemcpy(ctx->flags_dev, flags, sizeof(unsigned int*) * W, cudaMemcpyHostToDevice));
     ctx->epoch = 0;
+    return 0;
+}
+
+// both steps with the handles all-gathered through the NCCL communicator we already have
+static int peer_setup(dppo_ctx* ctx) {
+    const int W = ctx->world, R = ctx->rank;
+    PeerHandles mine;
+    if (int r = peer_alloc(ctx, &mine)) return r;
+    PeerHandles* d_all = nullptr;
+    DPPO_CHECK_CUDA(cudaMalloc((void**)&d_all, sizeof(PeerHandles) * W));
+    DPPO_CHECK_CUDA(cudaMemcpy(d_all + R, &mine, sizeof(PeerHandles), cudaMemcpyHostToDevice));
+    cudaStream_t s0 = 0;
+    const int rc = g_nccl.AllGather(d_all + R, d_all, sizeof(PeerHandles), /*ncclInt8*/ 0, (nccl_comm_t)ctx->nccl_comm, s0);
+    if (rc != 0) { cudaFree(d_all); DPPO_REQUIRE(false, "ncclAllGather of IPC handles: %s", g_nccl.GetErrorString(rc)); }
+    PeerHandles all[16];
+    DPPO_CHECK_CUDA(cudaStreamSynchronize(s0));
+    DPPO_CHECK_CUDA(cudaMemcpy(all, d_all, sizeof(PeerHandles) * W, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    return peer_map(ctx, all);
+}
+
+// ---- the same exchange without NCCL: the host moves the handle blobs (file, pipe, MPI, torch.distributed ...) ----
+int comm_peer_export(dppo_ctx* ctx, int rank, int world, void* handle_out) {
+    DPPO_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, "dppo_comm_peer_export: rank %d of %d (2..16 ranks)", rank, world);
+    DPPO_REQUIRE(ctx->nccl_comm == nullptr && ctx->peer_self == nullptr, "dppo_comm_peer_export: a communicator already exists");
+    ctx->rank = rank; ctx->world = world;
+    PeerHandles mine;
+    if (int r = peer_alloc(ctx, &mine)) { peer_teardown(ctx); ctx->world = 1; return r; }
+    memcpy(handle_out, &mine, sizeof(mine));
+    return 0;
+}
+
+int comm_peer_import(dppo_ctx* ctx, const void* all_handles) {
+    DPPO_REQUIRE(ctx->peer_self != nullptr && ctx->peer_bufs_dev == nullptr, "dppo_comm_peer_import: call dppo_comm_peer_export first");
+    PeerHandles all[16];
+    memcpy(all, all_handles, sizeof(PeerHandles) * ctx->world);
+    if (int r = peer_map(ctx, all)) { peer_teardown(ctx); ctx->world = 1; return r; }
     return 0;
 }
 

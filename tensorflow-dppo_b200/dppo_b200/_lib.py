@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(PKG, "lib", "libdppo_b200.so")
 MAX_HIDDEN = 8
 NUM_LOSS_SLOTS = 8
 NCCL_UNIQUE_ID_BYTES = 128
+PEER_HANDLE_BYTES = 128
 GAE_REFERENCE, GAE_STANDARD = 0, 1
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_BF16, GEMM_FP16X2 = 0, 1, 2, 3
 PD_DIAG_GAUSSIAN, PD_CATEGORICAL = 0, 1
@@ -44,6 +45,8 @@ _PROTOS = {
     "dppo_comm_unique_id": (C.c_int, [_p]),
     "dppo_comm_init": (C.c_int, [_p, C.c_int, C.c_int, _p]),
     "dppo_comm_destroy": (C.c_int, [_p]),
+    "dppo_comm_peer_export": (C.c_int, [_p, C.c_int, C.c_int, _p]),
+    "dppo_comm_peer_import": (C.c_int, [_p, _p]),
     "dppo_allreduce_avg": (C.c_int, [_p, _p, C.c_int64, _p]),
     "dppo_adam_apply": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, _p]),

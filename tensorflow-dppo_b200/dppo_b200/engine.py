@@ -167,6 +167,21 @@ class DppoEngine:
         self._check(self.lib.dppo_comm_init(self.ctx, rank, world, buf))
         self.world = world
 
+    def comm_peer_export(self, rank: int, world: int) -> bytes:
+        """NCCL-free bootstrap of the fused peer-memory exchange, step 1: this rank's IPC handle blob."""
+        buf = C.create_string_buffer(L.PEER_HANDLE_BYTES)
+        self._check(self.lib.dppo_comm_peer_export(self.ctx, int(rank), int(world), buf))
+        self._peer_world = int(world)
+        return buf.raw
+
+    def comm_peer_import(self, blobs):
+        """step 2: the blobs of ALL ranks, in rank order (moved between the processes by the caller)."""
+        data = b"".join(blobs)
+        if len(data) != self._peer_world * L.PEER_HANDLE_BYTES:
+            raise ValueError("comm_peer_import: need one handle blob per rank")
+        self._check(self.lib.dppo_comm_peer_import(self.ctx, C.create_string_buffer(data, len(data))))
+        self.world = self._peer_world
+
     def allreduce_avg(self, buf, n: Optional[int] = None):
         """In-place mean over ranks.  PPO._average_gradients, PPO.py:55-65."""
         n = buf.numel() if n is None else n
