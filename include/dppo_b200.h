@@ -205,6 +205,18 @@ int dppo_update_host(dppo_ctx* ctx, float* params_pi, const float* params_old,
                      float* adam_m, float* adam_v, int step, float lr, float beta1, float beta2, float eps,
                      float* losses_out_h, float* grad_out, void* stream);
 
+/* ---- checkpoint / resume -------------------------------------------------------------------------
+ * replaces save_state / load_state (Others/tf_util.py:271-279: tf.train.Saver over the session's variables): the flat
+ * parameter vectors of pi and oldpi (Model.py:17 order), the Adam slots m and v (PPO.py:20) and the optimiser step t.
+ * File: 128-byte header (magic "DPPOB200", version, obs_dim, act_dim, pd_type, n_hidden, hidden[8], n_params, step,
+ * which arrays are present) followed by the fp32 arrays; written to <path>.tmp and renamed.  adam_m / adam_v may be NULL
+ * (not saved / not restored).  load fails loudly when the header does not match the context's network.
+ * Both calls synchronise `stream`. */
+int dppo_save_state(dppo_ctx* ctx, const char* path, const float* params_pi, const float* params_old,
+                    const float* adam_m, const float* adam_v, int64_t step, void* stream);
+int dppo_load_state(dppo_ctx* ctx, const char* path, float* params_pi, float* params_old, float* adam_m,
+                    float* adam_v, int64_t* step_out, void* stream);
+
 /* ---- launch accounting -------------------------------------------------------------------------
  * Every kernel the library launches is counted per family; with enable_timing != 0 each launch
  * is also bracketed by CUDA events on its own stream (used by bench.py for the roofline line).

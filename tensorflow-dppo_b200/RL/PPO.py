@@ -94,6 +94,8 @@ class PPO(object):
             self._v = torch.zeros(n, dtype=torch.float32, device=self.device)
             self._t = 0
             self.train = Fetch(self, 'train')
+            from RL.Others import tf_util as U
+            U.set_default_ppo(self)            # what tf.train.Saver() (tf_util.py:271-279) would save / restore
             self.last_losses = None
 
     # -------------------------------------------------------------------------------------------

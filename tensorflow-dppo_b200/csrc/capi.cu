@@ -7,6 +7,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include <stddef.h>
 #include <new>
 
 namespace dppo {
@@ -756,6 +757,92 @@ int dppo_update_host(dppo_ctx* c, float* params_pi, const float* params_old, con
                                     cudaMemcpyDeviceToHost, st));
     DPPO_CHECK_CUDA(cudaStreamSynchronize(st));
     if (losses_out_h) memcpy(losses_out_h, c->losses_pinned, kLossSlots * sizeof(float));
+    return 0;
+}
+
+// ---- checkpoint / resume (Others/tf_util.py:271-279) -----------------------------------------------------------------
+struct StateHeader {
+    char magic[8];
+    int32_t version, obs_dim, act_dim, pd_type, n_hidden;
+    int32_t hidden[DPPO_MAX_HIDDEN];
+    int32_t has_adam;
+    int64_t n_params, step;
+    char pad[128 - 8 - 5 * 4 - DPPO_MAX_HIDDEN * 4 - 4 - 16];
+};
+static_assert(sizeof(StateHeader) == 128, "checkpoint header is 128 bytes");
+
+static void fill_header(const dppo_ctx* c, StateHeader* h, int has_adam, int64_t step) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h->magic, "DPPOB200", 8);
+    h->version = 1; h->obs_dim = c->cfg.obs_dim; h->act_dim = c->cfg.act_dim; h->pd_type = c->cfg.pd_type;
+    h->n_hidden = c->cfg.n_hidden;
+    for (int i = 0; i < c->cfg.n_hidden; ++i) h->hidden[i] = c->cfg.hidden[i];
+    h->has_adam = has_adam; h->n_params = c->shape.n_params; h->step = step;
+}
+
+int dppo_save_state(dppo_ctx* c, const char* path, const float* params_pi, const float* params_old, const float* adam_m,
+                    const float* adam_v, int64_t step, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(path && params_pi && params_old, "dppo_save_state: null argument");
+    DPPO_REQUIRE((adam_m == nullptr) == (adam_v == nullptr), "dppo_save_state: pass both Adam slots or neither");
+    const size_t n = (size_t)c->shape.n_params;
+    const int arrays = adam_m ? 4 : 2;
+    float* host = (float*)malloc(n * sizeof(float) * arrays);
+    DPPO_REQUIRE(host != nullptr, "dppo_save_state: out of host memory");
+    const float* src[4] = {params_pi, params_old, adam_m, adam_v};
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < arrays; ++i) {
+        const cudaError_t e = cudaMemcpyAsync(host + (size_t)i * n, src[i], n * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { free(host); set_error("dppo_save_state: %s", cudaGetErrorString(e)); return -2; }
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { free(host); set_error("dppo_save_state: stream synchronise failed"); return -2; }
+    StateHeader h;
+    fill_header(c, &h, adam_m ? 1 : 0, step);
+    char tmp[4096];
+    snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+    FILE* f = fopen(tmp, "wb");
+    if (!f) { free(host); set_error("dppo_save_state: cannot open %s", tmp); return -4; }
+    const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(host, sizeof(float), n * arrays, f) == n * arrays;
+    const bool closed = fclose(f) == 0;
+    free(host);
+    if (!ok || !closed || rename(tmp, path) != 0) { remove(tmp); set_error("dppo_save_state: write to %s failed", path); return -4; }
+    return 0;
+}
+
+int dppo_load_state(dppo_ctx* c, const char* path, float* params_pi, float* params_old, float* adam_m, float* adam_v,
+                    int64_t* step_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(path && params_pi && params_old, "dppo_load_state: null argument");
+    DPPO_REQUIRE((adam_m == nullptr) == (adam_v == nullptr), "dppo_load_state: pass both Adam slots or neither");
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("dppo_load_state: cannot open %s", path); return -4; }
+    StateHeader h, want;
+    if (fread(&h, sizeof(h), 1, f) != 1) { fclose(f); set_error("dppo_load_state: %s is truncated", path); return -4; }
+    fill_header(c, &want, h.has_adam, h.step);
+    if (memcmp(h.magic, "DPPOB200", 8) != 0 || h.version != 1) { fclose(f); set_error("dppo_load_state: %s is not a dppo_b200 checkpoint", path); return -4; }
+    if (memcmp(&h, &want, offsetof(StateHeader, has_adam)) != 0 || h.n_params != want.n_params) {
+        fclose(f);
+        set_error("dppo_load_state: %s holds a different network (obs %d act %d pd %d layers %d, %lld params; context has %lld)",
+                  path, h.obs_dim, h.act_dim, h.pd_type, h.n_hidden, (long long)h.n_params, (long long)want.n_params);
+        return -1;
+    }
+    if (adam_m && !h.has_adam) { fclose(f); set_error("dppo_load_state: %s holds no Adam slots", path); return -1; }
+    const size_t n = (size_t)c->shape.n_params;
+    const int arrays = adam_m ? 4 : 2;
+    float* host = nullptr;
+    if (cudaMallocHost((void**)&host, n * sizeof(float) * arrays) != cudaSuccess) { fclose(f); set_error("dppo_load_state: out of pinned host memory"); return -2; }
+    const bool ok = fread(host, sizeof(float), n * arrays, f) == n * arrays;
+    fclose(f);
+    if (!ok) { cudaFreeHost(host); set_error("dppo_load_state: %s is truncated", path); return -4; }
+    float* dst[4] = {params_pi, params_old, adam_m, adam_v};
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < arrays && e == cudaSuccess; ++i)
+        e = cudaMemcpyAsync(dst[i], host + (size_t)i * n, n * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeHost(host);
+    if (e != cudaSuccess) { set_error("dppo_load_state: %s", cudaGetErrorString(e)); return -2; }
+    if (step_out) *step_out = h.step;
     return 0;
 }
 

@@ -277,6 +277,25 @@ class DppoEngine:
             beta1, beta2, eps, losses, self._dev(g, self.grad_len, "grad_out"), self._stream()))
         return list(losses), g
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_state(self, path: str, params_pi, params_old, adam_m=None, adam_v=None, step: int = 0):
+        """save_state (Others/tf_util.py:276-279): pi, oldpi, Adam slots and the optimiser step to one file."""
+        n = self.n_params
+        self._check(self.lib.dppo_save_state(
+            self.ctx, str(path).encode(), self._dev(params_pi, n, "params_pi"), self._dev(params_old, n, "params_old"),
+            self._dev(adam_m, n, "adam_m") if adam_m is not None else None,
+            self._dev(adam_v, n, "adam_v") if adam_v is not None else None, int(step), self._stream()))
+
+    def load_state(self, path: str, params_pi, params_old, adam_m=None, adam_v=None) -> int:
+        """load_state (Others/tf_util.py:271-273) into the given tensors; returns the saved optimiser step."""
+        n = self.n_params
+        step = C.c_int64(0)
+        self._check(self.lib.dppo_load_state(
+            self.ctx, str(path).encode(), self._dev(params_pi, n, "params_pi"), self._dev(params_old, n, "params_old"),
+            self._dev(adam_m, n, "adam_m") if adam_m is not None else None,
+            self._dev(adam_v, n, "adam_v") if adam_v is not None else None, C.byref(step), self._stream()))
+        return int(step.value)
+
     # ------------------------------------------------------------------ CategoricalPd methods
     def categorical(self, op: str, logits, arg=None, seed: int = 0, offset: int = 0):
         """distributions.py:124-159 on a [B,ncat] logits tensor: neglogp(arg=int32 x[B]) / entropy / kl(arg=other logits)

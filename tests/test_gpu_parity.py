@@ -966,3 +966,41 @@ def test_loss_grad_vs_oracle_fp16x2(name, T, N, obs, hidden, A):
     errs = per_tensor_rel_err(g.cpu().numpy()[:lay.n_params], g_ref, lay)
     print(name, "fp16x2 per-tensor rel err", {k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) < (3e-5 if max(hidden or (0,)) >= 1024 else TOL), errs
+
+
+# ------------------------------------------------------------------------------- checkpoint / resume (tf_util.py:271-279)
+def test_save_load_state_resume_equals_continuous(tmp_path):
+    """4 updates in one go == 2 updates, dppo_save_state, fresh engine + dppo_load_state, 2 more updates: bit-identical
+    parameters and Adam slots; a checkpoint of a different network is refused loudly."""
+    T, N, obs, hidden, A = 64, 8, 17, (64, 64), 6
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]; n = lay.n_params; buf = c["buf"]
+    args = lambda: (dev(buf["obs"]), dev(c["act"]), dev(buf["rew"]), dev(buf["predv"]), dev(buf["done"]))   # noqa: E731
+
+    def run(eng, p, old, m, v, steps):
+        for t in steps:
+            eng.update(p, old, *args(), 0.99, 0.95, 0.7, adam_m=m, adam_v=v, step=t, lr=1e-3)
+        torch.cuda.synchronize()
+
+    eng = _engine(obs, hidden, A, T * N)
+    pa, old = dev(c["theta_pi"]), dev(c["theta_old"])
+    ma = torch.zeros(n, device="cuda"); va = torch.zeros(n, device="cuda")
+    run(eng, pa, old, ma, va, (1, 2, 3, 4))
+    pb = dev(c["theta_pi"]); mb = torch.zeros(n, device="cuda"); vb = torch.zeros(n, device="cuda")
+    run(eng, pb, old, mb, vb, (1, 2))
+    path = str(tmp_path / "ckpt" / "state.dppo")
+    os.makedirs(os.path.dirname(path))
+    eng.save_state(path, pb, old, mb, vb, step=2)
+    eng2 = _engine(obs, hidden, A, T * N)
+    pc = torch.zeros(n, device="cuda"); oc = torch.zeros(n, device="cuda")
+    mc = torch.zeros(n, device="cuda"); vc = torch.zeros(n, device="cuda")
+    t = eng2.load_state(path, pc, oc, mc, vc)
+    assert t == 2 and torch.equal(pc, pb) and torch.equal(oc, old) and torch.equal(mc, mb) and torch.equal(vc, vb)
+    run(eng2, pc, oc, mc, vc, (t + 1, t + 2))
+    assert torch.equal(pc, pa) and torch.equal(mc, ma) and torch.equal(vc, va)
+    other = _engine(obs, (32,), A, 128)
+    z = torch.zeros(other.n_params, device="cuda")
+    with pytest.raises(RuntimeError, match="different network"):
+        other.load_state(path, z, z.clone())
+    with pytest.raises(RuntimeError, match="cannot open"):
+        eng2.load_state(str(tmp_path / "missing.dppo"), pc, oc)

@@ -125,3 +125,29 @@ def test_cartpole_default_game_discrete_actions():
     with pytest.raises(RuntimeError, match="no CPU path"):
         CategoricalPd(torch.zeros(4, 2))
     assert np.isfinite(chief.ppo.last_losses.numpy()).all()
+
+
+def test_filewriter_writes_tensorboard_event_file(tmp_path):
+    """RL.session.FileWriter (tf.summary.FileWriter, main.py:46) emits a real event file: TensorBoard's own loader
+    reads back the scalars of PPO.summary_op (PPO.py:41-45)."""
+    from RL.session import FileWriter
+    w = FileWriter(str(tmp_path))
+    rows = [(1, dict(entropyLoss=-0.0144, policyLoss=0.0061, valueLoss=3.937, total_loss=3.929)),
+            (2, dict(entropyLoss=-0.0143, policyLoss=0.0055, valueLoss=3.5, total_loss=3.49))]
+    for step, sc in rows:
+        w.add_summary(sc, step)
+    w.close()
+    loader_mod = pytest.importorskip("tensorboard.backend.event_processing.event_file_loader")
+    got = []
+    for ev in loader_mod.EventFileLoader(w.event_path).Load():
+        if ev.HasField("summary") and len(ev.summary.value):
+            vals = {}
+            for v in ev.summary.value:
+                # newer TensorBoard loaders migrate simple_value into a rank-0 float tensor
+                vals[v.tag] = v.simple_value if v.HasField("simple_value") else float(v.tensor.float_val[0])
+            got.append((ev.step, vals))
+    assert [s for s, _ in got] == [1, 2]
+    for (_, ref), (_, vals) in zip(rows, got):
+        assert set(vals) == set(ref)
+        for k in ref:
+            assert abs(vals[k] - ref[k]) < 1e-6
