@@ -62,7 +62,19 @@ typedef struct dppo_config {
     float   clip_param;                 /* parameter_dict['CLIP_PARAM'] (main.py:17, PPO.py:10,19) */
     int32_t pd_type;                    /* DPPO_PD_*: what make_pdtype(env.action_space) returns    */
                                         /* (distributions.py:231-243)                               */
+    int32_t value_loss_mode;            /* DPPO_VLOSS_*: per-sample value loss, or PPO.py:36-39 as    */
+                                        /* literally written (pairwise broadcast, SURVEY A-D7)       */
 } dppo_config;
+
+/* Value loss (PPO.py:36-39).  As committed, `v` is [B,1,1] (Model.py:11,13) and `etr` [B,1] (PPO.py:28), so vfloss1/2
+ * broadcast to [B,B,1]: every value is paired with every return of its tower (one tower = one worker's rollout).
+ *   DPPO_VLOSS_PER_SAMPLE        the evident intent, (v_i - R_i)^2                     -- canonical, default;
+ *   DPPO_VLOSS_LITERAL_PAIRWISE  the as-written numbers: mean over all pairs (i,j) of one rollout of
+ *                                max((v_i - R_j)^2, (vclip_i - R_j)^2), averaged over the rollouts (tower mean).
+ *                                dppo_loss_grad treats its B rows as ONE tower; dppo_update / dppo_update_host /
+ *                                dppo_update_epochs (whole-buffer minibatches only) as N towers of T rows. */
+#define DPPO_VLOSS_PER_SAMPLE       0
+#define DPPO_VLOSS_LITERAL_PAIRWISE 1
 
 /* Policy distribution of the pi/oldpi heads (Model.py:9,14-15):
  *   DPPO_PD_DIAG_GAUSSIAN  spaces.Box      -> DiagGaussianPd; act_dim = A, policy head 2A wide (mean | logstd),

@@ -337,10 +337,12 @@ def mlp_backward(theta, obs, hs, d_out, lay: Layout, dtype=np.float64, q=_ident)
 
 
 def ppo_loss_grad(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout,
-                  hp: HParams = HParams(), dtype=np.float64, q=_ident):
+                  hp: HParams = HParams(), dtype=np.float64, q=_ident, literal_groups=None):
     """One tower: pi fwd + oldpi fwd + loss + backward  (PPO.py:21-22,29-40,46).
 
     Returns (losses[4] = policy, value, entropy, total ; flat_grad ; aux dict).
+    literal_groups = G: the as-written pairwise value loss (quirk D7) over G time-major rollouts instead of the
+    canonical per-sample one (value_literal_pairwise_grad).
     """
     obs = np.asarray(obs, dtype); act = np.asarray(act, dtype if lay.pd == "gauss" else np.int64)
     adv = np.asarray(adv, dtype).reshape(-1); ret = np.asarray(ret, dtype).reshape(-1)
@@ -348,9 +350,40 @@ def ppo_loss_grad(theta_pi, theta_old, obs, act, adv, ret, l_mul, lay: Layout,
     v_old, flat_old, _ = mlp_forward(theta_old, obs, lay, dtype, q)
     losses, d_out, aux = ppo_losses_from_heads(v, flat, v_old, flat_old, act, adv, ret,
                                                dtype(l_mul), hp, lay.pd)
+    if literal_groups:
+        vl, d_v, clipped = value_literal_pairwise_grad(v, v_old, ret, float(l_mul), int(literal_groups), hp)
+        losses = np.array([losses[0], vl, losses[2], losses[0] + losses[2] + vl])
+        d_out = d_out.copy(); d_out[:, 0] = d_v
+        aux["vclip_frac"] = float(clipped)
     grad = mlp_backward(theta_pi, obs, hs, d_out.astype(dtype), lay, dtype, q)
     aux.update(d_out=d_out, v=v, flat=flat, v_old=v_old, flat_old=flat_old, hs=hs)
     return losses, grad, aux
+
+
+def value_literal_pairwise_grad(v, v_old, ret, l_mul, groups=1, hp: HParams = HParams()):
+    """Quirk D7 as a trainable mode: PPO.py:36-39 as written pairs every value v_i with every return R_j of its tower
+    ([B,1,1] - [B,1] -> [B,B,1]).  A tower of the reference is ONE rollout; a time-major batch of `groups` rollouts
+    (row b = t*groups + n) is `groups` towers, whose losses / gradients are averaged (PPO.py:55-65).
+    Returns (value_loss, d value_loss / d v [B], fraction of pairs on the clipped branch with the clip active);
+    TF tie rules: maximum -> first arg iff x >= y, clip_by_value passes gradient iff lo <= x <= hi."""
+    c = hp.CLIP_PARAM * l_mul
+    v = np.asarray(v, np.float64).reshape(-1); v_old = np.asarray(v_old, np.float64).reshape(-1)
+    R = np.asarray(ret, np.float64).reshape(-1)
+    B = v.shape[0]; Tn = B // groups
+    loss = 0.0; clipped = 0.0
+    d_v = np.zeros(B)
+    for g in range(groups):
+        idx = np.arange(Tn) * groups + g
+        vi = v[idx][:, None]; vo = v_old[idx][:, None]; Rj = R[idx][None, :]
+        dv = vi - vo
+        vclip = vo + np.clip(dv, -c, c)
+        vf1 = np.square(vi - Rj); vf2 = np.square(vclip - Rj)
+        in_clip = (dv >= -c) & (dv <= c)
+        loss += hp.VCOEFF * np.mean(np.maximum(vf1, vf2)) / groups
+        clipped += np.mean((vf1 < vf2) & ~in_clip) / groups
+        d_v[idx] = (hp.VCOEFF / (groups * Tn * Tn)) * np.sum(
+            np.where(vf1 >= vf2, 2.0 * (vi - Rj), 2.0 * (vclip - Rj) * in_clip), axis=1)
+    return loss, d_v, clipped
 
 
 def value_loss_literal_pairwise(v, v_old, ret, l_mul, hp: HParams = HParams()):

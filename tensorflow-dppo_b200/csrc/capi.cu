@@ -276,7 +276,8 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
 static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
                           const float* act, const float* adv, const float* ret, int rows, int tile0,
                           int B_total, float l_mul, int accumulate, const int* active, cudaStream_t st,
-                          cudaEvent_t adv_ready = nullptr, const float* old_rows = nullptr) {
+                          cudaEvent_t adv_ready = nullptr, const float* old_rows = nullptr,
+                          const float* ret_all = nullptr, int row_off = 0, int groups = 1) {
     const NetShape& s = c->shape;
     Workspace& w = c->ws;
     // old_rows: the oldpi head outputs [rows, Pld] of exactly these rows, computed earlier (oldpi is frozen while the
@@ -287,6 +288,13 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const float clip = c->cfg.clip_param * l_mul;                       // PPO.py:19
     if (int r = launch_loss(s, w.out_pi, old_rows ? old_rows : w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
                             c->cfg.vcoeff, w.d_out, w.loss_part, st)) return r;
+    if (c->cfg.value_loss_mode == DPPO_VLOSS_LITERAL_PAIRWISE) {
+        // PPO.py:36-39 as written: every v_i against every R_j of its rollout (`groups` time-major rollouts of
+        // B_total / groups rows; ret_all = the returns of the whole batch, this call covers rows [row_off, row_off + rows))
+        if (int r = launch_value_pairwise(s, w.out_pi, old_rows ? old_rows : w.out_old, ret_all ? ret_all : ret, rows,
+                                          row_off, B_total / groups, groups, tile0, inv_B, clip, c->cfg.vcoeff, w.d_out,
+                                          w.loss_part, st)) return r;
+    }
 
     GemmEpi tn; tn.accumulate = accumulate;
     const int H = s.in_dim(s.L);
@@ -431,6 +439,8 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     NetShape s;
     if (int r = make_shape(cfg, &s)) return r;
     DPPO_REQUIRE(cfg->max_rows >= 1, "max_rows=%d must be >= 1", cfg->max_rows);
+    DPPO_REQUIRE(cfg->value_loss_mode == DPPO_VLOSS_PER_SAMPLE || cfg->value_loss_mode == DPPO_VLOSS_LITERAL_PAIRWISE,
+                 "value_loss_mode=%d unknown (DPPO_VLOSS_PER_SAMPLE=0, DPPO_VLOSS_LITERAL_PAIRWISE=1)", cfg->value_loss_mode);
     DPPO_REQUIRE(cfg->gemm_mode == DPPO_GEMM_FP32_SIMT || cfg->gemm_mode == DPPO_GEMM_TF32X3 ||
                      cfg->gemm_mode == DPPO_GEMM_BF16 || cfg->gemm_mode == DPPO_GEMM_FP16X2,
                  "gemm_mode=%d unknown (DPPO_GEMM_FP32_SIMT=0, DPPO_GEMM_TF32X3=1, DPPO_GEMM_BF16=2, DPPO_GEMM_FP16X2=3)",
@@ -553,7 +563,7 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
         const int rows = (B - r0 < rows_per) ? B - r0 : rows_per;
         if (int r = loss_grad_rows(c, params_pi, params_old, obs + (size_t)r0 * c->shape.obs, act + (size_t)r0 * c->shape.acols,
                                    c->ws.gae_adv + r0, c->ws.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active,
-                                   st, k == 0 ? c->chunk_ev[0] : nullptr)) return r;
+                                   st, k == 0 ? c->chunk_ev[0] : nullptr, nullptr, c->ws.gae_ret, r0, N)) return r;
     }
     return reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st);
 }
@@ -576,6 +586,9 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
     DPPO_REQUIRE(step0 >= 1, "dppo_update_epochs: step0=%d must be >= 1", step0);
     const int mb = minibatch_rows < B ? minibatch_rows : B;
     const int n_mb = (B + mb - 1) / mb;
+    DPPO_REQUIRE(c->cfg.value_loss_mode == DPPO_VLOSS_PER_SAMPLE || (n_mb == 1 && !shuffle),
+                 "dppo_update_epochs: DPPO_VLOSS_LITERAL_PAIRWISE pairs the rows of whole rollouts; use whole-buffer minibatches "
+                 "without shuffling");
     const NetShape& s = c->shape;
     Workspace& w = c->ws;
     cudaStream_t st = (cudaStream_t)stream;
@@ -614,7 +627,7 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
                 if (cache_old) old_rows = g_old;
             }
             if (int r = loss_grad_rows(c, params_pi, params_old, x, a, ad, rt, rows, 0, rows, l_mul, 0, active, st, nullptr,
-                                       old_rows)) return r;
+                                       old_rows, rt, 0, (n_mb == 1 && !shuffle) ? N : 1)) return r;
             if (int r = reduce_and_apply(c, active, rows, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st))
                 return r;
             if (losses_out)
@@ -749,7 +762,8 @@ int dppo_update_host(dppo_ctx* c, float* params_pi, const float* params_old, con
         const int r0 = chunk_r0[k], rows = chunk_rows[k];
         DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[k + 1], 0));
         if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.acols,
-                                   w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st))
+                                   w.gae_adv + r0, w.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st,
+                                   nullptr, nullptr, w.gae_ret, r0, N))
             return r;
     }
     if (int r = reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st)) return r;

@@ -242,6 +242,11 @@ int launch_categorical(int op, const float* logits, const void* arg, int B, int 
 int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, const float* act,
                 const float* adv, const float* ret, int rows, int tile0, float inv_B, float clip,
                 float entcoeff, float vcoeff, float* d_out, double* loss_part, cudaStream_t st);
+// literal pairwise value loss (quirk D7): overwrites d_out[:,0] and the value slots of the loss partials of rows
+// [row_off, row_off + rows) of a time-major batch of `groups` rollouts x T rows whose returns are ret_all[T*groups]
+int launch_value_pairwise(const NetShape& s, const float* out_pi, const float* out_old, const float* ret_all, int rows,
+                          int row_off, int T, int groups, int tile0, float inv_B, float clip, float vcoeff, float* d_out,
+                          double* loss_part, cudaStream_t st);
 // active[l] = number of split-K slices the dW launches of this update actually wrote (<= s.slices[l])
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st);

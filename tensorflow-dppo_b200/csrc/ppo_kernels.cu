@@ -325,6 +325,67 @@ int launch_loss(const NetShape& s, const float* out_pi, const float* out_old, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Literal value loss: PPO.py:36-39 as committed broadcasts v [B,1,1] against etr [B,1] to
+// [B,B,1], i.e. every value of a tower (= one rollout) is paired with every return of that rollout.  Runs AFTER the
+// loss kernel on the same 128-row tiles: thread = row i, loop over the T returns of its rollout (rows are time-major,
+// row b = t*groups + n, so a warp reads consecutive rollouts' R_j: coalesced; groups = 1 broadcasts), fp64 sums, then
+// replaces d_out[:,0] and the value-loss / clipped-fraction slots of the tile's loss partials.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossTileRows)
+value_pairwise_kernel(const float* __restrict__ out_pi, const float* __restrict__ out_old, const float* __restrict__ ret_all,
+                      int rows, int row_off, int T, int groups, int Pld, int tile0, float inv_B, float clip, float vcoeff,
+                      float* __restrict__ d_out, double* __restrict__ loss_part) {
+    __shared__ double s_red[kLossTileRows / 32][2];
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x * kLossTileRows + tid;
+    double e_sum = 0.0, g_sum = 0.0, c_sum = 0.0;
+    if (r < rows) {
+        const int b = row_off + r;
+        const int g = b % groups;
+        const float v = out_pi[(size_t)r * Pld], vo = out_old[(size_t)r * Pld];
+        const float dv = v - vo;
+        const float vclip = vo + fminf(fmaxf(dv, -clip), clip);
+        const bool inclip = (dv >= -clip) && (dv <= clip);
+        const float* R = ret_all + g;
+#pragma unroll 4
+        for (int j = 0; j < T; ++j) {
+            const float Rj = __ldg(R + (size_t)j * groups);
+            const float a1 = v - Rj, a2 = vclip - Rj;
+            const float e1 = a1 * a1, e2 = a2 * a2;
+            const bool first = (e1 >= e2);                                   // tf.maximum -> x iff x >= y
+            e_sum += (double)fmaxf(e1, e2);
+            g_sum += (double)(first ? 2.f * a1 : (inclip ? 2.f * a2 : 0.f));
+            c_sum += (!first && !inclip) ? 1.0 : 0.0;
+        }
+        const double invT = 1.0 / (double)T;
+        e_sum *= invT; g_sum *= invT; c_sum *= invT;
+        d_out[(size_t)r * Pld] = (float)((double)vcoeff * (double)inv_B * g_sum);
+    }
+    const int warp = tid / 32, lane = tid % 32;
+    const double we = warp_sum(e_sum), wc = warp_sum(c_sum);
+    if (lane == 0) { s_red[warp][0] = we; s_red[warp][1] = wc; }
+    __syncthreads();
+    if (tid < 2) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kLossTileRows / 32; ++w) t += s_red[w][tid];
+        loss_part[(size_t)(tile0 + blockIdx.x) * kLossSlots + (tid == 0 ? 1 : 5)] = t;
+    }
+}
+
+int launch_value_pairwise(const NetShape& s, const float* out_pi, const float* out_old, const float* ret_all, int rows,
+                          int row_off, int T, int groups, int tile0, float inv_B, float clip, float vcoeff, float* d_out,
+                          double* loss_part, cudaStream_t st) {
+    if (rows == 0) return 0;
+    const int grid = (rows + kLossTileRows - 1) / kLossTileRows;
+    ProfScope ps(KK_LOSS, st);
+    value_pairwise_kernel<<<grid, kLossTileRows, 0, st>>>(out_pi, out_old, ret_all, rows, row_off, T, groups, s.Pld, tile0,
+                                                          inv_B, clip, vcoeff, d_out, loss_part);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // finalize: deterministic split-K reduction of dW/db partials (internal layout) into the public
 // flat gradient (PPO.py:46 order), + the loss scalars at the tail.
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ PEER_HANDLE_BYTES = 128
 GAE_REFERENCE, GAE_STANDARD = 0, 1
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_BF16, GEMM_FP16X2 = 0, 1, 2, 3
 PD_DIAG_GAUSSIAN, PD_CATEGORICAL = 0, 1
+VLOSS_PER_SAMPLE, VLOSS_LITERAL_PAIRWISE = 0, 1
 
 
 class LibraryMissing(RuntimeError):
@@ -23,7 +24,7 @@ class DppoConfig(C.Structure):
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("n_hidden", C.c_int32),
         ("hidden", C.c_int32 * MAX_HIDDEN), ("max_rows", C.c_int32), ("device", C.c_int32),
         ("gemm_mode", C.c_int32), ("entcoeff", C.c_float), ("vcoeff", C.c_float), ("clip_param", C.c_float),
-        ("pd_type", C.c_int32),
+        ("pd_type", C.c_int32), ("value_loss_mode", C.c_int32),
     ]
 
 

@@ -23,7 +23,8 @@ class DppoEngine:
 
     def __init__(self, obs_dim: int, act_dim: int, hidden: Sequence[int], max_rows: int, device: int = 0,
                  entcoeff: float = 0.01, vcoeff: float = 0.5, clip_param: float = 0.2,
-                 gemm_mode: int = L.GEMM_FP32_SIMT, pd_type: int = L.PD_DIAG_GAUSSIAN):
+                 gemm_mode: int = L.GEMM_FP32_SIMT, pd_type: int = L.PD_DIAG_GAUSSIAN,
+                 value_loss_mode: int = L.VLOSS_PER_SAMPLE):
         """pd_type = L.PD_CATEGORICAL: act_dim is the number of classes, actions are int32 [B, 1] (PPO.py:26)."""
         self.lib = L.load_library()
         if not torch.cuda.is_available():
@@ -36,6 +37,7 @@ class DppoEngine:
         self.layout = ParamLayout(obs_dim, hidden, act_dim, self.pd_width)
         cfg = L.DppoConfig()
         cfg.pd_type = int(pd_type)
+        cfg.value_loss_mode = int(value_loss_mode)
         cfg.obs_dim, cfg.act_dim, cfg.n_hidden = obs_dim, act_dim, len(hidden)
         for i, h in enumerate(hidden):
             cfg.hidden[i] = int(h)
