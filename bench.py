@@ -125,8 +125,59 @@ def host_cores():
     return n
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and, by first touch, its pinned staging buffers) to the NUMA node its GPU hangs off:
+    the e2e number is a PCIe copy and moves by 20 % when the pages sit on the other socket.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id        # torch >= 2.1
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "single node / not reported"}
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as e:          # noqa: BLE001 -- binding is an optimisation, never a failure
+        return {"numa_node": None, "note": "not bound: %s" % type(e).__name__}
+
+
+GEMM_MODES = {"simt": 0, "tf32x3": 1, "bf16": 2, "fp16x2": 3}
+GEMM_TEXT = {"simt": "fp32 SIMT FFMA",
+             "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators",
+             "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (NOT fp32-parity)",
+             "fp16x2": "tcgen05 kind::f16, 2-term fp16 split x = hi + lo/2^11 (fp32-accurate), persistent kernels, TMEM "
+                       "accumulators; dW on the TMA-fed kind::tf32 kernel"}
+
+
+def make_config(args, world):
+    """The `config` object of the JSON line -- built by ONE function so that both arms print identical keys."""
+    from dppo_b200.synthetic import WORKLOADS
+    T, N, obs, act, hidden = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        N //= world
+    B = T * N
+    cfg = {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act, "hidden": list(hidden),
+           "rows_per_gpu": B, "parallelism": f"dp{world}", "gemm": GEMM_TEXT[args.gemm],
+           "l2": f"inputs larger than L2: obs buffer {B * obs * 4 / 1e6:.0f} MB + activations "
+                 f"{B * sum(hidden) * 4 * 2 / 1e6:.0f} MB stream through HBM every step (L2 126 MB)",
+           "step": "gae + pi/oldpi fwd + loss + bwd + allreduce(N>1) + adam"}
+    if args.minibatch:
+        cfg["minibatch_rows"] = args.minibatch
+        cfg["step"] = ("one epoch of shuffled minibatches through dppo_update_epochs: gae once, then per minibatch gather + "
+                       "pi fwd + loss + bwd + allreduce(N>1) + adam (oldpi heads cached per call)")
+    return cfg
+
+
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(workload, steps, warmup, sample_rows=131072):
+def cpu_reference_run(workload, steps, warmup, sample_rows=131072, budget_s=150.0):
     """The reference-equivalent CPU path on a bounded sample of the workload (first sample_T time
     steps of every rollout).  Returns (env-steps/s, cores, description, ms_per_step)."""
     import numpy as np
@@ -138,22 +189,17 @@ def cpu_reference_run(workload, steps, warmup, sample_rows=131072):
     th_pi, th_old = O.make_params_pair(lay)
     hp = O.HParams()
     towers = max(1, min(N, 8))
-    # calibrate on 64 time steps: pick the thread count that is actually fastest on this host (all
-    # the cores it can use -- more threads than usable cores only thrash), then size the sample for
-    # <= ~2 s of CPU work per step
-    cal = O.make_buffer(64, N, obs, act, 1)
-    best = None
-    for cand in sorted({min(host_cores(), c) for c in (8, 16, 32, 64, 128, 256)}):
-        torch.set_num_threads(cand)
-        O.cpu_update_torch(th_pi, th_old, cal, 64, N, lay, hp, 0.7, towers)
-        t0 = time.perf_counter()
-        O.cpu_update_torch(th_pi, th_old, cal, 64, N, lay, hp, 0.7, towers)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[0]:
-            best = (dt, cand)
-    per_row, cores = best[0] / (64 * N), best[1]
+    # fixed thread count = every core this process may use (affinity mask capped by the cgroup quota); one short
+    # calibration run only sizes the sample so that the whole (warmup + steps) run fits the time budget
+    cores = host_cores()
     torch.set_num_threads(cores)
-    budget_rows = int(2.0 / max(per_row, 1e-9))
+    cal = O.make_buffer(64, N, obs, act, 1)
+    O.cpu_update_torch(th_pi, th_old, cal, 64, N, lay, hp, 0.7, towers)
+    t0 = time.perf_counter()
+    O.cpu_update_torch(th_pi, th_old, cal, 64, N, lay, hp, 0.7, towers)
+    per_row = (time.perf_counter() - t0) / (64 * N)
+    per_step_s = min(2.0, max(0.2, budget_s / max(1, steps + warmup)))
+    budget_rows = int(per_step_s / max(per_row, 1e-9))
     Ts = max(16, min(T, sample_rows // N, budget_rows // N))
     buf = O.make_buffer(Ts, N, obs, act, 1234)
     times = []
@@ -165,28 +211,28 @@ def cpu_reference_run(workload, steps, warmup, sample_rows=131072):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    total = sum(times)
+    med = statistics.median(times)
     rows = Ts * N
     desc = (f"first {Ts} of {T} time steps x {N} rollouts = {rows} rows/step of {workload}; PyTorch-CPU fp32 "
             f"restatement of the reference graph ({towers} towers: pi+oldpi fwd, loss, autodiff bwd, tower mean, "
-            f"TF-Adam; vectorised GAE), {cores} threads")
-    return rows * len(times) / total, cores, desc, 1e3 * total / len(times)
+            f"TF-Adam; vectorised GAE), {cores} threads (all usable host cores), median of {len(times)} steps")
+    return rows / med, cores, desc, 1e3 * med
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
+    """Reference arm: the reference-equivalent CPU path (oracle port; TensorFlow 1.x is not installable) on the host cores,
+    same metric / unit / config object as the B200 arm, EXACTLY --steps timed steps after --warmup untimed ones, each step
+    a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    from dppo_b200.synthetic import WORKLOADS
-    T, N, obs, act, hidden = WORKLOADS[args.workload]
-    steps = min(args.steps, 10)
-    val, cores, desc, ms = cpu_reference_run(args.workload, steps, min(args.warmup, 2))
+    K, W = args.steps, max(args.warmup, 3)
+    val, cores, desc, ms = cpu_reference_run(args.workload, K, W)
     emit_json({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
-                   "hidden": list(hidden)},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
+        "config": make_config(args, max(world, args.gpus)),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -208,6 +254,7 @@ def run_b200(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)          # before the pinned host buffers are allocated (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -217,7 +264,7 @@ def run_b200(args):
         N //= world
     B = T * N
     gamma, lam, l_mul, lr = 0.99, 0.95, 0.7, 2e-5
-    eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode={"simt": 0, "tf32x3": 1, "bf16": 2}[args.gemm])
+    eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode=GEMM_MODES[args.gemm])
     if world > 1:
         init_engine_comm(eng, rank, world)
     host = rollout_buffer(T, N, obs, act, seed=1234 + rank, pin=True)      # weak scaling: own buffer per rank
@@ -333,7 +380,7 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, cores, desc, _ = cpu_reference_run(args.workload, steps=3, warmup=1)
+        val, cores, desc, _ = cpu_reference_run(args.workload, steps=10, warmup=2, budget_s=25.0)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
 
     if rank == 0:
@@ -341,26 +388,24 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "T": T, "N_per_gpu": N, "obs_dim": obs, "act_dim": act,
-                       "hidden": list(hidden), "rows_per_gpu": B, "parallelism": f"dp{world}",
-                       "gemm": {"simt": "fp32 SIMT FFMA", "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators",
-                                "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (NOT fp32-parity)"}[args.gemm],
-                       "l2": f"inputs larger than L2: obs buffer {B * obs * 4 / 1e6:.0f} MB + activations "
-                             f"{B * sum(hidden) * 4 * 2 / 1e6:.0f} MB stream through HBM every step (L2 126 MB)",
-                       "step": "gae + pi/oldpi fwd + loss + bwd + allreduce(N>1) + adam"},
+            "config": make_config(args, world),
             "roofline": {
                 "kernel": ("tc_gemm_kernel (tcgen05 fwd / dX / dW)" if args.gemm != "simt" else
                            "sgemm_kernel (fwd NN / dX NT / dW TN families)"), "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
-                "traffic_note": "DRAM bytes of all GEMM launches of one step (ncu capture under profiles/); algorithmic bytes "
-                                "of the whole update are %d -- the excess is fp32 activations (h1, h2, dh) round-tripping "
-                                "HBM between the per-layer kernels" % alg_bytes,
+                "traffic_source": "committed capture: profiles/traffic.json (ncu --set full of this command); NOT measured in this run",
+                "traffic_note": "DRAM bytes of all GEMM launches of one step; algorithmic bytes of the whole update are %d -- "
+                                "the excess is fp32 activations (h1, h2, dh) round-tripping HBM between the per-layer kernels"
+                                % alg_bytes,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "note": ("algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
-                         + ("fp32-parity path: every algorithmic MAC is issued as 3 TF32 MMAs (half the bf16 rate each), so the "
-                            "ceiling of this fraction is 1/6" if args.gemm == "tf32x3" else
-                            "this path runs the GEMMs as fp32 FFMA (fp32 FMA pipe, ~74 TFLOP/s), not on tensor cores")),
+                         + {"tf32x3": "fp32-parity path: every algorithmic MAC is issued as 3 TF32 MMAs (half the bf16 rate each), so "
+                                      "the ceiling of this fraction is 1/6",
+                            "fp16x2": "fp32-parity path: forward / dX MACs are issued as 3 fp16 MMAs (ceiling 1/3), dW MACs as 3 "
+                                      "TF32 MMAs (ceiling 1/6)",
+                            "bf16": "bf16 operands, one MMA per MAC: the ceiling of this fraction is 1",
+                            "simt": "this path runs the GEMMs as fp32 FFMA (fp32 FMA pipe, ~74 TFLOP/s), not on tensor cores"}[args.gemm]),
                 "launches_per_step": gemm_launches / K, "ms_per_step": gemm_ms / K,
                 "share_of_step": gemm_ms / ms_prof if ms_prof else None,
                 "family_ms_per_step": {k: v_ / K for k, v_ in fam_ms.items()},
@@ -377,10 +422,100 @@ def run_b200(args):
                                       "consumed per second when every rollout batch is trained on 4 times"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "exchange": ({"us_per_step": 1e3 * fam_ms.get("allreduce", 0.0) / K,
+                          "kind": "fused NVLink peer-memory allreduce + Adam (one kernel, includes waiting for the slowest rank)",
+                          "bytes": (eng.n_params + 8) * 4,
+                          "bus_GBps": (2 * (world - 1) / world * (eng.n_params + 8) * 4 / (fam_ms["allreduce"] / K * 1e-3) / 1e9)
+                          if fam_ms.get("allreduce") else None} if world > 1 else None),
+            "host_binding": numa,
         }
         if cpu:
             out["cpu_baseline"] = cpu
         emit_json(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_minibatch(args):
+    """BASELINE configs[4]: one bench step = one epoch over the workload's buffer in shuffled minibatches of --minibatch rows,
+    all on the device (dppo_update_epochs: GAE once, per minibatch gather + fwd + loss + bwd + exchange + Adam).  Reports the
+    time of one optimisation step, env-steps/s, algorithmic HBM GB/s and the gradient exchange's latency / bus GB/s."""
+    import torch
+    import torch.distributed as dist
+    from dppo_b200 import DppoEngine
+    from dppo_b200.dist import init_engine_comm, max_over_ranks
+    from dppo_b200.synthetic import WORKLOADS, rollout_buffer, params_pair
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, N, obs, act, hidden = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        N //= world
+    B = T * N
+    mb = min(args.minibatch, B); n_mb = (B + mb - 1) // mb
+    eng = DppoEngine(obs, act, hidden, B, device=local, gemm_mode=GEMM_MODES[args.gemm])
+    if world > 1:
+        init_engine_comm(eng, rank, world)
+    d = {k: v.to(dev) for k, v in rollout_buffer(T, N, obs, act, seed=1234 + rank).items()}
+    p_pi, p_old = (t.to(dev) for t in params_pair(eng.layout))
+    m = torch.zeros_like(p_pi); v = torch.zeros_like(p_pi); grad = eng.new_grad_buffer()
+    st = {"t": 0}
+
+    def epoch():
+        eng.update_epochs(p_pi, p_old, d["obs"], d["act"], d["rew"], d["predv"], d["done"], 0.99, 0.95, 0.7, m, v,
+                          step0=st["t"] + 1, lr=1e-6, n_epochs=1, minibatch_rows=mb, shuffle=mb < B, seed=3 + st["t"], grad_out=grad)
+        st["t"] += n_mb
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    for _ in range(W):
+        epoch()
+    if rank == 0:
+        sampler.start()
+    eng.profile_reset(False)
+    sync()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        epoch()
+    e1.record()
+    sync()
+    ms_total = max_over_ranks(e0.elapsed_time(e1), device=dev)
+    launches = sum(c for c, _ in eng.profile_read().values())
+    eng.profile_reset(True)
+    epoch()
+    prof = eng.profile_read(); eng.profile_reset(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ex_ms = prof["allreduce"][1] / max(prof["allreduce"][0], 1) if world > 1 else 0.0
+    ms_step = ms_total / K / n_mb
+    peaks = load_peaks()
+    grad_bytes = (eng.n_params + 8) * 4
+    hbm = mb * bytes_per_step(obs, act) / (ms_step * 1e-3) / 1e9
+    if rank == 0:
+        emit_json({
+            "metric": METRIC, "value": world * B * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic", "config": make_config(args, world),
+            "minibatch": {"rows_per_gpu_per_opt_step": mb, "opt_steps_per_epoch": n_mb, "ms_per_opt_step": ms_step,
+                          "graph": os.environ.get("DPPO_GRAPH", "1") != "0"},
+            "roofline": {"bound": "hbm", "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peaks["source"],
+                         "note": "algorithmic bytes of one optimisation step (1600 B/row at cfg3) over its time; small minibatches "
+                                 "are launch/latency-bound, not HBM-bound"},
+            "exchange": ({"us_per_opt_step": ex_ms * 1e3, "bytes": grad_bytes,
+                          "bus_GBps": 2 * (world - 1) / world * grad_bytes / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else None,
+                          "kind": "fused NVLink peer-memory allreduce + Adam"} if world > 1 else None),
+            "e2e": None, "gpu_launches": int(launches), "clocks": clocks, "host_binding": numa,
+        })
     if world > 1:
         dist.destroy_process_group()
 
@@ -419,11 +554,17 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the reference's semantics: every replica owns a full workload buffer) or strong "
                          "(the workload's N rollouts are divided over the ranks)")
-    ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3", "bf16"],
-                    help="dense-layer arithmetic: fp32 FFMA, or tcgen05 kind::tf32 with the 3-term fp32-accurate split")
+    ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3", "bf16", "fp16x2"],
+                    help="dense-layer arithmetic: fp32 FFMA, tcgen05 kind::tf32 with the 3-term fp32-accurate split, bf16 (config 4), "
+                         "or tcgen05 kind::f16 with the 2-term fp32-accurate fp16 split (persistent kernels)")
+    ap.add_argument("--minibatch", type=int, default=0,
+                    help="BASELINE configs[4]: rows per optimisation step; a bench step is then one epoch of shuffled minibatches "
+                         "(dppo_update_epochs).  0 = whole-buffer updates (the headline workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.minibatch:
+        run_minibatch(args)
     else:
         run_b200(args)
 

@@ -1004,3 +1004,50 @@ def test_save_load_state_resume_equals_continuous(tmp_path):
         other.load_state(path, z, z.clone())
     with pytest.raises(RuntimeError, match="cannot open"):
         eng2.load_state(str(tmp_path / "missing.dppo"), pc, oc)
+
+
+# ------------------------------------------------------------------------------- literal pairwise value loss (quirk D7)
+def test_literal_value_loss_matches_reference_lines_golden(golden_dir):
+    """PPO.py:29-40 executed from the reference source on the LITERAL rank-3 value head ([B,1,1] against etr [B,1],
+    tests/golden/ppo_loss_ref.npz `*_losses_literal`): DPPO_VLOSS_LITERAL_PAIRWISE, one tower = the whole batch."""
+    g = np.load(os.path.join(golden_dir, "ppo_loss_ref.npz"))
+    for tag in "abc":
+        flat, flat_old = g[f"{tag}_flat"], g[f"{tag}_flat_old"]
+        B, A2 = flat.shape
+        P = 1 + A2
+        obs = np.concatenate([g[f"{tag}_v"][:, None], flat, g[f"{tag}_v_old"][:, None], flat_old], 1).astype(np.float32)
+        lay, th_pi = _identity_head_params(P, False)
+        _, th_old = _identity_head_params(P, True)
+        eng = _engine(2 * P, (), A2 // 2, B, value_loss_mode=1)
+        losses, _ = eng.loss_grad(dev(th_pi), dev(th_old), dev(obs), dev(g[f"{tag}_act"]), dev(g[f"{tag}_adv"]),
+                                  dev(g[f"{tag}_etr"]), float(g[f"{tag}_l_mul"]))
+        np.testing.assert_allclose(losses.cpu().numpy()[:4], g[f"{tag}_losses_literal"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_literal_value_loss_update_vs_oracle(gemm_mode):
+    """The as-written mode through dppo_update: N towers of T rows (per-rollout [T,T] pairing, tower mean) and through
+    dppo_loss_grad (one tower = all rows), losses and every gradient tensor against the oracle's closed form."""
+    T, N, obs, hidden, A = 256, 8, 17, (64, 64), 6
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]; n = lay.n_params; buf = c["buf"]; B = T * N
+    eng = _engine(obs, hidden, A, B, gemm_mode=gemm_mode, value_loss_mode=1)
+    adv, ret = O.gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], 0.99, 0.95)
+    adv = adv.reshape(-1); ret = ret.reshape(-1)
+    l_ref, g_ref, aux = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], buf["obs"], c["act"], adv, ret, 0.7, lay,
+                                        literal_groups=N)
+    losses, g = eng.update(dev(c["theta_pi"]), dev(c["theta_old"]), dev(buf["obs"]), dev(c["act"]), dev(buf["rew"]),
+                           dev(buf["predv"]), dev(buf["done"]), 0.99, 0.95, 0.7)
+    got = losses.cpu().numpy()
+    np.testing.assert_allclose(got[:4], l_ref, rtol=TOL, atol=TOL)
+    assert abs(got[6] - aux["vclip_frac"]) < 1e-6
+    # the pairwise value gradient is small against the policy terms: compare per tensor, relative to its max
+    assert max(per_tensor_rel_err(g.cpu().numpy()[:n], g_ref, lay).values()) < 3 * TOL
+    l1, g1, _ = O.ppo_loss_grad(c["theta_pi"], c["theta_old"], buf["obs"], c["act"], adv, ret, 0.7, lay, literal_groups=1)
+    losses1, gg1 = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(buf["obs"]), dev(c["act"]), dev(adv), dev(ret), 0.7)
+    np.testing.assert_allclose(losses1.cpu().numpy()[:4], l1, rtol=TOL, atol=TOL)
+    assert max(per_tensor_rel_err(gg1.cpu().numpy()[:n], g1, lay).values()) < 3 * TOL
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    with pytest.raises(RuntimeError, match="LITERAL_PAIRWISE"):
+        eng.update_epochs(dev(c["theta_pi"]), dev(c["theta_old"]), dev(buf["obs"]), dev(c["act"]), dev(buf["rew"]),
+                          dev(buf["predv"]), dev(buf["done"]), 0.99, 0.95, 0.7, m, v, step0=1, lr=1e-4, minibatch_rows=512)

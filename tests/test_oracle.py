@@ -313,3 +313,27 @@ def test_update_epochs_whole_buffer_is_the_update_steps_loop():
         np.testing.assert_allclose(losses[step - 1], l, rtol=1e-12)
     np.testing.assert_array_equal(th, t2)
     assert losses.shape == (3, 4) and not np.allclose(losses[0], losses[2])
+
+
+def test_literal_pairwise_value_gradient_matches_autograd():
+    """Quirk D7 as a trainable mode: the oracle's closed-form d(valueLoss)/dv of the pairwise broadcast (per rollout,
+    tower mean over rollouts) against torch autograd of PPO.py:36-39 written with the literal ranks."""
+    import torch
+    rng = np.random.default_rng(5)
+    B, G, c = 48, 4, 0.2 * 0.7
+    v = rng.standard_normal(B); vo = v + 0.3 * rng.standard_normal(B); R = rng.standard_normal(B)
+    loss, d_v, _ = O.value_literal_pairwise_grad(v, vo, R, 0.7, G)
+    tv = torch.tensor(v, requires_grad=True); tvo = torch.tensor(vo); tR = torch.tensor(R)
+    T = B // G
+    tot = 0
+    for g in range(G):
+        idx = torch.arange(T) * G + g
+        vi = tv[idx].reshape(T, 1, 1); voi = tvo[idx].reshape(T, 1, 1); etr = tR[idx].reshape(T, 1)   # [T,1,1] vs [T,1]
+        vf1 = torch.square(vi - etr)                                                              # -> [T,T,1]
+        vf2 = torch.square(voi + torch.clamp(vi - voi, -c, c) - etr)
+        assert vf1.shape == (T, T, 1)
+        tot = tot + 0.5 * torch.maximum(vf1, vf2).mean() / G
+    tot.backward()
+    assert abs(float(tot.detach()) - loss) < 1e-12
+    np.testing.assert_allclose(tv.grad.numpy(), d_v, rtol=1e-10, atol=1e-14)
+    assert abs(O.value_loss_literal_pairwise(v, vo, R, 0.7) - O.value_literal_pairwise_grad(v, vo, R, 0.7, 1)[0]) < 1e-14
