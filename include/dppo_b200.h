@@ -13,8 +13,10 @@
  *     row-major, 16-byte aligned; nothing is retained after the call except inside dppo_ctx;
  *   - every launch takes the CUDA stream (cudaStream_t as void*) to enqueue on and is
  *     asynchronous; no call allocates device memory (the caller passes the workspace whose size
- *     dppo_workspace_bytes() reports) and none synchronises the host, except dppo_create,
- *     dppo_comm_init/destroy and the *_host entry point;
+ *     dppo_workspace_bytes() reports; the test hook dppo_dbg_gemm takes its scratch from it too) and
+ *     none synchronises the host, except dppo_create, dppo_comm_init / _peer_export / _peer_import /
+ *     _destroy (which own the exchange buffers), dppo_save_state / dppo_load_state and the *_host
+ *     entry points;
  *   - one dppo_ctx per GPU / process; a ctx is not thread-safe;
  *   - layouts: rollout buffers are time-major, sample row b = t*N + n; weights are [in,out]
  *     row-major (TF `kernel`); the flat parameter / gradient vector is
@@ -230,14 +232,14 @@ int dppo_load_state(dppo_ctx* ctx, const char* path, float* params_pi, float* pa
                     float* adam_v, int64_t* step_out, void* stream);
 
 /* ---- launch accounting -------------------------------------------------------------------------
- * Every kernel the library launches is counted per family; with enable_timing != 0 each launch
+ * Per context: every kernel the library launches on behalf of `ctx` is counted per family; with enable_timing != 0 each launch
  * is also bracketed by CUDA events on its own stream (used by bench.py for the roofline line).
  * Families, in order: gae, gemm_nn (forward), gemm_nt (dX), gemm_tn (dW), loss, finalize, misc,
  * adam, allreduce, tc_gemm.  dppo_profile_read synchronises the recorded events and returns the
  * number of families written. */
 #define DPPO_PROFILE_KINDS 10
-int dppo_profile_reset(int enable_timing);
-int dppo_profile_read(int64_t* launches, double* ms, int capacity);
+int dppo_profile_reset(dppo_ctx* ctx, int enable_timing);
+int dppo_profile_read(dppo_ctx* ctx, int64_t* launches, double* ms, int capacity);
 
 /* ---- unit-test hooks (exported so the parity tests can exercise kernels in isolation) ------ */
 /* C[M,N] = epilogue(A . B).  mode 0: A[M,K] B[K,N] (+bias, relu flag);  mode 1: A[M,K] B[N,K]^T,

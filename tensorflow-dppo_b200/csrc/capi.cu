@@ -21,7 +21,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-// ---- profiler ----------------------------------------------------------------------------------
+// ---- launch accounting: one ProfState per context.  Every C-ABI entry point binds the calling thread to its
+// context's state (CTX_GUARD); the kernel launchers, which only see a stream, account through that binding. ----
 struct ProfState {
     bool timing = false;
     long long launches[KK_COUNT] = {0};
@@ -31,22 +32,24 @@ struct ProfState {
     int kind_of[kMaxSlots];
     int created = 0, used = 0;
 };
-static ProfState g_prof;
+static thread_local ProfState* t_prof = nullptr;
 
 ProfScope::ProfScope(int k, cudaStream_t s) : kind(k), st(s), slot(-1) {
-    g_prof.launches[k]++;
-    if (!g_prof.timing || g_prof.used >= ProfState::kMaxSlots) return;
-    if (g_prof.used >= g_prof.created) {
-        if (cudaEventCreate(&g_prof.ev0[g_prof.created]) != cudaSuccess) return;
-        if (cudaEventCreate(&g_prof.ev1[g_prof.created]) != cudaSuccess) return;
-        g_prof.created++;
+    ProfState* p = t_prof;
+    if (!p) return;
+    p->launches[k]++;
+    if (!p->timing || p->used >= ProfState::kMaxSlots) return;
+    if (p->used >= p->created) {
+        if (cudaEventCreate(&p->ev0[p->created]) != cudaSuccess) return;
+        if (cudaEventCreate(&p->ev1[p->created]) != cudaSuccess) return;
+        p->created++;
     }
-    slot = g_prof.used++;
-    g_prof.kind_of[slot] = k;
-    cudaEventRecord(g_prof.ev0[slot], st);
+    slot = p->used++;
+    p->kind_of[slot] = k;
+    cudaEventRecord(p->ev0[slot], st);
 }
 ProfScope::~ProfScope() {
-    if (slot >= 0) cudaEventRecord(g_prof.ev1[slot], st);
+    if (slot >= 0 && t_prof) cudaEventRecord(t_prof->ev1[slot], st);
 }
 
 bool peer_available(const dppo_ctx* ctx);
@@ -394,6 +397,7 @@ using namespace dppo;
 
 #define CTX_GUARD(ctx)                                                     \
     DPPO_REQUIRE((ctx) != nullptr, "null dppo_ctx");                       \
+    t_prof = static_cast<ProfState*>((ctx)->prof);                         \
     DPPO_CHECK_CUDA(cudaSetDevice((ctx)->cfg.device))
 
 extern "C" {
@@ -462,6 +466,8 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     memset(c, 0, sizeof(*c));
     c->cfg = *cfg; c->shape = s; c->workspace = workspace; c->workspace_bytes = workspace_bytes;
     c->num_sms = prop.multiProcessorCount;
+    c->prof = new (std::nothrow) ProfState();
+    { const char* e = getenv("DPPO_NO_OLD_CACHE"); c->no_old_cache = (e && e[0] == '1') ? 1 : 0; }   // read once, per context
     carve(cfg, s, (char*)workspace, &c->ws);
     c->world = 1;
     cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -485,6 +491,11 @@ int dppo_destroy(dppo_ctx* c) {
     for (int i = 0; i < 64; ++i) if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
     if (c->done_ev) cudaEventDestroy(c->done_ev);
     if (c->losses_pinned) cudaFreeHost(c->losses_pinned);
+    if (ProfState* p = static_cast<ProfState*>(c->prof)) {
+        for (int i = 0; i < p->created; ++i) { cudaEventDestroy(p->ev0[i]); cudaEventDestroy(p->ev1[i]); }
+        if (t_prof == p) t_prof = nullptr;
+        delete p;
+    }
     delete c;
     return 0;
 }
@@ -553,18 +564,9 @@ int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const fl
                            side)) return r;
     DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[0], side));
     int active[kMaxLayers + 1];
-    // Optional row chunking (DPPO_UPDATE_CHUNK_ROWS=n): every layer kernel then works on a block of rows whose
-    // activations stay L2-resident between the per-layer launches; dW partials accumulate across the blocks.
-    static int chunk_rows = -1;
-    if (chunk_rows < 0) { const char* e = getenv("DPPO_UPDATE_CHUNK_ROWS"); chunk_rows = e ? atoi(e) : 0; }
-    int rows_per = (chunk_rows >= kLossTileRows && chunk_rows < B) ? (chunk_rows / kLossTileRows) * kLossTileRows : B;
-    active_slices(c, rows_per, active);
-    for (int r0 = 0, k = 0; r0 < B; r0 += rows_per, ++k) {
-        const int rows = (B - r0 < rows_per) ? B - r0 : rows_per;
-        if (int r = loss_grad_rows(c, params_pi, params_old, obs + (size_t)r0 * c->shape.obs, act + (size_t)r0 * c->shape.acols,
-                                   c->ws.gae_adv + r0, c->ws.gae_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active,
-                                   st, k == 0 ? c->chunk_ev[0] : nullptr, nullptr, c->ws.gae_ret, r0, N)) return r;
-    }
+    active_slices(c, B, active);
+    if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, c->ws.gae_adv, c->ws.gae_ret, B, 0, B, l_mul, 0, active, st,
+                               c->chunk_ev[0], nullptr, c->ws.gae_ret, 0, N)) return r;
     return reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps, grad_out, st);
 }
 
@@ -604,9 +606,7 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
     // oldpi does not change during the call (sync_pis happens in the worker, PPO.py:47 / Worker.py:42): evaluate its heads
     // ONCE over the whole buffer and reuse the rows in every minibatch of every epoch.  The reference re-evaluates oldpi
     // in-graph on every sess.run (PPO.py:22) and gets the same numbers.  DPPO_NO_OLD_CACHE=1 restores the recomputation.
-    static int no_cache = -1;
-    if (no_cache < 0) { const char* e = getenv("DPPO_NO_OLD_CACHE"); no_cache = (e && e[0] == '1') ? 1 : 0; }
-    const bool cache_old = !no_cache && (long long)n_epochs * n_mb > 1 && (!shuffle || s.hmax() >= s.Pld);
+    const bool cache_old = !c->no_old_cache && (long long)n_epochs * n_mb > 1 && (!shuffle || s.hmax() >= s.Pld);
     if (cache_old) {
         if (int r = forward_nets(c, params_old, nullptr, obs, B, st)) return r;          // oldpi through the "pi" slot
         DPPO_CHECK_CUDA(cudaMemcpyAsync(w.out_old, w.out_pi, (size_t)B * s.Pld * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -874,25 +874,30 @@ int dppo_categorical(dppo_ctx* c, int op, const float* logits, const void* arg, 
     return launch_categorical(op, logits, arg, B, ncat, seed, offset, out, (cudaStream_t)stream);
 }
 
-int dppo_profile_reset(int enable_timing) {
-    // fold finished timings, then reset
-    for (int i = 0; i < g_prof.used; ++i) cudaEventSynchronize(g_prof.ev1[i]);
-    g_prof.used = 0;
-    for (int k = 0; k < KK_COUNT; ++k) { g_prof.launches[k] = 0; g_prof.ms[k] = 0.0; }
-    g_prof.timing = enable_timing != 0;
+int dppo_profile_reset(dppo_ctx* c, int enable_timing) {
+    CTX_GUARD(c);
+    ProfState* p = static_cast<ProfState*>(c->prof);
+    DPPO_REQUIRE(p != nullptr, "dppo_profile_reset: no accounting state");
+    for (int i = 0; i < p->used; ++i) cudaEventSynchronize(p->ev1[i]);
+    p->used = 0;
+    for (int k = 0; k < KK_COUNT; ++k) { p->launches[k] = 0; p->ms[k] = 0.0; }
+    p->timing = enable_timing != 0;
     return 0;
 }
 
-int dppo_profile_read(int64_t* launches, double* ms, int capacity) {
+int dppo_profile_read(dppo_ctx* c, int64_t* launches, double* ms, int capacity) {
+    CTX_GUARD(c);
+    ProfState* p = static_cast<ProfState*>(c->prof);
+    DPPO_REQUIRE(p != nullptr, "dppo_profile_read: no accounting state");
     DPPO_REQUIRE(launches && ms && capacity >= KK_COUNT, "dppo_profile_read: need capacity %d", (int)KK_COUNT);
-    for (int i = 0; i < g_prof.used; ++i) {
-        DPPO_CHECK_CUDA(cudaEventSynchronize(g_prof.ev1[i]));
+    for (int i = 0; i < p->used; ++i) {
+        DPPO_CHECK_CUDA(cudaEventSynchronize(p->ev1[i]));
         float t = 0.f;
-        DPPO_CHECK_CUDA(cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]));
-        g_prof.ms[g_prof.kind_of[i]] += (double)t;
+        DPPO_CHECK_CUDA(cudaEventElapsedTime(&t, p->ev0[i], p->ev1[i]));
+        p->ms[p->kind_of[i]] += (double)t;
     }
-    g_prof.used = 0;
-    for (int k = 0; k < KK_COUNT; ++k) { launches[k] = g_prof.launches[k]; ms[k] = g_prof.ms[k]; }
+    p->used = 0;
+    for (int k = 0; k < KK_COUNT; ++k) { launches[k] = p->launches[k]; ms[k] = p->ms[k]; }
     return KK_COUNT;
 }
 
@@ -915,34 +920,6 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         DPPO_LAUNCH_CHECK();
         return 0;
     }
-    if (mode >= 80 && mode <= 83) {
-        // planes path (tc_gemm_pl.cu): A is split into hi/lo planes first, Bt[N,K] packed into 128-wide images.
-        // 80: C = relu?(A.Bt^T + bias);  81: C = (A.Bt^T) * (mask > 0);  82/83: same, but the result is returned as
-        // hi + lo of the planes the kernel wrote (what the next consumer would read).
-        // Test/microbenchmark hook only: scratch is allocated here, outside the caller's workspace.
-        static float* img = nullptr; static long long img_floats = 0;
-        static float* planes = nullptr; static long long plane_floats = 0;
-        static float* oplanes = nullptr; static long long oplane_floats = 0;
-        DPPO_REQUIRE(K % 4 == 0 && N % 4 == 0, "dppo_dbg_gemm planes modes need K %% 4 == 0 and N %% 4 == 0");
-        const long long need = tc_pl_image_floats(N, K), pneed = 2ll * M * K, oneed = 2ll * M * N;
-        if (need > img_floats) { if (img) cudaFree(img); DPPO_CHECK_CUDA(cudaMalloc((void**)&img, (size_t)need * 4)); img_floats = need; }
-        if (pneed > plane_floats) { if (planes) cudaFree(planes); DPPO_CHECK_CUDA(cudaMalloc((void**)&planes, (size_t)pneed * 4)); plane_floats = pneed; }
-        if (oneed > oplane_floats) { if (oplanes) cudaFree(oplanes); DPPO_CHECK_CUDA(cudaMalloc((void**)&oplanes, (size_t)oneed * 4)); oplane_floats = oneed; }
-        float* hi = planes; float* lo = planes + (size_t)M * K;
-        if (int r = tc_split_planes(A, (long long)M * K, hi, lo, st)) return r;
-        if (int r = tc_pack_one_ex(B, img, N, K, K, 0, 128, 32, st)) return r;
-        const bool want_planes = mode >= 82;
-        float* ohi = want_planes ? oplanes : nullptr; float* olo = want_planes ? oplanes + (size_t)M * N : nullptr;
-        const int nt = (mode & 1);
-        if (int r = tc_pl_gemm(nt, M, N, K, hi, lo, nullptr, nullptr, K, img, nullptr, want_planes ? nullptr : C, nullptr, ohi, olo,
-                               nullptr, nullptr, N, nt ? nullptr : bias, nullptr, nt ? 0 : relu, nt ? mask : nullptr, 1, st)) return r;
-        if (want_planes) {
-            ProfScope ps(KK_MISC, st);
-            reduce_slices_kernel<<<256, 256, 0, st>>>(oplanes, 2, (long long)M * N, (long long)M * N, C);
-            DPPO_LAUNCH_CHECK();
-        }
-        return 0;
-    }
     if (mode == 96 || mode == 97 || mode == 98) {
         // persistent fp16-split product (tc_gemm_h.cu): Bt[N,K] is packed into an fp16 hi|lo tile image first (scratch from
         // the caller's workspace).  96: C = relu?(A.Bt^T + bias); 97: C = (A.Bt^T) * (mask > 0), A pre-scaled by 2^17;
@@ -959,15 +936,13 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
                        nullptr, nullptr, mode == 98 ? reinterpret_cast<long long*>(bias_out) : nullptr);
     }
     if (mode == 48 || mode == 49) {
-        // weight-image product (the path the update uses): Bt[N,K] is packed into a smem-tile image first.
-        // Test/microbenchmark hook only: the image scratch is allocated here, outside the caller's workspace.
-        static float* scratch = nullptr; static long long scratch_floats = 0;
+        // weight-image product (the tf32 path of the update): Bt[N,K] is packed into a smem-tile image first (scratch from
+        // the caller's workspace)
         const long long need = tc_image_floats(N, K);
-        if (need > scratch_floats) {
-            if (scratch) cudaFree(scratch);
-            DPPO_CHECK_CUDA(cudaMalloc((void**)&scratch, (size_t)need * sizeof(float)));
-            scratch_floats = need;
-        }
+        float* scratch = nullptr;
+        if (c->shape.partial_floats >= need) scratch = c->ws.partial;
+        else if ((long long)c->ws.stage_floats >= need) scratch = c->ws.stage;
+        DPPO_REQUIRE(scratch != nullptr, "dppo_dbg_gemm: the workspace has no %lld-float scratch for the weight image", need);
         if (int r = tc_pack_one(B, scratch, N, K, K, 0, st)) return r;
         return tc_gemm_kk_img(mode == 49, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, bias, nullptr, relu,
                               mode == 49 ? mask : nullptr, 1, st);

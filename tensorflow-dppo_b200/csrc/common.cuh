@@ -114,6 +114,8 @@ struct dppo_ctx {
     cudaEvent_t chunk_ev[64];
     cudaEvent_t done_ev;
     float* losses_pinned;
+    int no_old_cache;            // DPPO_NO_OLD_CACHE=1 at dppo_create: dppo_update_epochs re-evaluates oldpi per minibatch
+    void* prof;                  // launch accounting of this context (capi.cu: ProfState)
 };
 
 namespace dppo {
@@ -192,15 +194,6 @@ int tc_pack_images(const NetShape& s, const float* params_pi, const float* head_
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
                    cudaStream_t st);
 int tc_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st);
-int tc_pack_one_ex(const float* src, float* dst, int N, int K, int ld, int transposed, int bn, int bk, cudaStream_t st);
-// planes path (tc_gemm_pl.cu): activations as RN-tf32 hi/lo planes, fed by TMA
-int tc_split_planes(const float* x, long long n, float* hi, float* lo, cudaStream_t st);
-bool tc_pl_supported(const float* a_hi, const float* a_lo, int lda);
-long long tc_pl_image_floats(int N, int K);
-int tc_pl_gemm(int epi_nt, int M, int N, int K, const float* Ahi0, const float* Alo0, const float* Ahi1, const float* Alo1,
-               int lda, const float* img0, const float* img1, float* C0, float* C1, float* Chi0, float* Clo0, float* Chi1,
-               float* Clo1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
-               cudaStream_t st);
 bool tc_bits_supported();
 // A kind::tf32 MMA reads only the upper 19 bits of an fp32 operand (verified on sm_100a: the parity tests pass with raw
 // tiles), i.e. it sees trunc(x).  The activation split can therefore be hi = x as it is (no conversion, and for the

@@ -440,237 +440,6 @@ __global__ void __launch_bounds__(kThreads, SmemPlan<BN, TERMS, KB>::kMinBlocks)
     }
 }
 
-// =====================================================================================================
-// Persistent variant for the K-major products whose B operand is a weight image (forward, dX).
-//   grid = #SMs; every CTA walks a contiguous range of 128x128 output tiles (n-tile inner, then net, then
-//   m-tile, so consecutive tiles re-use the same activation rows out of L2);
-//   TMEM holds TWO accumulator sets (main+correction, 256 columns each): the MMA warp fills set i&1 while
-//   four dedicated epilogue warps drain set (i-1)&1 -> the epilogue (TMEM -> smem staging -> coalesced
-//   global stores) overlaps the next tile's main loop instead of serialising with it;
-//   operand stages are a 2-deep ring that runs straight across tile boundaries.
-// Warps: 0-7 activation movers (registers, hi/lo split), 8 MMA issuer + TMEM owner, 9 weight-image
-// producer (cp.async.bulk), 10-13 epilogue.
-// =====================================================================================================
-constexpr int kPBN = 128;
-constexpr int kPStages = 2;
-constexpr int kPEpiWarp0 = kLoadWarps + 2;
-constexpr int kPThreads = (kLoadWarps + 2 + 4) * 32;
-constexpr int kPATile = BM * 128, kPBTile = kPBN * 128;
-constexpr int kPStage = 2 * (kPATile + kPBTile);                 // hi + lo of A and B: 64 KB
-constexpr int kPStgLd = kPBN + 4;
-constexpr int kPStaging = 4 * 32 * kPStgLd * 4;                  // 4 epilogue warps x 32 rows x 132 floats
-constexpr int kPSmemBytes = kPStages * kPStage + kPStaging + 1024 + 256;
-
-template <int EPI>
-__global__ void __launch_bounds__(kPThreads, 1) tc_gemm_persistent_kernel(const TcArgs g, int tiles_m, int total_tiles) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* staging = reinterpret_cast<float*>(smem + kPStages * kPStage);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * kPStage + kPStaging);
-    uint64_t* empty_bar = full_bar + kPStages;
-    uint64_t* acc_full = empty_bar + kPStages;
-    uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nkb = (g.K + BK - 1) / BK;
-    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const int t_begin = blockIdx.x * per_cta;
-    const int t_end = min(total_tiles, t_begin + per_cta);
-    const int my_tiles = max(0, t_end - t_begin);
-    const long long total_it = (long long)my_tiles * nkb;
-
-    if (tid == 0) {
-        for (int s = 0; s < kPStages; ++s) { mbar_init(&full_bar[s], kLoadThreads + 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
-        fence_barrier_init();
-    }
-    if (warp == kLoadWarps) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // tile t -> (m_tile, net, n_tile)
-    auto decode = [&](int t, int& mt, int& net, int& nt) {
-        nt = t % g.tiles_n; t /= g.tiles_n;
-        net = t % g.nets; mt = t / g.nets;
-    };
-
-    if (warp < kLoadWarps) {
-        // ---------------- activation movers ----------------
-        float4 ra[kPrefetch][BM / 32];
-        auto issue = [&](float4 (&r)[BM / 32], long long it) {
-            int mt, net, nt;
-            decode(t_begin + (int)(it / nkb), mt, net, nt);
-            tile_load<BM, false>(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * BK, g.K, g.vecA, tid);
-        };
-#pragma unroll
-        for (int j = 0; j < kPrefetch; ++j)
-            if (j < total_it) issue(ra[j], j);
-        for (long long it0 = 0; it0 < total_it; it0 += kPrefetch) {
-#pragma unroll
-            for (int j = 0; j < kPrefetch; ++j) {
-                const long long it = it0 + j;
-                if (it < total_it) {
-                    const int s = (int)(it % kPStages);
-                    mbar_wait(&empty_bar[s], (uint32_t)(((it / kPStages) & 1) ^ 1));
-                    uint8_t* st = smem + s * kPStage;
-                    tile_store<BM, false, 3>(ra[j], st, st + kPATile, tid);
-                    fence_proxy_async();
-                    mbar_arrive(&full_bar[s]);
-                    if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
-                }
-            }
-        }
-    } else if (warp == kLoadWarps + 1) {
-        // ---------------- weight-image producer ----------------
-        if (lane == 0) {
-            constexpr uint32_t kBytes = 2 * kPBTile;
-            for (long long it = 0; it < total_it; ++it) {
-                int mt, net, nt;
-                decode(t_begin + (int)(it / nkb), mt, net, nt);
-                const int s = (int)(it % kPStages);
-                mbar_wait(&empty_bar[s], (uint32_t)(((it / kPStages) & 1) ^ 1));
-                const uint8_t* img = reinterpret_cast<const uint8_t*>(g.Bimg[net]) +
-                                     (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
-                                     ((size_t)nt * nkb + (size_t)(it % nkb)) * kBytes;
-                mbar_arrive_expect_tx(&full_bar[s], kBytes);
-                bulk_copy_g2s(smem + s * kPStage + 2 * kPATile, img, kBytes, &full_bar[s]);
-            }
-        }
-    } else if (warp == kLoadWarps) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kPBN, false, false);
-            long long it = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 2 * kPBN);
-                mbar_wait(&acc_empty[i & 1], (uint32_t)(((i >> 1) & 1) ^ 1));      // epilogue has drained this set
-                tc_fence_after();
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = (int)(it % kPStages);
-                    mbar_wait(&full_bar[s], (uint32_t)((it / kPStages) & 1));
-                    tc_fence_after();
-                    const uint32_t st = smem_u32(smem + s * kPStage);
-                    const uint32_t a_hi = st, a_lo = st + kPATile, b_hi = st + 2 * kPATile, b_lo = b_hi + kPBTile;
-#pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t da_hi = make_sdesc(a_hi + k * 32, 0, 1024, kLayoutSW128);
-                        const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 1024, kLayoutSW128);
-                        const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 1024, kLayoutSW128);
-                        const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 1024, kLayoutSW128);
-                        umma_tf32(acc + kPBN, da_lo, db_hi, idesc, (kb | k) != 0);
-                        umma_tf32(acc + kPBN, da_hi, db_lo, idesc, 1u);
-                        umma_tf32(acc, da_hi, db_hi, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[s]);
-                }
-                umma_commit(&acc_full[i & 1]);
-            }
-            tc_fence_before();
-        }
-    } else {
-        // ---------------- epilogue warps ----------------
-        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
-        float* stg = staging + (size_t)(warp - kPEpiWarp0) * (32 * kPStgLd);
-        for (int i = 0; i < my_tiles; ++i) {
-            int mt, net, nt;
-            decode(t_begin + i, mt, net, nt);
-            const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 2 * kPBN) + ((uint32_t)(q * 32) << 16);
-            mbar_wait(&acc_full[i & 1], (uint32_t)((i >> 1) & 1));
-            tc_fence_after();
-#pragma unroll 1
-            for (int cb = 0; cb < kPBN; cb += 32) {
-                uint32_t v[32], w2[32];
-                tmem_ld32(acc + (uint32_t)cb, v);
-                tmem_ld32(acc + (uint32_t)(kPBN + cb), w2);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[j4 * 4 + 0]) + __uint_as_float(w2[j4 * 4 + 0]);
-                    o.y = __uint_as_float(v[j4 * 4 + 1]) + __uint_as_float(w2[j4 * 4 + 1]);
-                    o.z = __uint_as_float(v[j4 * 4 + 2]) + __uint_as_float(w2[j4 * 4 + 2]);
-                    o.w = __uint_as_float(v[j4 * 4 + 3]) + __uint_as_float(w2[j4 * 4 + 3]);
-                    *reinterpret_cast<float4*>(stg + lane * kPStgLd + cb + j4 * 4) = o;
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[i & 1]);                        // accumulator set free for tile i+2
-            __syncwarp();
-            // coalesced row-wise write-out: one 128-column row per warp instruction
-            float* __restrict__ C = g.C[net];
-            const float* __restrict__ bias = g.bias[net];
-            const int n = nt * kPBN + lane * 4;
-            const int nv = min(4, g.N - n);
-            float bv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (EPI == EPI_NN && bias) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (e < nv) bv[e] = __ldg(bias + n + e);
-            }
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                const int m = mt * BM + q * 32 + r;
-                if (m < g.M && nv > 0) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(stg + r * kPStgLd + lane * 4);
-                    float x[4] = {t4.x, t4.y, t4.z, t4.w};
-                    float* cp = C + (size_t)m * g.ldc + n;
-                    if (EPI == EPI_NN) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float y = x[e] + bv[e];
-                            x[e] = g.relu ? fmaxf(y, 0.f) : y;
-                        }
-                    } else if (g.mask) {
-                        const float* mp = g.mask + (size_t)m * g.ldc + n;
-                        if (g.vecC && nv == 4) {
-                            const float4 mk = __ldg(reinterpret_cast<const float4*>(mp));
-                            x[0] = mk.x > 0.f ? x[0] : 0.f; x[1] = mk.y > 0.f ? x[1] : 0.f;
-                            x[2] = mk.z > 0.f ? x[2] : 0.f; x[3] = mk.w > 0.f ? x[3] : 0.f;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (e < nv) x[e] = (__ldg(mp + e) > 0.f) ? x[e] : 0.f;
-                        }
-                    }
-                    if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
-                    else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (e < nv) cp[e] = x[e];
-                    }
-                }
-            }
-            __syncwarp();                                          // staging is rewritten by the next tile
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == kLoadWarps) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-template <int EPI>
-static int launch_persistent(TcArgs& g, cudaStream_t st) {
-    g.tiles_n = (g.N + kPBN - 1) / kPBN;
-    const int tiles_m = (g.M + BM - 1) / BM;
-    const long long total = (long long)tiles_m * g.tiles_n * g.nets;
-    DPPO_REQUIRE(total < (1ll << 30), "tc_gemm: too many tiles");
-    static PerDeviceOnce configured;
-    if (configured.need()) {
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_persistent_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kPSmemBytes));
-    }
-    const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
-    ProfScope ps(KK_TC_GEMM, st);
-    tc_gemm_persistent_kernel<EPI><<<grid, kPThreads, kPSmemBytes, st>>>(g, tiles_m, (int)total);
-    DPPO_LAUNCH_CHECK();
-    return 0;
-}
-
 static inline int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN, bool MN_MAJOR, int TERMS, int EPI, bool B_IMAGE, int KB = BK>
@@ -808,23 +577,8 @@ int tc_transpose_weights(const NetShape& s, const float* params_pi, const float*
     return 0;
 }
 
-// weight-image tile height: the persistent kernel walks 128-wide tiles; narrow products (heads) use 64
-static inline bool tc_use_persistent() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DPPO_TC_PERSISTENT"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-// DPPO_TC_BK16=1: 64-B operand rows (k-blocks of 16) + 128-wide tiles -> two co-resident CTAs per SM for every product
-// wider than 64 columns.  Measured SLOWER than the default 256-wide single-CTA tiles at cfg3 (1.45 vs 1.31 ms/update):
-// halving the tile width doubles the activation movers' LDG/convert/STS work per MMA and that, not the idle tensor pipe
-// during the epilogue, is then the limiter ("what did not work").  Kept as an opt-in experiment.
-static inline bool tc_use_bk16() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DPPO_TC_BK16"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1 && !tc_use_persistent();
-}
-static inline int tc_bk_for(int n) { return (n > 64 && tc_use_bk16()) ? 16 : tc::BK; }
-static inline int tc_bn_for(int n) { return n > 64 ? ((n > 128 && !tc_use_persistent() && !tc_use_bk16()) ? 256 : 128) : 64; }
+static inline int tc_bk_for(int) { return tc::BK; }
+static inline int tc_bn_for(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
 
 // floats of one weight image: B is [N,K]
 static long long tc_image_replica_floats(int N, int K) {
@@ -881,24 +635,8 @@ int tc_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
     return 0;
 }
 
-// one image with an explicit tile geometry (bn rows per n-tile, bk = 32 or 16 floats per k-block)
-int tc_pack_one_ex(const float* src, float* dst, int N, int K, int ld, int transposed, int bn, int bk, cudaStream_t st) {
-    tc::ImgPlan p; p.n = 1;
-    tc::ImgEntry& e = p.e[0];
-    e.src = src; e.dst = dst; e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = bn; e.bk = bk;
-    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + e.bk - 1) / e.bk) * e.bn * (e.bk / 4);
-    p.unit_end[0] = units;
-    int grid = (int)((units + 255) / 256);
-    if (grid > 148 * 8) grid = 148 * 8;
-    ProfScope ps(KK_MISC, st);
-    tc::pack_images_kernel<<<grid, 256, 0, st>>>(p, units);
-    DPPO_LAUNCH_CHECK();
-    return 0;
-}
-
 // C[M,N] = epi(A[M,K] . Bimg^T) with B given as weight images (see tc_pack_images)
-// the default 256/64-wide tc_gemm_kernel writes / reads the ReLU sign bitmap; the opt-in experimental tilings do not
-bool tc_bits_supported() { return !tc_use_persistent() && !tc_use_bk16(); }
+bool tc_bits_supported() { return true; }
 bool tc_raw_hi() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("DPPO_TC_RAWHI"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -923,14 +661,6 @@ int tc_gemm_kk_img(int epi_nt, int M, int N, int K, const float* A0, const float
     g.B[0] = A0; g.B[1] = A1;          // unused in image mode; keeps fill_vec_flags well-defined
     g.img_replica_bytes = tc_image_replica_floats(N, K) * 4;
     tc::fill_vec_flags(g);
-    if (N > 64 && tc_use_persistent()) {         // experimental: 128-wide persistent tiles, overlapped epilogue
-        if (epi_nt) return tc::launch_persistent<tc::EPI_NT>(g, st);
-        return tc::launch_persistent<tc::EPI_NN>(g, st);
-    }
-    if (N > 64 && tc_use_bk16()) {               // 128-wide tiles, 64-B operand rows, two CTAs per SM
-        if (epi_nt) return tc::launch<128, false, 3, tc::EPI_NT, true, 16>(g, 1, st);
-        return tc::launch<128, false, 3, tc::EPI_NN, true, 16>(g, 1, st);
-    }
     if (epi_nt) return tc::dispatch_bn<3, false, tc::EPI_NT, true>(g, 1, st);
     return tc::dispatch_bn<3, false, tc::EPI_NN, true>(g, 1, st);
 }

@@ -65,8 +65,8 @@ _PROTOS = {
     "dppo_diag_gaussian": (C.c_int, [_p, C.c_int, _p, _p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),
     "dppo_save_state": (C.c_int, [_p, C.c_char_p, _p, _p, _p, _p, C.c_int64, _p]),
     "dppo_load_state": (C.c_int, [_p, C.c_char_p, _p, _p, _p, _p, C.POINTER(C.c_int64), _p]),
-    "dppo_profile_reset": (C.c_int, [C.c_int]),
-    "dppo_profile_read": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int]),
+    "dppo_profile_reset": (C.c_int, [_p, C.c_int]),
+    "dppo_profile_read": (C.c_int, [_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int]),
     "dppo_dbg_gemm": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, C.c_int, _p, _p]),
 }
 EXPORTED = tuple(_PROTOS)

@@ -332,13 +332,13 @@ class DppoEngine:
 
     # ------------------------------------------------------------------ launch accounting
     def profile_reset(self, timing: bool = False):
-        self._check(self.lib.dppo_profile_reset(int(timing)))
+        self._check(self.lib.dppo_profile_reset(self.ctx, int(timing)))
 
     def profile_read(self):
         """{family: (launches, total_ms)} since the last reset."""
         n = len(L.PROFILE_KINDS)
         cnt = (C.c_int64 * n)(); ms = (C.c_double * n)()
-        k = self.lib.dppo_profile_read(cnt, ms, n)
+        k = self.lib.dppo_profile_read(self.ctx, cnt, ms, n)
         if k < 0:
             self._check(k)
         return {name: (int(cnt[i]), float(ms[i])) for i, name in enumerate(L.PROFILE_KINDS)}

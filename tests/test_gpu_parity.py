@@ -911,26 +911,6 @@ def test_reference_api_runs_on_engine(game, obs, pdw, discrete):
 
 
 # ------------------------------------------------------------------------------- planes path: TMA-fed persistent K-major kernel
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 256, 64), (1000, 256, 376), (130, 128, 100), (4096, 256, 256),
-                                   (20000, 256, 256), (777, 36, 256), (300, 256, 36), (129, 200, 36)])
-def test_tc_planes_gemm(M, N, K):
-    """tc_pl_kernel: activations as RN-tf32 hi/lo planes loaded by TMA, 128x128 persistent tiles, double-buffered TMEM;
-    fp32 result and the hi+lo planes it writes for the next consumer."""
-    eng = _engine(376, (256, 256), 17, 4096, gemm_mode=1)
-    rng = np.random.default_rng(M * 7 + N * 3 + K)
-    A = rng.standard_normal((M, K)).astype(np.float32); Bt = rng.standard_normal((N, K)).astype(np.float32)
-    bias = rng.standard_normal(N).astype(np.float32); mask = rng.standard_normal((M, N)).astype(np.float32)
-    ref = A.astype(np.float64) @ Bt.astype(np.float64).T
-    got = eng.dbg_gemm(80, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
-    assert rel_err(got, np.maximum(ref + bias, 0)) < 6e-6, "NN epilogue"
-    got = eng.dbg_gemm(81, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
-    assert rel_err(got, ref * (mask > 0)) < 6e-6, "NT epilogue"
-    got = eng.dbg_gemm(82, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
-    assert rel_err(got, np.maximum(ref + bias, 0)) < 6e-6, "NN epilogue, planes out"   # hi + lo loses < 2^-22
-    got = eng.dbg_gemm(83, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
-    assert rel_err(got, ref * (mask > 0)) < 6e-6, "NT epilogue, planes out"
-
-
 # ------------------------------------------------------------------------------- persistent fp16-split kernels (gemm_mode 3)
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (256, 256, 64), (1000, 256, 376), (777, 35, 256), (130, 128, 100),
                                    (4096, 256, 256), (20000, 256, 376), (129, 200, 33), (300, 64, 17), (5000, 1024, 1024)])

@@ -15,13 +15,6 @@ shapes = [  # (mode, M, N, K, label)
     (48, 131072, 35, 256, "img  fwd head"),
     (49, 131072, 256, 35, "img  dX head"),
     (49, 131072, 256, 256, "img  dX L2"),
-    (80, 18944, 256, 4096, "pl   one wave, long K"),
-    (80, 131072, 256, 376, "pl   fwd L1"),
-    (80, 131072, 256, 256, "pl   fwd L2"),
-    (82, 131072, 256, 256, "pl   fwd L2 -> planes"),
-    (81, 131072, 256, 256, "pl   dX L2"),
-    (83, 131072, 256, 256, "pl   dX L2 -> planes"),
-    (81, 131072, 256, 36, "pl   dX head"),
     (16, 18944, 256, 4096, "reg  one wave, long K"),
     (16, 131072, 256, 256, "reg  fwd L2"),
     (18, 376, 256, 131072, "tn   dW1"),
@@ -36,9 +29,9 @@ for mode, M, N, K, label in shapes:
         A = torch.randn(M, K, device="cuda"); B = torch.randn(K, N, device="cuda")
     else:
         A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
-    mask = torch.randn(M, N, device="cuda") if mode in (49, 81, 83) else None
-    bias = torch.randn(N, device="cuda") if mode in (48, 16, 0, 80, 82) else None
-    relu = mode in (48, 16, 0, 80, 82)
+    mask = torch.randn(M, N, device="cuda") if mode == 49 else None
+    bias = torch.randn(N, device="cuda") if mode in (48, 16, 0) else None
+    relu = mode in (48, 16, 0)
     for _ in range(3):
         eng.dbg_gemm(mode, A, B, M, N, K, bias=bias, mask=mask, relu=relu)
     torch.cuda.synchronize()
