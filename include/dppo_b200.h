@@ -219,6 +219,20 @@ int dppo_update_host(dppo_ctx* ctx, float* params_pi, const float* params_old,
                      float* adam_m, float* adam_v, int step, float lr, float beta1, float beta2, float eps,
                      float* losses_out_h, float* grad_out, void* stream);
 
+/* replaces the whole of Chief._train (Chief.py:54-64) for HOST-resident rollout batches: n_towers feeds (one per worker,
+ * Chief.py:58-63) of rows[k] samples each -- obs_h[k] [rows,obs_dim], act_h[k] [rows,act cols], adv_h[k] [rows],
+ * ret_h[k] [rows], host memory (pinned memory makes the upload asynchronous; pageable works) -- are uploaded ONCE, in
+ * row chunks overlapped with the first step's compute, and trained on n_steps (= UPDATE_STEPS, main.py:24) times on the
+ * device: [pi forward, loss, backward, tower mean (+ exchange across ranks), Adam] per step, step numbers step0,
+ * step0+1, ...; oldpi is evaluated once (it is frozen while the chief trains, PPO.py:47 / Worker.py:42).
+ * The tower mean of PPO.py:55-65 is taken as the mean over all rows (towers of equal length, as the reference's are).
+ * losses_out_h: host [n_steps, 8] (may be NULL).  grad_out: the last step's averaged gradient.  Synchronises `stream`.
+ * Per-sample value loss only (DPPO_VLOSS_LITERAL_PAIRWISE needs the [T,N] structure: use dppo_update). */
+int dppo_train_host(dppo_ctx* ctx, float* params_pi, const float* params_old, int n_towers, const float* const* obs_h,
+                    const void* const* act_h, const float* const* adv_h, const float* const* ret_h, const int* rows,
+                    int n_steps, float l_mul, float* adam_m, float* adam_v, int step0, float lr, float beta1, float beta2,
+                    float eps, float* losses_out_h, float* grad_out, void* stream);
+
 /* ---- checkpoint / resume -------------------------------------------------------------------------
  * replaces save_state / load_state (Others/tf_util.py:271-279: tf.train.Saver over the session's variables): the flat
  * parameter vectors of pi and oldpi (Model.py:17 order), the Adam slots m and v (PPO.py:20) and the optimiser step t.

@@ -60,8 +60,10 @@ class Chief(object):
             tower = worker.ppo
             feed.update({tower.s: batch[_S], tower.act: batch[_A], tower.adv: batch[_ADV], tower.str: batch[_RET],
                          tower.l_mul: l_mul})
-        for _ in range(self.UPDATE_STEPS):                                       # Chief.py:64
-            self.sess.run(self.ppo.train, feed_dict=feed)
+        # Chief.py:64 runs `train` UPDATE_STEPS times on this one feed; here the k steps are ONE fused engine call
+        # (one upload of the towers' batches, k x [forward, loss, backward, tower mean, Adam] on the device)
+        feed[self.ppo.update_steps] = self.UPDATE_STEPS
+        self.sess.run(self.ppo.train, feed_dict=feed)
         self._logs_writer(ranked)
 
     def _update_local_workers_weight(self):

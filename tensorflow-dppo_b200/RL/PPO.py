@@ -94,6 +94,9 @@ class PPO(object):
             self._v = torch.zeros(n, dtype=torch.float32, device=self.device)
             self._t = 0
             self.train = Fetch(self, 'train')
+            # feed `update_steps: k` next to `train` and the chief performs k optimisation steps on the same feed in ONE
+            # fused engine call (what Chief.py:64 spells as a loop of k sess.run calls); absent -> one step per run
+            self.update_steps = Placeholder(scope + '/update_steps', [])
             from RL.Others import tf_util as U
             U.set_default_ppo(self)            # what tf.train.Saver() (tf_util.py:271-279) would save / restore
             self.last_losses = None
@@ -105,6 +108,21 @@ class PPO(object):
         if cols is not None:
             t = t.reshape(-1, cols)
         return t.contiguous()
+
+    def _host_feeds(self, feed_dict):
+        """This tower's feed as contiguous HOST tensors (no copy when the worker queued fp32 / int32 arrays, as it does):
+        what dppo_train_host uploads itself, chunked and overlapped with compute."""
+        def host(x, dtype, cols=None):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            t = t.detach().to(device='cpu', dtype=dtype)
+            if cols is not None:
+                t = t.reshape(-1, cols)
+            return t.contiguous()
+        s = host(feed_dict[self.s], torch.float32, self.obs_dim)
+        a = host(feed_dict[self.a], torch.int32 if self.discrete else torch.float32, self.act_cols)
+        adv = host(feed_dict[self.adv], torch.float32).reshape(-1)
+        etr = host(feed_dict[self.etr], torch.float32).reshape(-1)
+        return s, a, adv, etr
 
     def _feeds(self, feed_dict):
         s = self._dev(feed_dict[self.s], self.obs_dim)
@@ -150,15 +168,29 @@ class PPO(object):
         if 'sync_pis' in kinds:
             be.sync_old(self.pipara.flat, self.oldpipara.flat)   # PPO.py:47
             vals['sync_pis'] = None
-        if 'train' in kinds:
+        if 'train' in kinds and getattr(self, 'update_steps', None) in feed_dict and hasattr(be, 'train_host'):
+            # Chief._train in ONE engine call (dppo_train_host): the towers' host batches are uploaded once (chunked,
+            # overlapped with the first step), UPDATE_STEPS x [fwd, loss, bwd, tower mean, Adam] run on the device
+            towers = [w.ppo for w in self.workerLists[:self.NUM_WORKERS]]
+            l_mul = float(feed_dict[self.l_mul])
+            k = int(feed_dict[self.update_steps])
+            losses, g = be.train_host(self.pipara.flat, towers[0].oldpipara.flat, [t._host_feeds(feed_dict) for t in towers],
+                                      k, l_mul, self._m, self._v, self._t + 1, self.LEARNING_RATE * l_mul)
+            self._t += k
+            self.last_losses = g[self.pipara.flat.numel():]
+            self.step_losses = losses
+            vals['train'] = None
+        elif 'train' in kinds:
+            # step-by-step path (a backend without the fused entry point, or `train` run without update_steps)
             towers = [w.ppo for w in self.workerLists[:self.NUM_WORKERS]]
             feeds = [t._feeds(feed_dict) for t in towers]
             s, a, adv, etr = (torch.cat([f[i] for f in feeds]) for i in range(4))
             l_mul = float(feed_dict[self.l_mul])
-            _, g = be.loss_grad(self.pipara.flat, towers[0].oldpipara.flat, s, a, adv, etr, l_mul)
-            g = self._average_gradients(g)
-            self._t += 1
-            be.adam_apply(self.pipara.flat, g, self._m, self._v, self._t, self.LEARNING_RATE * l_mul)   # PPO.py:20,53
+            for _ in range(int(feed_dict.get(getattr(self, 'update_steps', None), 1))):
+                _, g = be.loss_grad(self.pipara.flat, towers[0].oldpipara.flat, s, a, adv, etr, l_mul)
+                g = self._average_gradients(g)
+                self._t += 1
+                be.adam_apply(self.pipara.flat, g, self._m, self._v, self._t, self.LEARNING_RATE * l_mul)   # PPO.py:20,53
             self.last_losses = g[self.pipara.flat.numel():]
             vals['train'] = None
         return vals

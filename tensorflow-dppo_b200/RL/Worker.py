@@ -42,8 +42,13 @@ class Worker(object):
         that ended inside the rollout."""
         T, N = self.MAX_EPOCH_STEPS, self.NUM_ENVS
         act_dtype = np.int32 if self.ppo.discrete else np.float32
-        buf = dict(s=np.empty((T, N, self.ppo.obs_dim), np.float32), a=np.empty((T, N, self.ppo.act_cols), act_dtype),
-                   r=np.empty((T, N), np.float32), v=np.empty((T, N), np.float32), d=np.empty((T, N), np.float32))
+        # pinned host memory (when a CUDA device exists): the chief's fused update uploads these batches asynchronously
+        def alloc(shape, dtype):
+            t = torch.empty(shape, dtype=torch.int32 if dtype == np.int32 else torch.float32,
+                            pin_memory=torch.cuda.is_available())
+            return t.numpy()
+        buf = dict(s=alloc((T, N, self.ppo.obs_dim), np.float32), a=alloc((T, N, self.ppo.act_cols), act_dtype),
+                   r=alloc((T, N), np.float32), v=alloc((T, N), np.float32), d=alloc((T, N), np.float32))
         finished, running = [], np.zeros(N)
         state = self.env.reset()
         for t in range(T):
@@ -83,7 +88,10 @@ class Worker(object):
             dev = self.ppo.device
             adv, etr = self.ppo.backend.gae(*(torch.from_numpy(buf[k]).to(dev) for k in ('r', 'v', 'd')), self.GAMMA, self.LAM)
             rows = buf['r'].size
-            batch = [buf['s'].reshape(rows, -1), buf['a'].reshape(rows, -1), adv.reshape(-1, 1), etr.reshape(-1, 1), l_mul]
+            # queued as host arrays, like the numpy batches of Worker.py:94-95 (the chief's fused update uploads them)
+            adv_h, etr_h = (x.detach().to('cpu').reshape(-1, 1).numpy() if isinstance(x, torch.Tensor) else
+                            np.asarray(x, np.float32).reshape(-1, 1) for x in (adv, etr))
+            batch = [buf['s'].reshape(rows, -1), buf['a'].reshape(rows, -1), adv_h, etr_h, l_mul]
             tower = self.ppo
             feed = {tower.s: batch[0], tower.action: batch[1], tower.advantage: batch[2], tower.estimatedReturn: batch[3],
                     tower.l_mul: l_mul}

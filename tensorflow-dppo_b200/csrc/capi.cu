@@ -473,7 +473,7 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 64 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done_ev, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->losses_pinned, kLossSlots * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->losses_pinned, (size_t)kMaxTrainSteps * kLossSlots * sizeof(float));
     if (e != cudaSuccess) {
         set_error("dppo_create: %s", cudaGetErrorString(e));
         delete c;
@@ -771,6 +771,107 @@ int dppo_update_host(dppo_ctx* c, float* params_pi, const float* params_old, con
                                     cudaMemcpyDeviceToHost, st));
     DPPO_CHECK_CUDA(cudaStreamSynchronize(st));
     if (losses_out_h) memcpy(losses_out_h, c->losses_pinned, kLossSlots * sizeof(float));
+    return 0;
+}
+
+int dppo_train_host(dppo_ctx* c, float* params_pi, const float* params_old, int n_towers, const float* const* obs_h,
+                    const void* const* act_h, const float* const* adv_h, const float* const* ret_h, const int* rows_of,
+                    int n_steps, float l_mul, float* adam_m, float* adam_v, int step0, float lr, float beta1, float beta2,
+                    float eps, float* losses_out_h, float* grad_out, void* stream) {
+    CTX_GUARD(c);
+    DPPO_REQUIRE(params_pi && params_old && obs_h && act_h && adv_h && ret_h && rows_of && grad_out && adam_m && adam_v,
+                 "dppo_train_host: null argument");
+    DPPO_REQUIRE(n_towers >= 1 && n_towers <= 1024, "dppo_train_host: n_towers=%d out of [1, 1024]", n_towers);
+    DPPO_REQUIRE(n_steps >= 1 && n_steps <= kMaxTrainSteps, "dppo_train_host: n_steps=%d out of [1, %d]", n_steps, kMaxTrainSteps);
+    DPPO_REQUIRE(step0 >= 1, "dppo_train_host: step0=%d must be >= 1 (t after increment)", step0);
+    DPPO_REQUIRE(c->cfg.value_loss_mode == DPPO_VLOSS_PER_SAMPLE,
+                 "dppo_train_host: DPPO_VLOSS_LITERAL_PAIRWISE needs the [T,N] rollout structure: use dppo_update");
+    long long B64 = 0;
+    for (int k = 0; k < n_towers; ++k) {
+        DPPO_REQUIRE(rows_of[k] >= 1 && obs_h[k] && act_h[k] && adv_h[k] && ret_h[k], "dppo_train_host: tower %d is empty", k);
+        B64 += rows_of[k];
+    }
+    DPPO_REQUIRE(B64 <= c->cfg.max_rows, "dppo_train_host: %lld rows exceed max_rows=%d", B64, c->cfg.max_rows);
+    const int B = (int)B64;
+    const NetShape& s = c->shape;
+    Workspace& w = c->ws;
+    cudaStream_t st = (cudaStream_t)stream, cp = c->copy_stream;
+    float* d_obs = w.stage;
+    float* d_act = d_obs + (size_t)B * s.obs;
+    float* d_adv = d_act + (size_t)B * s.acols;
+    float* d_ret = d_adv + B;
+
+    DPPO_CHECK_CUDA(cudaEventRecord(c->done_ev, st));          // earlier work on `st` may still read the staging area
+    DPPO_CHECK_CUDA(cudaStreamWaitEvent(cp, c->done_ev, 0));
+    // the small per-row arrays first, then the big ones in row chunks of one full wave of forward CTAs
+    for (int k = 0, r0 = 0; k < n_towers; r0 += rows_of[k], ++k) {
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(d_adv + r0, adv_h[k], (size_t)rows_of[k] * 4, cudaMemcpyHostToDevice, cp));
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(d_ret + r0, ret_h[k], (size_t)rows_of[k] * 4, cudaMemcpyHostToDevice, cp));
+    }
+    int col_tiles = 1;
+    for (int l = 0; l < s.L; ++l) { const int t = (s.h[l] + 127) / 128; if (t > col_tiles) col_tiles = t; }
+    int rows_per = (2 * kPlanSMs / col_tiles) * 128;
+    if (rows_per < 4096) rows_per = 4096;
+    while ((B + rows_per - 1) / rows_per > 32) rows_per *= 2;
+    int chunk_r0[64], chunk_rows[64], n_chunks = 0;
+    {
+        int r0 = 0;
+        while (B - r0 > rows_per) { chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = rows_per; r0 += rows_per; }
+        const int left = B - r0;
+        const int q = ((left / 4 + kLossTileRows - 1) / kLossTileRows) * kLossTileRows;
+        const int first = ((left - 2 * q + kLossTileRows - 1) / kLossTileRows) * kLossTileRows;
+        if (n_chunks > 0 && q >= 1024 && first > 0 && left - first - q > 0) {
+            const int parts[3] = {first, q, left - first - q};
+            for (int i = 0; i < 3; ++i) { chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = parts[i]; r0 += parts[i]; }
+        } else {
+            chunk_r0[n_chunks] = r0; chunk_rows[n_chunks++] = left;
+        }
+    }
+    DPPO_REQUIRE(n_chunks <= 63, "dppo_train_host: too many chunks");
+    {
+        int seg = 0, seg_r0 = 0;                                  // tower that holds global row `r`, and its first global row
+        for (int k = 0; k < n_chunks; ++k) {
+            int r = chunk_r0[k];
+            const int end = r + chunk_rows[k];
+            while (r < end) {                                     // a chunk may straddle towers: one copy per piece
+                while (r >= seg_r0 + rows_of[seg]) { seg_r0 += rows_of[seg]; ++seg; }
+                const int off = r - seg_r0;
+                const int n = (end - r < rows_of[seg] - off) ? end - r : rows_of[seg] - off;
+                DPPO_CHECK_CUDA(cudaMemcpyAsync(d_obs + (size_t)r * s.obs, obs_h[seg] + (size_t)off * s.obs,
+                                                (size_t)n * s.obs * 4, cudaMemcpyHostToDevice, cp));
+                DPPO_CHECK_CUDA(cudaMemcpyAsync(d_act + (size_t)r * s.acols,
+                                                static_cast<const float*>(act_h[seg]) + (size_t)off * s.acols,
+                                                (size_t)n * s.acols * 4, cudaMemcpyHostToDevice, cp));
+                r += n;
+            }
+            DPPO_CHECK_CUDA(cudaEventRecord(c->chunk_ev[k + 1], cp));
+        }
+    }
+    int active[kMaxLayers + 1];
+    // step 0: chunk k's forward + loss + backward overlaps chunk k+1's upload
+    active_slices(c, rows_per < B ? rows_per : B, active);
+    for (int k = 0; k < n_chunks; ++k) {
+        const int r0 = chunk_r0[k], rows = chunk_rows[k];
+        DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, c->chunk_ev[k + 1], 0));
+        if (int r = loss_grad_rows(c, params_pi, params_old, d_obs + (size_t)r0 * s.obs, d_act + (size_t)r0 * s.acols,
+                                   d_adv + r0, d_ret + r0, rows, r0 / kLossTileRows, B, l_mul, k > 0, active, st)) return r;
+    }
+    if (int r = reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step0, lr, beta1, beta2, eps, grad_out, st)) return r;
+    DPPO_CHECK_CUDA(cudaMemcpyAsync(c->losses_pinned, grad_out + s.n_params, kLossSlots * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // steps 1..: the whole staged batch in one pass; oldpi's heads are cached once every row of them exists
+    bool old_cached = (n_chunks == 1);
+    if (n_steps > 1) active_slices(c, B, active);
+    for (int i = 1; i < n_steps; ++i) {
+        if (int r = loss_grad_rows(c, params_pi, params_old, d_obs, d_act, d_adv, d_ret, B, 0, B, l_mul, 0, active, st, nullptr,
+                                   old_cached ? w.out_old : nullptr)) return r;
+        old_cached = true;
+        if (int r = reduce_and_apply(c, active, B, params_pi, adam_m, adam_v, step0 + i, lr, beta1, beta2, eps, grad_out, st))
+            return r;
+        DPPO_CHECK_CUDA(cudaMemcpyAsync(c->losses_pinned + (size_t)i * kLossSlots, grad_out + s.n_params,
+                                        kLossSlots * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    DPPO_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (losses_out_h) memcpy(losses_out_h, c->losses_pinned, (size_t)n_steps * kLossSlots * sizeof(float));
     return 0;
 }
 

@@ -35,6 +35,7 @@ constexpr int kMaxLayers = DPPO_MAX_HIDDEN;
 constexpr int kLossSlots = DPPO_NUM_LOSS_SLOTS;
 constexpr int kLossTileRows = 128;          // rows per CTA of the loss kernel
 constexpr int kMaxSplitK = 148;             // upper bound of dW split-K slices per layer
+constexpr int kMaxTrainSteps = 64;          // UPDATE_STEPS bound of dppo_train_host (pinned loss read-back slots)
 constexpr int kPlanSMs = 148;               // B200: the split-K plan fills 2 CTAs/SM x 148 SMs in whole waves
 
 // Internal parameter layout: identical to the public one for the trunk; the two heads are packed

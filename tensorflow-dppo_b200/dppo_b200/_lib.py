@@ -63,6 +63,8 @@ _PROTOS = {
                                      C.c_float, C.c_float, C.c_float, _p, _p, _p]),
     "dppo_minibatch_perm": (C.c_int, [_p, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),
     "dppo_diag_gaussian": (C.c_int, [_p, C.c_int, _p, _p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _p, _p]),
+    "dppo_train_host": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, _p, _p, _p, C.c_int, C.c_float, _p, _p, C.c_int, C.c_float,
+                                  C.c_float, C.c_float, C.c_float, _p, _p, _p]),
     "dppo_save_state": (C.c_int, [_p, C.c_char_p, _p, _p, _p, _p, C.c_int64, _p]),
     "dppo_load_state": (C.c_int, [_p, C.c_char_p, _p, _p, _p, _p, C.POINTER(C.c_int64), _p]),
     "dppo_profile_reset": (C.c_int, [_p, C.c_int]),

@@ -279,6 +279,39 @@ class DppoEngine:
             beta1, beta2, eps, losses, self._dev(g, self.grad_len, "grad_out"), self._stream()))
         return list(losses), g
 
+    # ------------------------------------------------------------------ Chief._train in one call (host towers)
+    def train_host(self, params_pi, params_old, towers, n_steps: int, l_mul: float, adam_m, adam_v, step0: int, lr: float,
+                   beta1=0.9, beta2=0.999, eps=1e-8, grad_out=None):
+        """Chief.py:54-64: `towers` = [(obs, act, adv, ret), ...] HOST tensors (one tuple per worker's rollout batch; pinned
+        memory makes the upload asynchronous).  One upload, n_steps (= UPDATE_STEPS) x [forward, loss, backward, tower
+        mean, Adam] on the device, oldpi cached.  Returns (losses [n_steps][8] as a list of lists, gradient buffer)."""
+        k = len(towers)
+        if k < 1:
+            raise ValueError("train_host: no towers")
+        ptrs = [(C.c_void_p * k)() for _ in range(4)]
+        rows = (C.c_int * k)()
+        keep = []
+        for i, (obs, act, adv, ret) in enumerate(towers):
+            want_act = torch.int32 if self.is_categorical else torch.float32
+            n = int(obs.shape[0])
+            for name, t, dt, numel in (("obs", obs, torch.float32, n * self.obs_dim), ("act", act, want_act, n * self.act_cols),
+                                       ("adv", adv, torch.float32, n), ("ret", ret, torch.float32, n)):
+                if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != dt or not t.is_contiguous() or t.numel() != numel:
+                    raise TypeError(f"train_host: tower {i} `{name}` must be a contiguous {dt} host tensor with {numel} elements")
+            for j, t in enumerate((obs, act, adv, ret)):
+                ptrs[j][i] = t.data_ptr()
+            rows[i] = n
+            keep.append((obs, act, adv, ret))
+        g = grad_out if grad_out is not None else self.new_grad_buffer()
+        losses = (C.c_float * (L.NUM_LOSS_SLOTS * int(n_steps)))()
+        self._check(self.lib.dppo_train_host(
+            self.ctx, self._dev(params_pi, self.n_params, "params_pi"), self._dev(params_old, self.n_params, "params_old"), k,
+            ptrs[0], ptrs[1], ptrs[2], ptrs[3], rows, int(n_steps), float(l_mul), self._dev(adam_m, self.n_params, "adam_m"),
+            self._dev(adam_v, self.n_params, "adam_v"), int(step0), float(lr), beta1, beta2, eps, losses,
+            self._dev(g, self.grad_len, "grad_out"), self._stream()))
+        flat = list(losses)
+        return [flat[i * L.NUM_LOSS_SLOTS:(i + 1) * L.NUM_LOSS_SLOTS] for i in range(int(n_steps))], g
+
     # ------------------------------------------------------------------ checkpoint / resume
     def save_state(self, path: str, params_pi, params_old, adam_m=None, adam_v=None, step: int = 0):
         """save_state (Others/tf_util.py:276-279): pi, oldpi, Adam slots and the optimiser step to one file."""

@@ -1031,3 +1031,65 @@ def test_literal_value_loss_update_vs_oracle(gemm_mode):
     with pytest.raises(RuntimeError, match="LITERAL_PAIRWISE"):
         eng.update_epochs(dev(c["theta_pi"]), dev(c["theta_old"]), dev(buf["obs"]), dev(c["act"]), dev(buf["rew"]),
                           dev(buf["predv"]), dev(buf["done"]), 0.99, 0.95, 0.7, m, v, step0=1, lr=1e-4, minibatch_rows=512)
+
+
+# ------------------------------------------------------------------------------- Chief._train on the fused host-buffer call
+def _chief_with_batches(update_steps, gemm_mode=0):
+    """A Chief + 2 Workers on the HalfCheetah-shaped synthetic env with one queued rollout batch per worker."""
+    import main as dppo_main
+    from collections import deque
+    from RL.Chief import Chief
+    from RL.Worker import Worker
+    from RL.session import Session, Coordinator
+    import RL.PPO as rlppo
+    rlppo._ENGINES.clear()
+    pd = dppo_main.build_parameter_dict(GAME="HalfCheetah-v2", NUM_WORKERS=2, NUM_ENVS=4, MAX_EPOCH_STEPS=64, VERBOSE=False,
+                                        UPDATE_STEPS=update_steps, HIDDEN=(64, 64), SEED=3, LOG_FILE_PATH="/tmp/dppo_test_logs")
+    sess, coord, mem = Session(), Coordinator(), {}
+    workers = []
+    for i in range(2):
+        mem["Worker_N%i" % i] = deque()
+        workers.append(Worker("Worker_N%i" % i, pd, sess, mem, coord))
+    chief = Chief("Chief", pd, sess, mem, coord, workers)
+    rng = np.random.default_rng(11)
+    rows = 64 * 4
+    lay = O.make_layout(17, (64, 64), 6)
+    th_pi, th_old = O.make_params_pair(lay)
+    chief.ppo.pipara.flat.copy_(dev(th_pi))
+    batches = []
+    for i, wk in enumerate(workers):
+        wk.ppo.pipara.flat.copy_(dev(th_pi)); wk.ppo.oldpipara.flat.copy_(dev(th_old))
+        b = [rng.standard_normal((rows, 17)).astype(np.float32), rng.standard_normal((rows, 6)).astype(np.float32),
+             rng.standard_normal((rows, 1)).astype(np.float32), rng.standard_normal((rows, 1)).astype(np.float32), 0.7,
+             [1.0, -1.0, float(10 - i), 0.0, 0.0, 0.0, 0.0, 0.0, 1]]
+        mem[wk.name].append(b)
+        batches.append(b)
+    return chief, workers, batches, lay, th_pi, th_old, pd
+
+
+def test_chief_train_runs_the_fused_host_call_and_equals_the_engine_path():
+    """Chief._train (Chief.py:54-64) -> ONE dppo_train_host call: parameters bit-identical to the same UPDATE_STEPS
+    driven step by step through dppo_loss_grad + dppo_adam_apply on the concatenated towers, losses within 1e-5 of the oracle."""
+    K = 3
+    chief, workers, batches, lay, th_pi, th_old, pd = _chief_with_batches(K)
+    eng = chief.ppo.backend
+    eng.profile_reset(False)
+    chief._train()
+    torch.cuda.synchronize()
+    assert chief.ppo._t == K and len(chief.ppo.step_losses) == K
+    counts = {k: c for k, (c, _) in eng.profile_read().items()}
+    assert counts["adam"] == K and counts["loss"] == K                     # K steps on the device from one call
+    # the same K steps through the separate entry points
+    s = dev(np.concatenate([b[0] for b in batches])); a = dev(np.concatenate([b[1] for b in batches]))
+    adv = dev(np.concatenate([b[2] for b in batches]).reshape(-1)); etr = dev(np.concatenate([b[3] for b in batches]).reshape(-1))
+    p = dev(th_pi); old = dev(th_old); n = lay.n_params
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    th = th_pi.astype(np.float64); m_ref = np.zeros(n); v_ref = np.zeros(n)
+    for t in range(1, K + 1):
+        l_ref, g_ref, _ = O.ppo_loss_grad(th.astype(np.float32), th_old, s.cpu().numpy(), a.cpu().numpy(), adv.cpu().numpy(),
+                                          etr.cpu().numpy(), 0.7, lay)
+        np.testing.assert_allclose(chief.ppo.step_losses[t - 1][:4], l_ref, rtol=2e-5, atol=2e-6)
+        th, m_ref, v_ref = O.adam_tf(th, g_ref, m_ref, v_ref, t, pd["LEARNING_RATE"] * 0.7)
+        _, g = eng.loss_grad(p, old, s, a, adv, etr, 0.7)
+        eng.adam_apply(p, g, m, v, t, pd["LEARNING_RATE"] * 0.7)
+    assert torch.equal(chief.ppo.pipara.flat, p) and torch.equal(chief.ppo._m, m) and torch.equal(chief.ppo._v, v)
