@@ -356,6 +356,36 @@ def run_b200(args):
         step_host()
     ms_e2e = timed(step_host, K)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
+    # --- e2e through the reference-named API: Chief._train (Chief.py:54-64) on a queued host batch -> dppo_train_host ---
+    ms_api = None
+    try:
+        from collections import deque
+        import main as dppo_main
+        from RL.Chief import Chief
+        from RL.Worker import Worker
+        from RL.session import Session, Coordinator
+        game = {376: "Humanoid-v2", 17: "HalfCheetah-v2"}.get(obs)
+        if game is not None:
+            reset_state()
+            pdict = dppo_main.build_parameter_dict(GAME=game, NUM_WORKERS=1, NUM_ENVS=N, MAX_EPOCH_STEPS=T, VERBOSE=False,
+                                                   UPDATE_STEPS=1, HIDDEN=tuple(hidden), EPOCH_MAX=10 ** 9, BACKEND=eng,
+                                                   LEARNING_RATE=lr, LOG_FILE_PATH="/tmp/dppo_bench_logs")
+            sess, coord, mem = Session(), Coordinator(), {"Worker_N0": deque()}
+            wk = Worker("Worker_N0", pdict, sess, mem, coord)
+            chief = Chief("Chief", pdict, sess, mem, coord, [wk])
+            chief.ppo.pipara.flat.copy_(p_init); wk.ppo.oldpipara.flat.copy_(p_old)
+            adv_d, ret_d = eng.gae(d["rew"], d["predv"], d["done"], gamma, lam)
+            adv_h = adv_d.reshape(-1, 1).cpu().pin_memory().numpy(); ret_h = ret_d.reshape(-1, 1).cpu().pin_memory().numpy()
+            batch = [host["obs"].numpy(), host["act"].numpy(), adv_h, ret_h, l_mul, [1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1]]
+
+            def step_api():            # what main.run does per update once the worker has queued its rollout batch
+                mem["Worker_N0"].append(batch)
+                chief._train()
+            for _ in range(max(W, 10)):
+                step_api()
+            ms_api = timed(step_api, K)
+    except Exception as e:             # noqa: BLE001 -- the API pass must never take the bench line down
+        sys.stderr.write("e2e_api pass failed: %r\n" % (e,))
     # --- the reference's UPDATE_STEPS=4 loop (main.py:24, Chief.py:64) as ONE call: GAE once, 4 x [fwd, loss, bwd, mean, Adam]
     reset_state()
     us4_losses = torch.empty(4, 8, device=dev)
@@ -417,6 +447,11 @@ def run_b200(args):
                     "h2d_copy_only_ms": ms_copy, "frac_of_copy_floor": ms_copy / (ms_e2e / K),
                     "api": "DppoEngine.update_host -> dppo_update_host (pinned host rollout, chunked H2D with a tapered tail "
                            "overlapped with fwd/loss/bwd, then mean + Adam, losses read back)"},
+            "e2e_api": ({"value": world * B * K / (ms_api * 1e-3), "unit": UNIT, "ms_per_step": ms_api / K,
+                         "frac_of_e2e": (ms_e2e / K) / (ms_api / K),
+                         "api": "RL.Chief._train (Chief.py:54-64) on one queued pinned host batch -> RL.PPO train -> dppo_train_host "
+                                "(chunked H2D overlapped with fwd/loss/bwd, mean + Adam, losses read back); the worker-side GAE "
+                                "(Worker.py:82-92 -> dppo_gae) is outside this call, as in the reference"} if ms_api else None),
             "update_steps4": {"ms_per_rollout_batch": ms_us4, "value": world * B / (ms_us4 * 1e-3), "unit": UNIT,
                               "note": "Chief.py:64 loop, UPDATE_STEPS=4 (main.py:24) through dppo_update_epochs: env-steps "
                                       "consumed per second when every rollout batch is trained on 4 times"},
