@@ -55,7 +55,8 @@ ProfScope::~ProfScope() {
 bool peer_available(const dppo_ctx* ctx);
 float* peer_exchange_buffer(dppo_ctx* ctx);
 int peer_allreduce_adam(dppo_ctx* ctx, float* params, float* m, float* v, int step, float lr, float b1, float b2, float eps,
-                        float* grad_out, cudaStream_t st);
+                        float* grad_out, cudaStream_t st, const StepParams* sp = nullptr, const int* counter = nullptr);
+float* peer_exchange_half(dppo_ctx* ctx, int sel);
 int comm_unique_id(void* out);
 int comm_init(dppo_ctx* ctx, int rank, int world, const void* id_bytes);
 int comm_destroy(dppo_ctx* ctx);
@@ -167,6 +168,8 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     w.gae_ret = (float*)take(R * sizeof(float));
     w.stage_floats = R * ((size_t)s.obs + s.acols + 3);
     w.stage = (float*)take(w.stage_floats * sizeof(float));
+    w.step_params = (StepParams*)take((size_t)kMaxGraphSteps * sizeof(StepParams));
+    w.step_counter = (int*)take(256);
     if (ws) *ws = w;
     return off;
 }
@@ -363,22 +366,24 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
 
 // ---- tail of every update: split-K partials -> flat gradient (+8 loss scalars) -> tower mean over the ranks -> Adam ----
 static int reduce_and_apply(dppo_ctx* c, const int* active, int rows, float* params_pi, float* adam_m, float* adam_v,
-                            int step, float lr, float beta1, float beta2, float eps, float* grad_out, cudaStream_t st) {
+                            int step, float lr, float beta1, float beta2, float eps, float* grad_out, cudaStream_t st,
+                            const StepParams* sp = nullptr, const int* counter = nullptr) {
     const int tiles = (rows + kLossTileRows - 1) / kLossTileRows;
     if (c->world > 1 && peer_available(c)) {
         // NVLink peer path: the rank's gradient goes straight into its exchange buffer; ONE kernel then averages over
         // the ranks through peer loads and applies Adam (PPO.py:53,55-65)
         if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
-                                    peer_exchange_buffer(c), nullptr, st)) return r;
+                                    sp ? peer_exchange_half(c, 0) : peer_exchange_buffer(c), nullptr, st,
+                                    sp ? peer_exchange_half(c, 1) : nullptr, sp, counter)) return r;
         return peer_allreduce_adam(c, params_pi, (adam_m && adam_v) ? adam_m : nullptr, adam_v, step, lr, beta1, beta2, eps,
-                                   grad_out, st);
+                                   grad_out, st, sp, counter);
     }
     if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
                                 grad_out, nullptr, st)) return r;
     if (c->nccl_comm && c->world > 1)
         if (int r = allreduce_avg(c, grad_out, c->shape.n_params + kLossSlots, st)) return r;
     if (adam_m && adam_v)
-        return launch_adam(params_pi, grad_out, adam_m, adam_v, c->shape.n_params, step, lr, beta1, beta2, eps, st);
+        return launch_adam(params_pi, grad_out, adam_m, adam_v, c->shape.n_params, step, lr, beta1, beta2, eps, st, sp, counter);
     return 0;
 }
 
@@ -467,6 +472,7 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     c->cfg = *cfg; c->shape = s; c->workspace = workspace; c->workspace_bytes = workspace_bytes;
     c->num_sms = prop.multiProcessorCount;
     c->prof = new (std::nothrow) ProfState();
+    { const char* e = getenv("DPPO_GRAPH"); c->use_graph = (e && e[0] == '0') ? 0 : 1; }
     { const char* e = getenv("DPPO_NO_OLD_CACHE"); c->no_old_cache = (e && e[0] == '1') ? 1 : 0; }   // read once, per context
     carve(cfg, s, (char*)workspace, &c->ws);
     c->world = 1;
@@ -491,6 +497,7 @@ int dppo_destroy(dppo_ctx* c) {
     for (int i = 0; i < 64; ++i) if (c->chunk_ev[i]) cudaEventDestroy(c->chunk_ev[i]);
     if (c->done_ev) cudaEventDestroy(c->done_ev);
     if (c->losses_pinned) cudaFreeHost(c->losses_pinned);
+    if (c->step_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)c->step_graph_exec);
     if (ProfState* p = static_cast<ProfState*>(c->prof)) {
         for (int i = 0; i < p->created; ++i) { cudaEventDestroy(p->ev0[i]); cudaEventDestroy(p->ev1[i]); }
         if (t_prof == p) t_prof = nullptr;
@@ -612,6 +619,95 @@ int dppo_update_epochs(dppo_ctx* c, float* params_pi, const float* params_old, c
         DPPO_CHECK_CUDA(cudaMemcpyAsync(w.out_old, w.out_pi, (size_t)B * s.Pld * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     float* g_old = w.scratch[1];         // gathered oldpi rows of a shuffled minibatch (free until the backward pass)
+    const long long total_steps = (long long)n_epochs * n_mb;
+
+    // ---- small shuffled minibatches are launch-bound (~15 kernels of a few microseconds each): ONE minibatch step is captured
+    // as a CUDA graph and replayed; what differs from step to step (permutation key, first row, Adam step size, loss slot,
+    // exchange epoch) is read by the kernels from a device array of per-step records through a device-side step counter ----
+    ProfState* prof = static_cast<ProfState*>(c->prof);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const bool use_graph = c->use_graph && shuffle && n_mb >= 2 && total_steps <= kMaxGraphSteps && !(prof && prof->timing) &&
+                           cap == cudaStreamCaptureStatusNone && !(c->nccl_comm && c->world > 1 && !peer_available(c));
+    if (use_graph) {
+        StepParams* host_sp = (StepParams*)malloc((size_t)total_steps * sizeof(StepParams));
+        DPPO_REQUIRE(host_sp != nullptr, "dppo_update_epochs: out of host memory");
+        const bool peer = c->world > 1 && peer_available(c);
+        for (int e = 0, i = 0; e < n_epochs; ++e) {
+            const PermKey key = make_perm_key((uint32_t)B, seed, (uint64_t)e);
+            for (int k = 0; k < n_mb; ++k, ++i) {
+                StepParams& q = host_sp[i];
+                memset(&q, 0, sizeof(q));
+                q.key = key; q.first = k * mb; q.rows = (B - k * mb < mb) ? B - k * mb : mb;
+                q.lr_t = (float)adam_lr_t(lr, beta1, beta2, step0 + i);
+                q.loss_slot = i;
+                if (peer) { c->epoch += 1; q.peer_epoch = c->epoch; q.peer_sel = (int)(c->epoch & 1); }
+            }
+        }
+        // pageable source: the runtime stages it before returning, so host_sp can be freed right away
+        cudaError_t e1 = cudaMemcpyAsync(w.step_params, host_sp, (size_t)total_steps * sizeof(StepParams), cudaMemcpyHostToDevice, st);
+        free(host_sp);
+        DPPO_CHECK_CUDA(e1);
+        DPPO_CHECK_CUDA(cudaMemsetAsync(w.step_counter, 0, sizeof(int), st));
+        // one graph per (minibatch rows, buffers, hyper-parameters); re-captured when any of them changes
+        struct GraphKey { const void* p[10]; int mb, B, cache_old, world; float l_mul, b1, b2, eps; } key;
+        memset(&key, 0, sizeof(key));
+        key.p[0] = params_pi; key.p[1] = params_old; key.p[2] = obs; key.p[3] = act; key.p[4] = adam_m; key.p[5] = adam_v;
+        key.p[6] = grad_out; key.p[7] = losses_out; key.mb = mb; key.B = B; key.cache_old = cache_old ? 1 : 0; key.world = c->world;
+        key.l_mul = l_mul; key.b1 = beta1; key.b2 = beta2; key.eps = eps;
+        static_assert(sizeof(GraphKey) <= sizeof(c->step_graph_key), "graph key storage");
+        if (!c->step_graph_exec || memcmp(&key, c->step_graph_key, sizeof(key)) != 0) {
+            if (c->step_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)c->step_graph_exec); c->step_graph_exec = nullptr; }
+            cudaStream_t cs = c->copy_stream;                // the caller's stream may be the legacy default stream: capture elsewhere
+            long long before[KK_COUNT];
+            for (int k = 0; k < KK_COUNT; ++k) before[k] = prof ? prof->launches[k] : 0;
+            DPPO_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_gather_rows(make_perm_key((uint32_t)B, seed, 0), 0, mb, s.obs, s.acols, obs, act, w.gae_adv, w.gae_ret, g_obs,
+                                        g_act, g_adv, g_ret, cache_old ? w.out_old : nullptr, g_old, s.Pld, cs, w.step_params, w.step_counter);
+            if (!rc) rc = loss_grad_rows(c, params_pi, params_old, g_obs, g_act, g_adv, g_ret, mb, 0, mb, l_mul, 0, active, cs, nullptr,
+                                         cache_old ? g_old : nullptr);
+            if (!rc) rc = reduce_and_apply(c, active, mb, params_pi, adam_m, adam_v, step0, lr, beta1, beta2, eps, grad_out, cs,
+                                           w.step_params, w.step_counter);
+            if (!rc) rc = launch_step_advance(grad_out + s.n_params, losses_out, w.step_params, w.step_counter, cs);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            DPPO_CHECK_CUDA(ce);
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            DPPO_CHECK_CUDA(ie);
+            c->step_graph_exec = exec;
+            memcpy(c->step_graph_key, &key, sizeof(key));
+            for (int k = 0; k < KK_COUNT; ++k) {
+                c->step_graph_counts[k] = prof ? prof->launches[k] - before[k] : 0;
+                if (prof) prof->launches[k] = before[k];     // captured, not launched
+            }
+        }
+        for (int e = 0, i = 0; e < n_epochs; ++e) {
+            const PermKey pkey = make_perm_key((uint32_t)B, seed, (uint64_t)e);
+            for (int k = 0; k < n_mb; ++k, ++i) {
+                const int r0 = k * mb, rows = (B - r0 < mb) ? B - r0 : mb;
+                if (rows == mb) {
+                    DPPO_CHECK_CUDA(cudaGraphLaunch((cudaGraphExec_t)c->step_graph_exec, st));
+                    if (prof) for (int q = 0; q < KK_COUNT; ++q) prof->launches[q] += c->step_graph_counts[q];
+                    continue;
+                }
+                // the ragged last minibatch of an epoch: direct launches, same per-step records
+                if (int r = launch_gather_rows(pkey, r0, rows, s.obs, s.acols, obs, act, w.gae_adv, w.gae_ret, g_obs, g_act, g_adv, g_ret,
+                                               cache_old ? w.out_old : nullptr, g_old, s.Pld, st)) return r;
+                int active_r[kMaxLayers + 1];
+                active_slices(c, rows, active_r);
+                if (int r = loss_grad_rows(c, params_pi, params_old, g_obs, g_act, g_adv, g_ret, rows, 0, rows, l_mul, 0, active_r, st,
+                                           nullptr, cache_old ? g_old : nullptr)) return r;
+                if (int r = reduce_and_apply(c, active_r, rows, params_pi, adam_m, adam_v, step0 + i, lr, beta1, beta2, eps, grad_out, st,
+                                             w.step_params, w.step_counter)) return r;
+                if (int r = launch_step_advance(grad_out + s.n_params, losses_out, w.step_params, w.step_counter, st)) return r;
+            }
+        }
+        return 0;
+    }
+
     int step = step0, slot = 0;
     for (int e = 0; e < n_epochs; ++e) {
         const PermKey key = make_perm_key((uint32_t)B, seed, (uint64_t)e);
@@ -1029,6 +1125,7 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         float* scratch = nullptr;
         if (c->shape.partial_floats >= need) scratch = c->ws.partial;
         else if ((long long)c->ws.stage_floats >= need) scratch = c->ws.stage;
+        else if ((long long)c->cfg.max_rows * (c->shape.hmax() > 0 ? c->shape.hmax() : 1) >= need) scratch = c->ws.scratch[0];
         DPPO_REQUIRE(scratch != nullptr, "dppo_dbg_gemm: the workspace has no %lld-float scratch for the weight image", need);
         if (int r = th_pack_one(B, scratch, N, K, K, 0, st)) return r;
         if (mode == 97)

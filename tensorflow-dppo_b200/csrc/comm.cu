@@ -181,7 +181,11 @@ peer_allreduce_adam_kernel(float* const* __restrict__ bufs, unsigned int* const*
                            unsigned int epoch, long long buf_off, long long n_params, long long n_valid, long long n_total,
                            float* __restrict__ params,
                            float* __restrict__ m, float* __restrict__ v, float lr_t, float b1, float b2, float eps,
-                           float* __restrict__ grad_out) {
+                           float* __restrict__ grad_out, const StepParams* __restrict__ sp, const int* __restrict__ counter) {
+    if (sp) {                                                          // graph replay: this step's epoch / buffer half / step size
+        const StepParams& q = sp[*counter];
+        epoch = q.peer_epoch; buf_off = (long long)q.peer_sel * n_total; lr_t = q.lr_t;
+    }
     unsigned int* my_flags = flags[rank];
     unsigned int* go = my_flags + world;
     if (blockIdx.x == 0) {
@@ -224,10 +228,12 @@ float* peer_exchange_buffer(dppo_ctx* ctx) {         // where finalize_kernel wr
 }
 
 // grad (already in this rank's exchange buffer for epoch+1) -> mean over ranks in grad_out (+ Adam when m, v given)
+float* peer_exchange_half(dppo_ctx* ctx, int sel) { return ctx->peer_self + (size_t)sel * ctx->peer_len; }
+
 int peer_allreduce_adam(dppo_ctx* ctx, float* params, float* m, float* v, int step, float lr, float b1, float b2, float eps,
-                        float* grad_out, cudaStream_t st) {
+                        float* grad_out, cudaStream_t st, const StepParams* sp, const int* counter) {
     DPPO_REQUIRE(peer_available(ctx), "peer exchange is not set up");
-    ctx->epoch += 1;
+    if (!sp) ctx->epoch += 1;                      // graph replay: the host advanced the epoch when it filled the step records
     const long long n_total = ctx->peer_len;
     double lr_t = 0.0;
     if (m) {
@@ -241,7 +247,7 @@ int peer_allreduce_adam(dppo_ctx* ctx, float* params, float* m, float* v, int st
     peer_allreduce_adam_kernel<<<grid, 256, 0, st>>>(ctx->peer_bufs_dev, ctx->flags_dev, ctx->rank, ctx->world, ctx->epoch,
                                                      (long long)(ctx->epoch & 1) * ctx->peer_len, ctx->shape.n_params,
                                                      ctx->shape.n_params + kLossSlots, n_total,
-                                                     params, m, v, (float)lr_t, b1, b2, eps, grad_out);
+                                                     params, m, v, (float)lr_t, b1, b2, eps, grad_out, sp, counter);
     DPPO_LAUNCH_CHECK();
     return 0;
 }

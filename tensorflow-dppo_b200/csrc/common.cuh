@@ -64,6 +64,21 @@ struct NetShape {
 
 int make_shape(const dppo_config* cfg, NetShape* s);
 
+// Per-step values of the device-scheduled minibatch loop, read by the kernels of a CUDA-graph replay through
+// params[*counter] (dppo_update_epochs): everything else of a minibatch step is identical from step to step.
+struct StepParams {
+    PermKey key;            // row permutation of this step's epoch
+    int first;              // first permuted index of the minibatch
+    int rows;
+    float lr_t;             // Adam step size with the bias corrections of this step number
+    int loss_slot;          // row of losses_out this step reports to
+    unsigned peer_epoch;    // arrival epoch of the fused peer exchange
+    int peer_sel;           // which half of the double-buffered exchange buffer this step writes / reads
+    int pad[4];
+};
+static_assert(sizeof(StepParams) == 64, "StepParams is one 64-byte record");
+constexpr int kMaxGraphSteps = 4096;
+
 struct Workspace {
     // all device pointers into the caller's workspace
     float* head_pi;      // packed head W|b of pi      [H_L*P + P]
@@ -86,6 +101,8 @@ struct Workspace {
     float* gae_ret;      // [max_rows]
     float* stage;        // device staging for dppo_update_host: obs|act|rew|predv|done
     size_t stage_floats;
+    StepParams* step_params;   // [kMaxGraphSteps] per-step records of the graph-replayed minibatch loop
+    int* step_counter;         // index of the step the next replay executes
 };
 
 }  // namespace dppo
@@ -115,6 +132,11 @@ struct dppo_ctx {
     cudaEvent_t chunk_ev[64];
     cudaEvent_t done_ev;
     float* losses_pinned;
+    // dppo_update_epochs: one minibatch step captured as a CUDA graph and replayed (small minibatches are launch-bound)
+    void* step_graph_exec;       // cudaGraphExec_t
+    unsigned char step_graph_key[160];
+    long long step_graph_counts[16];   // kernel launches per replay, per family
+    int use_graph;               // DPPO_GRAPH != 0 at dppo_create
     int no_old_cache;            // DPPO_NO_OLD_CACHE=1 at dppo_create: dppo_update_epochs re-evaluates oldpi per minibatch
     void* prof;                  // launch accounting of this context (capi.cu: ProfState)
 };
@@ -243,18 +265,23 @@ int launch_value_pairwise(const NetShape& s, const float* out_pi, const float* o
                           double* loss_part, cudaStream_t st);
 // active[l] = number of split-K slices the dW launches of this update actually wrote (<= s.slices[l])
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
-                    float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st);
+                    float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st,
+                    float* grad_out_alt = nullptr, const StepParams* sp = nullptr, const int* counter = nullptr);
 int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
                        cudaStream_t st);
 int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,
-                float b1, float b2, float eps, cudaStream_t st);
+                float b1, float b2, float eps, cudaStream_t st, const StepParams* sp = nullptr, const int* counter = nullptr);
+double adam_lr_t(float lr, float b1, float b2, int step);
+// end of a graph-replayed step: report the 8 loss scalars to losses_out[slot] and advance the step counter
+int launch_step_advance(const float* grad_tail, float* losses_out, const StepParams* sp, int* counter, cudaStream_t st);
 int launch_diag_gaussian(int op, const float* flat, const float* arg, int B, int A, uint64_t seed, uint64_t offset,
                          float* out, cudaStream_t st);
 int launch_sample(const NetShape& s, const float* out, int rows, uint64_t seed, uint64_t offset,
                   float* action, float* v_out, cudaStream_t st);
 int launch_gather_rows(const PermKey& key, int first, int rows, int obs_dim, int act_dim, const float* obs,
                        const float* act, const float* adv, const float* ret, float* obs_o, float* act_o, float* adv_o,
-                       float* ret_o, const float* old_src, float* old_dst, int pld, cudaStream_t st);
+                       float* ret_o, const float* old_src, float* old_dst, int pld, cudaStream_t st,
+                       const StepParams* sp = nullptr, const int* counter = nullptr);
 int launch_perm_fill(const PermKey& key, int32_t* out, cudaStream_t st);
 
 }  // namespace dppo

@@ -400,8 +400,10 @@ struct FinalizePlan {
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, FinalizePlan plan, long long n_params,
                                 long long head_off, int H, int W, const double* __restrict__ loss_part, int n_tiles,
                                 float entcoeff, float vcoeff, float* __restrict__ grad_out,
-                                float* __restrict__ losses_out) {
+                                float* __restrict__ losses_out, float* __restrict__ grad_out_alt,
+                                const StepParams* __restrict__ sp, const int* __restrict__ counter) {
     const int P = 1 + W;                     // W = policy-head width (2A or ncat)
+    if (sp && sp[*counter].peer_sel) grad_out = grad_out_alt;      // graph replay: the exchange buffer half of this step
     // A block owns 32 consecutive parameters.  Warp w streams slices w, w+8, ... of them: every load instruction
     // is one full 128-byte line (32 lanes x consecutive parameters of ONE slice), 8 lines in flight per warp; the 8
     // warps' sums are then combined in a fixed order through shared memory -> deterministic and DRAM-friendly.
@@ -481,7 +483,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 }
 
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
-                    float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st) {
+                    float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st, float* grad_out_alt,
+                    const StepParams* sp, const int* counter) {
     FinalizePlan plan;
     plan.n_regions = s.L + 1;
     for (int l = 0; l <= s.L; ++l) {
@@ -494,7 +497,7 @@ int launch_finalize(const NetShape& s, const int* active, const float* partial, 
     if (grid < 1) grid = 1;
     ProfScope ps(KK_FINALIZE, st);
     finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.pdw, loss_part,
-                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out);
+                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out, grad_out_alt, sp, counter);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -532,7 +535,9 @@ int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_o
 //   theta -= lr_t * m / (sqrt(v) + eps)
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps) {
+                            float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+                            const StepParams* __restrict__ sp, const int* __restrict__ counter) {
+    if (sp) lr_t = sp[*counter].lr_t;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float gi = g[i];
@@ -543,15 +548,34 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+double adam_lr_t(float lr, float b1, float b2, int step) {
+    return (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
+}
+
+__global__ void step_advance_kernel(const float* __restrict__ grad_tail, float* __restrict__ losses_out,
+                                    const StepParams* __restrict__ sp, int* __restrict__ counter) {
+    const int i = *counter;
+    if (losses_out && threadIdx.x < kLossSlots) losses_out[(size_t)sp[i].loss_slot * kLossSlots + threadIdx.x] = grad_tail[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = i + 1;
+}
+
+int launch_step_advance(const float* grad_tail, float* losses_out, const StepParams* sp, int* counter, cudaStream_t st) {
+    ProfScope ps(KK_MISC, st);
+    step_advance_kernel<<<1, 32, 0, st>>>(grad_tail, losses_out, sp, counter);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,
-                float b1, float b2, float eps, cudaStream_t st) {
+                float b1, float b2, float eps, cudaStream_t st, const StepParams* sp, const int* counter) {
     DPPO_REQUIRE(step >= 1, "dppo_adam_apply: step=%d must be >= 1 (t after increment)", step);
     if (n == 0) return 0;
-    const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
+    const double lr_t = adam_lr_t(lr, b1, b2, step);
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     ProfScope ps(KK_ADAM, st);
-    adam_kernel<<<grid, 256, 0, st>>>(params, grad, m, v, (long long)n, (float)lr_t, b1, b2, eps);
+    adam_kernel<<<grid, 256, 0, st>>>(params, grad, m, v, (long long)n, (float)lr_t, b1, b2, eps, sp, counter);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -566,7 +590,8 @@ __global__ void gather_rows_kernel(PermKey key, int first, int rows, int obs_dim
                                    const float* __restrict__ adv, const float* __restrict__ ret,
                                    float* __restrict__ obs_o, float* __restrict__ act_o, float* __restrict__ adv_o,
                                    float* __restrict__ ret_o, const float* __restrict__ old_src, float* __restrict__ old_dst,
-                                   int pld) {
+                                   int pld, const StepParams* __restrict__ sp, const int* __restrict__ counter) {
+    if (sp) { const StepParams& q = sp[*counter]; key = q.key; first = q.first; rows = q.rows; }
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < rows; j += warps) {
@@ -592,13 +617,14 @@ __global__ void gather_rows_kernel(PermKey key, int first, int rows, int obs_dim
 
 int launch_gather_rows(const PermKey& key, int first, int rows, int obs_dim, int act_dim, const float* obs,
                        const float* act, const float* adv, const float* ret, float* obs_o, float* act_o, float* adv_o,
-                       float* ret_o, const float* old_src, float* old_dst, int pld, cudaStream_t st) {
+                       float* ret_o, const float* old_src, float* old_dst, int pld, cudaStream_t st, const StepParams* sp,
+                       const int* counter) {
     if (rows <= 0) return 0;
     int grid = (rows + 7) / 8;                  // 8 warps per CTA, one row per warp per pass
     if (grid > 148 * 8) grid = 148 * 8;
     ProfScope ps(KK_MISC, st);
     gather_rows_kernel<<<grid, 256, 0, st>>>(key, first, rows, obs_dim, act_dim, obs, act, adv, ret, obs_o, act_o, adv_o,
-                                             ret_o, old_src, old_dst, pld);
+                                             ret_o, old_src, old_dst, pld, sp, counter);
     DPPO_LAUNCH_CHECK();
     return 0;
 }

@@ -58,7 +58,9 @@ struct HArgs {
     int tiles_n, nets, relu, vecA, vecC, bits_wpr;
     float a_scale, out_scale;          // powers of two: operand pre-scale and its inverse
     long long img_replica_bytes;
-    long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_timeline.py)
+    long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
+    int dbg;                           // microbenchmark-only ablations (wrong results): 1 no global loads, 2 no conversion,
+                                       // 4 no global stores, 8 no staging at all, 16 one MMA per k-step instead of three
 };
 
 template <int BN>
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
         auto issue = [&](MoverRegs& r, long long it) {
             int mt, net, nt;
             decode(t_begin + (int)(it / nkb), mt, net, nt);
+            if (g.dbg & 1) return;
             mover_load(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * kKB, g.K, g.vecA, tid);
         };
 #pragma unroll
@@ -201,6 +204,15 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                     const int sa = (int)(it % kASlots);
                     mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
                     uint8_t* slot = a_ring + sa * P::kASlot;
+                    if (g.dbg & 2) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int row = (tid >> 2) + u * 64, cc = tid & 3;
+                            const uint32_t off = (uint32_t)row * 64u + (uint32_t)((cc ^ ((row >> 1) & 3)) << 4);
+                            *reinterpret_cast<float4*>(slot + off) = ra[j].v[u][0];
+                            *reinterpret_cast<float4*>(slot + P::kAHalf + off) = ra[j].v[u][1];
+                        }
+                    } else
                     mover_store(ra[j], slot, slot + P::kAHalf, s, tid);
                     fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
                     mbar_arrive(&full_a[sa]);
@@ -246,8 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                         const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
-                        umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                        umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                        if (!(g.dbg & 16)) {
+                            umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                            umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                        }
                         umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_a[sa]);         // the slots may be refilled once these MMAs retire
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                         o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3])) * oscale;
                         const int c = (ch * kDrainCols + cb) / 4 + j4;               // 16-B chunk of the staged row
                         const int pc = (c & ~7) | ((c ^ r) & 7);                      // XOR swizzle: conflict-free both ways
-                        *reinterpret_cast<float4*>(stg + r * kRowBytes + pc * 16) = o;
+                        if (!(g.dbg & 8)) *reinterpret_cast<float4*>(stg + r * kRowBytes + pc * 16) = o;
                     }
                 }
                 if (p == P::kPhases - 1) {                         // every column of this tile is out of TMEM
@@ -338,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                     const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * kRowBytes + pc * 16);
                     float x[4] = {t4.x, t4.y, t4.z, t4.w};
                     uint32_t nib = 0u;
-                    const bool ok = (m < g.M) && (nv > 0);
+                    const bool ok = (m < g.M) && (nv > 0) && !(g.dbg & 12);
                     if (EPI == EPI_NN) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -509,6 +523,8 @@ int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
 int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
             float a_scale, cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; }      // microbenchmark ablations only
     if (M == 0) return 0;
     th::HArgs g{};
     g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = reinterpret_cast<const uint8_t*>(img0); g.Bimg[1] = reinterpret_cast<const uint8_t*>(img1);
@@ -519,6 +535,7 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.a_scale = a_scale; g.out_scale = 1.0f / a_scale;
     g.img_replica_bytes = th_image_replica_bytes(N, K);
     g.timeline = timeline;
+    g.dbg = dbg;
     g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
     const int bn = th_bn_for(N);
