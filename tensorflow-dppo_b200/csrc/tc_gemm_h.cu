@@ -17,16 +17,22 @@
 //     128-column phases, releases TMEM as soon as the last column is read, and only then streams the second phase to
 //     HBM: the next tile's MMAs overlap the write-out (all 512 TMEM columns are one 128x256 tile's main + correction
 //     accumulators, so TMEM itself cannot be double-buffered);
-//   * separate rings for the activation operand (2 slots, filled by 8 mover warps: LDG fp32 -> fp16 hi/lo -> swizzled
-//     st.shared, 3 k-blocks in flight in registers) and for the weight operand (4 slots, ONE cp.async.bulk of a ready-made
-//     tile image per k-block), so the weight stream can run 3 k-blocks ahead;
+//   * the activation operand arrives by TMA: one thread issues cp.async.bulk.tensor.2d boxes {32 fp32 x 128 rows,
+//     SWIZZLE_128B} into a raw ring (2 slots); 8 converter warps read their 16-B chunks back, split them into fp16 hi / lo
+//     and write the K-major SWIZZLE_64B operand tiles (2 slots).  Measured on the first version of this kernel: register-
+//     staged movers (LDG -> cvt -> STS, 48 KB in flight per SM) delivered only 7 B/clk/SM and left the tensor pipe at 26 %
+//     -- the L1 miss path cannot hold enough loads in flight; the TMA queue can.  Rows whose stride or base is not 16-B
+//     aligned (obs_dim 3, 17, ...) keep the LDG movers (template flag);
+//   * the weight operand has its own ring (3 slots, ONE cp.async.bulk of a ready-made tile image per k-block);
 //   * ReLU sign bitmaps are plain row-major bit matrices (1 bit / activation), written by the forward epilogue and read by
 //     the dX epilogue of the same width.
 // Warps: 0-7 movers | 8 TMEM owner + MMA issuer (one thread) | 9 weight-image producer (one thread) | 10-17 epilogue.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace dppo {
 namespace th {
@@ -42,7 +48,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;      // 576
 constexpr int kKB = 32;                                      // reduction elements per k-block: 32 fp16 = one 64-B swizzle row
-constexpr int kASlots = 2, kBSlots = 4;
+constexpr int kASlots = 2, kBSlots = 3, kRSlots = 2;
 constexpr int kPrefetch = 3;                                 // activation k-blocks in flight per mover thread
 constexpr int kImgReplicas = 8;                              // copies of every weight image (spreads the hot L2 lines)
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
@@ -59,8 +65,6 @@ struct HArgs {
     float a_scale, out_scale;          // powers of two: operand pre-scale and its inverse
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
-    int dbg;                           // microbenchmark-only ablations (wrong results): 1 no global loads, 2 no conversion,
-                                       // 4 no global stores, 8 no staging at all, 16 one MMA per k-step instead of three
 };
 
 template <int BN>
@@ -72,7 +76,9 @@ struct HPlan {
     static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
     static constexpr int kPhases = BN / kPhaseCols;
     static constexpr int kStaging = BM * kPhaseCols * 4;
-    static constexpr int kBOff = kASlots * kASlot;
+    static constexpr int kRawSlot = BM * 128;                // raw fp32 k-block: 128 rows x 32 floats
+    static constexpr int kRawOff = kASlots * kASlot;
+    static constexpr int kBOff = kRawOff + kRSlots * kRawSlot;
     static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
     static constexpr int kBytes = kBarOff + 256 + 1024;
@@ -88,6 +94,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // D = f32, A = B = fp16 (format 0), both K-major, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// shared-memory accesses by 32-bit shared-space address (a pointer derived from the aligned dynamic buffer is a GENERIC
+// pointer to the compiler, which then emits generic LD/ST)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst_smem), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
@@ -126,7 +155,7 @@ __device__ __forceinline__ void mover_load(MoverRegs& r, const float* __restrict
     }
 }
 
-__device__ __forceinline__ void mover_store(const MoverRegs& r, uint8_t* hi_tile, uint8_t* lo_tile, float s, int tid) {
+__device__ __forceinline__ void mover_store(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, float s, int tid) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int row = (tid >> 2) + j * 64, c = tid & 3;
@@ -135,24 +164,38 @@ __device__ __forceinline__ void mover_store(const MoverRegs& r, uint8_t* hi_tile
         uint4 h, l;
         split2(a.x * s, a.y * s, h.x, l.x); split2(a.z * s, a.w * s, h.y, l.y);
         split2(b.x * s, b.y * s, h.z, l.z); split2(b.z * s, b.w * s, h.w, l.w);
-        *reinterpret_cast<uint4*>(hi_tile + off) = h;
-        *reinterpret_cast<uint4*>(lo_tile + off) = l;
+        sts128(hi_tile + off, h);
+        sts128(lo_tile + off, l);
     }
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int total_tiles) {
+// the same two units of a k-block read back from the raw tile TMA wrote (128-B rows, SWIZZLE_128B: chunk ^= row % 8)
+__device__ __forceinline__ void raw_load(MoverRegs& r, uint32_t raw_tile, int tid) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (tid >> 2) + j * 64, c = tid & 3;
+        const uint32_t base = raw_tile + (uint32_t)row * 128u;
+        r.v[j][0] = lds128f(base + (uint32_t)(((2 * c) ^ (row & 7)) << 4));
+        r.v[j][1] = lds128f(base + (uint32_t)(((2 * c + 1) ^ (row & 7)) << 4));
+    }
+}
+
+template <int BN, int EPI, bool TMA_A>
+__global__ void __launch_bounds__(kThreads, 1)
+h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const HArgs g, int total_tiles) {
     using P = HPlan<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + P::kBOff;
-    uint8_t* stg = smem + P::kStgOff;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t a_ring = smem_base, raw_ring = smem_base + P::kRawOff, b_ring = smem_base + P::kBOff;
+    const uint32_t stg = smem_base + P::kStgOff;
     uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + P::kBarOff);
     uint64_t* empty_a = full_a + kASlots;
     uint64_t* full_b = empty_a + kASlots;
     uint64_t* empty_b = full_b + kBSlots;
-    uint64_t* acc_full = empty_b + kBSlots;
+    uint64_t* raw_full = empty_b + kBSlots;
+    uint64_t* raw_empty = raw_full + kRSlots;
+    uint64_t* acc_full = raw_empty + kRSlots;
     uint64_t* acc_empty = acc_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
@@ -167,6 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
     if (tid == 0) {
         for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], kMoverThreads); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < kRSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverThreads); }
         mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
         fence_barrier_init();
     }
@@ -184,62 +228,86 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
     };
 
     if (warp < kMoverWarps) {
-        // ================= activation movers =================
-        MoverRegs ra[kPrefetch];
-        auto issue = [&](MoverRegs& r, long long it) {
-            int mt, net, nt;
-            decode(t_begin + (int)(it / nkb), mt, net, nt);
-            if (g.dbg & 1) return;
-            mover_load(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * kKB, g.K, g.vecA, tid);
-        };
-#pragma unroll
-        for (int j = 0; j < kPrefetch; ++j)
-            if (j < total_it) issue(ra[j], j);
         const float s = g.a_scale;
-        for (long long it0 = 0; it0 < total_it; it0 += kPrefetch) {
+        if (TMA_A) {
+            // ================= converters: raw fp32 tile (TMA) -> fp16 hi / lo operand tiles =================
+            for (long long it = 0; it < total_it; ++it) {
+                const int rs = (int)(it % kRSlots), sa = (int)(it % kASlots);
+                MoverRegs r;
+                mbar_wait(&raw_full[rs], (uint32_t)((it / kRSlots) & 1));
+                raw_load(r, raw_ring + rs * P::kRawSlot, tid);
+                mbar_arrive(&raw_empty[rs]);               // release: the loads above are complete; TMA may refill the slot
+                mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
+                const uint32_t slot = a_ring + sa * P::kASlot;
+                mover_store(r, slot, slot + P::kAHalf, s, tid);
+                fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(&full_a[sa]);
+            }
+        } else {
+            // ================= movers: LDG fp32 -> fp16 hi / lo (rows that TMA cannot address: unaligned strides) ==========
+            MoverRegs ra[kPrefetch];
+            auto issue = [&](MoverRegs& r, long long it) {
+                int mt, net, nt;
+                decode(t_begin + (int)(it / nkb), mt, net, nt);
+                mover_load(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * kKB, g.K, g.vecA, tid);
+            };
 #pragma unroll
-            for (int j = 0; j < kPrefetch; ++j) {
-                const long long it = it0 + j;
-                if (it < total_it) {
-                    const int sa = (int)(it % kASlots);
-                    mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
-                    uint8_t* slot = a_ring + sa * P::kASlot;
-                    if (g.dbg & 2) {
+            for (int j = 0; j < kPrefetch; ++j)
+                if (j < total_it) issue(ra[j], j);
+            for (long long it0 = 0; it0 < total_it; it0 += kPrefetch) {
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int row = (tid >> 2) + u * 64, cc = tid & 3;
-                            const uint32_t off = (uint32_t)row * 64u + (uint32_t)((cc ^ ((row >> 1) & 3)) << 4);
-                            *reinterpret_cast<float4*>(slot + off) = ra[j].v[u][0];
-                            *reinterpret_cast<float4*>(slot + P::kAHalf + off) = ra[j].v[u][1];
-                        }
-                    } else
-                    mover_store(ra[j], slot, slot + P::kAHalf, s, tid);
-                    fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
-                    mbar_arrive(&full_a[sa]);
-                    if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
+                for (int j = 0; j < kPrefetch; ++j) {
+                    const long long it = it0 + j;
+                    if (it < total_it) {
+                        const int sa = (int)(it % kASlots);
+                        mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
+                        const uint32_t slot = a_ring + sa * P::kASlot;
+                        mover_store(ra[j], slot, slot + P::kAHalf, s, tid);
+                        fence_proxy_async();
+                        mbar_arrive(&full_a[sa]);
+                        if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
+                    }
                 }
             }
         }
     } else if (warp == kProdWarp) {
-        // ================= weight-image producer (one thread) =================
+        // ================= producer (one thread): weight-image bulk copies and activation TMA boxes =================
+        // two independent streams polled without blocking, so that a full ring of one never holds the other back
         if (lane == 0) {
-            for (long long it = 0; it < total_it; ++it) {
-                int mt, net, nt;
-                decode(t_begin + (int)(it / nkb), mt, net, nt);
-                const int kb = (int)(it % nkb);
-                const int sb = (int)(it % kBSlots);
-                mbar_wait(&empty_b[sb], (uint32_t)(((it / kBSlots) & 1) ^ 1));
-                const uint8_t* img = g.Bimg[net] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
-                                     ((size_t)nt * nkb + (size_t)kb) * P::kBSlot;
-                mbar_arrive_expect_tx(&full_b[sb], (uint32_t)P::kBSlot);
-                bulk_copy_g2s(b_ring + sb * P::kBSlot, img, (uint32_t)P::kBSlot, &full_b[sb]);
+            long long ib = 0, ia = TMA_A ? 0 : total_it;
+            while (ib < total_it || ia < total_it) {
+                if (ib < total_it) {
+                    const int sb = (int)(ib % kBSlots);
+                    if (mbar_test(&empty_b[sb], (uint32_t)(((ib / kBSlots) & 1) ^ 1))) {
+                        int mt, net, nt;
+                        decode(t_begin + (int)(ib / nkb), mt, net, nt);
+                        const int kb = (int)(ib % nkb);
+                        const uint8_t* img = g.Bimg[net] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
+                                             ((size_t)nt * nkb + (size_t)kb) * P::kBSlot;
+                        mbar_arrive_expect_tx(&full_b[sb], (uint32_t)P::kBSlot);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(b_ring + sb * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[sb]))
+                                     : "memory");
+                        ++ib;
+                    }
+                }
+                if (ia < total_it) {
+                    const int rs = (int)(ia % kRSlots);
+                    if (mbar_test(&raw_empty[rs], (uint32_t)(((ia / kRSlots) & 1) ^ 1))) {
+                        int mt, net, nt;
+                        decode(t_begin + (int)(ia / nkb), mt, net, nt);
+                        mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)P::kRawSlot);
+                        tma_load_2d(raw_ring + rs * P::kRawSlot, net ? &mapA1 : &mapA0, (int)(ia % nkb) * kKB, mt * BM, &raw_full[rs]);
+                        ++ia;
+                    }
+                }
             }
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(BN);
-            const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+            const uint32_t a_base = a_ring, b_base = b_ring;
             long long it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));          // the epilogue has read tile i-1 out of TMEM
@@ -258,10 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                         const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
-                        if (!(g.dbg & 16)) {
-                            umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                            umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
-                        }
+                        umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                        umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
                         umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_a[sa]);         // the slots may be refilled once these MMAs retire
@@ -315,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                         o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3])) * oscale;
                         const int c = (ch * kDrainCols + cb) / 4 + j4;               // 16-B chunk of the staged row
                         const int pc = (c & ~7) | ((c ^ r) & 7);                      // XOR swizzle: conflict-free both ways
-                        if (!(g.dbg & 8)) *reinterpret_cast<float4*>(stg + r * kRowBytes + pc * 16) = o;
+                        sts128f(stg + (uint32_t)(r * kRowBytes + pc * 16), o);
                     }
                 }
                 if (p == P::kPhases - 1) {                         // every column of this tile is out of TMEM
@@ -334,8 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                         mw[it] = (m < g.M && n < g.N) ? __ldg(g.bits_in + (size_t)m * g.bits_wpr + (n >> 5)) : 0u;
                     }
                 }
-                epi_bar();                                         // staging complete
-                // ---- write-out: one staged row (or two) per warp instruction, coalesced ----
+                // the bias of this lane's four columns, likewise ahead of the barrier
                 const int n = nt * BN + p * PC + cl * 4;
                 const int nv = min(4, g.N - n);
                 float bv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -344,15 +409,17 @@ __global__ void __launch_bounds__(kThreads, 1) h_gemm_kernel(const HArgs g, int 
                     for (int e = 0; e < 4; ++e)
                         if (e < nv) bv[e] = __ldg(bias + n + e);
                 }
+                epi_bar();                                         // staging complete
+                // ---- write-out: one staged row (or two) per warp instruction, coalesced ----
 #pragma unroll
                 for (int it = 0; it < kIters; ++it) {
                     const int rr = ew * 16 + it * kRowsPerIter + lr;
                     const int m = mt * BM + rr;
                     const int pc = (cl & ~7) | ((cl ^ rr) & 7);
-                    const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * kRowBytes + pc * 16);
+                    const float4 t4 = lds128f(stg + (uint32_t)(rr * kRowBytes + pc * 16));
                     float x[4] = {t4.x, t4.y, t4.z, t4.w};
                     uint32_t nib = 0u;
-                    const bool ok = (m < g.M) && (nv > 0) && !(g.dbg & 12);
+                    const bool ok = (m < g.M) && (nv > 0);
                     if (EPI == EPI_NN) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -440,21 +507,59 @@ __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
 
 static inline int aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+typedef CUresult (*HEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static HEncodeFn h_encode() {
+    static HEncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<HEncodeFn>(p);
+    }
+    return fn;
+}
+// row-major [rows, cols] fp32 activation matrix, box {32 cols, 128 rows}, SWIZZLE_128B; out-of-range reads give zeros
+static bool h_make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld) {
+    HEncodeFn enc = h_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int EPI, bool TMA_A>
+static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, HArgs& g, int grid, int total, cudaStream_t st) {
+    using P = HPlan<BN>;
+    static PerDeviceOnce configured;
+    if (configured.need())
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    ProfScope ps(KK_TC_GEMM, st);
+    h_gemm_kernel<BN, EPI, TMA_A><<<grid, kThreads, P::kBytes, st>>>(m0, m1, g, total);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int BN, int EPI>
 static int launch_h(HArgs& g, cudaStream_t st) {
-    using P = HPlan<BN>;
     g.tiles_n = (g.N + BN - 1) / BN;
     const int tiles_m = (g.M + BM - 1) / BM;
     const long long total = (long long)tiles_m * g.tiles_n * g.nets;
     DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
-    static PerDeviceOnce configured;
-    if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
-    ProfScope ps(KK_TC_GEMM, st);
-    h_gemm_kernel<BN, EPI><<<grid, kThreads, P::kBytes, st>>>(g, (int)total);
-    DPPO_LAUNCH_CHECK();
-    return 0;
+    // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, 35-wide heads' gradients ...) takes the LDG movers
+    CUtensorMap m0, m1;
+    memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1));
+    bool tma = g.vecA && h_make_map(&m0, g.A[0], g.M, g.K, g.lda);
+    if (tma) { if (g.nets > 1) tma = h_make_map(&m1, g.A[1], g.M, g.K, g.lda); else m1 = m0; }
+    if (tma) return launch_h2<BN, EPI, true>(m0, m1, g, grid, (int)total, st);
+    return launch_h2<BN, EPI, false>(m0, m1, g, grid, (int)total, st);
 }
 
 }  // namespace th
@@ -523,8 +628,7 @@ int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
 int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
             float a_scale, cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline) {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; }      // microbenchmark ablations only
+
     if (M == 0) return 0;
     th::HArgs g{};
     g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = reinterpret_cast<const uint8_t*>(img0); g.Bimg[1] = reinterpret_cast<const uint8_t*>(img1);
@@ -535,7 +639,6 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.a_scale = a_scale; g.out_scale = 1.0f / a_scale;
     g.img_replica_bytes = th_image_replica_bytes(N, K);
     g.timeline = timeline;
-    g.dbg = dbg;
     g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
     const int bn = th_bn_for(N);

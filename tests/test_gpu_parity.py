@@ -918,7 +918,7 @@ def test_h_gemm_fp16_split(M, N, K):
     """tc_gemm_h.cu through dppo_dbg_gemm: persistent tcgen05 kind::f16 product with the 2-term fp16 split vs an fp64
     product, forward epilogue (bias + ReLU) and dX epilogue (fp32 mask, operand pre-scaled by 2^17)."""
     rng = np.random.default_rng(M * 7 + N * 3 + K)
-    eng = _engine(376, (256, 256), 17, max(M, 4096), gemm_mode=1)
+    eng = _engine(376, (256, 256), 17, max(M, 32768), gemm_mode=1)      # the weight image is taken from the workspace
     A = rng.standard_normal((M, K)).astype(np.float32)
     Bt = (rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
