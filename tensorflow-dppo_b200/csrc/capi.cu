@@ -267,7 +267,7 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
             const int W = 2 * kPlanSMs / g;
             const int up = ((want + W - 1) / W) * W;
             if (up * 4 <= want * 5) want = up;
-            const int kps = (((rows + want - 1) / want + 15) / 16) * 16;
+            const int kps = (((rows + want - 1) / want + 31) / 32) * 32;     // whole k-blocks of the fp16 (32-row) and tf32 (16-row) kernels
             want = (rows + kps - 1) / kps;
             if (want < a) a = want;
         } else {
@@ -322,6 +322,9 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
                 return r;
             return tc_colsum(dY, rows, out, ldy, active[l], p + (size_t)in * out, s.region[l], accumulate, st);
         }
+        if (fp16x2 && th_dw_supported(x_in, in, dY, ldy))     // persistent fp16-split kernel, bias column sums fused
+            return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,
+                              dx_scale, st);
         if (tcore) {
             if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
                 return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l],
@@ -1115,6 +1118,26 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         ProfScope ps(KK_MISC, st);
         reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
         DPPO_LAUNCH_CHECK();
+        return 0;
+    }
+    if (mode == 99) {
+        // persistent fp16-split dW product (tc_dw_h.cu): C[M,N] = A[K,M]^T . B[K,N], bias_out[N] = column sums of B, with B
+        // pre-scaled by 2^17 inside the kernel (B holds 1/B-sized gradients)
+        const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
+        int slices = (int)(c->shape.partial_floats / stride);
+        const int want = (K + 511) / 512;
+        if (slices > want) slices = want;
+        DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
+        DPPO_REQUIRE(th_dw_supported(A, M, B, N), "dppo_dbg_gemm: the fp16 dW kernel needs 16-byte aligned rows");
+        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, 131072.0f, st))
+            return r;
+        ProfScope ps(KK_MISC, st);
+        reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
+        DPPO_LAUNCH_CHECK();
+        if (bias_out) {
+            reduce_slices_kernel<<<4, 256, 0, st>>>(c->ws.partial + (int64_t)M * N, slices, stride, N, bias_out);
+            DPPO_LAUNCH_CHECK();
+        }
         return 0;
     }
     if (mode == 96 || mode == 97 || mode == 98) {

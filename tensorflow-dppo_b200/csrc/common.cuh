@@ -243,6 +243,9 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
             float a_scale, cudaStream_t st, uint32_t* bits_out0 = nullptr, const uint32_t* bits_in = nullptr,
             long long* timeline = nullptr);
+bool th_dw_supported(const float* X, int ldx, const float* G, int ldg);
+int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int ldg, float* C, int ldc, float* bias_out,
+               int slices, long long slice_stride, int accumulate, float g_scale, cudaStream_t st);
 // tensor-core gemm modes whose dW runs on the tf32 TMA kernel with the 512-row accumulation bound
 inline bool tc_mode(int gemm_mode) { return gemm_mode == DPPO_GEMM_TF32X3 || gemm_mode == DPPO_GEMM_FP16X2; }
 int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,

@@ -1,0 +1,383 @@
+// Persistent fp16-split dW product:  C[s][M,N] (+)= X[rows_s, M]^T . G[rows_s, N]  over the rows of slice s  (sm_100a)
+//
+// The weight-gradient part of TF's auto-diff (/root/reference/PPO.py:46) for the dense layers of Model.py:12-14, on
+// tcgen05 kind::f16 with the 2-term fp16 split of tc_gemm_h.cu (x = hi + lo / 2^11, three MMAs per product, main and
+// correction accumulators in TMEM).  Both operands are activations whose reduction dimension (rollout rows) is the slow
+// axis of a row-major matrix, i.e. MN-major UMMA operands (SWIZZLE_128B: 64 fp16 of M or N per 128-B row, 8 k-rows per
+// atom, the layout tc_gemm_bf16.cu validated).  CTAs are persistent over (slice, m-tile, n-tile) work items:
+//
+//   warp 9 (one thread) : cp.async.bulk.tensor.2d boxes {32 fp32 features x 32 rows, SWIZZLE_128B} of X and of G into a
+//                         raw ring (2 slots x 48 KB at BN = 256);
+//   warps 0-7           : converters, lane = k-row, a fixed set of 8-feature column groups per warp: LDS raw -> fp16 hi/lo
+//                         -> operand tiles (2 slots); the same pass adds up G's columns (the bias gradient) in registers --
+//                         every column group belongs to ONE warp, so a warp shuffle finishes the sum, deterministically;
+//   warp 8 (one thread) : 6 MMAs per 32-row k-block (2 k-steps x {lo.hi, hi.lo -> correction; hi.hi -> main});
+//   warps 10-17         : epilogue, as in tc_gemm_h.cu: TMEM -> staging (64-column phases) -> coalesced partial-slice rows
+//                         (+= when the update accumulates over row chunks); TMEM is released after the last phase's drain.
+// G carries 1/B-scaled gradients: it is multiplied by a power of two (g_scale) on its way into the operand tiles and the
+// result scaled back.  Rows per slice are bounded by the split-K plan (fp32 TMEM accumulation truncates: DESIGN.md).
+#include "tc_h.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+namespace dppo {
+namespace th {
+
+constexpr int kDwRaw = 2, kDwOp = 2;               // ring depths
+constexpr int kDwPC = 64;                          // staged columns per epilogue phase
+
+struct DwArgs {
+    float* C; float* bias_out;
+    int M, N, K;                  // C is [M,N] (ldc); K = rollout rows
+    int ldc, k_per_slice, slices, accumulate, vecC;
+    int tiles_m, tiles_n;
+    long long slice_stride;
+    float g_scale, out_scale;
+};
+
+template <int BN>
+struct DwPlan {
+    static constexpr int kARaw = 32 * BM * 4;            // 4 boxes of {32 features x 32 rows} fp32
+    static constexpr int kBRaw = 32 * BN * 4;
+    static constexpr int kRawSlot = kARaw + kBRaw;
+    static constexpr int kAHalf = 32 * BM * 2;           // fp16 hi (or lo) operand tile: BM/64 atoms x 32 k-rows x 128 B
+    static constexpr int kBHalf = 32 * BN * 2;
+    static constexpr int kOpSlot = 2 * (kAHalf + kBHalf);
+    static constexpr int kPC = BN < kDwPC ? BN : kDwPC;
+    static constexpr int kPhases = BN / kPC;
+    static constexpr int kStaging = BM * kPC * 4;
+    static constexpr int kOpOff = kDwRaw * kRawSlot;
+    static constexpr int kStgOff = kOpOff + kDwOp * kOpSlot;
+    static constexpr int kBarOff = kStgOff + kStaging;
+    static constexpr int kBytes = kBarOff + 256 + 1024;
+    static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
+};
+
+// D = f32, A = B = fp16, both MN-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// one 8-feature unit (k-row `k`, box `box`, unit `j` of the box): raw fp32 -> hi / lo chunk of the MN-major operand tile
+__device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_tile, uint32_t lo_tile, int box, int j, int k, float s,
+                                                float (&csum)[8], bool sum) {
+    const uint32_t rbase = raw_op + (uint32_t)box * 4096u + (uint32_t)k * 128u;
+    const float4 a = lds128f(rbase + (uint32_t)(((2 * j) ^ (k & 7)) << 4));
+    const float4 b = lds128f(rbase + (uint32_t)(((2 * j + 1) ^ (k & 7)) << 4));
+    if (sum) {
+        csum[0] += a.x; csum[1] += a.y; csum[2] += a.z; csum[3] += a.w;
+        csum[4] += b.x; csum[5] += b.y; csum[6] += b.z; csum[7] += b.w;
+    }
+    uint4 h, l;
+    split2(a.x * s, a.y * s, h.x, l.x); split2(a.z * s, a.w * s, h.y, l.y);
+    split2(b.x * s, b.y * s, h.z, l.z); split2(b.z * s, b.w * s, h.w, l.w);
+    const int c = (box & 1) * 4 + j;                                  // 16-B chunk of the 64-feature atom
+    const uint32_t off = (uint32_t)(box >> 1) * 4096u + (uint32_t)k * 128u + (uint32_t)((c ^ (k & 7)) << 4);
+    sts128(hi_tile + off, h);
+    sts128(lo_tile + off, l);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG, const DwArgs g, int total_tiles) {
+    using P = DwPlan<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t raw_ring = smem_base, op_ring = smem_base + P::kOpOff, stg = smem_base + P::kStgOff;
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + P::kBarOff);
+    uint64_t* raw_empty = raw_full + kDwRaw;
+    uint64_t* op_full = raw_empty + kDwRaw;
+    uint64_t* op_empty = op_full + kDwOp;
+    uint64_t* acc_full = op_empty + kDwOp;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per_cta;
+    const int t_end = min(total_tiles, t_begin + per_cta);
+    const int my_tiles = max(0, t_end - t_begin);
+    const int tiles_mn = g.tiles_m * g.tiles_n;
+
+    // work item t -> (slice, m-tile, n-tile); the tiles of one slice are neighbours (they share X / G rows through L2)
+    auto decode = [&](int t, int& slice, int& mt, int& nt, int& nkb, int& k0) {
+        slice = t / tiles_mn;
+        const int r = t - slice * tiles_mn;
+        mt = r / g.tiles_n; nt = r - mt * g.tiles_n;
+        k0 = slice * g.k_per_slice;
+        const int k1 = min(g.K, k0 + g.k_per_slice);
+        nkb = max(0, (k1 - k0 + kKB - 1) / kKB);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kDwRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverThreads); }
+        for (int s = 0; s < kDwOp; ++s) { mbar_init(&op_full[s], kMoverThreads); mbar_init(&op_empty[s], 1); }
+        mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
+        fence_barrier_init();
+    }
+    constexpr uint32_t kTmemCols = 2 * BN;
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kMoverWarps) {
+        // ================= converters (+ column sums of G = the bias gradient) =================
+        constexpr int kAPairs = (BM / 32) * 4 / kMoverWarps;          // (box, j) column groups of X per warp: 2
+        constexpr int kBPairs = (BN / 32) * 4 / kMoverWarps;          // ... of G per warp: BN / 64
+        static_assert(kBPairs >= 1, "BN >= 64");
+        const int k = lane;
+        const float gs = g.g_scale;
+        long long it = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            int slice, mt, nt, nkb, k0;
+            decode(t_begin + i, slice, mt, nt, nkb, k0);
+            const bool want_bias = (g.bias_out != nullptr) && (mt == 0);
+            float csum[kBPairs][8];
+#pragma unroll
+            for (int u = 0; u < kBPairs; ++u)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) csum[u][e] = 0.f;
+            float dummy[8];
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int rs = (int)(it % kDwRaw), os = (int)(it % kDwOp);
+                mbar_wait(&raw_full[rs], (uint32_t)((it / kDwRaw) & 1));
+                mbar_wait(&op_empty[os], (uint32_t)(((it / kDwOp) & 1) ^ 1));
+                const uint32_t raw = raw_ring + rs * P::kRawSlot;
+                const uint32_t op = op_ring + os * P::kOpSlot;
+                const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+#pragma unroll
+                for (int u = 0; u < kAPairs; ++u) {
+                    const int p = warp + u * kMoverWarps;
+                    dw_convert_unit(raw, a_hi, a_lo, p >> 2, p & 3, k, 1.0f, dummy, false);
+                }
+#pragma unroll
+                for (int u = 0; u < kBPairs; ++u) {
+                    const int p = warp + u * kMoverWarps;
+                    dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, gs, csum[u], want_bias);
+                }
+                fence_proxy_async();
+                mbar_arrive(&op_full[os]);
+                mbar_arrive(&raw_empty[rs]);
+            }
+            if (want_bias) {            // warp-uniform: fold the 32 k-rows (lanes), lane 0 writes the slice's bias partials
+#pragma unroll
+                for (int u = 0; u < kBPairs; ++u) {
+                    const int p = warp + u * kMoverWarps;
+                    const int n = nt * BN + (p >> 2) * 32 + (p & 3) * 8;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float v = csum[u][e];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == 0 && n + e < g.N) {
+                            float* bo = g.bias_out + (size_t)slice * g.slice_stride + n + e;
+                            *bo = g.accumulate ? *bo + v : v;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == kProdWarp) {
+        // ================= TMA producer (one thread) =================
+        if (lane == 0) {
+            long long it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int slice, mt, nt, nkb, k0;
+                decode(t_begin + i, slice, mt, nt, nkb, k0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int rs = (int)(it % kDwRaw);
+                    mbar_wait(&raw_empty[rs], (uint32_t)(((it / kDwRaw) & 1) ^ 1));
+                    const uint32_t raw = raw_ring + rs * P::kRawSlot;
+                    mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)P::kRawSlot);
+                    const int row = k0 + kb * kKB;
+#pragma unroll
+                    for (int b = 0; b < BM / 32; ++b) tma_load_2d(raw + b * 4096, &mapX, mt * BM + b * 32, row, &raw_full[rs]);
+#pragma unroll
+                    for (int b = 0; b < BN / 32; ++b)
+                        tma_load_2d(raw + P::kARaw + b * 4096, &mapG, nt * BN + b * 32, row, &raw_full[rs]);
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_mn(BN);
+            constexpr uint32_t kLbo = 4096u, kSbo = 1024u, kStep = 2048u;     // MN atoms / 8-row k groups / one UMMA_K = 16 rows
+            long long it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int slice, mt, nt, nkb, k0;
+                decode(t_begin + i, slice, mt, nt, nkb, k0);
+                mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int os = (int)(it % kDwOp);
+                    mbar_wait(&op_full[os], (uint32_t)((it / kDwOp) & 1));
+                    tc_fence_after();
+                    const uint32_t op = op_ring + os * P::kOpSlot;
+                    const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+#pragma unroll
+                    for (int k = 0; k < kKB / 16; ++k) {
+                        const uint64_t da_hi = make_sdesc(a_hi + k * kStep, kLbo, kSbo, kLayoutSW128);
+                        const uint64_t da_lo = make_sdesc(a_lo + k * kStep, kLbo, kSbo, kLayoutSW128);
+                        const uint64_t db_hi = make_sdesc(b_hi + k * kStep, kLbo, kSbo, kLayoutSW128);
+                        const uint64_t db_lo = make_sdesc(b_lo + k * kStep, kLbo, kSbo, kLayoutSW128);
+                        umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                        umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                        umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&op_empty[os]);
+                }
+                umma_commit(acc_full);                 // fires at once when the slice holds no rows (nkb == 0)
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ================= epilogue warps =================
+        constexpr int PC = P::kPC;
+        constexpr int kRowBytes = PC * 4;
+        constexpr int kDrainCols = PC / 2;                        // 32 (or 16 when BN = 32: not built)
+        constexpr int kLanesPerRow = PC / 4;                      // 16
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;           // 2
+        constexpr int kIters = (BM / kEpiWarps) / kRowsPerIter;   // 8
+        static_assert(kDrainCols == 32, "one 32-column TMEM load per warp and phase");
+        const int ew = warp - kEpiWarp0;
+        const int q = warp & 3;
+        const int ch = ew >> 2;
+        const int lr = lane / kLanesPerRow, cl = lane % kLanesPerRow;
+        const float oscale = g.out_scale;
+        for (int i = 0; i < my_tiles; ++i) {
+            int slice, mt, nt, nkb, k0;
+            decode(t_begin + i, slice, mt, nt, nkb, k0);
+            float* __restrict__ C = g.C + (size_t)slice * g.slice_stride;
+            mbar_wait(acc_full, (uint32_t)(i & 1));
+            tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int p = 0; p < P::kPhases; ++p) {
+                epi_bar();
+                const int r = q * 32 + lane;
+                {
+                    const int col = p * PC + ch * kDrainCols;
+                    uint32_t v[32], w2[32];
+                    if (nkb > 0) {
+                        tmem_ld32(acc + (uint32_t)col, v);
+                        tmem_ld32(acc + (uint32_t)(BN + col), w2);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[j] = 0u; w2[j] = 0u; }
+                    }
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 o;
+                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0])) * oscale;
+                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1])) * oscale;
+                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2])) * oscale;
+                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3])) * oscale;
+                        const int c = (ch * kDrainCols) / 4 + j4;
+                        const int pc = (c & ~7) | ((c ^ r) & 7);
+                        sts128f(stg + (uint32_t)(r * kRowBytes + pc * 16), o);
+                    }
+                }
+                if (p == P::kPhases - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+                const int n = nt * BN + p * PC + cl * 4;
+                const int nv = min(4, g.N - n);
+                // accumulate over row chunks: the partial tile is requested ahead of the barrier
+                float4 aux[kIters];
+#pragma unroll
+                for (int it = 0; it < kIters; ++it) {
+                    const int m = mt * BM + ew * 16 + it * kRowsPerIter + lr;
+                    aux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.accumulate && m < g.M && nv > 0) {
+                        const float* sp = C + (size_t)m * g.ldc + n;
+                        if (g.vecC && nv == 4) aux[it] = *reinterpret_cast<const float4*>(sp);
+                        else {
+                            aux[it].x = sp[0];
+                            if (nv > 1) aux[it].y = sp[1];
+                            if (nv > 2) aux[it].z = sp[2];
+                            if (nv > 3) aux[it].w = sp[3];
+                        }
+                    }
+                }
+                epi_bar();
+#pragma unroll
+                for (int it = 0; it < kIters; ++it) {
+                    const int rr = ew * 16 + it * kRowsPerIter + lr;
+                    const int m = mt * BM + rr;
+                    const int pc = (cl & ~7) | ((cl ^ rr) & 7);
+                    const float4 t4 = lds128f(stg + (uint32_t)(rr * kRowBytes + pc * 16));
+                    if (m < g.M && nv > 0) {
+                        const float x[4] = {t4.x + aux[it].x, t4.y + aux[it].y, t4.z + aux[it].z, t4.w + aux[it].w};
+                        float* cp = C + (size_t)m * g.ldc + n;
+                        if (g.vecC && nv == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv) cp[e] = x[e];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <int BN>
+static int launch_dw(const CUtensorMap& mX, const CUtensorMap& mG, DwArgs& g, cudaStream_t st) {
+    using P = DwPlan<BN>;
+    g.tiles_m = (g.M + BM - 1) / BM;
+    g.tiles_n = (g.N + BN - 1) / BN;
+    const long long total = (long long)g.tiles_m * g.tiles_n * g.slices;
+    DPPO_REQUIRE(total < (1ll << 30), "h_dw: too many work items");
+    static PerDeviceOnce configured;
+    if (configured.need())
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_dw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
+    ProfScope ps(KK_TC_GEMM, st);
+    h_dw_kernel<BN><<<grid, kThreads, P::kBytes, st>>>(mX, mG, g, (int)total);
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace th
+
+// true when the TMA-fed dW kernel can take this product (16-byte aligned rows of both operands)
+bool th_dw_supported(const float* X, int ldx, const float* G, int ldg) {
+    return th::h_encode() != nullptr && (ldx % 4 == 0) && (ldg % 4 == 0) && th::aligned16(X) && th::aligned16(G);
+}
+
+// C[s][M,N] (+)= X[rows,M]^T . G[rows,N] over the rows of slice s (k_per_slice rows, a multiple of 32);
+// bias_out[s][N] (+)= column sums of G (may be null).  g_scale: power of two applied to G's operand tiles.
+int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int ldg, float* C, int ldc, float* bias_out,
+               int slices, long long slice_stride, int accumulate, float g_scale, cudaStream_t st) {
+    CUtensorMap mX, mG;
+    DPPO_REQUIRE(th::h_make_map(&mX, X, K, M, ldx, 32), "cuTensorMapEncodeTiled failed for X [%d x %d] ld %d", K, M, ldx);
+    DPPO_REQUIRE(th::h_make_map(&mG, G, K, N, ldg, 32), "cuTensorMapEncodeTiled failed for G [%d x %d] ld %d", K, N, ldg);
+    th::DwArgs g{};
+    g.C = C; g.bias_out = bias_out; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.accumulate = accumulate;
+    g.slice_stride = slice_stride;
+    if (slices < 1) slices = 1;
+    int kps = (K + slices - 1) / slices;
+    kps = ((kps + th::kKB - 1) / th::kKB) * th::kKB;
+    if (kps == 0) kps = th::kKB;
+    g.k_per_slice = kps; g.slices = slices;
+    g.vecC = (ldc % 4 == 0) && th::aligned16(C) && (slice_stride % 4 == 0);
+    g.g_scale = g_scale; g.out_scale = 1.0f / g_scale;
+    if (N > 128) return th::launch_dw<256>(mX, mG, g, st);
+    if (N > 64) return th::launch_dw<128>(mX, mG, g, st);
+    return th::launch_dw<64>(mX, mG, g, st);
+}
+
+}  // namespace dppo

@@ -932,6 +932,21 @@ def test_h_gemm_fp16_split(M, N, K):
     assert rel_err(got2, ref2) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,Kr", [(128, 256, 32), (376, 256, 1000), (256, 36, 2048), (120, 64, 333), (256, 256, 4096),
+                                    (376, 256, 20000), (256, 128, 1500), (1024, 1024, 2048)])
+def test_h_dw_fp16_split(M, N, Kr):
+    """tc_dw_h.cu through dppo_dbg_gemm mode 99: C = X^T . G over the rows (split-K slices, fused column sums of G) vs fp64;
+    G holds 1/B-sized gradients (pre-scaled by 2^17 inside the kernel)."""
+    rng = np.random.default_rng(M + 3 * N + 7 * Kr)
+    eng = _engine(376, (1024, 1024), 17, 4096, gemm_mode=1)
+    X = rng.standard_normal((Kr, M)).astype(np.float32)
+    G = (rng.standard_normal((Kr, N)) / 131072.0).astype(np.float32)
+    got, bias = eng.dbg_gemm(99, dev(X), dev(G), M, N, Kr, want_bias_out=True)
+    ref = X.astype(np.float64).T @ G.astype(np.float64)
+    assert rel_err(got.cpu().numpy(), ref) < 2e-6
+    assert rel_err(bias.cpu().numpy(), G.astype(np.float64).sum(0)) < 2e-6
+
+
 @pytest.mark.parametrize("name,T,N,obs,hidden,A", CASES)
 def test_loss_grad_vs_oracle_fp16x2(name, T, N, obs, hidden, A):
     """The whole tower on the persistent fp16-split kernels (forward, dX; dW on the TMA-fed tf32 kernel), 1e-5 bar."""

@@ -22,9 +22,18 @@ shapes = [  # (mode, M, N, K, label)
     (48, 18944, 256, 4096, "tf32 one wave, long K"),
     (96, 18944, 256, 4096, "h    one wave, long K"),
     (96, 131072, 128, 256, "h    N=128"),
+    (19, 376, 256, 131072, "tf32 dW L1 (TMA)"),
+    (99, 376, 256, 131072, "h    dW L1"),
+    (19, 256, 256, 131072, "tf32 dW L2 (TMA)"),
+    (99, 256, 256, 131072, "h    dW L2"),
+    (19, 256, 36, 131072, "tf32 dW head (TMA)"),
+    (99, 256, 36, 131072, "h    dW head"),
 ]
 for mode, M, N, K, label in shapes:
-    A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
+    if mode in (19, 99):
+        A = torch.randn(K, M, device="cuda"); B = torch.randn(K, N, device="cuda")
+    else:
+        A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda")
     mask = torch.randn(M, N, device="cuda") if mode in (49, 97) else None
     bias = torch.randn(N, device="cuda") if mode in (48, 96) else None
     relu = mode in (48, 96)
