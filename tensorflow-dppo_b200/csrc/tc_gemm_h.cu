@@ -34,7 +34,7 @@
 namespace dppo {
 namespace th {
 
-constexpr int kASlots = 2, kBSlots = 3, kRSlots = 2;
+constexpr int kASlots = 2, kRSlots = 2, kPeerSlots = 4;
 constexpr int kPrefetch = 3;                                 // activation k-blocks in flight per mover thread
 constexpr int kImgReplicas = 8;                              // copies of every weight image (spreads the hot L2 lines)
 
@@ -52,11 +52,13 @@ struct HArgs {
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 struct HPlan {
+    static constexpr int kBSlots = PAIR ? 4 : 3;
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
     static constexpr int kASlot = 2 * kAHalf;
-    static constexpr int kBHalf = BN * 64;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;        // a CTA of a pair holds half of the weight tile's rows
+    static constexpr int kBHalf = kBRows * 64;
     static constexpr int kBSlot = 2 * kBHalf;
     static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
     static constexpr int kPhases = BN / kPhaseCols;
@@ -121,10 +123,16 @@ __device__ __forceinline__ void raw_load(MoverRegs& r, uint32_t raw_tile, int ti
     }
 }
 
-template <int BN, int EPI, bool TMA_A>
+// PAIR: two CTAs of a cluster work on a 256-row super-tile with cta_group::2 MMAs (M = 256): each CTA streams its own 128
+// activation rows and HALF of the weight tile's rows, so the weight bytes a CTA pulls through its L2 port halve (the
+// single-CTA kernel is bound by exactly that port).  The leader (rank 0) issues every MMA once both CTAs' slots are full
+// (the peer's MMA warp relays its local full barriers to the leader) and releases slots / publishes accumulators with
+// multicast commits; each CTA drains its own TMEM rows.
+template <int BN, int EPI, bool TMA_A, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const HArgs g, int total_tiles) {
-    using P = HPlan<BN>;
+    using P = HPlan<BN, PAIR>;
+    constexpr int kBSlots = P::kBSlots;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
@@ -138,12 +146,16 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     uint64_t* raw_empty = raw_full + kRSlots;
     uint64_t* acc_full = raw_empty + kRSlots;
     uint64_t* acc_empty = acc_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* peer_full = acc_empty + 1;            // PAIR, leader only: "the peer's slots of iteration it are full"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + kPeerSlots);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (g.K + kKB - 1) / kKB;
-    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const int t_begin = blockIdx.x * per_cta;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int n_groups = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;         // a group = one CTA, or one CTA pair
+    const int group = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    const int per_cta = (total_tiles + n_groups - 1) / n_groups;
+    const int t_begin = group * per_cta;
     const int t_end = min(total_tiles, t_begin + per_cta);
     const int my_tiles = max(0, t_end - t_begin);
     const long long total_it = (long long)my_tiles * nkb;
@@ -152,11 +164,13 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], kMoverThreads); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kRSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverThreads); }
-        mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
+        mbar_init(acc_full, 1); mbar_init(acc_empty, PAIR ? 2 * kEpiWarps : kEpiWarps);
+        for (int s = 0; s < kPeerSlots; ++s) mbar_init(&peer_full[s], 1);
         fence_barrier_init();
     }
+    if (PAIR) cluster_sync_all();                   // both CTAs' barriers exist before anything arrives on them remotely
     constexpr uint32_t kTmemCols = 2 * BN;          // [0,BN) main (hi.hi), [BN,2BN) correction (lo.hi + hi.lo, scaled 2^11)
-    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == kMmaWarp) { if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -166,6 +180,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     auto decode = [&](int t, int& mt, int& net, int& nt) {
         nt = t % g.tiles_n; t /= g.tiles_n;
         net = t % g.nets; mt = t / g.nets;
+        if (PAIR) mt = mt * 2 + (int)rank;          // the pair's 256-row super-tile: rank r takes rows [r*128, r*128+128)
     };
 
     if (warp < kMoverWarps) {
@@ -223,8 +238,8 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                         int mt, net, nt;
                         decode(t_begin + (int)(ib / nkb), mt, net, nt);
                         const int kb = (int)(ib % nkb);
-                        const uint8_t* img = g.Bimg[net] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
-                                             ((size_t)nt * nkb + (size_t)kb) * P::kBSlot;
+                        const uint8_t* img = g.Bimg[net] + (size_t)(group % kImgReplicas) * g.img_replica_bytes +
+                                             (((size_t)nt * nkb + (size_t)kb) * (PAIR ? 2 : 1) + (PAIR ? rank : 0u)) * P::kBSlot;
                         mbar_arrive_expect_tx(&full_b[sb], (uint32_t)P::kBSlot);
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                      ::"r"(b_ring + sb * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[sb]))
@@ -245,19 +260,31 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             }
         }
     } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BN);
+        // ================= MMA issuer (one thread; in a pair: the leader issues, the peer relays its full barriers) ==========
+        if (lane == 0 && PAIR && rank != 0) {
+            uint32_t remote[kPeerSlots];
+#pragma unroll
+            for (int s = 0; s < kPeerSlots; ++s) remote[s] = mapa_u32(smem_u32(&peer_full[s]), 0);
+            for (long long it = 0; it < total_it; ++it) {
+                const int sa = (int)(it % kASlots), sb = (int)(it % kBSlots);
+                mbar_wait(&full_a[sa], (uint32_t)((it / kASlots) & 1));
+                mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
+                mbar_arrive_remote(remote[it % kPeerSlots]);
+            }
+        } else if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BN, PAIR ? 2 * BM : BM);
             const uint32_t a_base = a_ring, b_base = b_ring;
             long long it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));          // the epilogue has read tile i-1 out of TMEM
+                // the epilogue (of both CTAs) has read tile i-1 out of TMEM
+                if (PAIR) mbar_wait_cluster(acc_empty, (uint32_t)((i & 1) ^ 1)); else mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));
                 tc_fence_after();
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 0] = clock64();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int sa = (int)(it % kASlots), sb = (int)(it % kBSlots);
                     mbar_wait(&full_a[sa], (uint32_t)((it / kASlots) & 1));
                     mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
+                    if (PAIR) mbar_wait_cluster(&peer_full[it % kPeerSlots], (uint32_t)((it / kPeerSlots) & 1));
                     tc_fence_after();
                     const uint32_t a_hi = a_base + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
                     const uint32_t b_hi = b_base + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
@@ -267,14 +294,20 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                         const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
-                        umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                        umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
-                        umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                        if (PAIR) {
+                            umma_f16_pair(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                            umma_f16_pair(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                            umma_f16_pair(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                        } else {
+                            umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                            umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                            umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                        }
                     }
-                    umma_commit(&empty_a[sa]);         // the slots may be refilled once these MMAs retire
-                    umma_commit(&empty_b[sb]);
+                    if (PAIR) { umma_commit_pair(&empty_a[sa]); umma_commit_pair(&empty_b[sb]); }     // slots free in BOTH CTAs
+                    else { umma_commit(&empty_a[sa]); umma_commit(&empty_b[sb]); }
                 }
-                umma_commit(acc_full);                 // accumulators of tile i complete
+                if (PAIR) umma_commit_pair(acc_full); else umma_commit(acc_full);     // accumulators of tile i complete
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 1] = clock64();
             }
             tc_fence_before();
@@ -328,7 +361,10 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 if (p == P::kPhases - 1) {                         // every column of this tile is out of TMEM
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
+                    if (lane == 0) {
+                        if (PAIR && rank != 0) mbar_arrive_remote(mapa_u32(smem_u32(acc_empty), 0));
+                        else mbar_arrive(acc_empty);
+                    }
                     if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 3] = clock64();
                 }
                 // NT: the mask words of this warp's rows are requested before the barrier
@@ -402,16 +438,17 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();       // the leader's MMAs read the peer's shared memory and signal its barriers until the very end
+    else __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
 // ---- weight images: per (n-tile, k-block) the fp16 hi tile then the lo tile, K-major SWIZZLE_64B, exactly as the MMA
 // reads them from shared memory -> one cp.async.bulk per k-block ----
-struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn; };
+struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn, pair; };
 struct HImgPlan { int n; HImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
 
 __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
@@ -434,44 +471,63 @@ __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
         uint4 h, l;
         split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
         const size_t ntiles = (size_t)((e.N + e.bn - 1) / e.bn);
-        const size_t half = (size_t)e.bn * 64;
-        const size_t replica_bytes = ntiles * kbs * 2 * half;
-        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+        // single CTA: [hi (bn rows) | lo];  CTA pair: [rank 0: hi (bn/2 rows) | lo] [rank 1: hi | lo]
+        const int rows_per = e.pair ? e.bn / 2 : e.bn;
+        const int part = r / rows_per, rr = r % rows_per;
+        const size_t half = (size_t)rows_per * 64;
+        const size_t replica_bytes = ntiles * kbs * 2 * (size_t)e.bn * 64;
+        const uint32_t off = (uint32_t)rr * 64u + (uint32_t)((c ^ ((rr >> 1) & 3)) << 4);
 #pragma unroll
         for (int rep = 0; rep < kImgReplicas; ++rep) {
-            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * half;
+            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * (size_t)e.bn * 64 + (size_t)part * 2 * half;
             *reinterpret_cast<uint4*>(tile + off) = h;
             *reinterpret_cast<uint4*>(tile + half + off) = l;
         }
     }
 }
 
-template <int BN, int EPI, bool TMA_A>
-static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, HArgs& g, int grid, int total, cudaStream_t st) {
-    using P = HPlan<BN>;
+// DPPO_H_PAIR=1: every product on CTA pairs (cta_group::2); the weight images are then packed in the pair layout
+static bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DPPO_H_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+template <int BN, int EPI, bool TMA_A, bool PAIR>
+static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, HArgs& g, cudaStream_t st) {
+    using P = HPlan<BN, PAIR>;
+    const int tiles_m = (g.M + BM - 1) / BM;
+    const long long total = (long long)(PAIR ? (tiles_m + 1) / 2 : tiles_m) * g.tiles_n * g.nets;     // (super-)tiles
+    DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    const int groups = (int)(total < (PAIR ? kPlanSMs / 2 : kPlanSMs) ? total : (PAIR ? kPlanSMs / 2 : kPlanSMs));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(PAIR ? 2 * groups : groups); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = P::kBytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     ProfScope ps(KK_TC_GEMM, st);
-    h_gemm_kernel<BN, EPI, TMA_A><<<grid, kThreads, P::kBytes, st>>>(m0, m1, g, total);
-    DPPO_LAUNCH_CHECK();
+    DPPO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, h_gemm_kernel<BN, EPI, TMA_A, PAIR>, m0, m1, g, (int)total));
     return 0;
 }
 
 template <int BN, int EPI>
-static int launch_h(HArgs& g, cudaStream_t st) {
+static int launch_h(HArgs& g, bool pair, cudaStream_t st) {
     g.tiles_n = (g.N + BN - 1) / BN;
-    const int tiles_m = (g.M + BM - 1) / BM;
-    const long long total = (long long)tiles_m * g.tiles_n * g.nets;
-    DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
-    const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
-    // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, 35-wide heads' gradients ...) takes the LDG movers
+    // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, ...) takes the LDG movers
     CUtensorMap m0, m1;
     memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1));
     bool tma = g.vecA && h_make_map(&m0, g.A[0], g.M, g.K, g.lda, BM);
     if (tma) { if (g.nets > 1) tma = h_make_map(&m1, g.A[1], g.M, g.K, g.lda, BM); else m1 = m0; }
-    if (tma) return launch_h2<BN, EPI, true>(m0, m1, g, grid, (int)total, st);
-    return launch_h2<BN, EPI, false>(m0, m1, g, grid, (int)total, st);
+    if (pair) {
+        if (tma) return launch_h2<BN, EPI, true, true>(m0, m1, g, st);
+        return launch_h2<BN, EPI, false, true>(m0, m1, g, st);
+    }
+    if (tma) return launch_h2<BN, EPI, true, false>(m0, m1, g, st);
+    return launch_h2<BN, EPI, false, false>(m0, m1, g, st);
 }
 
 }  // namespace th
@@ -497,7 +553,7 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
         if (!src || !dst) return;
         th::HImgEntry& e = p.e[p.n];
         e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed;
-        e.bn = th_bn_for(N);
+        e.bn = th_bn_for(N); e.pair = th::pair_enabled() ? 1 : 0;
         units += (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
         p.unit_end[p.n++] = units;
     };
@@ -523,6 +579,7 @@ int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
     th::HImgPlan p; p.n = 1;
     th::HImgEntry& e = p.e[0];
     e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N);
+    e.pair = th::pair_enabled() ? 1 : 0;
     const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
     p.unit_end[0] = units;
     int grid = (int)((units + 255) / 256);
@@ -554,14 +611,15 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
     const int bn = th_bn_for(N);
+    const bool pair = th::pair_enabled();         // the weight images were packed for the same choice (th_pack_images)
     if (epi_nt) {
-        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, st);
-        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, st);
-        return th::launch_h<64, th::EPI_NT>(g, st);
+        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, pair, st);
+        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, pair, st);
+        return th::launch_h<64, th::EPI_NT>(g, pair, st);
     }
-    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, st);
-    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, st);
-    return th::launch_h<64, th::EPI_NN>(g, st);
+    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, pair, st);
+    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, pair, st);
+    return th::launch_h<64, th::EPI_NN>(g, pair, st);
 }
 
 }  // namespace dppo
