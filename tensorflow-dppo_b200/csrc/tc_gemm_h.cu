@@ -502,13 +502,29 @@ static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, HArgs& g, cud
     static PerDeviceOnce configured;
     if (configured.need())
         DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
-    const int groups = (int)(total < (PAIR ? kPlanSMs / 2 : kPlanSMs) ? total : (PAIR ? kPlanSMs / 2 : kPlanSMs));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(PAIR ? 2 * groups : groups); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = P::kBytes; cfg.stream = st;
+    cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = P::kBytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    // persistent grid = what is co-resident: pairs must sit in one GPC, so fewer than #SMs / 2 of them may fit
+    static int max_groups[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (max_groups[dev] == 0) {
+        int n = PAIR ? kPlanSMs / 2 : kPlanSMs;
+        if (PAIR) {
+            cfg.gridDim = dim3(kPlanSMs);
+            int q = 0;
+            if (cudaOccupancyMaxActiveClusters(&q, h_gemm_kernel<BN, EPI, TMA_A, PAIR>, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+            else (void)cudaGetLastError();
+        }
+        max_groups[dev] = n;
+    }
+    const int groups = (int)(total < max_groups[dev] ? total : max_groups[dev]);
+    cfg.gridDim = dim3(PAIR ? 2 * groups : groups);
     ProfScope ps(KK_TC_GEMM, st);
     DPPO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, h_gemm_kernel<BN, EPI, TMA_A, PAIR>, m0, m1, g, (int)total));
     return 0;
