@@ -219,13 +219,15 @@ def test_loss_grad_vs_oracle(name, T, N, obs, hidden, A):
     assert aux["clip_frac"] > 0.01 and all(0.1 < float((h > 0).mean()) < 0.9 for h in aux["hs"])
 
 
-def test_loss_grad_reference_regime_pi_equals_old():
-    """The reference's own regime (Appendix A-D9): pi == oldpi, normc(0.01) init -> ratio == 1, clips idle."""
+@pytest.mark.parametrize("gemm_mode", [0, 1, 3])
+def test_loss_grad_reference_regime_pi_equals_old(gemm_mode):
+    """The reference's own regime (Appendix A-D9): pi == oldpi, normc(0.01) init -> ratio == 1, clips idle.  Activations are
+    1e-2 ... 1e-5 here: the fp16-split path (mode 3) must hold the bar where `hi` alone would be subnormal."""
     lay = O.make_layout(17, (256, 256), 6)
     th = O.init_params(lay, np.random.default_rng(3))
     buf = O.make_buffer(64, 16, 17, 6, 5)
     adv, ret = O.gae_batch_vectorized(buf["rew"], buf["predv"], buf["done"], 0.99, 0.95)
-    eng = _engine(17, (256, 256), 6, 1024)
+    eng = _engine(17, (256, 256), 6, 1024, gemm_mode=gemm_mode)
     losses, g = eng.loss_grad(dev(th), dev(th), dev(buf["obs"]), dev(buf["act"]), dev(adv.reshape(-1)),
                               dev(ret.reshape(-1)), 1.0)
     l_ref, g_ref, aux = O.ppo_loss_grad(th, th, buf["obs"], buf["act"], adv.reshape(-1), ret.reshape(-1), 1.0, lay)
