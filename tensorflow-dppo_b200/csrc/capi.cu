@@ -322,7 +322,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
                 return r;
             return tc_colsum(dY, rows, out, ldy, active[l], p + (size_t)in * out, s.region[l], accumulate, st);
         }
-        if (fp16x2 && th_dw_supported(x_in, in, dY, ldy))     // persistent fp16-split kernel, bias column sums fused
+        if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, in, dY, ldy))     // persistent fp16-split kernel, bias column sums fused
             return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,
                               dx_scale, st);
         if (tcore) {
@@ -475,6 +475,7 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     c->cfg = *cfg; c->shape = s; c->workspace = workspace; c->workspace_bytes = workspace_bytes;
     c->num_sms = prop.multiProcessorCount;
     c->prof = new (std::nothrow) ProfState();
+    { const char* e = getenv("DPPO_H_DW"); c->use_h_dw = (e && e[0] == '1') ? 1 : 0; }     // fp16-split dW kernel (tc_dw_h.cu)
     { const char* e = getenv("DPPO_GRAPH"); c->use_graph = (e && e[0] == '0') ? 0 : 1; }
     { const char* e = getenv("DPPO_NO_OLD_CACHE"); c->no_old_cache = (e && e[0] == '1') ? 1 : 0; }   // read once, per context
     carve(cfg, s, (char*)workspace, &c->ws);

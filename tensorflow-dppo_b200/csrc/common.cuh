@@ -137,6 +137,7 @@ struct dppo_ctx {
     unsigned char step_graph_key[160];
     long long step_graph_counts[16];   // kernel launches per replay, per family
     int use_graph;               // DPPO_GRAPH != 0 at dppo_create
+    int use_h_dw;                // DPPO_H_DW: dW of the fp16x2 mode on the persistent fp16-split kernel (else the tf32 TMA kernel)
     int no_old_cache;            // DPPO_NO_OLD_CACHE=1 at dppo_create: dppo_update_epochs re-evaluates oldpi per minibatch
     void* prof;                  // launch accounting of this context (capi.cu: ProfState)
 };
