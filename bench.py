@@ -420,8 +420,10 @@ def run_b200(args):
             "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
             "config": make_config(args, world),
             "roofline": {
-                "kernel": ("tc_gemm_kernel (tcgen05 fwd / dX / dW)" if args.gemm != "simt" else
-                           "sgemm_kernel (fwd NN / dX NT / dW TN families)"), "bound": "tensor",
+                "kernel": {"fp16x2": "h_gemm_kernel / h_dw_kernel (persistent tcgen05 kind::f16 fwd / dX / dW; dW on tc_tn_tma_kernel when DPPO_H_DW=0)",
+                           "tf32x3": "tc_gemm_kernel / tc_tn_tma_kernel (tcgen05 kind::tf32 fwd / dX / dW)",
+                           "bf16": "bf16_gemm_kernel (tcgen05 kind::f16, bf16 operands)",
+                           "simt": "sgemm_kernel (fwd NN / dX NT / dW TN families)"}[args.gemm], "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
                 "traffic_source": "committed capture: profiles/traffic.json (ncu --set full of this command); NOT measured in this run",
@@ -589,7 +591,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the reference's semantics: every replica owns a full workload buffer) or strong "
                          "(the workload's N rollouts are divided over the ranks)")
-    ap.add_argument("--gemm", default="tf32x3", choices=["simt", "tf32x3", "bf16", "fp16x2"],
+    ap.add_argument("--gemm", default="fp16x2", choices=["simt", "tf32x3", "bf16", "fp16x2"],
                     help="dense-layer arithmetic: fp32 FFMA, tcgen05 kind::tf32 with the 3-term fp32-accurate split, bf16 (config 4), "
                          "or tcgen05 kind::f16 with the 2-term fp32-accurate fp16 split (persistent kernels)")
     ap.add_argument("--minibatch", type=int, default=0,
