@@ -340,7 +340,8 @@ def run_b200(args):
     peaks = load_peaks()
     traffic = None
     try:        # measured DRAM bytes of the GEMM family for one step, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.gemm)
+        tj = json.load(open(tpath if os.path.exists(tpath) else os.path.join(ROOT, "profiles", "traffic.json")))
         if tj.get("workload") == args.workload and tj.get("gemm") == args.gemm:
             traffic = tj["family_bytes_per_step"]
     except (OSError, ValueError, KeyError):
@@ -426,7 +427,7 @@ def run_b200(args):
                            "simt": "sgemm_kernel (fwd NN / dX NT / dW TN families)"}[args.gemm], "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
-                "traffic_source": "committed capture: profiles/traffic.json (ncu --set full of this command); NOT measured in this run",
+                "traffic_source": "committed capture: profiles/traffic_<gemm>.json (ncu --set full of this command); NOT measured in this run",
                 "traffic_note": "DRAM bytes of all GEMM launches of one step; algorithmic bytes of the whole update are %d -- "
                                 "the excess is fp32 activations (h1, h2, dh) round-tripping HBM between the per-layer kernels"
                                 % alg_bytes,

@@ -86,6 +86,39 @@ for rep in sorted(glob.glob(f"gpurun_out/prof_*_{TAG}.ncu-rep")):
                 md.append(f"| {label} (`{k}`) | {r[idx[k]]} {units[idx[k]]} |")
         md.append("")
 
+# measured DRAM traffic of the GEMM family for ONE step (bench.py reports it as roofline.traffic): all launches of the
+# tensor-core capture of this visit, which gpu_prof.sh takes over exactly one step
+tc_rep = f"gpurun_out/prof_tc_{TAG}.ncu-rep"
+if os.path.exists(tc_rep):
+    raw = subprocess.run(["ncu", "-i", tc_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) >= 3:
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per, total = {}, 0.0
+        for n, r in enumerate(rows[2:]):
+            rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_read.sum"]]]
+            wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_write.sum"]]]
+            total += rd + wr
+            per[f"{n}: {r[idx['Kernel Name']][:70]} grid {r[idx['Grid Size']]}"] = {
+                "dram_read_MB": rd / 1e6, "dram_write_MB": wr / 1e6,
+                "duration_us": float(r[idx["gpu__time_duration.sum"]].replace(",", "")),
+                "tensor_pipe_active_pct": float(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]])}
+        meta = {}
+        try:
+            meta = json.load(open(f"gpurun_out/bench_{TAG}.json"))["config"]
+        except Exception:
+            pass
+        gemm = "fp16x2" if "2-term fp16" in meta.get("gemm", "") else ("tf32x3" if "tf32" in meta.get("gemm", "") else
+                                                                        ("bf16" if "bf16" in meta.get("gemm", "") else "simt"))
+        json.dump({"source": f"profiles/prof_tc_{TAG}_raw_selected.csv (ncu --set full --clock-control none, dram__bytes_read.sum + "
+                             "dram__bytes_write.sum, the tensor-core GEMM launches of one step)",
+                   "workload": meta.get("workload", "humanoid-cfg3"), "gemm": gemm, "family_bytes_per_step": total,
+                   "launches": len(per), "per_launch": per}, open(f"{OUT}/traffic_{gemm}.json", "w"), indent=1)
+        md += [f"## DRAM traffic of the GEMM family, one step: {total / 1e9:.3f} GB over {len(per)} launches "
+               f"(`profiles/traffic_{gemm}.json`)", ""]
+
 bench = f"gpurun_out/bench_{TAG}.json"
 if os.path.exists(bench) and os.path.getsize(bench):
     shutil.copy(bench, f"{OUT}/{TAG}_bench.json")
