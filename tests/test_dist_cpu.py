@@ -23,6 +23,11 @@ def _worker(rank, world, port, out_dir):
     from dppo_b200.dist import shard_rollouts, exchange_unique_id, max_over_ranks
     uid = exchange_unique_id(lambda: bytes(range(128)), rank, world)
     assert uid == bytes(range(128))
+    # Chief.check's "train now?" must be unanimous (the train step contains the exchange): collective AND
+    from dppo_b200.dist import all_ranks_true
+    assert all_ranks_true(True) is True
+    assert all_ranks_true(rank == 0) is False          # one rank without data -> nobody trains
+    assert all_ranks_true(False) is False
     assert max_over_ranks(float(rank + 1)) == float(world)
     T, N, obs, hidden, A = 64, 8, 11, (16, 12), 3
     c = O.make_case(T, N, obs, hidden, A)
@@ -66,3 +71,16 @@ def test_shard_rollouts_partitions():
             assert abs(sum(wi * 1.0 for wi in w) / world - 1.0) < 1e-12 or n < world
     with pytest.raises(ValueError):
         shard_rollouts(8, 2, 2)
+
+
+def test_stable_seed_is_process_independent_and_rank_dependent():
+    """Seeds come from a stable hash (str hash() is salted per process) and differ per rank (advisor finding, round 1)."""
+    import subprocess, sys
+    from dppo_b200.dist import stable_seed
+    code = ("import sys; sys.path.insert(0, %r); from dppo_b200.dist import stable_seed; "
+            "print(stable_seed('Worker_N0', 0, 0), stable_seed('Worker_N0', 0, 1))" % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tensorflow-dppo_b200"))
+    outs = {subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONHASHSEED=str(h))).stdout.strip()
+            for h in (1, 2)}
+    assert len(outs) == 1
+    a, b = (int(x) for x in outs.pop().split())
+    assert a == stable_seed("Worker_N0", 0, 0) and a != b and 0 <= a < 2 ** 31
