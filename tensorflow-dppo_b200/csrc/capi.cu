@@ -210,7 +210,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
             if (int r = th_gemm(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
-                                head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, 1.0f, st,
+                                head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st,
                                 head ? nullptr : w.act_bits[l], nullptr)) return r;
             in0 = o0; in1 = o1;
         }
@@ -278,6 +278,13 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
     }
 }
 
+// fp16-split mode: the loss kernel emits d_out multiplied by this power of two (the backward operands must sit in fp16's
+// range; raw they are ~1/B), every backward product carries the factor and finalize_kernel divides it out (exact in fp32)
+static float grad_prescale(const dppo_ctx* c, int B_total) {
+    if (c->cfg.gemm_mode != DPPO_GEMM_FP16X2) return 1.0f;
+    return exp2f(floorf(log2f((float)(B_total > 1 ? B_total : 1))));
+}
+
 // ---- fwd + loss + bwd over one block of rows; dW/db land in the split-K partial buffer --------
 static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
                           const float* act, const float* adv, const float* ret, int rows, int tile0,
@@ -290,7 +297,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     // chief trains, so epochs after the first need not re-evaluate it); nullptr -> evaluate both nets here
     if (int r = forward_nets(c, params_pi, old_rows ? nullptr : params_old, obs, rows, st)) return r;
     if (adv_ready) DPPO_CHECK_CUDA(cudaStreamWaitEvent(st, adv_ready, 0));   // adv/ret come from a side stream
-    const float inv_B = 1.0f / (float)B_total;
+    const float inv_B = grad_prescale(c, B_total) / (float)B_total;     // 1/B of the batch means (x the fp16-mode gradient scale)
     const float clip = c->cfg.clip_param * l_mul;                       // PPO.py:19
     if (int r = launch_loss(s, w.out_pi, old_rows ? old_rows : w.out_old, act, adv, ret, rows, tile0, inv_B, clip, c->cfg.entcoeff,
                             c->cfg.vcoeff, w.d_out, w.loss_part, st)) return r;
@@ -308,9 +315,6 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
     const bool tcore = tc_mode(c->cfg.gemm_mode);
     const bool fp16x2 = (c->cfg.gemm_mode == DPPO_GEMM_FP16X2);
-    // the dX operands are 1/B-scaled gradients: bring them to O(1) for the fp16 split (exact power of two, divided out in
-    // the epilogue)
-    const float dx_scale = exp2f(floorf(log2f((float)(B_total > 1 ? B_total : 1))));
     const bool bf16 = (c->cfg.gemm_mode == DPPO_GEMM_BF16);
     // dW_l (+ db_l) into layer l's split-K partial region
     auto dense_dw = [&](int l, const float* x_in, const float* dY) -> int {
@@ -323,8 +327,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
             return tc_colsum(dY, rows, out, ldy, active[l], p + (size_t)in * out, s.region[l], accumulate, st);
         }
         if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, in, dY, ldy))     // persistent fp16-split kernel, bias column sums fused
-            return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,
-                              dx_scale, st);
+            return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate, st);
         if (tcore) {
             if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
                 return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l],
@@ -341,7 +344,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     auto dense_dx = [&](int l_, int M_, int N_, int K_, const float* dY, int ldy, const float* W, float* dX,
                         const float* mask) -> int {
         if (fp16x2) return th_gemm(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_, nullptr, nullptr,
-                                   0, mask, 1, dx_scale, st, nullptr, w.act_bits[l_ - 1]);
+                                   0, mask, 1, st, nullptr, w.act_bits[l_ - 1]);
         if (tcore) return tc_gemm_kk_img(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_,
                                          nullptr, nullptr, 0, mask, 1, st, nullptr, w.act_bits[l_ - 1]);
         if (bf16) return bf16_gemm_kk(1, M_, N_, K_, dY, nullptr, ldy, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr, 0,
@@ -377,12 +380,12 @@ static int reduce_and_apply(dppo_ctx* c, const int* active, int rows, float* par
         // the ranks through peer loads and applies Adam (PPO.py:53,55-65)
         if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
                                     sp ? peer_exchange_half(c, 0) : peer_exchange_buffer(c), nullptr, st,
-                                    sp ? peer_exchange_half(c, 1) : nullptr, sp, counter)) return r;
+                                    sp ? peer_exchange_half(c, 1) : nullptr, sp, counter, 1.0f / grad_prescale(c, rows))) return r;
         return peer_allreduce_adam(c, params_pi, (adam_m && adam_v) ? adam_m : nullptr, adam_v, step, lr, beta1, beta2, eps,
                                    grad_out, st, sp, counter);
     }
     if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
-                                grad_out, nullptr, st)) return r;
+                                grad_out, nullptr, st, nullptr, nullptr, nullptr, 1.0f / grad_prescale(c, rows))) return r;
     if (c->nccl_comm && c->world > 1)
         if (int r = allreduce_avg(c, grad_out, c->shape.n_params + kLossSlots, st)) return r;
     if (adam_m && adam_v)
@@ -475,7 +478,7 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     c->cfg = *cfg; c->shape = s; c->workspace = workspace; c->workspace_bytes = workspace_bytes;
     c->num_sms = prop.multiProcessorCount;
     c->prof = new (std::nothrow) ProfState();
-    { const char* e = getenv("DPPO_H_DW"); c->use_h_dw = (e && e[0] == '1') ? 1 : 0; }     // fp16-split dW kernel (tc_dw_h.cu)
+    { const char* e = getenv("DPPO_H_DW"); c->use_h_dw = (e && e[0] == '0') ? 0 : 1; }     // fp16-split dW kernel (tc_dw_h.cu); 0 = tf32 TMA kernel
     { const char* e = getenv("DPPO_GRAPH"); c->use_graph = (e && e[0] == '0') ? 0 : 1; }
     { const char* e = getenv("DPPO_NO_OLD_CACHE"); c->no_old_cache = (e && e[0] == '1') ? 1 : 0; }   // read once, per context
     carve(cfg, s, (char*)workspace, &c->ws);
@@ -554,7 +557,7 @@ int dppo_loss_grad(dppo_ctx* c, const float* params_pi, const float* params_old,
     if (int r = loss_grad_rows(c, params_pi, params_old, obs, act, adv, ret, B, 0, B, l_mul, 0, active, st)) return r;
     const int tiles = (B + kLossTileRows - 1) / kLossTileRows;
     return launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff, grad_out,
-                           losses_out, st);
+                           losses_out, st, nullptr, nullptr, nullptr, 1.0f / grad_prescale(c, B));
 }
 
 int dppo_update(dppo_ctx* c, float* params_pi, const float* params_old, const float* obs, const float* act,
@@ -1122,15 +1125,14 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         return 0;
     }
     if (mode == 99) {
-        // persistent fp16-split dW product (tc_dw_h.cu): C[M,N] = A[K,M]^T . B[K,N], bias_out[N] = column sums of B, with B
-        // pre-scaled by 2^17 inside the kernel (B holds 1/B-sized gradients)
+        // persistent fp16-split dW product (tc_dw_h.cu): C[M,N] = A[K,M]^T . B[K,N], bias_out[N] = column sums of B
         const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
         int slices = (int)(c->shape.partial_floats / stride);
         const int want = (K + 511) / 512;
         if (slices > want) slices = want;
         DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
         DPPO_REQUIRE(th_dw_supported(A, M, B, N), "dppo_dbg_gemm: the fp16 dW kernel needs 16-byte aligned rows");
-        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, 131072.0f, st))
+        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, st))
             return r;
         ProfScope ps(KK_MISC, st);
         reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
@@ -1143,7 +1145,7 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
     }
     if (mode == 96 || mode == 97 || mode == 98) {
         // persistent fp16-split product (tc_gemm_h.cu): Bt[N,K] is packed into an fp16 hi|lo tile image first (scratch from
-        // the caller's workspace).  96: C = relu?(A.Bt^T + bias); 97: C = (A.Bt^T) * (mask > 0), A pre-scaled by 2^17;
+        // the caller's workspace).  96: C = relu?(A.Bt^T + bias); 97: C = (A.Bt^T) * (mask > 0);
         // 98: as 96, and bias_out receives the kernel's clock64 time line (bias_out must hold 128 int64)
         const long long need = th_image_floats(N, K);
         float* scratch = nullptr;
@@ -1153,8 +1155,8 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         DPPO_REQUIRE(scratch != nullptr, "dppo_dbg_gemm: the workspace has no %lld-float scratch for the weight image", need);
         if (int r = th_pack_one(B, scratch, N, K, K, 0, st)) return r;
         if (mode == 97)
-            return th_gemm(1, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, nullptr, nullptr, 0, mask, 1, 131072.0f, st);
-        return th_gemm(0, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, bias, nullptr, relu, nullptr, 1, 1.0f, st,
+            return th_gemm(1, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, nullptr, nullptr, 0, mask, 1, st);
+        return th_gemm(0, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, bias, nullptr, relu, nullptr, 1, st,
                        nullptr, nullptr, mode == 98 ? reinterpret_cast<long long*>(bias_out) : nullptr);
     }
     if (mode == 48 || mode == 49) {

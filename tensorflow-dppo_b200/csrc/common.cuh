@@ -242,11 +242,11 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
 int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st);
 int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
-            float a_scale, cudaStream_t st, uint32_t* bits_out0 = nullptr, const uint32_t* bits_in = nullptr,
+            cudaStream_t st, uint32_t* bits_out0 = nullptr, const uint32_t* bits_in = nullptr,
             long long* timeline = nullptr);
 bool th_dw_supported(const float* X, int ldx, const float* G, int ldg);
 int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int ldg, float* C, int ldc, float* bias_out,
-               int slices, long long slice_stride, int accumulate, float g_scale, cudaStream_t st);
+               int slices, long long slice_stride, int accumulate, cudaStream_t st);
 // tensor-core gemm modes whose dW runs on the tf32 TMA kernel with the 512-row accumulation bound
 inline bool tc_mode(int gemm_mode) { return gemm_mode == DPPO_GEMM_TF32X3 || gemm_mode == DPPO_GEMM_FP16X2; }
 int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,
@@ -270,7 +270,8 @@ int launch_value_pairwise(const NetShape& s, const float* out_pi, const float* o
 // active[l] = number of split-K slices the dW launches of this update actually wrote (<= s.slices[l])
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st,
-                    float* grad_out_alt = nullptr, const StepParams* sp = nullptr, const int* counter = nullptr);
+                    float* grad_out_alt = nullptr, const StepParams* sp = nullptr, const int* counter = nullptr,
+                    float grad_scale = 1.0f);
 int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
                        cudaStream_t st);
 int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                                 long long head_off, int H, int W, const double* __restrict__ loss_part, int n_tiles,
                                 float entcoeff, float vcoeff, float* __restrict__ grad_out,
                                 float* __restrict__ losses_out, float* __restrict__ grad_out_alt,
-                                const StepParams* __restrict__ sp, const int* __restrict__ counter) {
+                                const StepParams* __restrict__ sp, const int* __restrict__ counter, float grad_scale) {
     const int P = 1 + W;                     // W = policy-head width (2A or ncat)
     if (sp && sp[*counter].peer_sel) grad_out = grad_out_alt;      // graph replay: the exchange buffer half of this step
     // A block owns 32 consecutive parameters.  Warp w streams slices w, w+8, ... of them: every load instruction
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                     pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + (long long)W * H + (c - 1));
                 }
             }
-            grad_out[pub] = t;
+            grad_out[pub] = t * grad_scale;      // 1 / the power of two the loss kernel put on d_out (fp16-split mode), else 1
         }
         __syncthreads();
     }
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st, float* grad_out_alt,
-                    const StepParams* sp, const int* counter) {
+                    const StepParams* sp, const int* counter, float grad_scale) {
     FinalizePlan plan;
     plan.n_regions = s.L + 1;
     for (int l = 0; l <= s.L; ++l) {
@@ -497,7 +497,7 @@ int launch_finalize(const NetShape& s, const int* active, const float* partial, 
     if (grid < 1) grid = 1;
     ProfScope ps(KK_FINALIZE, st);
     finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.pdw, loss_part,
-                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out, grad_out_alt, sp, counter);
+                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out, grad_out_alt, sp, counter, grad_scale);
     DPPO_LAUNCH_CHECK();
     return 0;
 }

@@ -14,8 +14,8 @@
 //   warp 8 (one thread) : 6 MMAs per 32-row k-block (2 k-steps x {lo.hi, hi.lo -> correction; hi.hi -> main});
 //   warps 10-17         : epilogue, as in tc_gemm_h.cu: TMEM -> staging (64-column phases) -> coalesced partial-slice rows
 //                         (+= when the update accumulates over row chunks); TMEM is released after the last phase's drain.
-// G carries 1/B-scaled gradients: it is multiplied by a power of two (g_scale) on its way into the operand tiles and the
-// result scaled back.  Rows per slice are bounded by the split-K plan (fp32 TMEM accumulation truncates: DESIGN.md).
+// G carries gradients the loss kernel pre-scaled by a power of two (capi.cu: grad_prescale); finalize_kernel divides it
+// out after the split-K sum.  Rows per slice are bounded by the split-K plan (fp32 TMEM accumulation truncates: DESIGN.md).
 #include "tc_h.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -32,7 +32,6 @@ struct DwArgs {
     int ldc, k_per_slice, slices, accumulate, vecC;
     int tiles_m, tiles_n;
     long long slice_stride;
-    float g_scale, out_scale;
 };
 
 template <int BN>
@@ -59,7 +58,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
 }
 
 // one 8-feature unit (k-row `k`, box `box`, unit `j` of the box): raw fp32 -> hi / lo chunk of the MN-major operand tile
-__device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_tile, uint32_t lo_tile, int box, int j, int k, float s,
+__device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_tile, uint32_t lo_tile, int box, int j, int k,
                                                 float (&csum)[8], bool sum) {
     const uint32_t rbase = raw_op + (uint32_t)box * 4096u + (uint32_t)k * 128u;
     const float4 a = lds128f(rbase + (uint32_t)(((2 * j) ^ (k & 7)) << 4));
@@ -69,8 +68,8 @@ __device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_til
         csum[4] += b.x; csum[5] += b.y; csum[6] += b.z; csum[7] += b.w;
     }
     uint4 h, l;
-    split2(a.x * s, a.y * s, h.x, l.x); split2(a.z * s, a.w * s, h.y, l.y);
-    split2(b.x * s, b.y * s, h.z, l.z); split2(b.z * s, b.w * s, h.w, l.w);
+    split2(a.x, a.y, h.x, l.x); split2(a.z, a.w, h.y, l.y);
+    split2(b.x, b.y, h.z, l.z); split2(b.z, b.w, h.w, l.w);
     const int c = (box & 1) * 4 + j;                                  // 16-B chunk of the 64-feature atom
     const uint32_t off = (uint32_t)(box >> 1) * 4096u + (uint32_t)k * 128u + (uint32_t)((c ^ (k & 7)) << 4);
     sts128(hi_tile + off, h);
@@ -129,7 +128,6 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         constexpr int kBPairs = (BN / 32) * 4 / kMoverWarps;          // ... of G per warp: BN / 64
         static_assert(kBPairs >= 1, "BN >= 64");
         const int k = lane;
-        const float gs = g.g_scale;
         long long it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             int slice, mt, nt, nkb, k0;
@@ -151,12 +149,12 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
 #pragma unroll
                 for (int u = 0; u < kAPairs; ++u) {
                     const int p = warp + u * kMoverWarps;
-                    dw_convert_unit(raw, a_hi, a_lo, p >> 2, p & 3, k, 1.0f, dummy, false);
+                    dw_convert_unit(raw, a_hi, a_lo, p >> 2, p & 3, k, dummy, false);
                 }
 #pragma unroll
                 for (int u = 0; u < kBPairs; ++u) {
                     const int p = warp + u * kMoverWarps;
-                    dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, gs, csum[u], want_bias);
+                    dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, csum[u], want_bias);
                 }
                 fence_proxy_async();
                 mbar_arrive(&op_full[os]);
@@ -247,7 +245,6 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         const int q = warp & 3;
         const int ch = ew >> 2;
         const int lr = lane / kLanesPerRow, cl = lane % kLanesPerRow;
-        const float oscale = g.out_scale;
         for (int i = 0; i < my_tiles; ++i) {
             int slice, mt, nt, nkb, k0;
             decode(t_begin + i, slice, mt, nt, nkb, k0);
@@ -272,10 +269,10 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float4 o;
-                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0])) * oscale;
-                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1])) * oscale;
-                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2])) * oscale;
-                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3])) * oscale;
+                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0]));
+                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1]));
+                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2]));
+                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3]));
                         const int c = (ch * kDrainCols) / 4 + j4;
                         const int pc = (c & ~7) | ((c ^ r) & 7);
                         sts128f(stg + (uint32_t)(r * kRowBytes + pc * 16), o);
@@ -359,9 +356,9 @@ bool th_dw_supported(const float* X, int ldx, const float* G, int ldg) {
 }
 
 // C[s][M,N] (+)= X[rows,M]^T . G[rows,N] over the rows of slice s (k_per_slice rows, a multiple of 32);
-// bias_out[s][N] (+)= column sums of G (may be null).  g_scale: power of two applied to G's operand tiles.
+// bias_out[s][N] (+)= column sums of G (may be null).
 int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int ldg, float* C, int ldc, float* bias_out,
-               int slices, long long slice_stride, int accumulate, float g_scale, cudaStream_t st) {
+               int slices, long long slice_stride, int accumulate, cudaStream_t st) {
     CUtensorMap mX, mG;
     DPPO_REQUIRE(th::h_make_map(&mX, X, K, M, ldx, 32), "cuTensorMapEncodeTiled failed for X [%d x %d] ld %d", K, M, ldx);
     DPPO_REQUIRE(th::h_make_map(&mG, G, K, N, ldg, 32), "cuTensorMapEncodeTiled failed for G [%d x %d] ld %d", K, N, ldg);
@@ -374,7 +371,6 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     if (kps == 0) kps = th::kKB;
     g.k_per_slice = kps; g.slices = slices;
     g.vecC = (ldc % 4 == 0) && th::aligned16(C) && (slice_stride % 4 == 0);
-    g.g_scale = g_scale; g.out_scale = 1.0f / g_scale;
     if (N > 128) return th::launch_dw<256>(mX, mG, g, st);
     if (N > 64) return th::launch_dw<128>(mX, mG, g, st);
     return th::launch_dw<64>(mX, mG, g, st);

@@ -6,9 +6,10 @@
 //        A.B ~= A_hi.B_hi + (A_lo.B_hi + A_hi.B_lo) / 2^11                                the same 22 as the tf32 split)
 // The 2^11 pre-scale keeps `lo` inside fp16's normal range, and the correction products live in their own TMEM
 // accumulator anyway (the tensor core truncates on every fp32 add: DESIGN.md, precision), so the scale costs nothing.
-// Operands whose magnitude is far from 1 (the 1/B-scaled gradients of the dX products) are multiplied by a power of two
-// (`a_scale`) on their way into shared memory and the result is scaled back in the epilogue.  fp16 range: |x * a_scale|
-// must stay below 65504 (observations / activations / weights of a working policy are; DESIGN.md states the bound).
+// Operands must lie in fp16's range (|x| < 65504; far below 1e-4 only `lo` carries precision).  Observations, activations
+// and weights of a working policy do; the 1/B-sized gradients of the backward products do not, so the loss kernel emits
+// d_out pre-multiplied by a power of two, the whole backward chain carries that factor and finalize_kernel divides it out
+// (exact in fp32) -- no kernel of the chain spends an instruction on scaling.
 //
 // What is new against tc_gemm.cu, whose one-tile-per-CTA kernels leave the tensor pipe idle during every prologue and
 // epilogue (45 % of their time at cfg3):
@@ -34,7 +35,7 @@
 namespace dppo {
 namespace th {
 
-constexpr int kASlots = 2, kRSlots = 2, kPeerSlots = 4;
+constexpr int kPeerSlots = 4;
 constexpr int kPrefetch = 3;                                 // activation k-blocks in flight per mover thread
 constexpr int kImgReplicas = 8;                              // copies of every weight image (spreads the hot L2 lines)
 
@@ -47,7 +48,6 @@ struct HArgs {
     uint32_t* bits_out[2];             // NN: sign bitmap of the result (nullable per net)
     int M, N, K, lda, ldc;
     int tiles_n, nets, relu, vecA, vecC, bits_wpr;
-    float a_scale, out_scale;          // powers of two: operand pre-scale and its inverse
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
 };
@@ -55,6 +55,7 @@ struct HArgs {
 template <int BN, bool PAIR>
 struct HPlan {
     static constexpr int kBSlots = PAIR ? 4 : 3;
+    static constexpr int kASlots = PAIR ? 3 : 2, kRSlots = PAIR ? 3 : 2;     // a pair's weight slots are half as big: deeper rings fit
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
     static constexpr int kASlot = 2 * kAHalf;
     static constexpr int kBRows = PAIR ? BN / 2 : BN;        // a CTA of a pair holds half of the weight tile's rows
@@ -98,15 +99,15 @@ __device__ __forceinline__ void mover_load(MoverRegs& r, const float* __restrict
     }
 }
 
-__device__ __forceinline__ void mover_store(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, float s, int tid) {
+__device__ __forceinline__ void mover_store(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, int tid) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int row = (tid >> 2) + j * 64, c = tid & 3;
         const uint32_t off = (uint32_t)row * 64u + (uint32_t)((c ^ ((row >> 1) & 3)) << 4);     // SWIZZLE_64B
         const float4 a = r.v[j][0], b = r.v[j][1];
         uint4 h, l;
-        split2(a.x * s, a.y * s, h.x, l.x); split2(a.z * s, a.w * s, h.y, l.y);
-        split2(b.x * s, b.y * s, h.z, l.z); split2(b.z * s, b.w * s, h.w, l.w);
+        split2(a.x, a.y, h.x, l.x); split2(a.z, a.w, h.y, l.y);
+        split2(b.x, b.y, h.z, l.z); split2(b.z, b.w, h.w, l.w);
         sts128(hi_tile + off, h);
         sts128(lo_tile + off, l);
     }
@@ -132,7 +133,7 @@ template <int BN, int EPI, bool TMA_A, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const HArgs g, int total_tiles) {
     using P = HPlan<BN, PAIR>;
-    constexpr int kBSlots = P::kBSlots;
+    constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
@@ -184,7 +185,6 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     };
 
     if (warp < kMoverWarps) {
-        const float s = g.a_scale;
         if (TMA_A) {
             // ================= converters: raw fp32 tile (TMA) -> fp16 hi / lo operand tiles =================
             for (long long it = 0; it < total_it; ++it) {
@@ -195,7 +195,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 mbar_arrive(&raw_empty[rs]);               // release: the loads above are complete; TMA may refill the slot
                 mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
                 const uint32_t slot = a_ring + sa * P::kASlot;
-                mover_store(r, slot, slot + P::kAHalf, s, tid);
+                mover_store(r, slot, slot + P::kAHalf, tid);
                 fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core (async proxy)
                 mbar_arrive(&full_a[sa]);
             }
@@ -218,7 +218,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                         const int sa = (int)(it % kASlots);
                         mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
                         const uint32_t slot = a_ring + sa * P::kASlot;
-                        mover_store(ra[j], slot, slot + P::kAHalf, s, tid);
+                        mover_store(ra[j], slot, slot + P::kAHalf, tid);
                         fence_proxy_async();
                         mbar_arrive(&full_a[sa]);
                         if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
@@ -324,7 +324,6 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         const int q = warp & 3;                                   // TMEM lane quarter this warp may read
         const int ch = ew >> 2;
         const int lr = lane / kLanesPerRow, cl = lane % kLanesPerRow;
-        const float oscale = g.out_scale;
         for (int i = 0; i < my_tiles; ++i) {
             int mt, net, nt;
             decode(t_begin + i, mt, net, nt);
@@ -349,10 +348,10 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float4 o;
-                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0])) * oscale;
-                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1])) * oscale;
-                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2])) * oscale;
-                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3])) * oscale;
+                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0]));
+                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1]));
+                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2]));
+                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3]));
                         const int c = (ch * kDrainCols + cb) / 4 + j4;               // 16-B chunk of the staged row
                         const int pc = (c & ~7) | ((c ^ r) & 7);                      // XOR swizzle: conflict-free both ways
                         sts128f(stg + (uint32_t)(r * kRowBytes + pc * 16), o);
@@ -609,10 +608,11 @@ int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
 // C[M,N] = epi(A[M,K] . B^T) with B given as fp16 hi/lo weight images (th_pack_images).  nets = 1 or 2 products sharing
 // shapes.  epi_nt = 0: C = relu?(acc + bias), optional sign bitmap of C to bits_out0 (net 0 only);
 // epi_nt = 1: C = acc * mask, mask = bits_in (sign bitmap) or the fp32 matrix `mask`.
-// a_scale: power of two applied to A on its way into shared memory (and divided out of the result).
+// Operands must lie in fp16's range: the backward products therefore run on gradients the loss kernel pre-scaled by a
+// power of two (capi.cu: grad_prescale), and finalize_kernel divides it out again.
 int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
-            float a_scale, cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline) {
+            cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline) {
 
     if (M == 0) return 0;
     th::HArgs g{};
@@ -621,7 +621,6 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.bits_out[0] = bits_out0; g.bits_out[1] = nullptr;
     g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldc = ldc; g.nets = nets; g.relu = relu;
     g.bits_wpr = (N + 31) / 32;
-    g.a_scale = a_scale; g.out_scale = 1.0f / a_scale;
     g.img_replica_bytes = th_image_replica_bytes(N, K);
     g.timeline = timeline;
     g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));

@@ -58,9 +58,6 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 
 // two fp32 -> packed fp16 hi pair and packed fp16 lo pair (lo pre-scaled by 2^11)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    // saturate at fp16's largest finite value: an out-of-range operand degrades the result instead of turning it into inf/NaN
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
     const __half2 h = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);

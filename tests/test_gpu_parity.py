@@ -918,7 +918,7 @@ def test_reference_api_runs_on_engine(game, obs, pdw, discrete):
                                    (4096, 256, 256), (20000, 256, 376), (129, 200, 33), (300, 64, 17), (5000, 1024, 1024)])
 def test_h_gemm_fp16_split(M, N, K):
     """tc_gemm_h.cu through dppo_dbg_gemm: persistent tcgen05 kind::f16 product with the 2-term fp16 split vs an fp64
-    product, forward epilogue (bias + ReLU) and dX epilogue (fp32 mask, operand pre-scaled by 2^17)."""
+    product, forward epilogue (bias + ReLU) and dX epilogue (fp32 mask)."""
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     eng = _engine(376, (256, 256), 17, max(M, 32768), gemm_mode=1)      # the weight image is taken from the workspace
     A = rng.standard_normal((M, K)).astype(np.float32)
@@ -928,21 +928,19 @@ def test_h_gemm_fp16_split(M, N, K):
     got = eng.dbg_gemm(96, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
     assert rel_err(got, np.maximum(ref, 0)) < 2e-6
     mask = rng.standard_normal((M, N)).astype(np.float32)
-    G = (A / 131072.0).astype(np.float32)                 # 1/B-scaled gradients, as the dX products see them
-    ref2 = (G.astype(np.float64) @ Bt.astype(np.float64).T) * (mask > 0)
-    got2 = eng.dbg_gemm(97, dev(G), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    ref2 = (A.astype(np.float64) @ Bt.astype(np.float64).T) * (mask > 0)
+    got2 = eng.dbg_gemm(97, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
     assert rel_err(got2, ref2) < 2e-6
 
 
 @pytest.mark.parametrize("M,N,Kr", [(128, 256, 32), (376, 256, 1000), (256, 36, 2048), (120, 64, 333), (256, 256, 4096),
                                     (376, 256, 20000), (256, 128, 1500), (1024, 1024, 2048)])
 def test_h_dw_fp16_split(M, N, Kr):
-    """tc_dw_h.cu through dppo_dbg_gemm mode 99: C = X^T . G over the rows (split-K slices, fused column sums of G) vs fp64;
-    G holds 1/B-sized gradients (pre-scaled by 2^17 inside the kernel)."""
+    """tc_dw_h.cu through dppo_dbg_gemm mode 99: C = X^T . G over the rows (split-K slices, fused column sums of G) vs fp64."""
     rng = np.random.default_rng(M + 3 * N + 7 * Kr)
     eng = _engine(376, (1024, 1024), 17, 4096, gemm_mode=1)
     X = rng.standard_normal((Kr, M)).astype(np.float32)
-    G = (rng.standard_normal((Kr, N)) / 131072.0).astype(np.float32)
+    G = rng.standard_normal((Kr, N)).astype(np.float32)       # the update feeds gradients pre-scaled to O(1) (capi.cu: grad_prescale)
     got, bias = eng.dbg_gemm(99, dev(X), dev(G), M, N, Kr, want_bias_out=True)
     ref = X.astype(np.float64).T @ G.astype(np.float64)
     assert rel_err(got.cpu().numpy(), ref) < 2e-6
