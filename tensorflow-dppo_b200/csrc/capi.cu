@@ -256,15 +256,23 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
     for (int l = 0; l <= s.L; ++l) {
         int a = s.slices[l];
         if (tc_mode(c->cfg.gemm_mode)) {
-            int want = (rows + 511) / 512;                  // <= 512 rows per TMEM accumulation chain
+            // <= 512 rows per TMEM accumulation chain (64 truncating adds of a K = 8 tf32 MMA); the fp16 dW kernel covers
+            // K = 16 per MMA, so 1024 rows are the same 64 adds -- half the partial slices to write and to sum
+            const bool h_dw = c->cfg.gemm_mode == DPPO_GEMM_FP16X2 && c->use_h_dw && s.in_dim(l) % 4 == 0 &&
+                              (l == s.L ? s.Pld : s.out_dim(l)) % 4 == 0;
+            const int chain = h_dw ? 1024 : 512;
+            int want = (rows + chain - 1) / chain;
             // whole waves: the dW grid is tiles x slices CTAs on 2 x 148 slots (two CTAs per SM).  Round the slice count
             // up to the next count that fills its last wave when that costs <= 25 % more slices (cfg3: 256 -> 296, the
             // 6-tile layer-1 grid goes from 5.2 to 6.0 waves of 12 % shorter CTAs), then drop slices left without rows.
+            // (the persistent fp16 kernel: 148 CTAs walk tiles x slices work items, 128 x 256 / 128 / 64 tiles)
             const int in = s.in_dim(l), out = s.out_dim(l);
-            const int tiles = ((in + 127) / 128) * ((out + (out > 64 ? 127 : 63)) / (out > 64 ? 128 : 64));
-            int g = 2 * kPlanSMs, t = tiles;
+            const int bn = h_dw ? (out > 128 ? 256 : (out > 64 ? 128 : 64)) : (out > 64 ? 128 : 64);
+            const int tiles = ((in + 127) / 128) * ((out + bn - 1) / bn);
+            const int slots = h_dw ? kPlanSMs : 2 * kPlanSMs;
+            int g = slots, t = tiles;
             while (t) { const int r = g % t; g = t; t = r; }            // gcd(slots, tiles)
-            const int W = 2 * kPlanSMs / g;
+            const int W = slots / g;
             const int up = ((want + W - 1) / W) * W;
             if (up * 4 <= want * 5) want = up;
             const int kps = (((rows + want - 1) / want + 31) / 32) * 32;     // whole k-blocks of the fp16 (32-row) and tf32 (16-row) kernels

@@ -23,7 +23,7 @@
 namespace dppo {
 namespace th {
 
-constexpr int kDwRaw = 2, kDwOp = 2;               // ring depths
+constexpr int kDwOp = 2;                            // operand ring depth
 constexpr int kDwPC = 64;                          // staged columns per epilogue phase
 
 struct DwArgs {
@@ -36,6 +36,7 @@ struct DwArgs {
 
 template <int BN>
 struct DwPlan {
+    static constexpr int kDwRaw = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);     // raw (TMA) ring depth: what shared memory allows
     static constexpr int kARaw = 32 * BM * 4;            // 4 boxes of {32 features x 32 rows} fp32
     static constexpr int kBRaw = 32 * BN * 4;
     static constexpr int kRawSlot = kARaw + kBRaw;
@@ -80,6 +81,7 @@ template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG, const DwArgs g, int total_tiles) {
     using P = DwPlan<BN>;
+    constexpr int kDwRaw = P::kDwRaw;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t smem_base = smem_u32(smem);
