@@ -32,6 +32,7 @@ struct DwArgs {
     int ldc, k_per_slice, slices, accumulate, vecC;
     int tiles_m, tiles_n;
     long long slice_stride;
+    int fold;                     // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
 };
 
 template <int BN>
@@ -49,7 +50,8 @@ struct DwPlan {
     static constexpr int kOpOff = kDwRaw * kRawSlot;
     static constexpr int kStgOff = kOpOff + kDwOp * kOpSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
-    static constexpr int kBytes = kBarOff + 256 + 1024;
+    static constexpr int kFoldOff = kBarOff + 256;
+    static constexpr int kBytes = kBarOff + 256 + kFoldBytes + 1024;
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
@@ -117,6 +119,7 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
         fence_barrier_init();
     }
+    if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
     constexpr uint32_t kTmemCols = 2 * BN;
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
@@ -230,6 +233,7 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
                     }
                     umma_commit(&op_empty[os]);
                 }
+                if (g.fold && nkb > 0) fold_issue<BN>(tmem_base, smem_base + P::kFoldOff);
                 umma_commit(acc_full);                 // fires at once when the slice holds no rows (nkb == 0)
             }
             tc_fence_before();
@@ -260,21 +264,23 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
                 const int r = q * 32 + lane;
                 {
                     const int col = p * PC + ch * kDrainCols;
-                    uint32_t v[32], w2[32];
+                    uint32_t v[32];
                     if (nkb > 0) {
                         tmem_ld32(acc + (uint32_t)col, v);
-                        tmem_ld32(acc + (uint32_t)(BN + col), w2);
+                        if (!g.fold) {
+                            uint32_t w2[32];
+                            tmem_ld32(acc + (uint32_t)(BN + col), w2);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(w2[j]), kLoInv, __uint_as_float(v[j])));
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { v[j] = 0u; w2[j] = 0u; }
+                        for (int j = 0; j < 32; ++j) v[j] = 0u;
                     }
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 o;
-                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0]));
-                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1]));
-                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2]));
-                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3]));
+                        const float4 o = make_float4(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1]),
+                                                     __uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3]));
                         const int c = (ch * kDrainCols) / 4 + j4;
                         const int pc = (c & ~7) | ((c ^ r) & 7);
                         sts128f(stg + (uint32_t)(r * kRowBytes + pc * 16), o);
@@ -367,6 +373,7 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     th::DwArgs g{};
     g.C = C; g.bias_out = bias_out; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.accumulate = accumulate;
     g.slice_stride = slice_stride;
+    g.fold = th::fold_enabled() ? 1 : 0;
     if (slices < 1) slices = 1;
     int kps = (K + slices - 1) / slices;
     kps = ((kps + th::kKB - 1) / th::kKB) * th::kKB;

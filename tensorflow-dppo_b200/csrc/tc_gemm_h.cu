@@ -50,6 +50,7 @@ struct HArgs {
     int tiles_n, nets, relu, vecA, vecC, bits_wpr;
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
+    int fold;                          // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
 };
 
 template <int BN, bool PAIR>
@@ -71,7 +72,8 @@ struct HPlan {
     static constexpr int kBOff = kRawOff + kRSlots * kRawSlot;
     static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
-    static constexpr int kBytes = kBarOff + 256 + 1024;
+    static constexpr int kFoldOff = kBarOff + 256;            // the two fold patterns (tc_h.cuh)
+    static constexpr int kBytes = kBarOff + 256 + kFoldBytes + 1024;
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
@@ -171,6 +173,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         for (int s = 0; s < kPeerSlots; ++s) mbar_init(&peer_full[s], 1);
         fence_barrier_init();
     }
+    if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
     if (PAIR) cluster_sync_all();                   // both CTAs' barriers exist before anything arrives on them remotely
     constexpr uint32_t kTmemCols = 2 * BN;          // [0,BN) main (hi.hi), [BN,2BN) correction (lo.hi + hi.lo, scaled 2^11)
     if (warp == kMmaWarp) { if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
@@ -309,6 +312,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     if (PAIR) { umma_commit_pair(&empty_a[sa]); umma_commit_pair(&empty_b[sb]); }     // slots free in BOTH CTAs
                     else { umma_commit(&empty_a[sa]); umma_commit(&empty_b[sb]); }
                 }
+                if (!PAIR && g.fold) fold_issue<BN>(tmem_base, smem_base + P::kFoldOff);
                 if (PAIR) umma_commit_pair(acc_full); else umma_commit(acc_full);     // accumulators of tile i complete
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 1] = clock64();
             }
@@ -344,16 +348,18 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
 #pragma unroll 1
                 for (int cb = 0; cb < kDrainCols; cb += 32) {
                     const int col = p * PC + ch * kDrainCols + cb;
-                    uint32_t v[32], w2[32];
+                    uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)col, v);
-                    tmem_ld32(acc + (uint32_t)(BN + col), w2);
+                    if (!g.fold) {                                  // warp-uniform: main + correction / 2^11 here, not on the tensor core
+                        uint32_t w2[32];
+                        tmem_ld32(acc + (uint32_t)(BN + col), w2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(w2[j]), kLoInv, __uint_as_float(v[j])));
+                    }
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        float4 o;
-                        o.x = fmaf(__uint_as_float(w2[j4 * 4 + 0]), kLoInv, __uint_as_float(v[j4 * 4 + 0]));
-                        o.y = fmaf(__uint_as_float(w2[j4 * 4 + 1]), kLoInv, __uint_as_float(v[j4 * 4 + 1]));
-                        o.z = fmaf(__uint_as_float(w2[j4 * 4 + 2]), kLoInv, __uint_as_float(v[j4 * 4 + 2]));
-                        o.w = fmaf(__uint_as_float(w2[j4 * 4 + 3]), kLoInv, __uint_as_float(v[j4 * 4 + 3]));
+                        const float4 o = make_float4(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1]),
+                                                     __uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3]));
                         const int c = (ch * kDrainCols + cb) / 4 + j4;               // 16-B chunk of the staged row
                         const int pc = (c & ~7) | ((c ^ r) & 7);                      // XOR swizzle: conflict-free both ways
                         sts128f(stg + (uint32_t)(r * kRowBytes + pc * 16), o);
@@ -625,6 +631,7 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.bits_wpr = (N + 31) / 32;
     g.img_replica_bytes = th_image_replica_bytes(N, K);
     g.timeline = timeline;
+    g.fold = (th::fold_enabled() && !th::pair_enabled()) ? 1 : 0;
     g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
     const int bn = th_bn_for(N);
