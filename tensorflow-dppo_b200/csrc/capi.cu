@@ -273,6 +273,10 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
             int g = slots, t = tiles;
             while (t) { const int r = g % t; g = t; t = r; }            // gcd(slots, tiles)
             const int W = slots / g;
+            // short row blocks (minibatches, the H2D chunks of the host-buffer path): at least one work item per CTA slot,
+            // as long as an item keeps >= 128 rows
+            const int fill = (slots + tiles - 1) / tiles;
+            if (want < fill) { const int cap = rows / 128 > 1 ? rows / 128 : 1; want = fill < cap ? fill : cap; }
             const int up = ((want + W - 1) / W) * W;
             if (up * 4 <= want * 5) want = up;
             const int kps = (((rows + want - 1) / want + 31) / 32) * 32;     // whole k-blocks of the fp16 (32-row) and tf32 (16-row) kernels

@@ -57,7 +57,7 @@ template <int BN, bool PAIR>
 struct HPlan {
     static constexpr int kBSlots = PAIR ? 4 : 3;
     // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight
-    static constexpr int kASlots = PAIR ? 3 : 2;
+    static constexpr int kASlots = PAIR ? 3 : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
     static constexpr int kRSlots = PAIR ? 3 : (BN >= 256 ? 2 : (BN >= 128 ? 4 : 6));
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
     static constexpr int kASlot = 2 * kAHalf;
