@@ -154,7 +154,8 @@ GEMM_TEXT = {"simt": "fp32 SIMT FFMA",
              "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators",
              "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (NOT fp32-parity)",
              "fp16x2": "tcgen05 kind::f16, 2-term fp16 split x = hi + lo/2^11 (fp32-accurate), persistent kernels, TMEM "
-                       "accumulators; dW on the TMA-fed kind::tf32 kernel"}
+                       "accumulators; forward / dX / dW all on the fp16-split kernels (dW falls back to the TMA-fed "
+                       "kind::tf32 kernel only with DPPO_H_DW=0)"}
 
 
 def make_config(args, world):
