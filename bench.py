@@ -436,8 +436,8 @@ def run_b200(args):
                 "note": ("algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "
                          + {"tf32x3": "fp32-parity path: every algorithmic MAC is issued as 3 TF32 MMAs (half the bf16 rate each), so "
                                       "the ceiling of this fraction is 1/6",
-                            "fp16x2": "fp32-parity path: forward / dX MACs are issued as 3 fp16 MMAs (ceiling 1/3), dW MACs as 3 "
-                                      "TF32 MMAs (ceiling 1/6)",
+                            "fp16x2": "fp32-parity path: every algorithmic MAC (forward, dX, dW) is issued as 3 fp16 MMAs, so the "
+                                      "ceiling of this fraction is 1/3",
                             "bf16": "bf16 operands, one MMA per MAC: the ceiling of this fraction is 1",
                             "simt": "this path runs the GEMMs as fp32 FFMA (fp32 FMA pipe, ~74 TFLOP/s), not on tensor cores"}[args.gemm]),
                 "launches_per_step": gemm_launches / K, "ms_per_step": gemm_ms / K,

@@ -114,8 +114,8 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     };
 
     if (tid == 0) {
-        for (int s = 0; s < kDwRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverThreads); }
-        for (int s = 0; s < kDwOp; ++s) { mbar_init(&op_full[s], kMoverThreads); mbar_init(&op_empty[s], 1); }
+        for (int s = 0; s < kDwRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverWarps); }
+        for (int s = 0; s < kDwOp; ++s) { mbar_init(&op_full[s], kMoverWarps); mbar_init(&op_empty[s], 1); }
         mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
         fence_barrier_init();
     }
@@ -162,8 +162,8 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
                     dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, csum[u], want_bias);
                 }
                 fence_proxy_async();
-                mbar_arrive(&op_full[os]);
-                mbar_arrive(&raw_empty[rs]);
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&op_full[os]); mbar_arrive(&raw_empty[rs]); }
             }
             if (want_bias) {            // warp-uniform: fold the 32 k-rows (lanes), lane 0 writes the slice's bias partials
 #pragma unroll

@@ -14,10 +14,14 @@
 // What is new against tc_gemm.cu, whose one-tile-per-CTA kernels leave the tensor pipe idle during every prologue and
 // epilogue (45 % of their time at cfg3):
 //   * persistent CTAs (grid = #SMs) walk output tiles; the operand rings run straight across tile boundaries;
-//   * the epilogue has its own 8 warps and drains TMEM -> registers -> a swizzled shared-memory staging buffer in two
-//     128-column phases, releases TMEM as soon as the last column is read, and only then streams the second phase to
-//     HBM: the next tile's MMAs overlap the write-out (all 512 TMEM columns are one 128x256 tile's main + correction
-//     accumulators, so TMEM itself cannot be double-buffered);
+//   * the epilogue has its own 8 warps, thread = accumulator row: 64-column sub-phases leave TMEM, are finished in
+//     registers (correction / 2^11, bias, ReLU + sign word | mask word) and staged as 128-B rows of SWIZZLE_128B boxes
+//     that ONE thread hands to TMA (cp.async.bulk.tensor store, clipped at the matrix edge); two staging buffers, so the
+//     store of sub-phase k runs under the drain of k+1 and TMEM is held for the drains only.  (C rows TMA cannot address
+//     -- a stride that is not a multiple of 16 B -- keep a coalesced st.global write-out.)
+//   * all 512 TMEM columns are one 128x256 tile's main + correction accumulators, so a 256-wide tile cannot overlap its
+//     drain with the next tile's MMAs; tiles of <= 128 columns get TWO accumulator stages and do.  Products with a short
+//     reduction (K < 65: the dX of the heads) therefore run as 128-wide tiles even when N = 256;
 //   * the activation operand arrives by TMA: one thread issues cp.async.bulk.tensor.2d boxes {32 fp32 x 128 rows,
 //     SWIZZLE_128B} into a raw ring (2 slots); 8 converter warps read their 16-B chunks back, split them into fp16 hi / lo
 //     and write the K-major SWIZZLE_64B operand tiles (2 slots).  Measured on the first version of this kernel: register-
@@ -35,7 +39,6 @@
 namespace dppo {
 namespace th {
 
-constexpr int kPeerSlots = 4;
 constexpr int kPrefetch = 3;                                 // activation k-blocks in flight per mover thread
 constexpr int kImgReplicas = 8;                              // copies of every weight image (spreads the hot L2 lines)
 
@@ -51,18 +54,20 @@ struct HArgs {
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
     int fold;                          // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
+    int dbg;                           // DPPO_H_DBG: timing-only ablations (WRONG results), tools/h_ablate.py
 };
+enum { DBG_NO_A = 1, DBG_NO_SPLIT = 2, DBG_ONE_MMA = 4, DBG_NO_W = 8, DBG_NO_STORE = 16, DBG_NO_FENCE = 32,
+       DBG_EARLY_RELEASE = 512 };     // 512: release the raw slot right after ISSUING its loads (the race described in the converter loop)
 
-template <int BN, bool PAIR>
+template <int BN>
 struct HPlan {
-    static constexpr int kBSlots = PAIR ? 4 : 3;
+    static constexpr int kBSlots = 3;
     // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight
-    static constexpr int kASlots = PAIR ? 3 : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
-    static constexpr int kRSlots = PAIR ? 3 : (BN >= 256 ? 2 : (BN >= 128 ? 4 : 6));
+    static constexpr int kASlots = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);   // operand ring: latency-bound when k-blocks are short
+    static constexpr int kRSlots = BN >= 256 ? 2 : (BN >= 128 ? 4 : 6);
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
     static constexpr int kASlot = 2 * kAHalf;
-    static constexpr int kBRows = PAIR ? BN / 2 : BN;        // a CTA of a pair holds half of the weight tile's rows
-    static constexpr int kBHalf = kBRows * 64;
+    static constexpr int kBHalf = BN * 64;
     static constexpr int kBSlot = 2 * kBHalf;
     static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
     static constexpr int kPhases = BN / kPhaseCols;
@@ -73,7 +78,9 @@ struct HPlan {
     static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
     static constexpr int kFoldOff = kBarOff + 256;            // the two fold patterns (tc_h.cuh)
-    static constexpr int kBytes = kBarOff + 256 + kFoldBytes + 1024;
+    static constexpr int kBiasOff = kFoldOff + kFoldBytes;    // the tile's bias vector (TMA write-out epilogue)
+    static constexpr int kBytes = kBiasOff + BN * 4;
+    static_assert(kStgOff % 1024 == 0, "staging boxes are SWIZZLE_128B");
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
@@ -103,17 +110,39 @@ __device__ __forceinline__ void mover_load(MoverRegs& r, const float* __restrict
     }
 }
 
-__device__ __forceinline__ void mover_store(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, int tid) {
+struct OperandRegs { uint4 h[2], l[2]; };
+__device__ __forceinline__ void mover_split(const MoverRegs& r, OperandRegs& o) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float4 a = r.v[j][0], b = r.v[j][1];
+        split2(a.x, a.y, o.h[j].x, o.l[j].x); split2(a.z, a.w, o.h[j].y, o.l[j].y);
+        split2(b.x, b.y, o.h[j].z, o.l[j].z); split2(b.z, b.w, o.h[j].w, o.l[j].w);
+    }
+}
+__device__ __forceinline__ void mover_store_split(const OperandRegs& o, uint32_t hi_tile, uint32_t lo_tile, int tid) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int row = (tid >> 2) + j * 64, c = tid & 3;
         const uint32_t off = (uint32_t)row * 64u + (uint32_t)((c ^ ((row >> 1) & 3)) << 4);     // SWIZZLE_64B
+        sts128(hi_tile + off, o.h[j]);
+        sts128(lo_tile + off, o.l[j]);
+    }
+}
+__device__ __forceinline__ void mover_store(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, int tid) {
+    OperandRegs o;
+    mover_split(r, o);
+    mover_store_split(o, hi_tile, lo_tile, tid);
+}
+
+// timing ablation: the same stores without the fp32 -> fp16 split (bit patterns, wrong values)
+__device__ __forceinline__ void mover_store_raw(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, int tid) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (tid >> 2) + j * 64, c = tid & 3;
+        const uint32_t off = (uint32_t)row * 64u + (uint32_t)((c ^ ((row >> 1) & 3)) << 4);
         const float4 a = r.v[j][0], b = r.v[j][1];
-        uint4 h, l;
-        split2(a.x, a.y, h.x, l.x); split2(a.z, a.w, h.y, l.y);
-        split2(b.x, b.y, h.z, l.z); split2(b.z, b.w, h.w, l.w);
-        sts128(hi_tile + off, h);
-        sts128(lo_tile + off, l);
+        sts128(hi_tile + off, make_uint4(__float_as_uint(a.x) & 0x3bff3bffu, __float_as_uint(a.y) & 0x3bff3bffu, __float_as_uint(a.z) & 0x3bff3bffu, __float_as_uint(a.w) & 0x3bff3bffu));
+        sts128(lo_tile + off, make_uint4(__float_as_uint(b.x) & 0x3bff3bffu, __float_as_uint(b.y) & 0x3bff3bffu, __float_as_uint(b.z) & 0x3bff3bffu, __float_as_uint(b.w) & 0x3bff3bffu));
     }
 }
 
@@ -128,18 +157,17 @@ __device__ __forceinline__ void raw_load(MoverRegs& r, uint32_t raw_tile, int ti
     }
 }
 
-// PAIR: two CTAs of a cluster work on a 256-row super-tile with cta_group::2 MMAs (M = 256): each CTA streams its own 128
-// activation rows and HALF of the weight tile's rows, so the weight bytes a CTA pulls through its L2 port halve (the
-// single-CTA kernel is bound by exactly that port).  The leader (rank 0) issues every MMA once both CTAs' slots are full
-// (the peer's MMA warp relays its local full barriers to the leader) and releases slots / publishes accumulators with
-// multicast commits; each CTA drains its own TMEM rows.
-template <int BN, int EPI, bool TMA_A, bool PAIR>
+// The accumulators of a tile: main (hi.hi) and correction (lo.hi + hi.lo, scaled 2^11), BN columns each.  Tiles of up to 128
+// columns leave room for TWO such stages in the 512 TMEM columns: the MMAs of tile i+1 run while tile i is drained.
+template <int BN> struct HAcc { static constexpr int kStages = BN >= 256 ? 1 : 2; };
+
+template <int BN, int EPI, bool TMA_A, bool TMA_C>
 __global__ void __launch_bounds__(kThreads, 1)
-h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const HArgs g, int total_tiles) {
-    using P = HPlan<BN, PAIR>;
-    constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+              const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1, const HArgs g, int total_tiles) {
+    using P = HPlan<BN>;
+    constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots, kAcc = HAcc<BN>::kStages;
+    extern __shared__ __align__(1024) uint8_t smem[];         // SWIZZLE_128B boxes and UMMA tiles need 1024-B alignment
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t a_ring = smem_base, raw_ring = smem_base + P::kRawOff, b_ring = smem_base + P::kBOff;
     const uint32_t stg = smem_base + P::kStgOff;
@@ -150,33 +178,30 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     uint64_t* raw_full = empty_b + kBSlots;
     uint64_t* raw_empty = raw_full + kRSlots;
     uint64_t* acc_full = raw_empty + kRSlots;
-    uint64_t* acc_empty = acc_full + 1;
-    uint64_t* peer_full = acc_empty + 1;            // PAIR, leader only: "the peer's slots of iteration it are full"
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + kPeerSlots);
+    uint64_t* acc_empty = acc_full + kAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+    float* s_bias = reinterpret_cast<float*>(smem + P::kBiasOff);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (g.K + kKB - 1) / kKB;
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-    const int n_groups = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;         // a group = one CTA, or one CTA pair
-    const int group = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
-    const int per_cta = (total_tiles + n_groups - 1) / n_groups;
-    const int t_begin = group * per_cta;
+    const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = (int)blockIdx.x * per_cta;
     const int t_end = min(total_tiles, t_begin + per_cta);
     const int my_tiles = max(0, t_end - t_begin);
     const long long total_it = (long long)my_tiles * nkb;
 
     if (tid == 0) {
-        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], kMoverThreads); mbar_init(&empty_a[s], 1); }
+        if (smem_base & 1023u) __trap();
+        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], kMoverWarps); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < kRSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverThreads); }
-        mbar_init(acc_full, 1); mbar_init(acc_empty, PAIR ? 2 * kEpiWarps : kEpiWarps);
-        for (int s = 0; s < kPeerSlots; ++s) mbar_init(&peer_full[s], 1);
+        for (int s = 0; s < kRSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverWarps); }
+        for (int s = 0; s < kAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
         fence_barrier_init();
     }
     if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
-    if (PAIR) cluster_sync_all();                   // both CTAs' barriers exist before anything arrives on them remotely
-    constexpr uint32_t kTmemCols = 2 * BN;          // [0,BN) main (hi.hi), [BN,2BN) correction (lo.hi + hi.lo, scaled 2^11)
-    if (warp == kMmaWarp) { if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
+    constexpr uint32_t kStageCols = 2 * BN;         // [0,BN) main, [BN,2BN) correction
+    constexpr uint32_t kTmemCols = kAcc * kStageCols;
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -186,7 +211,6 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     auto decode = [&](int t, int& mt, int& net, int& nt) {
         nt = t % g.tiles_n; t /= g.tiles_n;
         net = t % g.nets; mt = t / g.nets;
-        if (PAIR) mt = mt * 2 + (int)rank;          // the pair's 256-row super-tile: rank r takes rows [r*128, r*128+128)
     };
 
     if (warp < kMoverWarps) {
@@ -195,14 +219,31 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             for (long long it = 0; it < total_it; ++it) {
                 const int rs = (int)(it % kRSlots), sa = (int)(it % kASlots);
                 MoverRegs r;
-                mbar_wait(&raw_full[rs], (uint32_t)((it / kRSlots) & 1));
-                raw_load(r, raw_ring + rs * P::kRawSlot, tid);
-                mbar_arrive(&raw_empty[rs]);               // release: the loads above are complete; TMA may refill the slot
+                OperandRegs o;
+                const bool old_order = (g.dbg & DBG_EARLY_RELEASE) != 0;
+                if (!(g.dbg & DBG_NO_A)) {
+                    mbar_wait(&raw_full[rs], (uint32_t)((it / kRSlots) & 1));
+                    raw_load(r, raw_ring + rs * P::kRawSlot, tid);
+                    if (old_order) warp_arrive(&raw_empty[rs], lane);
+                } else {
+                    r.v[0][0] = r.v[0][1] = r.v[1][0] = r.v[1][1] = make_float4(1.f, 2.f, 3.f, 4.f);
+                }
+                // The raw slot is released only after its values have been USED (the split below cannot issue before the
+                // shared-memory loads have returned) and behind a proxy fence: the refill is an async-proxy write, and a
+                // barrier arrive alone does not keep it behind this thread's still outstanding generic-proxy reads.
+                // Releasing straight after issuing the loads let TMA overwrite rows that had not been read yet (seen as
+                // "k-block kb+2 instead of kb" in rows of a tile's first k-blocks whenever the epilogue kept the LSU busy).
+                mover_split(r, o);
+                if (!(g.dbg & DBG_NO_A) && !old_order) {
+                    fence_proxy_async();
+                    warp_arrive(&raw_empty[rs], lane);
+                }
                 mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
                 const uint32_t slot = a_ring + sa * P::kASlot;
-                mover_store(r, slot, slot + P::kAHalf, tid);
-                fence_proxy_async();                       // generic-proxy stores -> visible to the tensor core (async proxy)
-                mbar_arrive(&full_a[sa]);
+                if (g.dbg & DBG_NO_SPLIT) mover_store_raw(r, slot, slot + P::kAHalf, tid);
+                else mover_store_split(o, slot, slot + P::kAHalf, tid);
+                if (!(g.dbg & DBG_NO_FENCE)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                warp_arrive(&full_a[sa], lane);
             }
         } else {
             // ================= movers: LDG fp32 -> fp16 hi / lo (rows that TMA cannot address: unaligned strides) ==========
@@ -225,7 +266,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                         const uint32_t slot = a_ring + sa * P::kASlot;
                         mover_store(ra[j], slot, slot + P::kAHalf, tid);
                         fence_proxy_async();
-                        mbar_arrive(&full_a[sa]);
+                        warp_arrive(&full_a[sa], lane);
                         if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
                     }
                 }
@@ -235,7 +276,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         // ================= producer (one thread): weight-image bulk copies and activation TMA boxes =================
         // two independent streams polled without blocking, so that a full ring of one never holds the other back
         if (lane == 0) {
-            long long ib = 0, ia = TMA_A ? 0 : total_it;
+            long long ib = (g.dbg & DBG_NO_W) ? total_it : 0, ia = (TMA_A && !(g.dbg & DBG_NO_A)) ? 0 : total_it;
             while (ib < total_it || ia < total_it) {
                 if (ib < total_it) {
                     const int sb = (int)(ib % kBSlots);
@@ -243,8 +284,8 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                         int mt, net, nt;
                         decode(t_begin + (int)(ib / nkb), mt, net, nt);
                         const int kb = (int)(ib % nkb);
-                        const uint8_t* img = g.Bimg[net] + (size_t)(group % kImgReplicas) * g.img_replica_bytes +
-                                             (((size_t)nt * nkb + (size_t)kb) * (PAIR ? 2 : 1) + (PAIR ? rank : 0u)) * P::kBSlot;
+                        const uint8_t* img = g.Bimg[net] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
+                                             ((size_t)nt * nkb + (size_t)kb) * P::kBSlot;
                         mbar_arrive_expect_tx(&full_b[sb], (uint32_t)P::kBSlot);
                         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                      ::"r"(b_ring + sb * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[sb]))
@@ -265,61 +306,164 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             }
         }
     } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one thread; in a pair: the leader issues, the peer relays its full barriers) ==========
-        if (lane == 0 && PAIR && rank != 0) {
-            uint32_t remote[kPeerSlots];
-#pragma unroll
-            for (int s = 0; s < kPeerSlots; ++s) remote[s] = mapa_u32(smem_u32(&peer_full[s]), 0);
-            for (long long it = 0; it < total_it; ++it) {
-                const int sa = (int)(it % kASlots), sb = (int)(it % kBSlots);
-                mbar_wait(&full_a[sa], (uint32_t)((it / kASlots) & 1));
-                mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
-                mbar_arrive_remote(remote[it % kPeerSlots]);
-            }
-        } else if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BN, PAIR ? 2 * BM : BM);
-            const uint32_t a_base = a_ring, b_base = b_ring;
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BN);
             long long it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                // the epilogue (of both CTAs) has read tile i-1 out of TMEM
-                if (PAIR) mbar_wait_cluster(acc_empty, (uint32_t)((i & 1) ^ 1)); else mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));
+                const int as = i % kAcc;
+                const uint32_t acc = tmem_base + (uint32_t)as * kStageCols;
+                mbar_wait(&acc_empty[as], (uint32_t)(((i / kAcc) & 1) ^ 1));      // the epilogue has read tile i - kAcc out of this stage
                 tc_fence_after();
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 0] = clock64();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int sa = (int)(it % kASlots), sb = (int)(it % kBSlots);
                     mbar_wait(&full_a[sa], (uint32_t)((it / kASlots) & 1));
-                    mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
-                    if (PAIR) mbar_wait_cluster(&peer_full[it % kPeerSlots], (uint32_t)((it / kPeerSlots) & 1));
+                    if (!(g.dbg & DBG_NO_W)) mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
                     tc_fence_after();
-                    const uint32_t a_hi = a_base + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
-                    const uint32_t b_hi = b_base + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
+                    const uint32_t a_hi = a_ring + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
+                    const uint32_t b_hi = b_ring + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
 #pragma unroll
                     for (int k = 0; k < kKB / 16; ++k) {
                         const uint64_t da_hi = make_sdesc(a_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
-                        if (PAIR) {
-                            umma_f16_pair(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                            umma_f16_pair(tmem_base + BN, da_hi, db_lo, idesc, 1u);
-                            umma_f16_pair(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
-                        } else {
-                            umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                            umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
-                            umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
+                        if (!(g.dbg & DBG_ONE_MMA)) {
+                            umma_f16(acc + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                            umma_f16(acc + BN, da_hi, db_lo, idesc, 1u);
                         }
+                        umma_f16(acc, da_hi, db_hi, idesc, (kb | k) != 0);
                     }
-                    if (PAIR) { umma_commit_pair(&empty_a[sa]); umma_commit_pair(&empty_b[sb]); }     // slots free in BOTH CTAs
-                    else { umma_commit(&empty_a[sa]); umma_commit(&empty_b[sb]); }
+                    umma_commit(&empty_a[sa]);
+                    umma_commit(&empty_b[sb]);
                 }
-                if (!PAIR && g.fold) fold_issue<BN>(tmem_base, smem_base + P::kFoldOff);
-                if (PAIR) umma_commit_pair(acc_full); else umma_commit(acc_full);     // accumulators of tile i complete
+                if (g.fold) fold_issue<BN>(acc, smem_base + P::kFoldOff);
+                umma_commit(&acc_full[as]);                 // accumulators of tile i complete
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 1] = clock64();
             }
             tc_fence_before();
         }
+    } else if (TMA_C) {
+        // ================= epilogue warps, TMA write-out =================
+        // thread = accumulator row.  A tile leaves TMEM in 64-column sub-phases; each thread finishes its 32 columns of the
+        // sub-phase in registers (correction, bias, ReLU + sign word | mask word) and stages them as one 128-B row of a
+        // SWIZZLE_128B box; one thread then hands the two boxes of the sub-phase to TMA (cp.async.bulk.tensor store, clipped
+        // at the matrix edge).  With two staging buffers the store of sub-phase k runs under the drain of k+1, so TMEM is
+        // held for the drains only.
+        constexpr int kSubs = BN / 64;
+        constexpr int kBufs = P::kStaging / (BM * 64 * 4);         // 2 (BN >= 128) or 1
+        static_assert(kBufs == 1 || kBufs == 2, "staging holds one or two 64-column sub-phases");
+        const int ew = warp - kEpiWarp0;
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+        const int ch = ew >> 2;                                   // which 32 columns of the sub-phase
+        const int r = q * 32 + lane;
+        const bool t0 = (ew == 0 && lane == 0);
+        const uint32_t row_off = (uint32_t)r * 128u;
+        uint32_t gsp = 0;                                         // sub-phases staged so far (buffer choice)
+        for (int i = 0; i < my_tiles; ++i) {
+            int mt, net, nt;
+            decode(t_begin + i, mt, net, nt);
+            const int m = mt * BM + r;
+            const CUtensorMap* mapC = net ? &mapC1 : &mapC0;
+            uint32_t* __restrict__ bits_out = (EPI == EPI_NN) ? g.bits_out[net] : nullptr;
+            uint32_t mw[kSubs];
+            if (EPI == EPI_NN) {
+                // the tile's bias vector -> shared memory (everybody finished reading the previous tile's at its last barrier)
+                const int e = (warp - kEpiWarp0) * 32 + lane;
+                const float* __restrict__ bias = g.bias[net];
+                if (e < BN) s_bias[e] = (bias && nt * BN + e < g.N) ? __ldg(bias + nt * BN + e) : 0.f;
+                epi_bar();
+            } else if (g.bits_in) {
+#pragma unroll
+                for (int sp = 0; sp < kSubs; ++sp) {
+                    const int wi = nt * (BN / 32) + sp * 2 + ch;
+                    mw[sp] = (m < g.M && wi < g.bits_wpr) ? __ldg(g.bits_in + (size_t)m * g.bits_wpr + wi) : 0u;
+                }
+            }
+            const int as = i % kAcc;
+            mbar_wait(&acc_full[as], (uint32_t)((i / kAcc) & 1));
+            tc_fence_after();
+            if (g.timeline && blockIdx.x == 0 && i < 16 && t0) g.timeline[i * 8 + 2] = clock64();
+            const uint32_t acc = tmem_base + (uint32_t)as * kStageCols + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+            for (int sp = 0; sp < kSubs; ++sp, ++gsp) {
+                const uint32_t buf = stg + (gsp % kBufs) * (uint32_t)(BM * 64 * 4) + (uint32_t)ch * (uint32_t)(BM * 128);
+                const int col = sp * 64 + ch * 32;               // first of this thread's 32 columns within the tile
+                if (kBufs == 1) {                                 // one buffer: its previous store must have read it
+                    if (t0) bulk_wait_read0();
+                    epi_bar();
+                }
+                uint32_t v[32];
+                if (!g.fold) {
+                    uint32_t w2[32];
+                    tmem_ld32x2(acc + (uint32_t)col, v, acc + (uint32_t)(BN + col), w2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(w2[j]), kLoInv, __uint_as_float(v[j])));
+                } else {
+                    tmem_ld32(acc + (uint32_t)col, v);
+                }
+                if (sp == kSubs - 1) {                            // every column of this tile is out of TMEM
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[as]);
+                    if (g.timeline && blockIdx.x == 0 && i < 16 && t0) g.timeline[i * 8 + 3] = clock64();
+                }
+                if (EPI == EPI_NN) {
+                    uint32_t sign = 0u;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + col + j4 * 4);
+                        float x0 = __uint_as_float(v[j4 * 4 + 0]) + b4.x, x1 = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+                        float x2 = __uint_as_float(v[j4 * 4 + 2]) + b4.z, x3 = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+                        if (g.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                        sign |= ((x0 > 0.f ? 1u : 0u) | (x1 > 0.f ? 2u : 0u) | (x2 > 0.f ? 4u : 0u) | (x3 > 0.f ? 8u : 0u)) << (j4 * 4);
+                        sts128f(buf + row_off + (uint32_t)(((j4 ^ r) & 7) << 4), make_float4(x0, x1, x2, x3));
+                    }
+                    const int wi = (nt * BN + col) >> 5;
+                    if (bits_out && m < g.M && wi < g.bits_wpr) bits_out[(size_t)m * g.bits_wpr + wi] = sign;
+                } else {
+                    uint32_t keep = 0xffffffffu;
+                    if (g.bits_in) keep = mw[sp];
+                    else if (g.mask) {
+                        keep = 0u;
+                        const int n0 = nt * BN + col;
+                        if (m < g.M && n0 + 32 <= g.N) {           // (TMA_C implies 16-B aligned rows)
+                            const float4* mp = reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldc + n0);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 k = __ldg(mp + j4);
+                                keep |= ((k.x > 0.f ? 1u : 0u) | (k.y > 0.f ? 2u : 0u) | (k.z > 0.f ? 4u : 0u) | (k.w > 0.f ? 8u : 0u)) << (j4 * 4);
+                            }
+                        } else if (m < g.M) {
+                            for (int j = 0; j < 32; ++j)
+                                if (n0 + j < g.N && __ldg(g.mask + (size_t)m * g.ldc + n0 + j) > 0.f) keep |= 1u << j;
+                        }
+                    }
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const uint32_t k4 = keep >> (j4 * 4);
+                        const float4 o = make_float4((k4 & 1u) ? __uint_as_float(v[j4 * 4 + 0]) : 0.f, (k4 & 2u) ? __uint_as_float(v[j4 * 4 + 1]) : 0.f,
+                                                     (k4 & 4u) ? __uint_as_float(v[j4 * 4 + 2]) : 0.f, (k4 & 8u) ? __uint_as_float(v[j4 * 4 + 3]) : 0.f);
+                        sts128f(buf + row_off + (uint32_t)(((j4 ^ r) & 7) << 4), o);
+                    }
+                }
+                fence_proxy_async();                              // staged rows -> visible to TMA (async proxy)
+                if (kBufs == 2 && t0) bulk_wait_read0();         // the other buffer's store (previous sub-phase) has read it
+                epi_bar();                                        // sub-phase staged; the other buffer is free
+                if (t0) {
+                    const uint32_t b0 = stg + (gsp % kBufs) * (uint32_t)(BM * 64 * 4);
+                    const int n0 = nt * BN + sp * 64;
+                    if (n0 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0, n0, mt * BM);
+                    if (n0 + 32 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0 + (uint32_t)(BM * 128), n0 + 32, mt * BM);
+                    bulk_commit();
+                }
+            }
+            if (g.timeline && blockIdx.x == 0 && i < 16 && t0) g.timeline[i * 8 + 4] = clock64();
+        }
+        if (t0) bulk_wait_read0();                                // shared memory stays valid until TMA has read it
     } else {
-        // ================= epilogue warps =================
+        // ================= epilogue warps, st.global write-out (C rows that TMA cannot address) =================
         constexpr int PC = P::kPhaseCols;
         constexpr int kRowBytes = PC * 4;
         constexpr int kDrainCols = PC / 2;                        // columns each of the two warps of a lane quarter drains
@@ -336,10 +480,11 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             float* __restrict__ C = g.C[net];
             const float* __restrict__ bias = g.bias[net];
             uint32_t* __restrict__ bits_out = (EPI == EPI_NN) ? g.bits_out[net] : nullptr;
-            mbar_wait(acc_full, (uint32_t)(i & 1));
+            const int as = i % kAcc;
+            mbar_wait(&acc_full[as], (uint32_t)((i / kAcc) & 1));
             tc_fence_after();
             if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 2] = clock64();
-            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t acc = tmem_base + (uint32_t)as * kStageCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int p = 0; p < P::kPhases; ++p) {
                 epi_bar();                                         // the staging buffer has been written out
@@ -368,10 +513,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 if (p == P::kPhases - 1) {                         // every column of this tile is out of TMEM
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) {
-                        if (PAIR && rank != 0) mbar_arrive_remote(mapa_u32(smem_u32(acc_empty), 0));
-                        else mbar_arrive(acc_empty);
-                    }
+                    if (lane == 0) mbar_arrive(&acc_empty[as]);
                     if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 3] = clock64();
                 }
                 // NT: the mask words of this warp's rows are requested before the barrier
@@ -445,17 +587,16 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         }
     }
     tc_fence_before();
-    if (PAIR) cluster_sync_all();       // the leader's MMAs read the peer's shared memory and signal its barriers until the very end
-    else __syncthreads();
+    __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
 // ---- weight images: per (n-tile, k-block) the fp16 hi tile then the lo tile, K-major SWIZZLE_64B, exactly as the MMA
 // reads them from shared memory -> one cp.async.bulk per k-block ----
-struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn, pair; };
+struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn; };
 struct HImgPlan { int n; HImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
 
 __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
@@ -478,88 +619,73 @@ __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
         uint4 h, l;
         split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
         const size_t ntiles = (size_t)((e.N + e.bn - 1) / e.bn);
-        // single CTA: [hi (bn rows) | lo];  CTA pair: [rank 0: hi (bn/2 rows) | lo] [rank 1: hi | lo]
-        const int rows_per = e.pair ? e.bn / 2 : e.bn;
-        const int part = r / rows_per, rr = r % rows_per;
-        const size_t half = (size_t)rows_per * 64;
-        const size_t replica_bytes = ntiles * kbs * 2 * (size_t)e.bn * 64;
-        const uint32_t off = (uint32_t)rr * 64u + (uint32_t)((c ^ ((rr >> 1) & 3)) << 4);
+        const size_t half = (size_t)e.bn * 64;                  // a tile image = [hi (bn rows x 64 B) | lo]
+        const size_t replica_bytes = ntiles * kbs * 2 * half;
+        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 #pragma unroll
         for (int rep = 0; rep < kImgReplicas; ++rep) {
-            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * (size_t)e.bn * 64 + (size_t)part * 2 * half;
+            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * half;
             *reinterpret_cast<uint4*>(tile + off) = h;
             *reinterpret_cast<uint4*>(tile + half + off) = l;
         }
     }
 }
 
-// DPPO_H_PAIR=1: every product on CTA pairs (cta_group::2); the weight images are then packed in the pair layout
-static bool pair_enabled() {
+// DPPO_H_TMAC=0: keep the st.global write-out even where TMA could store C (A/B switch for measurements)
+static bool tmac_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("DPPO_H_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("DPPO_H_TMAC"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 
-template <int BN, int EPI, bool TMA_A, bool PAIR>
-static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, HArgs& g, cudaStream_t st) {
-    using P = HPlan<BN, PAIR>;
-    const int tiles_m = (g.M + BM - 1) / BM;
-    const long long total = (long long)(PAIR ? (tiles_m + 1) / 2 : tiles_m) * g.tiles_n * g.nets;     // (super-)tiles
+template <int BN, int EPI, bool TMA_A, bool TMA_C>
+static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& c0, const CUtensorMap& c1, HArgs& g, cudaStream_t st) {
+    using P = HPlan<BN>;
+    const long long total = (long long)((g.M + BM - 1) / BM) * g.tiles_n * g.nets;
     DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = P::kBytes; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    // persistent grid = what is co-resident: pairs must sit in one GPC, so fewer than #SMs / 2 of them may fit
-    static int max_groups[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (max_groups[dev] == 0) {
-        int n = PAIR ? kPlanSMs / 2 : kPlanSMs;
-        if (PAIR) {
-            cfg.gridDim = dim3(kPlanSMs);
-            int q = 0;
-            if (cudaOccupancyMaxActiveClusters(&q, h_gemm_kernel<BN, EPI, TMA_A, PAIR>, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
-            else (void)cudaGetLastError();
-        }
-        max_groups[dev] = n;
-    }
-    const int groups = (int)(total < max_groups[dev] ? total : max_groups[dev]);
-    cfg.gridDim = dim3(PAIR ? 2 * groups : groups);
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A, TMA_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);
-    DPPO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, h_gemm_kernel<BN, EPI, TMA_A, PAIR>, m0, m1, g, (int)total));
+    h_gemm_kernel<BN, EPI, TMA_A, TMA_C><<<grid, kThreads, P::kBytes, st>>>(m0, m1, c0, c1, g, (int)total);
+    DPPO_LAUNCH_CHECK();
     return 0;
 }
 
 template <int BN, int EPI>
-static int launch_h(HArgs& g, bool pair, cudaStream_t st) {
+static int launch_h(HArgs& g, cudaStream_t st) {
     g.tiles_n = (g.N + BN - 1) / BN;
-    // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, ...) takes the LDG movers
-    CUtensorMap m0, m1;
-    memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1));
+    // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, ...) takes the LDG movers / the st.global write-out
+    CUtensorMap m0, m1, c0, c1;
+    memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1)); memset(&c0, 0, sizeof(c0)); memset(&c1, 0, sizeof(c1));
     bool tma = g.vecA && h_make_map(&m0, g.A[0], g.M, g.K, g.lda, BM);
     if (tma) { if (g.nets > 1) tma = h_make_map(&m1, g.A[1], g.M, g.K, g.lda, BM); else m1 = m0; }
-    if (pair) {
-        if (tma) return launch_h2<BN, EPI, true, true>(m0, m1, g, st);
-        return launch_h2<BN, EPI, false, true>(m0, m1, g, st);
+    bool tmc = g.vecC && tmac_enabled() && h_make_map(&c0, g.C[0], g.M, g.N, g.ldc, BM);
+    if (tmc) { if (g.nets > 1) tmc = h_make_map(&c1, g.C[1], g.M, g.N, g.ldc, BM); else c1 = c0; }
+    if (tma) {
+        if (tmc) return launch_h2<BN, EPI, true, true>(m0, m1, c0, c1, g, st);
+        return launch_h2<BN, EPI, true, false>(m0, m1, c0, c1, g, st);
     }
-    if (tma) return launch_h2<BN, EPI, true, false>(m0, m1, g, st);
-    return launch_h2<BN, EPI, false, false>(m0, m1, g, st);
+    if (tmc) return launch_h2<BN, EPI, false, true>(m0, m1, c0, c1, g, st);
+    return launch_h2<BN, EPI, false, false>(m0, m1, c0, c1, g, st);
 }
 
 }  // namespace th
 
-static inline int th_bn_for(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+// Tile width.  256 columns halve the activation re-reads but fill TMEM (no overlap of drain and MMAs); with a short
+// reduction the drain dominates such a tile, so products with K < kWideMinK take two 128-wide tiles instead, whose two TMEM
+// stages hide it (DPPO_H_WIDE_MINK overrides the threshold for measurements).
+static int th_wide_min_k() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DPPO_H_WIDE_MINK"); v = e ? atoi(e) : 65; if (v < 0) v = 0; }
+    return v;
+}
+static inline int th_bn_for(int n, int k) { return n > 128 ? (k >= th_wide_min_k() ? 256 : 128) : (n > 64 ? 128 : 64); }
 
 // bytes of one replica of the weight image of B[N,K]
 static long long th_image_replica_bytes(int N, int K) {
-    const int bn = th_bn_for(N);
+    const int bn = th_bn_for(N, K);
     return (long long)((N + bn - 1) / bn) * ((K + th::kKB - 1) / th::kKB) * bn * 64 * 2;
 }
 long long th_image_floats(int N, int K) { return th::kImgReplicas * th_image_replica_bytes(N, K) / 4; }
@@ -576,7 +702,7 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
         if (!src || !dst) return;
         th::HImgEntry& e = p.e[p.n];
         e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed;
-        e.bn = th_bn_for(N); e.pair = th::pair_enabled() ? 1 : 0;
+        e.bn = th_bn_for(N, K);
         units += (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
         p.unit_end[p.n++] = units;
     };
@@ -601,8 +727,7 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
 int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st) {
     th::HImgPlan p; p.n = 1;
     th::HImgEntry& e = p.e[0];
-    e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N);
-    e.pair = th::pair_enabled() ? 1 : 0;
+    e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N, K);
     const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
     p.unit_end[0] = units;
     int grid = (int)((units + 255) / 256);
@@ -631,19 +756,19 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.bits_wpr = (N + 31) / 32;
     g.img_replica_bytes = th_image_replica_bytes(N, K);
     g.timeline = timeline;
-    g.fold = (th::fold_enabled() && !th::pair_enabled()) ? 1 : 0;
+    g.fold = th::fold_enabled() ? 1 : 0;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
-    const int bn = th_bn_for(N);
-    const bool pair = th::pair_enabled();         // the weight images were packed for the same choice (th_pack_images)
+    const int bn = th_bn_for(N, K);
     if (epi_nt) {
-        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, pair, st);
-        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, pair, st);
-        return th::launch_h<64, th::EPI_NT>(g, pair, st);
+        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, st);
+        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, st);
+        return th::launch_h<64, th::EPI_NT>(g, st);
     }
-    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, pair, st);
-    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, pair, st);
-    return th::launch_h<64, th::EPI_NN>(g, pair, st);
+    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, st);
+    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, st);
+    return th::launch_h<64, th::EPI_NN>(g, st);
 }
 
 }  // namespace dppo

@@ -40,6 +40,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("DPPO_NVCC_EXTRA", "").split()          # e.g. -DDPPO_H_DEEP_RAW=1 for a kernel experiment
     procs = []
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")

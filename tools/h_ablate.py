@@ -20,6 +20,6 @@ tl = torch.zeros(128, dtype=torch.int64, device="cuda")
 eng.dbg_gemm(98, A, B, M, N, K, bias=bias, relu=True, aux_out=tl)
 torch.cuda.synchronize()
 t = tl.cpu().numpy().reshape(16, 8)
-i = 3
-print(f"DPPO_H_DBG={os.environ.get('DPPO_H_DBG', '0'):>3s} M={M} N={N} K={K}: {us:7.1f} us | tile 3: mainloop {t[i,1]-t[i,0]:6d}  acc {t[i,2]-t[i,1]:5d}  "
+i = int(os.environ.get('H_TILE', '3'))
+print(f"DPPO_H_DBG={os.environ.get('DPPO_H_DBG', '0'):>3s} M={M} N={N} K={K}: {us:7.1f} us | tile {i}: mainloop {t[i,1]-t[i,0]:6d}  acc {t[i,2]-t[i,1]:5d}  "
       f"tmem hold {t[i,3]-t[i,2]:6d}  write2 {t[i,4]-t[i,3]:6d}  period {t[i+1,0]-t[i,0]:6d}", flush=True)
