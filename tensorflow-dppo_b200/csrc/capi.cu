@@ -4,6 +4,7 @@
 //     -> loss + d_out (PPO.py:29-40,46) -> dense backward -> split-K finalize
 //     -> allreduce (PPO.py:55-65) -> Adam (PPO.py:53).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
@@ -174,6 +175,15 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     return off;
 }
 
+// fp16x2 mode: hidden activations and their gradients are stored as fp16 hi | lo planes (same bytes as fp32) whenever every
+// hidden width keeps the plane rows 16-byte aligned (DPPO_H_PLANES=0 at dppo_create keeps fp32 matrices + converter warps)
+static bool h_planes(const dppo_ctx* c) {
+    if (c->cfg.gemm_mode != DPPO_GEMM_FP16X2 || !c->use_h_planes || !c->use_h_dw) return false;
+    for (int l = 0; l < c->shape.L; ++l)
+        if (c->shape.h[l] % 8 != 0) return false;
+    return c->shape.L > 0;
+}
+
 // ---- forward of pi (and oldpi) over rows [0, rows) of obs ------------------------------------
 static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params_old, const float* obs,
                         int rows, cudaStream_t st) {
@@ -202,6 +212,10 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
         // persistent fp16-split kernels: weight images (fp16 hi | lo tiles) refreshed from the current parameters
         if (int r = th_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
                                    w.img_dx_pi, st)) return r;
+        // hidden activations live as fp16 hi | lo planes (h_planes): the epilogue that produces them applies the split the
+        // consumer's converter warps would apply, so every later product reads its operand tiles straight from TMA
+        const bool planes = h_planes(c);
+        const long long R = c->cfg.max_rows;
         for (int l = 0; l <= s.L; ++l) {
             const bool head = (l == s.L);
             float* o0 = head ? w.out_pi : w.act_pi[l];
@@ -209,9 +223,12 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const int in = s.in_dim(l), out = s.out_dim(l);
             const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
+            ThPlanes pl{};
+            pl.a_planes = planes && l > 0; pl.a_lo_off = R * in;
+            pl.c_planes = planes && !head; pl.c_lo_off = R * out;
             if (int r = th_gemm(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
                                 head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st,
-                                head ? nullptr : w.act_bits[l], nullptr)) return r;
+                                head ? nullptr : w.act_bits[l], nullptr, nullptr, &pl)) return r;
             in0 = o0; in1 = o1;
         }
         return 0;
@@ -328,8 +345,10 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const bool tcore = tc_mode(c->cfg.gemm_mode);
     const bool fp16x2 = (c->cfg.gemm_mode == DPPO_GEMM_FP16X2);
     const bool bf16 = (c->cfg.gemm_mode == DPPO_GEMM_BF16);
+    const bool planes = h_planes(c);
     // dW_l (+ db_l) into layer l's split-K partial region
-    auto dense_dw = [&](int l, const float* x_in, const float* dY) -> int {
+    // (tmp: a free [rows, hmax] buffer -- planes mode joins dY back to fp32 there when layer 0's obs rows cannot be read by TMA)
+    auto dense_dw = [&](int l, const float* x_in, const float* dY, float* tmp) -> int {
         const int in = s.in_dim(l), out = s.out_dim(l);
         const int ldy = (l == s.L) ? s.Pld : out;
         float* p = w.partial + s.part_off[l];
@@ -337,6 +356,19 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
             if (int r = bf16_gemm_tn_splitk(in, out, rows, x_in, in, dY, ldy, p, out, active[l], s.region[l], accumulate, st))
                 return r;
             return tc_colsum(dY, rows, out, ldy, active[l], p + (size_t)in * out, s.region[l], accumulate, st);
+        }
+        if (planes) {                                       // X = a hidden activation, G = a hidden gradient: fp16 planes
+            ThPlanes pl{};
+            pl.a_planes = l > 0; pl.a_lo_off = (long long)c->cfg.max_rows * in;
+            pl.c_planes = l < s.L; pl.c_lo_off = (long long)c->cfg.max_rows * out;
+            if ((pl.a_planes || th_dw_supported(x_in, in, x_in, in)) && (pl.c_planes || th_dw_supported(dY, ldy, dY, ldy)))
+                return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,
+                                  st, &pl);
+            // obs rows TMA cannot address (obs_dim 3, 17, ...): the tf32 kernels below take fp32 operands
+            DPPO_REQUIRE(pl.c_planes && tmp != nullptr, "fp16 planes: layer %d has an fp32 operand TMA cannot address", l);
+            const __half* hi = reinterpret_cast<const __half*>(dY);
+            if (int r = th_join_planes(hi, hi + pl.c_lo_off, (long long)rows * out, tmp, st)) return r;
+            dY = tmp;
         }
         if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, in, dY, ldy))     // persistent fp16-split kernel, bias column sums fused
             return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate, st);
@@ -355,8 +387,13 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     // mask = activations of hidden layer l_ - 1 (N_ wide); the tensor-core path reads their sign bitmap instead
     auto dense_dx = [&](int l_, int M_, int N_, int K_, const float* dY, int ldy, const float* W, float* dX,
                         const float* mask) -> int {
-        if (fp16x2) return th_gemm(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_, nullptr, nullptr,
-                                   0, mask, 1, st, nullptr, w.act_bits[l_ - 1]);
+        if (fp16x2) {
+            ThPlanes pl{};                                    // dY of a hidden layer and every dX are planes
+            pl.a_planes = planes && l_ < s.L; pl.a_lo_off = (long long)c->cfg.max_rows * K_;
+            pl.c_planes = planes; pl.c_lo_off = (long long)c->cfg.max_rows * N_;
+            return th_gemm(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_, nullptr, nullptr,
+                           0, mask, 1, st, nullptr, w.act_bits[l_ - 1], nullptr, &pl);
+        }
         if (tcore) return tc_gemm_kk_img(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_,
                                          nullptr, nullptr, 0, mask, 1, st, nullptr, w.act_bits[l_ - 1]);
         if (bf16) return bf16_gemm_kk(1, M_, N_, K_, dY, nullptr, ldy, W, nullptr, K_, dX, nullptr, N_, nullptr, nullptr, 0,
@@ -364,7 +401,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
         GemmEpi nt; nt.mask = mask;
         return gemm_nt(M_, N_, K_, dY, ldy, W, K_, dX, N_, nt, st);
     };
-    if (int r = dense_dw(s.L, head_in, w.d_out)) return r;
+    if (int r = dense_dw(s.L, head_in, w.d_out, nullptr)) return r;
     if (s.L == 0) return 0;
     // dh_L = (d_out . Wh^T) * [h_L > 0]
     int cur = 0;
@@ -372,7 +409,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     for (int l = s.L - 1; l >= 0; --l) {
         const float* dY = w.scratch[cur];
         const float* x_in = l ? w.act_pi[l - 1] : obs;
-        if (int r = dense_dw(l, x_in, dY)) return r;
+        if (int r = dense_dw(l, x_in, dY, w.scratch[cur ^ 1])) return r;
         if (l > 0) {
             if (int r = dense_dx(l, rows, s.h[l - 1], s.h[l], dY, s.h[l], params_pi + s.w_off[l], w.scratch[cur ^ 1],
                                  w.act_pi[l - 1])) return r;
@@ -490,7 +527,9 @@ int dppo_create(const dppo_config* cfg, void* workspace, size_t workspace_bytes,
     c->cfg = *cfg; c->shape = s; c->workspace = workspace; c->workspace_bytes = workspace_bytes;
     c->num_sms = prop.multiProcessorCount;
     c->prof = new (std::nothrow) ProfState();
-    { const char* e = getenv("DPPO_H_DW"); c->use_h_dw = (e && e[0] == '0') ? 0 : 1; }     // fp16-split dW kernel (tc_dw_h.cu); 0 = tf32 TMA kernel
+    { const char* e = getenv("DPPO_H_DW"); c->use_h_dw = (e && e[0] == '0') ? 0 : 1; }
+     // fp16-split dW kernel (tc_dw_h.cu); 0 = tf32 TMA kernel
+    { const char* e = getenv("DPPO_H_PLANES"); c->use_h_planes = (e && e[0] == '0') ? 0 : 1; }   // fp16 hi | lo activation planes
     { const char* e = getenv("DPPO_GRAPH"); c->use_graph = (e && e[0] == '0') ? 0 : 1; }
     { const char* e = getenv("DPPO_NO_OLD_CACHE"); c->no_old_cache = (e && e[0] == '1') ? 1 : 0; }   // read once, per context
     carve(cfg, s, (char*)workspace, &c->ws);
@@ -1136,15 +1175,34 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         DPPO_LAUNCH_CHECK();
         return 0;
     }
-    if (mode == 99) {
+    if (mode == 99 || (mode >= 101 && mode <= 103)) {
         // persistent fp16-split dW product (tc_dw_h.cu): C[M,N] = A[K,M]^T . B[K,N], bias_out[N] = column sums of B
+        // 101 / 102 / 103: B / A / both operands first converted to fp16 hi | lo planes (scratch[1] / scratch[0])
+        ThPlanes pl{};
+        const long long cap = (long long)c->cfg.max_rows * (c->shape.hmax() > 0 ? c->shape.hmax() : 1);
+        if (mode >= 101) {
+            pl.a_planes = (mode & 2) ? 1 : 0; pl.c_planes = (mode & 1) ? 1 : 0;
+            pl.a_lo_off = ((long long)K * M + 7) & ~7LL; pl.c_lo_off = ((long long)K * N + 7) & ~7LL;
+            DPPO_REQUIRE(2 * pl.a_lo_off <= 2 * cap && 2 * pl.c_lo_off <= 2 * cap, "dppo_dbg_gemm: operand planes exceed the scratch buffers");
+            if (pl.a_planes) {
+                __half* hi = reinterpret_cast<__half*>(c->ws.scratch[0]);
+                if (int r = th_split_planes(A, (long long)K * M, hi, hi + pl.a_lo_off, st)) return r;
+                A = c->ws.scratch[0];
+            }
+            if (pl.c_planes) {
+                __half* hi = reinterpret_cast<__half*>(c->ws.scratch[1]);
+                if (int r = th_split_planes(B, (long long)K * N, hi, hi + pl.c_lo_off, st)) return r;
+                B = c->ws.scratch[1];
+            }
+        }
         const int64_t stride = ((int64_t)M * N + N + 3) & ~3LL;
         int slices = (int)(c->shape.partial_floats / stride);
         const int want = (K + 511) / 512;
         if (slices > want) slices = want;
         DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
         DPPO_REQUIRE(th_dw_supported(A, M, B, N), "dppo_dbg_gemm: the fp16 dW kernel needs 16-byte aligned rows");
-        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, st))
+        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, st,
+                               mode >= 101 ? &pl : nullptr))
             return r;
         ProfScope ps(KK_MISC, st);
         reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
@@ -1154,6 +1212,30 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
             DPPO_LAUNCH_CHECK();
         }
         return 0;
+    }
+    if (mode == 92 || mode == 94 || mode == 95) {        // 92: as 94, bias_out receives the kernel's clock64 time line (128 int64)
+        // as 96 / 97 with A given to the kernel as fp16 hi | lo planes and C written as planes (then joined back to fp32):
+        // the operand path of the update's hidden layers
+        const long long need = th_image_floats(N, K);
+        DPPO_REQUIRE(c->shape.partial_floats >= need, "dppo_dbg_gemm: the partial buffer cannot hold the %lld-float weight image", need);
+        const long long cap = (long long)c->cfg.max_rows * (c->shape.hmax() > 0 ? c->shape.hmax() : 1);
+        ThPlanes pl{};
+        pl.a_planes = pl.c_planes = 1;
+        pl.a_lo_off = ((long long)M * K + 7) & ~7LL; pl.c_lo_off = ((long long)M * N + 7) & ~7LL;
+        DPPO_REQUIRE(pl.a_lo_off <= cap && pl.c_lo_off <= cap, "dppo_dbg_gemm: planes exceed the scratch buffers");
+        __half* a_hi = reinterpret_cast<__half*>(c->ws.scratch[0]);
+        __half* c_hi = reinterpret_cast<__half*>(c->ws.scratch[1]);
+        if (int r = th_split_planes(A, (long long)M * K, a_hi, a_hi + pl.a_lo_off, st)) return r;
+        if (int r = th_pack_one(B, c->ws.partial, N, K, K, 0, st)) return r;
+        if (mode == 95) {
+            if (int r = th_gemm(1, M, N, K, c->ws.scratch[0], nullptr, K, c->ws.partial, nullptr, c->ws.scratch[1], nullptr, N, nullptr,
+                                nullptr, 0, mask, 1, st, nullptr, nullptr, nullptr, &pl)) return r;
+        } else {
+            if (int r = th_gemm(0, M, N, K, c->ws.scratch[0], nullptr, K, c->ws.partial, nullptr, c->ws.scratch[1], nullptr, N, bias,
+                                nullptr, relu, nullptr, 1, st, nullptr, nullptr,
+                                mode == 92 ? reinterpret_cast<long long*>(bias_out) : nullptr, &pl)) return r;
+        }
+        return th_join_planes(c_hi, c_hi + pl.c_lo_off, (long long)M * N, C, st);
     }
     if (mode == 96 || mode == 97 || mode == 98) {
         // persistent fp16-split product (tc_gemm_h.cu): Bt[N,K] is packed into an fp16 hi|lo tile image first (scratch from

@@ -23,7 +23,6 @@
 namespace dppo {
 namespace th {
 
-constexpr int kDwOp = 2;                            // operand ring depth
 constexpr int kDwPC = 64;                          // staged columns per epilogue phase
 
 struct DwArgs {
@@ -35,23 +34,33 @@ struct DwArgs {
     int fold;                     // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
 };
 
-template <int BN>
+// XP / GP: the X / G operand is stored as fp16 hi | lo planes (written by the forward / dX epilogues of tc_gemm_h.cu): TMA
+// boxes {64 fp16 features x 32 rows, SWIZZLE_128B} ARE the MN-major operand atoms, so that operand needs no raw slot and no
+// converter pass; the bias gradient (column sums of G) is then read back from the operand tiles by the otherwise idle warps.
+template <int BN, bool XP, bool GP>
 struct DwPlan {
-    static constexpr int kDwRaw = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);     // raw (TMA) ring depth: what shared memory allows
-    static constexpr int kARaw = 32 * BM * 4;            // 4 boxes of {32 features x 32 rows} fp32
-    static constexpr int kBRaw = 32 * BN * 4;
+    static constexpr int kARaw = XP ? 0 : 32 * BM * 4;   // 4 boxes of {32 features x 32 rows} fp32
+    static constexpr int kBRaw = GP ? 0 : 32 * BN * 4;
     static constexpr int kRawSlot = kARaw + kBRaw;
     static constexpr int kAHalf = 32 * BM * 2;           // fp16 hi (or lo) operand tile: BM/64 atoms x 32 k-rows x 128 B
     static constexpr int kBHalf = 32 * BN * 2;
     static constexpr int kOpSlot = 2 * (kAHalf + kBHalf);
+    static constexpr int kPlaneBytes = (XP ? 2 * kAHalf : 0) + (GP ? 2 * kBHalf : 0);   // what TMA writes into an operand slot
     static constexpr int kPC = BN < kDwPC ? BN : kDwPC;
     static constexpr int kPhases = BN / kPC;
     static constexpr int kStaging = BM * kPC * 4;
-    static constexpr int kOpOff = kDwRaw * kRawSlot;
+    // ring depth (raw and operand rings alike): what shared memory allows, at most 4
+    static constexpr int kRoom = 232448 - 256 - kFoldBytes - kStaging;
+    static constexpr int kFit = kRoom / (kOpSlot + kRawSlot);
+    static constexpr int kDepth = kFit > 4 ? 4 : kFit;
+    static_assert(kDepth >= 2, "two slots per ring at least");
+    static constexpr int kDwRaw = kRawSlot ? kDepth : 0;
+    static constexpr int kDwOp = kDepth;
+    static constexpr int kOpOff = kDepth * kRawSlot;
     static constexpr int kStgOff = kOpOff + kDwOp * kOpSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
     static constexpr int kFoldOff = kBarOff + 256;
-    static constexpr int kBytes = kBarOff + 256 + kFoldBytes + 1024;
+    static constexpr int kBytes = kBarOff + 256 + kFoldBytes;
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
@@ -79,28 +88,34 @@ __device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_til
     sts128(lo_tile + off, l);
 }
 
-template <int BN>
+struct DwMaps { CUtensorMap x, xl, g, gl; };          // fp32 matrix or hi plane, lo plane
+
+template <int BN, bool XP, bool GP>
 __global__ void __launch_bounds__(kThreads, 1)
-h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG, const DwArgs g, int total_tiles) {
-    using P = DwPlan<BN>;
-    constexpr int kDwRaw = P::kDwRaw;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles) {
+    using P = DwPlan<BN, XP, GP>;
+    constexpr int kDwRaw = P::kDwRaw > 0 ? P::kDwRaw : 1, kDwOp = P::kDwOp;
+    constexpr bool kConv = !(XP && GP);                  // some operand still arrives as fp32 and is converted here
+    extern __shared__ __align__(1024) uint8_t smem[];         // SWIZZLE_128B boxes and UMMA tiles need 1024-B alignment
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t raw_ring = smem_base, op_ring = smem_base + P::kOpOff, stg = smem_base + P::kStgOff;
     uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + P::kBarOff);
     uint64_t* raw_empty = raw_full + kDwRaw;
     uint64_t* op_full = raw_empty + kDwRaw;
+    static_assert((2 * kDwRaw + 2 * kDwOp + 2) * 8 + 4 <= 256, "barrier block");
     uint64_t* op_empty = op_full + kDwOp;
     uint64_t* acc_full = op_empty + kDwOp;
     uint64_t* acc_empty = acc_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const int t_begin = blockIdx.x * per_cta;
-    const int t_end = min(total_tiles, t_begin + per_cta);
-    const int my_tiles = max(0, t_end - t_begin);
+    // Work items are dealt out round-robin (CTA b takes b, b + grid, ...): the m-tiles of one slice are neighbours in the list,
+    // so they run AT THE SAME TIME on neighbouring CTAs and the G rows they share are fetched from HBM once and found in L2 by
+    // the others.  (Contiguous chunks per CTA, the first version, had one CTA walk a slice's m-tiles one after the other, a full
+    // item apart: measured DRAM reads of 662 MB where the operands are 331 MB, and the kernel sat at HBM bandwidth.)
+    const int t_begin = blockIdx.x;
+    const int t_stride = gridDim.x;
+    const int my_tiles = total_tiles > t_begin ? (total_tiles - t_begin + t_stride - 1) / t_stride : 0;
     const int tiles_mn = g.tiles_m * g.tiles_n;
 
     // work item t -> (slice, m-tile, n-tile); the tiles of one slice are neighbours (they share X / G rows through L2)
@@ -114,8 +129,14 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     };
 
     if (tid == 0) {
+        if (smem_base & 1023u) __trap();
         for (int s = 0; s < kDwRaw; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverWarps); }
-        for (int s = 0; s < kDwOp; ++s) { mbar_init(&op_full[s], kMoverWarps); mbar_init(&op_empty[s], 1); }
+        // an operand slot is full when the converters have stored their part AND the plane boxes have landed; it is empty when
+        // its MMAs have completed AND (planes of G) the column-sum readers are done with it
+        for (int s = 0; s < kDwOp; ++s) {
+            mbar_init(&op_full[s], (kConv ? kMoverWarps : 0) + ((XP || GP) ? 1 : 0));
+            mbar_init(&op_empty[s], 1 + (GP ? kMoverWarps : 0));
+        }
         mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
         fence_barrier_init();
     }
@@ -136,7 +157,7 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         long long it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             int slice, mt, nt, nkb, k0;
-            decode(t_begin + i, slice, mt, nt, nkb, k0);
+            decode(t_begin + i * t_stride, slice, mt, nt, nkb, k0);
             const bool want_bias = (g.bias_out != nullptr) && (mt == 0);
             float csum[kBPairs][8];
 #pragma unroll
@@ -146,24 +167,55 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
             float dummy[8];
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int rs = (int)(it % kDwRaw), os = (int)(it % kDwOp);
-                mbar_wait(&raw_full[rs], (uint32_t)((it / kDwRaw) & 1));
-                mbar_wait(&op_empty[os], (uint32_t)(((it / kDwOp) & 1) ^ 1));
                 const uint32_t raw = raw_ring + rs * P::kRawSlot;
                 const uint32_t op = op_ring + os * P::kOpSlot;
                 const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+                if (kConv) {
+                    mbar_wait(&raw_full[rs], (uint32_t)((it / kDwRaw) & 1));
+                    mbar_wait(&op_empty[os], (uint32_t)(((it / kDwOp) & 1) ^ 1));
+                    if (!XP) {
 #pragma unroll
-                for (int u = 0; u < kAPairs; ++u) {
-                    const int p = warp + u * kMoverWarps;
-                    dw_convert_unit(raw, a_hi, a_lo, p >> 2, p & 3, k, dummy, false);
-                }
+                        for (int u = 0; u < kAPairs; ++u) {
+                            const int p = warp + u * kMoverWarps;
+                            dw_convert_unit(raw, a_hi, a_lo, p >> 2, p & 3, k, dummy, false);
+                        }
+                    }
+                    if (!GP) {
 #pragma unroll
-                for (int u = 0; u < kBPairs; ++u) {
-                    const int p = warp + u * kMoverWarps;
-                    dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, csum[u], want_bias);
+                        for (int u = 0; u < kBPairs; ++u) {
+                            const int p = warp + u * kMoverWarps;
+                            dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, csum[u], want_bias);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&op_full[os]); mbar_arrive(&raw_empty[rs]); }
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&op_full[os]); mbar_arrive(&raw_empty[rs]); }
+                if (GP) {
+                    // G arrived as planes: its column sums are read back from the operand tiles (lane = k-row, the same
+                    // column groups as above).  Every warp passes through the slot's full barrier before it releases the slot,
+                    // so that no warp can run a whole ring ahead of the barrier phases.
+                    mbar_wait(&op_full[os], (uint32_t)((it / kDwOp) & 1));
+                    if (want_bias) {
+#pragma unroll
+                        for (int u = 0; u < kBPairs; ++u) {
+                            const int p = warp + u * kMoverWarps;          // columns [8p, 8p + 8): atom p / 8, chunk p % 8
+                            const uint32_t off = (uint32_t)(p >> 3) * 4096u + (uint32_t)k * 128u + (uint32_t)((((p & 7) ^ k) & 7) << 4);
+                            const uint4 h = lds128(b_hi + off), l = lds128(b_lo + off);
+                            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                                csum[u][2 * e] += fmaf(lf.x, kLoInv, hf.x);
+                                csum[u][2 * e + 1] += fmaf(lf.y, kLoInv, hf.y);
+                            }
+                        }
+                        fence_proxy_async();       // the refill of this slot is an async-proxy write behind these generic reads
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&op_empty[os]);
+                }
             }
             if (want_bias) {            // warp-uniform: fold the 32 k-rows (lanes), lane 0 writes the slice's bias partials
 #pragma unroll
@@ -184,23 +236,73 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
             }
         }
     } else if (warp == kProdWarp) {
-        // ================= TMA producer (one thread) =================
+        // ================= TMA producer (one thread): raw fp32 boxes and / or plane boxes, polled without blocking =========
         if (lane == 0) {
-            long long it = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                int slice, mt, nt, nkb, k0;
-                decode(t_begin + i, slice, mt, nt, nkb, k0);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int rs = (int)(it % kDwRaw);
-                    mbar_wait(&raw_empty[rs], (uint32_t)(((it / kDwRaw) & 1) ^ 1));
-                    const uint32_t raw = raw_ring + rs * P::kRawSlot;
-                    mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)P::kRawSlot);
-                    const int row = k0 + kb * kKB;
+            struct Cursor { int i, kb, nkb, slice, mt, nt, k0; long long it; bool done; };
+            auto start = [&](Cursor& c) {
+                c.i = 0; c.kb = 0; c.it = 0; c.done = (my_tiles == 0); c.nkb = 0;
+                while (!c.done) {                                   // first work item that holds rows
+                    decode(t_begin + c.i * t_stride, c.slice, c.mt, c.nt, c.nkb, c.k0);
+                    if (c.nkb > 0) break;
+                    if (++c.i >= my_tiles) c.done = true;
+                }
+            };
+            auto advance = [&](Cursor& c) {
+                ++c.it;
+                if (++c.kb < c.nkb) return;
+                c.kb = 0;
+                for (;;) {
+                    if (++c.i >= my_tiles) { c.done = true; return; }
+                    decode(t_begin + c.i * t_stride, c.slice, c.mt, c.nt, c.nkb, c.k0);
+                    if (c.nkb > 0) return;
+                }
+            };
+            Cursor cr, cp;
+            start(cr); start(cp);
+            if (!kConv) cr.done = true;
+            if (!(XP || GP)) cp.done = true;
+            while (!cr.done || !cp.done) {
+                if (!cr.done) {
+                    const int rs = (int)(cr.it % kDwRaw);
+                    if (mbar_test(&raw_empty[rs], (uint32_t)(((cr.it / kDwRaw) & 1) ^ 1))) {
+                        const uint32_t raw = raw_ring + rs * P::kRawSlot;
+                        mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)P::kRawSlot);
+                        const int row = cr.k0 + cr.kb * kKB;
+                        if (!XP) {
 #pragma unroll
-                    for (int b = 0; b < BM / 32; ++b) tma_load_2d(raw + b * 4096, &mapX, mt * BM + b * 32, row, &raw_full[rs]);
+                            for (int b = 0; b < BM / 32; ++b) tma_load_2d(raw + b * 4096, &maps.x, cr.mt * BM + b * 32, row, &raw_full[rs]);
+                        }
+                        if (!GP) {
 #pragma unroll
-                    for (int b = 0; b < BN / 32; ++b)
-                        tma_load_2d(raw + P::kARaw + b * 4096, &mapG, nt * BN + b * 32, row, &raw_full[rs]);
+                            for (int b = 0; b < BN / 32; ++b)
+                                tma_load_2d(raw + P::kARaw + b * 4096, &maps.g, cr.nt * BN + b * 32, row, &raw_full[rs]);
+                        }
+                        advance(cr);
+                    }
+                }
+                if (!cp.done) {
+                    const int os = (int)(cp.it % kDwOp);
+                    if (mbar_test(&op_empty[os], (uint32_t)(((cp.it / kDwOp) & 1) ^ 1))) {
+                        const uint32_t op = op_ring + os * P::kOpSlot;
+                        const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+                        mbar_arrive_expect_tx(&op_full[os], (uint32_t)P::kPlaneBytes);
+                        const int row = cp.k0 + cp.kb * kKB;
+                        if (XP) {
+#pragma unroll
+                            for (int b = 0; b < BM / 64; ++b) {
+                                tma_load_2d(a_hi + b * 4096, &maps.x, cp.mt * BM + b * 64, row, &op_full[os]);
+                                tma_load_2d(a_lo + b * 4096, &maps.xl, cp.mt * BM + b * 64, row, &op_full[os]);
+                            }
+                        }
+                        if (GP) {
+#pragma unroll
+                            for (int b = 0; b < BN / 64; ++b) {
+                                tma_load_2d(b_hi + b * 4096, &maps.g, cp.nt * BN + b * 64, row, &op_full[os]);
+                                tma_load_2d(b_lo + b * 4096, &maps.gl, cp.nt * BN + b * 64, row, &op_full[os]);
+                            }
+                        }
+                        advance(cp);
+                    }
                 }
             }
         }
@@ -212,7 +314,7 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
             long long it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 int slice, mt, nt, nkb, k0;
-                decode(t_begin + i, slice, mt, nt, nkb, k0);
+                decode(t_begin + i * t_stride, slice, mt, nt, nkb, k0);
                 mbar_wait(acc_empty, (uint32_t)((i & 1) ^ 1));
                 tc_fence_after();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -253,7 +355,7 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
         const int lr = lane / kLanesPerRow, cl = lane % kLanesPerRow;
         for (int i = 0; i < my_tiles; ++i) {
             int slice, mt, nt, nkb, k0;
-            decode(t_begin + i, slice, mt, nt, nkb, k0);
+            decode(t_begin + i * t_stride, slice, mt, nt, nkb, k0);
             float* __restrict__ C = g.C + (size_t)slice * g.slice_stride;
             mbar_wait(acc_full, (uint32_t)(i & 1));
             tc_fence_after();
@@ -339,21 +441,28 @@ h_dw_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CU
     }
 }
 
-template <int BN>
-static int launch_dw(const CUtensorMap& mX, const CUtensorMap& mG, DwArgs& g, cudaStream_t st) {
-    using P = DwPlan<BN>;
+template <int BN, bool XP, bool GP>
+static int launch_dw(const DwMaps& maps, DwArgs& g, cudaStream_t st) {
+    using P = DwPlan<BN, XP, GP>;
     g.tiles_m = (g.M + BM - 1) / BM;
     g.tiles_n = (g.N + BN - 1) / BN;
     const long long total = (long long)g.tiles_m * g.tiles_n * g.slices;
     DPPO_REQUIRE(total < (1ll << 30), "h_dw: too many work items");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_dw_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_dw_kernel<BN, XP, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);
-    h_dw_kernel<BN><<<grid, kThreads, P::kBytes, st>>>(mX, mG, g, (int)total);
+    h_dw_kernel<BN, XP, GP><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
     DPPO_LAUNCH_CHECK();
     return 0;
+}
+template <int BN>
+static int launch_dw_bn(const DwMaps& maps, int xp, int gp, DwArgs& g, cudaStream_t st) {
+    if (xp && gp) return launch_dw<BN, true, true>(maps, g, st);
+    if (xp) return launch_dw<BN, true, false>(maps, g, st);
+    if (gp) return launch_dw<BN, false, true>(maps, g, st);
+    return launch_dw<BN, false, false>(maps, g, st);
 }
 
 }  // namespace th
@@ -366,10 +475,28 @@ bool th_dw_supported(const float* X, int ldx, const float* G, int ldg) {
 // C[s][M,N] (+)= X[rows,M]^T . G[rows,N] over the rows of slice s (k_per_slice rows, a multiple of 32);
 // bias_out[s][N] (+)= column sums of G (may be null).
 int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int ldg, float* C, int ldc, float* bias_out,
-               int slices, long long slice_stride, int accumulate, cudaStream_t st) {
-    CUtensorMap mX, mG;
-    DPPO_REQUIRE(th::h_make_map(&mX, X, K, M, ldx, 32), "cuTensorMapEncodeTiled failed for X [%d x %d] ld %d", K, M, ldx);
-    DPPO_REQUIRE(th::h_make_map(&mG, G, K, N, ldg, 32), "cuTensorMapEncodeTiled failed for G [%d x %d] ld %d", K, N, ldg);
+               int slices, long long slice_stride, int accumulate, cudaStream_t st, const ThPlanes* planes) {
+    th::DwMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const int xp = planes && planes->a_planes, gp = planes && planes->c_planes;
+    if (xp) {
+        const __half* hi = reinterpret_cast<const __half*>(X);
+        DPPO_REQUIRE(ldx % 8 == 0 && th::aligned16(hi) && planes->a_lo_off % 8 == 0, "h_dw: fp16 planes need 16-byte aligned rows");
+        DPPO_REQUIRE(th::h_make_map16(&maps.x, hi, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                     th::h_make_map16(&maps.xl, hi + planes->a_lo_off, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B),
+                     "cuTensorMapEncodeTiled failed for the X planes [%d x %d] ld %d", K, M, ldx);
+    } else {
+        DPPO_REQUIRE(th::h_make_map(&maps.x, X, K, M, ldx, 32), "cuTensorMapEncodeTiled failed for X [%d x %d] ld %d", K, M, ldx);
+    }
+    if (gp) {
+        const __half* hi = reinterpret_cast<const __half*>(G);
+        DPPO_REQUIRE(ldg % 8 == 0 && th::aligned16(hi) && planes->c_lo_off % 8 == 0, "h_dw: fp16 planes need 16-byte aligned rows");
+        DPPO_REQUIRE(th::h_make_map16(&maps.g, hi, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                     th::h_make_map16(&maps.gl, hi + planes->c_lo_off, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B),
+                     "cuTensorMapEncodeTiled failed for the G planes [%d x %d] ld %d", K, N, ldg);
+    } else {
+        DPPO_REQUIRE(th::h_make_map(&maps.g, G, K, N, ldg, 32), "cuTensorMapEncodeTiled failed for G [%d x %d] ld %d", K, N, ldg);
+    }
     th::DwArgs g{};
     g.C = C; g.bias_out = bias_out; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.accumulate = accumulate;
     g.slice_stride = slice_stride;
@@ -380,9 +507,9 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     if (kps == 0) kps = th::kKB;
     g.k_per_slice = kps; g.slices = slices;
     g.vecC = (ldc % 4 == 0) && th::aligned16(C) && (slice_stride % 4 == 0);
-    if (N > 128) return th::launch_dw<256>(mX, mG, g, st);
-    if (N > 64) return th::launch_dw<128>(mX, mG, g, st);
-    return th::launch_dw<64>(mX, mG, g, st);
+    if (N > 128) return th::launch_dw_bn<256>(maps, xp, gp, g, st);
+    if (N > 64) return th::launch_dw_bn<128>(maps, xp, gp, g, st);
+    return th::launch_dw_bn<64>(maps, xp, gp, g, st);
 }
 
 }  // namespace dppo

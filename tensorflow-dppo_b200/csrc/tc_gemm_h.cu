@@ -49,7 +49,7 @@ struct HArgs {
     const float* mask;                 // NT: fp32 mask [M,N] (row stride ldc), C *= (mask > 0); used when bits_in == nullptr
     const uint32_t* bits_in;           // NT: ReLU sign bitmap [M, bits_wpr]
     uint32_t* bits_out[2];             // NN: sign bitmap of the result (nullable per net)
-    int M, N, K, lda, ldc;
+    int M, N, K, lda, ldc, ldmask;
     int tiles_n, nets, relu, vecA, vecC, bits_wpr;
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
@@ -59,12 +59,22 @@ struct HArgs {
 enum { DBG_NO_A = 1, DBG_NO_SPLIT = 2, DBG_ONE_MMA = 4, DBG_NO_W = 8, DBG_NO_STORE = 16, DBG_NO_FENCE = 32,
        DBG_EARLY_RELEASE = 512 };     // 512: release the raw slot right after ISSUING its loads (the race described in the converter loop)
 
-template <int BN>
+// How the activation operand reaches shared memory / how the result leaves it
+enum { A_LDG = 0,        // LDG movers: fp32 rows TMA cannot address (unaligned stride)
+       A_RAW = 1,        // TMA boxes of fp32 into a raw ring, converter warps split them into fp16 hi / lo
+       A_PLANES = 2 };   // the producer kernel already stored fp16 hi | lo planes: TMA writes the operand tiles directly
+enum { C_STG = 0,        // st.global write-out (fp32)
+       C_TMA = 1,        // fp32 boxes by TMA store
+       C_PLANES = 2 };   // fp16 hi | lo planes by TMA store (the next product's A_PLANES operand, the dW kernel's plane operands)
+
+template <int BN, int AMODE = A_RAW>
 struct HPlan {
     static constexpr int kBSlots = 3;
-    // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight
-    static constexpr int kASlots = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);   // operand ring: latency-bound when k-blocks are short
-    static constexpr int kRSlots = BN >= 256 ? 2 : (BN >= 128 ? 4 : 6);
+    // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight.
+    // With fp16 planes there is no raw ring and no converter hand-off: its bytes go to a deeper operand ring.
+    static constexpr int kASlots = AMODE == A_PLANES ? (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8))
+                                                     : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
+    static constexpr int kRSlots = AMODE == A_PLANES ? 0 : (BN >= 256 ? 2 : (BN >= 128 ? 4 : 6));
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
     static constexpr int kASlot = 2 * kAHalf;
     static constexpr int kBHalf = BN * 64;
@@ -161,11 +171,15 @@ __device__ __forceinline__ void raw_load(MoverRegs& r, uint32_t raw_tile, int ti
 // columns leave room for TWO such stages in the 512 TMEM columns: the MMAs of tile i+1 run while tile i is drained.
 template <int BN> struct HAcc { static constexpr int kStages = BN >= 256 ? 1 : 2; };
 
-template <int BN, int EPI, bool TMA_A, bool TMA_C>
+// the tensor maps of one launch: [net] x {fp32 matrix or hi plane, lo plane}
+struct HMaps { CUtensorMap a[2], al[2], c[2], cl[2]; };
+
+template <int BN, int EPI, int AMODE, int CMODE>
 __global__ void __launch_bounds__(kThreads, 1)
-h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-              const __grid_constant__ CUtensorMap mapC0, const __grid_constant__ CUtensorMap mapC1, const HArgs g, int total_tiles) {
-    using P = HPlan<BN>;
+h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles) {
+    using P = HPlan<BN, AMODE>;
+    constexpr bool TMA_A = (AMODE == A_RAW);
+    constexpr bool TMA_C = (CMODE != C_STG);
     constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots, kAcc = HAcc<BN>::kStages;
     extern __shared__ __align__(1024) uint8_t smem[];         // SWIZZLE_128B boxes and UMMA tiles need 1024-B alignment
     const uint32_t smem_base = smem_u32(smem);
@@ -192,7 +206,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
 
     if (tid == 0) {
         if (smem_base & 1023u) __trap();
-        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], kMoverWarps); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], AMODE == A_PLANES ? 1 : kMoverWarps); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kRSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverWarps); }
         for (int s = 0; s < kAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
@@ -214,15 +228,18 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     };
 
     if (warp < kMoverWarps) {
-        if (TMA_A) {
+        if (AMODE == A_PLANES) {
+            // nothing to convert: TMA writes the fp16 hi / lo operand tiles
+        } else if (TMA_A) {
             // ================= converters: raw fp32 tile (TMA) -> fp16 hi / lo operand tiles =================
             for (long long it = 0; it < total_it; ++it) {
-                const int rs = (int)(it % kRSlots), sa = (int)(it % kASlots);
+                constexpr int kRS = kRSlots > 0 ? kRSlots : 1;
+                const int rs = (int)(it % kRS), sa = (int)(it % kASlots);
                 MoverRegs r;
                 OperandRegs o;
                 const bool old_order = (g.dbg & DBG_EARLY_RELEASE) != 0;
                 if (!(g.dbg & DBG_NO_A)) {
-                    mbar_wait(&raw_full[rs], (uint32_t)((it / kRSlots) & 1));
+                    mbar_wait(&raw_full[rs], (uint32_t)((it / kRS) & 1));
                     raw_load(r, raw_ring + rs * P::kRawSlot, tid);
                     if (old_order) warp_arrive(&raw_empty[rs], lane);
                 } else {
@@ -275,32 +292,42 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     } else if (warp == kProdWarp) {
         // ================= producer (one thread): weight-image bulk copies and activation TMA boxes =================
         // two independent streams polled without blocking, so that a full ring of one never holds the other back
+        // (stream positions are kept as (tile, k-block, slot, phase) counters: no division in this loop)
         if (lane == 0) {
-            long long ib = (g.dbg & DBG_NO_W) ? total_it : 0, ia = (TMA_A && !(g.dbg & DBG_NO_A)) ? 0 : total_it;
-            while (ib < total_it || ia < total_it) {
-                if (ib < total_it) {
-                    const int sb = (int)(ib % kBSlots);
-                    if (mbar_test(&empty_b[sb], (uint32_t)(((ib / kBSlots) & 1) ^ 1))) {
-                        int mt, net, nt;
-                        decode(t_begin + (int)(ib / nkb), mt, net, nt);
-                        const int kb = (int)(ib % nkb);
-                        const uint8_t* img = g.Bimg[net] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes +
-                                             ((size_t)nt * nkb + (size_t)kb) * P::kBSlot;
-                        mbar_arrive_expect_tx(&full_b[sb], (uint32_t)P::kBSlot);
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(b_ring + sb * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[sb]))
-                                     : "memory");
-                        ++ib;
-                    }
+            struct Pos { int i, kb, slot; uint32_t phase; int mt, net, nt; };
+            auto start = [&](Pos& p) { p.i = 0; p.kb = 0; p.slot = 0; p.phase = 1u; if (my_tiles > 0) decode(t_begin, p.mt, p.net, p.nt); };
+            auto advance = [&](Pos& p, int slots) {
+                if (++p.slot == slots) { p.slot = 0; p.phase ^= 1u; }
+                if (++p.kb == nkb) { p.kb = 0; if (++p.i < my_tiles) decode(t_begin + p.i, p.mt, p.net, p.nt); }
+            };
+            Pos pb, pa;
+            start(pb); start(pa);
+            if (g.dbg & DBG_NO_W) pb.i = my_tiles;
+            if (AMODE == A_LDG || (g.dbg & DBG_NO_A)) pa.i = my_tiles;
+            const uint8_t* img_base[2] = {g.Bimg[0] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes,
+                                          g.Bimg[1] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes};
+            while (pb.i < my_tiles || pa.i < my_tiles) {
+                if (pb.i < my_tiles && mbar_test(&empty_b[pb.slot], pb.phase)) {
+                    const uint8_t* img = img_base[pb.net] + ((size_t)pb.nt * nkb + (size_t)pb.kb) * P::kBSlot;
+                    mbar_arrive_expect_tx(&full_b[pb.slot], (uint32_t)P::kBSlot);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(b_ring + pb.slot * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[pb.slot]))
+                                 : "memory");
+                    advance(pb, kBSlots);
                 }
-                if (ia < total_it) {
-                    const int rs = (int)(ia % kRSlots);
-                    if (mbar_test(&raw_empty[rs], (uint32_t)(((ia / kRSlots) & 1) ^ 1))) {
-                        int mt, net, nt;
-                        decode(t_begin + (int)(ia / nkb), mt, net, nt);
-                        mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)P::kRawSlot);
-                        tma_load_2d(raw_ring + rs * P::kRawSlot, net ? &mapA1 : &mapA0, (int)(ia % nkb) * kKB, mt * BM, &raw_full[rs]);
-                        ++ia;
+                if (AMODE == A_PLANES) {
+                    if (pa.i < my_tiles && mbar_test(&empty_a[pa.slot], pa.phase)) {
+                        const uint32_t slot = a_ring + pa.slot * P::kASlot;
+                        mbar_arrive_expect_tx(&full_a[pa.slot], (uint32_t)P::kASlot);
+                        tma_load_2d(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                        tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                        advance(pa, kASlots);
+                    }
+                } else if (AMODE == A_RAW) {
+                    if (pa.i < my_tiles && mbar_test(&raw_empty[pa.slot], pa.phase)) {
+                        mbar_arrive_expect_tx(&raw_full[pa.slot], (uint32_t)P::kRawSlot);
+                        tma_load_2d(raw_ring + pa.slot * P::kRawSlot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &raw_full[pa.slot]);
+                        advance(pa, kRSlots > 0 ? kRSlots : 1);
                     }
                 }
             }
@@ -309,17 +336,17 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(BN);
-            long long it = 0;
+            int sa = 0, sb = 0;
+            uint32_t pha = 0u, phb = 0u;
             for (int i = 0; i < my_tiles; ++i) {
                 const int as = i % kAcc;
                 const uint32_t acc = tmem_base + (uint32_t)as * kStageCols;
                 mbar_wait(&acc_empty[as], (uint32_t)(((i / kAcc) & 1) ^ 1));      // the epilogue has read tile i - kAcc out of this stage
                 tc_fence_after();
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 0] = clock64();
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int sa = (int)(it % kASlots), sb = (int)(it % kBSlots);
-                    mbar_wait(&full_a[sa], (uint32_t)((it / kASlots) & 1));
-                    if (!(g.dbg & DBG_NO_W)) mbar_wait(&full_b[sb], (uint32_t)((it / kBSlots) & 1));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (!(AMODE == A_PLANES && (g.dbg & DBG_NO_A))) mbar_wait(&full_a[sa], pha);
+                    if (!(g.dbg & DBG_NO_W)) mbar_wait(&full_b[sb], phb);
                     tc_fence_after();
                     const uint32_t a_hi = a_ring + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
                     const uint32_t b_hi = b_ring + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
@@ -337,6 +364,8 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     }
                     umma_commit(&empty_a[sa]);
                     umma_commit(&empty_b[sb]);
+                    if (++sa == kASlots) { sa = 0; pha ^= 1u; }
+                    if (++sb == kBSlots) { sb = 0; phb ^= 1u; }
                 }
                 if (g.fold) fold_issue<BN>(acc, smem_base + P::kFoldOff);
                 umma_commit(&acc_full[as]);                 // accumulators of tile i complete
@@ -365,7 +394,8 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             int mt, net, nt;
             decode(t_begin + i, mt, net, nt);
             const int m = mt * BM + r;
-            const CUtensorMap* mapC = net ? &mapC1 : &mapC0;
+            const CUtensorMap* mapC = &maps.c[net];
+            const CUtensorMap* mapCl = &maps.cl[net];
             uint32_t* __restrict__ bits_out = (EPI == EPI_NN) ? g.bits_out[net] : nullptr;
             uint32_t mw[kSubs];
             if (EPI == EPI_NN) {
@@ -409,6 +439,8 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     if (lane == 0) mbar_arrive(&acc_empty[as]);
                     if (g.timeline && blockIdx.x == 0 && i < 16 && t0) g.timeline[i * 8 + 3] = clock64();
                 }
+                // this thread's 32 finished columns
+                float f[32];
                 if (EPI == EPI_NN) {
                     uint32_t sign = 0u;
 #pragma unroll
@@ -418,7 +450,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                         float x2 = __uint_as_float(v[j4 * 4 + 2]) + b4.z, x3 = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
                         if (g.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
                         sign |= ((x0 > 0.f ? 1u : 0u) | (x1 > 0.f ? 2u : 0u) | (x2 > 0.f ? 4u : 0u) | (x3 > 0.f ? 8u : 0u)) << (j4 * 4);
-                        sts128f(buf + row_off + (uint32_t)(((j4 ^ r) & 7) << 4), make_float4(x0, x1, x2, x3));
+                        f[j4 * 4 + 0] = x0; f[j4 * 4 + 1] = x1; f[j4 * 4 + 2] = x2; f[j4 * 4 + 3] = x3;
                     }
                     const int wi = (nt * BN + col) >> 5;
                     if (bits_out && m < g.M && wi < g.bits_wpr) bits_out[(size_t)m * g.bits_wpr + wi] = sign;
@@ -428,8 +460,8 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     else if (g.mask) {
                         keep = 0u;
                         const int n0 = nt * BN + col;
-                        if (m < g.M && n0 + 32 <= g.N) {           // (TMA_C implies 16-B aligned rows)
-                            const float4* mp = reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldc + n0);
+                        if (m < g.M && n0 + 32 <= g.N) {           // (a 16-B aligned fp32 mask row)
+                            const float4* mp = reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + n0);
 #pragma unroll
                             for (int j4 = 0; j4 < 8; ++j4) {
                                 const float4 k = __ldg(mp + j4);
@@ -437,15 +469,29 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                             }
                         } else if (m < g.M) {
                             for (int j = 0; j < 32; ++j)
-                                if (n0 + j < g.N && __ldg(g.mask + (size_t)m * g.ldc + n0 + j) > 0.f) keep |= 1u << j;
+                                if (n0 + j < g.N && __ldg(g.mask + (size_t)m * g.ldmask + n0 + j) > 0.f) keep |= 1u << j;
                         }
                     }
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const uint32_t k4 = keep >> (j4 * 4);
-                        const float4 o = make_float4((k4 & 1u) ? __uint_as_float(v[j4 * 4 + 0]) : 0.f, (k4 & 2u) ? __uint_as_float(v[j4 * 4 + 1]) : 0.f,
-                                                     (k4 & 4u) ? __uint_as_float(v[j4 * 4 + 2]) : 0.f, (k4 & 8u) ? __uint_as_float(v[j4 * 4 + 3]) : 0.f);
-                        sts128f(buf + row_off + (uint32_t)(((j4 ^ r) & 7) << 4), o);
+                    for (int j = 0; j < 32; ++j) f[j] = ((keep >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+                }
+                if (CMODE == C_TMA) {
+                    // one 128-B row of this warp half's {32 fp32 x 128 rows} SWIZZLE_128B box
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        sts128f(buf + row_off + (uint32_t)(((j4 ^ r) & 7) << 4), make_float4(f[j4 * 4 + 0], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]));
+                } else {
+                    // fp16 planes: 64 B of this row in the hi box and in the lo box ({64 fp16 x 128 rows}, SWIZZLE_128B); the split
+                    // is the one the next product's converters would have applied to the fp32 value, so results do not change
+                    const uint32_t hb = stg + (gsp % kBufs) * (uint32_t)(BM * 64 * 4) + row_off, lb = hb + (uint32_t)(BM * 128);
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint4 h, l;
+                        split2(f[j4 * 8 + 0], f[j4 * 8 + 1], h.x, l.x); split2(f[j4 * 8 + 2], f[j4 * 8 + 3], h.y, l.y);
+                        split2(f[j4 * 8 + 4], f[j4 * 8 + 5], h.z, l.z); split2(f[j4 * 8 + 6], f[j4 * 8 + 7], h.w, l.w);
+                        const uint32_t ck = (uint32_t)((((ch * 4 + j4) ^ r) & 7) << 4);
+                        sts128(hb + ck, h);
+                        sts128(lb + ck, l);
                     }
                 }
                 fence_proxy_async();                              // staged rows -> visible to TMA (async proxy)
@@ -454,8 +500,13 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 if (t0) {
                     const uint32_t b0 = stg + (gsp % kBufs) * (uint32_t)(BM * 64 * 4);
                     const int n0 = nt * BN + sp * 64;
-                    if (n0 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0, n0, mt * BM);
-                    if (n0 + 32 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0 + (uint32_t)(BM * 128), n0 + 32, mt * BM);
+                    if (CMODE == C_TMA) {
+                        if (n0 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0, n0, mt * BM);
+                        if (n0 + 32 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0 + (uint32_t)(BM * 128), n0 + 32, mt * BM);
+                    } else if (n0 < g.N && !(g.dbg & DBG_NO_STORE)) {
+                        tma_store_2d(mapC, b0, n0, mt * BM);
+                        tma_store_2d(mapCl, b0 + (uint32_t)(BM * 128), n0, mt * BM);
+                    }
                     bulk_commit();
                 }
             }
@@ -566,7 +617,7 @@ h_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                             x[0] = (b4 & 1u) ? x[0] : 0.f; x[1] = (b4 & 2u) ? x[1] : 0.f;
                             x[2] = (b4 & 4u) ? x[2] : 0.f; x[3] = (b4 & 8u) ? x[3] : 0.f;
                         } else if (g.mask && ok) {
-                            const float* mp = g.mask + (size_t)m * g.ldc + n;
+                            const float* mp = g.mask + (size_t)m * g.ldmask + n;
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
                                 if (e < nv) x[e] = (__ldg(mp + e) > 0.f) ? x[e] : 0.f;
@@ -638,37 +689,82 @@ static bool tmac_enabled() {
     return v == 1;
 }
 
-template <int BN, int EPI, bool TMA_A, bool TMA_C>
-static int launch_h2(const CUtensorMap& m0, const CUtensorMap& m1, const CUtensorMap& c0, const CUtensorMap& c1, HArgs& g, cudaStream_t st) {
-    using P = HPlan<BN>;
+template <int BN, int EPI, int AMODE, int CMODE>
+static int launch_h2(const HMaps& maps, HArgs& g, cudaStream_t st) {
+    using P = HPlan<BN, AMODE>;
     const long long total = (long long)((g.M + BM - 1) / BM) * g.tiles_n * g.nets;
     DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, TMA_A, TMA_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, AMODE, CMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);
-    h_gemm_kernel<BN, EPI, TMA_A, TMA_C><<<grid, kThreads, P::kBytes, st>>>(m0, m1, c0, c1, g, (int)total);
+    h_gemm_kernel<BN, EPI, AMODE, CMODE><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
 
+template <int BN, int EPI, int AMODE>
+static int launch_h1(const HMaps& maps, int cmode, HArgs& g, cudaStream_t st) {
+    if (cmode == C_PLANES) return launch_h2<BN, EPI, AMODE, C_PLANES>(maps, g, st);
+    if (cmode == C_TMA) return launch_h2<BN, EPI, AMODE, C_TMA>(maps, g, st);
+    return launch_h2<BN, EPI, AMODE, C_STG>(maps, g, st);
+}
+
 template <int BN, int EPI>
-static int launch_h(HArgs& g, cudaStream_t st) {
+static int launch_h(HArgs& g, const ThPlanes& pl, cudaStream_t st) {
     g.tiles_n = (g.N + BN - 1) / BN;
-    // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, ...) takes the LDG movers / the st.global write-out
-    CUtensorMap m0, m1, c0, c1;
-    memset(&m0, 0, sizeof(m0)); memset(&m1, 0, sizeof(m1)); memset(&c0, 0, sizeof(c0)); memset(&c1, 0, sizeof(c1));
-    bool tma = g.vecA && h_make_map(&m0, g.A[0], g.M, g.K, g.lda, BM);
-    if (tma) { if (g.nets > 1) tma = h_make_map(&m1, g.A[1], g.M, g.K, g.lda, BM); else m1 = m0; }
-    bool tmc = g.vecC && tmac_enabled() && h_make_map(&c0, g.C[0], g.M, g.N, g.ldc, BM);
-    if (tmc) { if (g.nets > 1) tmc = h_make_map(&c1, g.C[1], g.M, g.N, g.ldc, BM); else c1 = c0; }
-    if (tma) {
-        if (tmc) return launch_h2<BN, EPI, true, true>(m0, m1, c0, c1, g, st);
-        return launch_h2<BN, EPI, true, false>(m0, m1, c0, c1, g, st);
+    HMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int amode = A_LDG, cmode = C_STG;
+    if (pl.a_planes) {
+        // fp16 hi | lo planes, K-major operand tiles of {32 fp16 x 128 rows}, SWIZZLE_64B: exactly what the MMA reads
+        for (int n = 0; n < g.nets; ++n) {
+            const __half* hi = reinterpret_cast<const __half*>(g.A[n]);
+            DPPO_REQUIRE(g.lda % 8 == 0 && aligned16(hi) && pl.a_lo_off % 8 == 0, "h_gemm: fp16 planes need 16-byte aligned rows");
+            DPPO_REQUIRE(h_make_map16(&maps.a[n], hi, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B) &&
+                         h_make_map16(&maps.al[n], hi + pl.a_lo_off, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B),
+                         "cuTensorMapEncodeTiled failed for the A planes [%d x %d]", g.M, g.K);
+        }
+        amode = A_PLANES;
+    } else {
+        // TMA needs 16-byte aligned rows; anything else (obs_dim 3, 17, ...) takes the LDG movers
+        bool tma = g.vecA && h_make_map(&maps.a[0], g.A[0], g.M, g.K, g.lda, BM);
+        if (tma && g.nets > 1) tma = h_make_map(&maps.a[1], g.A[1], g.M, g.K, g.lda, BM);
+        if (tma) amode = A_RAW;
     }
-    if (tmc) return launch_h2<BN, EPI, false, true>(m0, m1, c0, c1, g, st);
-    return launch_h2<BN, EPI, false, false>(m0, m1, c0, c1, g, st);
+    if (pl.c_planes) {
+        for (int n = 0; n < g.nets; ++n) {
+            __half* hi = reinterpret_cast<__half*>(g.C[n]);
+            DPPO_REQUIRE(g.ldc % 8 == 0 && aligned16(hi) && pl.c_lo_off % 8 == 0, "h_gemm: fp16 planes need 16-byte aligned rows");
+            DPPO_REQUIRE(h_make_map16(&maps.c[n], hi, g.M, g.N, g.ldc, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+                         h_make_map16(&maps.cl[n], hi + pl.c_lo_off, g.M, g.N, g.ldc, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B),
+                         "cuTensorMapEncodeTiled failed for the C planes [%d x %d]", g.M, g.N);
+        }
+        cmode = C_PLANES;
+    } else {
+        bool tmc = g.vecC && tmac_enabled() && h_make_map(&maps.c[0], g.C[0], g.M, g.N, g.ldc, BM);
+        if (tmc && g.nets > 1) tmc = h_make_map(&maps.c[1], g.C[1], g.M, g.N, g.ldc, BM);
+        if (tmc) cmode = C_TMA;
+    }
+    if (amode == A_PLANES) return launch_h1<BN, EPI, A_PLANES>(maps, cmode, g, st);
+    if (amode == A_RAW) return launch_h1<BN, EPI, A_RAW>(maps, cmode, g, st);
+    return launch_h1<BN, EPI, A_LDG>(maps, cmode, g, st);
+}
+
+// ---- fp32 <-> fp16 hi | lo planes (the split the converters apply; tests and one-off conversions) ----
+__global__ void split_planes_kernel(const float* __restrict__ src, long long n, __half* __restrict__ hi, __half* __restrict__ lo) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (long long)gridDim.x * blockDim.x * 2) {
+        const float a = src[i], b = (i + 1 < n) ? src[i + 1] : 0.f;
+        uint32_t h, l;
+        split2(a, b, h, l);
+        if (i + 1 < n) { *reinterpret_cast<uint32_t*>(hi + i) = h; *reinterpret_cast<uint32_t*>(lo + i) = l; }
+        else { hi[i] = __ushort_as_half((unsigned short)(h & 0xffffu)); lo[i] = __ushort_as_half((unsigned short)(l & 0xffffu)); }
+    }
+}
+__global__ void join_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n, float* __restrict__ dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = fmaf(__half2float(lo[i]), kLoInv, __half2float(hi[i]));
 }
 
 }  // namespace th
@@ -745,30 +841,52 @@ int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transpos
 // power of two (capi.cu: grad_prescale), and finalize_kernel divides it out again.
 int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
-            cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline) {
+            cudaStream_t st, uint32_t* bits_out0, const uint32_t* bits_in, long long* timeline, const ThPlanes* planes) {
 
     if (M == 0) return 0;
     th::HArgs g{};
     g.A[0] = A0; g.A[1] = A1; g.Bimg[0] = reinterpret_cast<const uint8_t*>(img0); g.Bimg[1] = reinterpret_cast<const uint8_t*>(img1);
     g.C[0] = C0; g.C[1] = C1; g.bias[0] = bias0; g.bias[1] = bias1; g.mask = mask; g.bits_in = bits_in;
     g.bits_out[0] = bits_out0; g.bits_out[1] = nullptr;
-    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldc = ldc; g.nets = nets; g.relu = relu;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldc = ldc; g.ldmask = N; g.nets = nets; g.relu = relu;
+    ThPlanes pl{};
+    if (planes) pl = *planes;
     g.bits_wpr = (N + 31) / 32;
     g.img_replica_bytes = th_image_replica_bytes(N, K);
     g.timeline = timeline;
     g.fold = th::fold_enabled() ? 1 : 0;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
-    g.vecA = (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
-    g.vecC = (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
+    g.vecA = !pl.a_planes && (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
+    g.vecC = !pl.c_planes && (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
     const int bn = th_bn_for(N, K);
     if (epi_nt) {
-        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, st);
-        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, st);
-        return th::launch_h<64, th::EPI_NT>(g, st);
+        if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, pl, st);
+        if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, pl, st);
+        return th::launch_h<64, th::EPI_NT>(g, pl, st);
     }
-    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, st);
-    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, st);
-    return th::launch_h<64, th::EPI_NN>(g, st);
+    if (bn == 256) return th::launch_h<256, th::EPI_NN>(g, pl, st);
+    if (bn == 128) return th::launch_h<128, th::EPI_NN>(g, pl, st);
+    return th::launch_h<64, th::EPI_NN>(g, pl, st);
+}
+
+// x[n] fp32 -> hi[n] | lo[n] fp16 planes and back (x ~= hi + lo / 2^11)
+int th_split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n / 2 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps(KK_MISC, st);
+    th::split_planes_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(src, n, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo));
+    DPPO_LAUNCH_CHECK();
+    return 0;
+}
+int th_join_planes(const void* hi, const void* lo, long long n, float* dst, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps(KK_MISC, st);
+    th::join_planes_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), n, dst);
+    DPPO_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace dppo

@@ -947,6 +947,75 @@ def test_h_dw_fp16_split(M, N, Kr):
     assert rel_err(bias.cpu().numpy(), G.astype(np.float64).sum(0)) < 2e-6
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (1000, 256, 376), (777, 256, 256), (129, 200, 40), (4096, 64, 256),
+                                   (300, 128, 64), (20000, 256, 256), (3000, 1024, 1024)])
+def test_h_gemm_fp16_planes(M, N, K):
+    """tc_gemm_h.cu with the activation operand given as fp16 hi | lo planes (TMA writes the MMA operand tiles, no converter
+    warps) and the result written as planes by TMA store -- the operand path of the update's hidden layers (modes 94 / 95)."""
+    rng = np.random.default_rng(M * 5 + N * 3 + K)
+    eng = _engine(376, (1024, 1024), 17, max(M, 8192), gemm_mode=1)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = (rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = A.astype(np.float64) @ Bt.astype(np.float64).T + bias
+    got = eng.dbg_gemm(94, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(ref, 0)) < 2e-6
+    mask = rng.standard_normal((M, N)).astype(np.float32)
+    ref2 = (A.astype(np.float64) @ Bt.astype(np.float64).T) * (mask > 0)
+    got2 = eng.dbg_gemm(95, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    assert rel_err(got2, ref2) < 2e-6
+    # the planes hold exactly the split the converter warps apply to an fp32 operand: feeding the SAME values as fp32 gives the
+    # same accumulators, so the two paths differ only by the final rounding of C to hi + lo / 2^11
+    got_f32 = eng.dbg_gemm(96, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(got, got_f32) < 5e-7
+
+
+@pytest.mark.parametrize("mode", [101, 102, 103])
+@pytest.mark.parametrize("M,N,Kr", [(128, 256, 32), (376, 256, 1000), (256, 40, 2048), (120, 64, 333), (256, 256, 4096),
+                                    (376, 256, 20000), (256, 128, 1500), (1024, 1024, 2048)])
+def test_h_dw_fp16_planes(M, N, Kr, mode):
+    """tc_dw_h.cu with G (101), X (102) or both (103) given as fp16 hi | lo planes: TMA boxes are the MN-major operand atoms,
+    the bias gradient is read back from the operand tiles."""
+    rng = np.random.default_rng(M + 3 * N + 7 * Kr)
+    eng = _engine(376, (1024, 1024), 17, 8192, gemm_mode=1)
+    X = rng.standard_normal((Kr, M)).astype(np.float32)
+    G = rng.standard_normal((Kr, N)).astype(np.float32)
+    if Kr * max(M, N) > 8192 * 1024:
+        pytest.skip("operand planes exceed the scratch buffers of this engine")
+    got, bias = eng.dbg_gemm(mode, dev(X), dev(G), M, N, Kr, want_bias_out=True)
+    ref = X.astype(np.float64).T @ G.astype(np.float64)
+    assert rel_err(got.cpu().numpy(), ref) < 2e-6
+    assert rel_err(bias.cpu().numpy(), G.astype(np.float64).sum(0)) < 2e-6
+    # identical operand values as the fp32-fed kernel -> identical products
+    got0, _ = eng.dbg_gemm(99, dev(X), dev(G), M, N, Kr, want_bias_out=True)
+    assert torch.equal(got, got0)
+
+
+@pytest.mark.parametrize("obs,hidden,A,T,N", [(376, (256, 256), 17, 64, 48), (17, (256, 256), 6, 128, 16), (24, (64,), 4, 100, 9),
+                                             (376, (1024, 1024, 1024, 1024), 17, 32, 16)])
+def test_fp16x2_planes_equal_fp32_activations(obs, hidden, A, T, N, monkeypatch):
+    """Hidden activations / gradients as fp16 hi | lo planes (default) against DPPO_H_PLANES=0 (fp32 matrices + converter
+    warps): the operands of every product are the same numbers, so losses and weight gradients are bit-identical; bias gradients
+    are summed from hi + lo / 2^11 instead of the fp32 value."""
+    c = O.make_case(T, N, obs, hidden, A)
+    lay = c["lay"]; B = T * N
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DPPO_H_PLANES", flag)
+        eng = _engine(obs, hidden, A, B, gemm_mode=3)
+        losses, g = eng.loss_grad(dev(c["theta_pi"]), dev(c["theta_old"]), dev(c["buf"]["obs"]), dev(c["act"]),
+                                  dev(c["adv"]), dev(c["ret"]), c["l_mul"])
+        out[flag] = (losses.cpu().numpy().copy(), g.cpu().numpy()[:lay.n_params].copy())
+    np.testing.assert_array_equal(out["1"][0], out["0"][0])
+    for name, shape, off in lay.entries:
+        n = int(np.prod(shape))
+        a, b = out["1"][1][off:off + n], out["0"][1][off:off + n]
+        if len(shape) == 2 and not (name == "W1" and obs % 4 != 0):      # (unaligned obs rows: layer 1's dW joins dh back to fp32)
+            np.testing.assert_array_equal(a, b, err_msg=name)
+        else:
+            assert rel_err(a, b) < 2e-6, name
+
+
 @pytest.mark.parametrize("name,T,N,obs,hidden,A", CASES)
 def test_loss_grad_vs_oracle_fp16x2(name, T, N, obs, hidden, A):
     """The whole tower on the persistent fp16-split kernels (forward, dX; dW on the TMA-fed tf32 kernel), 1e-5 bar."""
