@@ -147,7 +147,7 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     for (int l = 0; l < s.L; ++l) w.act_pi[l] = (float*)take(R * s.h[l] * sizeof(float));
     if (cfg->gemm_mode == DPPO_GEMM_TF32X3)
         for (int l = 0; l < s.L; ++l) w.act_bits[l] = (uint32_t*)take((size_t)tc_bits_words((long long)R, s.h[l]) * sizeof(uint32_t));
-    if (cfg->gemm_mode == DPPO_GEMM_FP16X2) {
+    if (cfg->gemm_mode == DPPO_GEMM_FP16X2 || cfg->gemm_mode == DPPO_GEMM_BF16) {     // (bf16: the one-term mode of the same kernels)
         for (int l = 0; l <= s.L; ++l) {
             const size_t fwd = (size_t)th_image_floats(s.out_dim(l), s.in_dim(l)) * sizeof(float);
             w.img_fwd_pi[l] = (float*)take(fwd);
@@ -178,10 +178,21 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
 // fp16x2 mode: hidden activations and their gradients are stored as fp16 hi | lo planes (same bytes as fp32) whenever every
 // hidden width keeps the plane rows 16-byte aligned (DPPO_H_PLANES=0 at dppo_create keeps fp32 matrices + converter warps)
 static bool h_planes(const dppo_ctx* c) {
-    if (c->cfg.gemm_mode != DPPO_GEMM_FP16X2 || !c->use_h_planes || !c->use_h_dw) return false;
+    const bool bf16 = c->cfg.gemm_mode == DPPO_GEMM_BF16;
+    if ((c->cfg.gemm_mode != DPPO_GEMM_FP16X2 && !bf16) || !c->use_h_planes || !c->use_h_dw) return false;
     for (int l = 0; l < c->shape.L; ++l)
         if (c->shape.h[l] % 8 != 0) return false;
+    // DPPO_GEMM_BF16 runs on these kernels in their one-term mode (one bf16 plane per activation, one MMA per product) only
+    // when every operand can be read by TMA; other shapes keep the round-1 bf16 kernels (tc_gemm_bf16.cu)
+    if (bf16 && c->shape.obs % 4 != 0) return false;
     return c->shape.L > 0;
+}
+// the persistent kernel family of tc_gemm_h.cu / tc_dw_h.cu: 2 = fp16 hi + lo operands (DPPO_GEMM_FP16X2), 1 = bf16 operands
+// (DPPO_GEMM_BF16 on TMA-addressable shapes), 0 = not on this family
+static int th_terms(const dppo_ctx* c) {
+    if (c->cfg.gemm_mode == DPPO_GEMM_FP16X2) return 2;
+    if (c->cfg.gemm_mode == DPPO_GEMM_BF16 && h_planes(c)) return 1;
+    return 0;
 }
 
 // ---- forward of pi (and oldpi) over rows [0, rows) of obs ------------------------------------
@@ -192,7 +203,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
     const int nets = params_old ? 2 : 1;
     if (int r = launch_pack_heads(s, params_pi, params_old, w.head_pi, w.head_old, st)) return r;
     const float* in0 = obs; const float* in1 = obs;
-    if (c->cfg.gemm_mode == DPPO_GEMM_BF16) {
+    if (c->cfg.gemm_mode == DPPO_GEMM_BF16 && th_terms(c) == 0) {
         // bf16 tensor cores: B operand K-major = transposed kernels (fp32 in HBM, rounded to bf16 by the movers)
         if (int r = tc_transpose_weights(s, params_pi, w.head_pi, w.wt_pi, params_old, w.head_old, w.wt_old, st)) return r;
         for (int l = 0; l <= s.L; ++l) {
@@ -208,10 +219,12 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
         }
         return 0;
     }
-    if (c->cfg.gemm_mode == DPPO_GEMM_FP16X2) {
-        // persistent fp16-split kernels: weight images (fp16 hi | lo tiles) refreshed from the current parameters
+    if (th_terms(c)) {
+        // persistent fp16-split kernels: weight images (fp16 hi | lo tiles; bf16 tiles in one-term mode) refreshed from the
+        // current parameters
+        const int terms = th_terms(c);
         if (int r = th_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
-                                   w.img_dx_pi, st)) return r;
+                                   w.img_dx_pi, st, terms)) return r;
         // hidden activations live as fp16 hi | lo planes (h_planes): the epilogue that produces them applies the split the
         // consumer's converter warps would apply, so every later product reads its operand tiles straight from TMA
         const bool planes = h_planes(c);
@@ -224,6 +237,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const float* b0 = head ? w.head_pi + (size_t)in * out : params_pi + s.b_off[l];
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
             ThPlanes pl{};
+            pl.terms = terms;
             pl.a_planes = planes && l > 0; pl.a_lo_off = R * in;
             pl.c_planes = planes && !head; pl.c_lo_off = R * out;
             if (int r = th_gemm(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
@@ -343,8 +357,9 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const float* head_in = s.L ? w.act_pi[s.L - 1] : obs;
     // heads: dWh = h_L^T . d_out, dbh = colsum(d_out)
     const bool tcore = tc_mode(c->cfg.gemm_mode);
-    const bool fp16x2 = (c->cfg.gemm_mode == DPPO_GEMM_FP16X2);
-    const bool bf16 = (c->cfg.gemm_mode == DPPO_GEMM_BF16);
+    const int terms = th_terms(c);
+    const bool fp16x2 = (terms != 0);                                   // the persistent kernel family (two- or one-term)
+    const bool bf16 = (c->cfg.gemm_mode == DPPO_GEMM_BF16) && terms == 0;   // round-1 bf16 kernels
     const bool planes = h_planes(c);
     // dW_l (+ db_l) into layer l's split-K partial region
     // (tmp: a free [rows, hmax] buffer -- planes mode joins dY back to fp32 there when layer 0's obs rows cannot be read by TMA)
@@ -359,6 +374,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
         }
         if (planes) {                                       // X = a hidden activation, G = a hidden gradient: fp16 planes
             ThPlanes pl{};
+            pl.terms = terms;
             pl.a_planes = l > 0; pl.a_lo_off = (long long)c->cfg.max_rows * in;
             pl.c_planes = l < s.L; pl.c_lo_off = (long long)c->cfg.max_rows * out;
             if ((pl.a_planes || th_dw_supported(x_in, in, x_in, in)) && (pl.c_planes || th_dw_supported(dY, ldy, dY, ldy)))
@@ -367,11 +383,15 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
             // obs rows TMA cannot address (obs_dim 3, 17, ...): the tf32 kernels below take fp32 operands
             DPPO_REQUIRE(pl.c_planes && tmp != nullptr, "fp16 planes: layer %d has an fp32 operand TMA cannot address", l);
             const __half* hi = reinterpret_cast<const __half*>(dY);
-            if (int r = th_join_planes(hi, hi + pl.c_lo_off, (long long)rows * out, tmp, st)) return r;
+            if (int r = th_join_planes(hi, hi + pl.c_lo_off, (long long)rows * out, tmp, st, terms)) return r;
             dY = tmp;
         }
-        if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, in, dY, ldy))     // persistent fp16-split kernel, bias column sums fused
-            return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate, st);
+        if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, in, dY, ldy)) {    // persistent fp16-split kernel, bias column sums fused
+            ThPlanes pl{};
+            pl.terms = terms;
+            return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate, st,
+                              &pl);
+        }
         if (tcore) {
             if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
                 return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l],
@@ -389,6 +409,7 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
                         const float* mask) -> int {
         if (fp16x2) {
             ThPlanes pl{};                                    // dY of a hidden layer and every dX are planes
+            pl.terms = terms;
             pl.a_planes = planes && l_ < s.L; pl.a_lo_off = (long long)c->cfg.max_rows * K_;
             pl.c_planes = planes; pl.c_lo_off = (long long)c->cfg.max_rows * N_;
             return th_gemm(1, M_, N_, K_, dY, nullptr, ldy, w.img_dx_pi[l_], nullptr, dX, nullptr, N_, nullptr, nullptr,
@@ -1161,6 +1182,9 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
     CTX_GUARD(c);
     cudaStream_t st = (cudaStream_t)stream;
     GemmEpi e; e.bias = bias; e.relu = relu; e.mask = mask;
+    // 192 / 194 / 195 / 196 / 197 / 199 / 201-203: the persistent kernels of modes 92 ... 103 in their ONE-TERM mode (bf16 operands)
+    int terms = 2;
+    if (mode >= 192 && mode <= 203) { terms = 1; mode -= 100; }
     if (mode >= 64 && mode <= 66) {
         // bf16 tensor-core products: 64 C = relu?(A[M,K].Bt[N,K]^T + bias); 65 same product * (mask>0); 66 C = A[K,M]^T.B[K,N]
         if (mode == 64) return bf16_gemm_kk(0, M, N, K, A, nullptr, K, B, nullptr, K, C, nullptr, N, bias, nullptr, relu, nullptr, 1, st);
@@ -1179,6 +1203,7 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         // persistent fp16-split dW product (tc_dw_h.cu): C[M,N] = A[K,M]^T . B[K,N], bias_out[N] = column sums of B
         // 101 / 102 / 103: B / A / both operands first converted to fp16 hi | lo planes (scratch[1] / scratch[0])
         ThPlanes pl{};
+        pl.terms = terms;
         const long long cap = (long long)c->cfg.max_rows * (c->shape.hmax() > 0 ? c->shape.hmax() : 1);
         if (mode >= 101) {
             pl.a_planes = (mode & 2) ? 1 : 0; pl.c_planes = (mode & 1) ? 1 : 0;
@@ -1186,12 +1211,12 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
             DPPO_REQUIRE(2 * pl.a_lo_off <= 2 * cap && 2 * pl.c_lo_off <= 2 * cap, "dppo_dbg_gemm: operand planes exceed the scratch buffers");
             if (pl.a_planes) {
                 __half* hi = reinterpret_cast<__half*>(c->ws.scratch[0]);
-                if (int r = th_split_planes(A, (long long)K * M, hi, hi + pl.a_lo_off, st)) return r;
+                if (int r = th_split_planes(A, (long long)K * M, hi, hi + pl.a_lo_off, st, terms)) return r;
                 A = c->ws.scratch[0];
             }
             if (pl.c_planes) {
                 __half* hi = reinterpret_cast<__half*>(c->ws.scratch[1]);
-                if (int r = th_split_planes(B, (long long)K * N, hi, hi + pl.c_lo_off, st)) return r;
+                if (int r = th_split_planes(B, (long long)K * N, hi, hi + pl.c_lo_off, st, terms)) return r;
                 B = c->ws.scratch[1];
             }
         }
@@ -1201,8 +1226,7 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         if (slices > want) slices = want;
         DPPO_REQUIRE(slices >= 1, "dppo_dbg_gemm: M*N+N exceeds the partial buffer");
         DPPO_REQUIRE(th_dw_supported(A, M, B, N), "dppo_dbg_gemm: the fp16 dW kernel needs 16-byte aligned rows");
-        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, st,
-                               mode >= 101 ? &pl : nullptr))
+        if (int r = th_gemm_dw(M, N, K, A, M, B, N, c->ws.partial, N, c->ws.partial + (int64_t)M * N, slices, stride, 0, st, &pl))
             return r;
         ProfScope ps(KK_MISC, st);
         reduce_slices_kernel<<<256, 256, 0, st>>>(c->ws.partial, slices, stride, (long long)M * N, C);
@@ -1220,13 +1244,14 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         DPPO_REQUIRE(c->shape.partial_floats >= need, "dppo_dbg_gemm: the partial buffer cannot hold the %lld-float weight image", need);
         const long long cap = (long long)c->cfg.max_rows * (c->shape.hmax() > 0 ? c->shape.hmax() : 1);
         ThPlanes pl{};
+        pl.terms = terms;
         pl.a_planes = pl.c_planes = 1;
         pl.a_lo_off = ((long long)M * K + 7) & ~7LL; pl.c_lo_off = ((long long)M * N + 7) & ~7LL;
         DPPO_REQUIRE(pl.a_lo_off <= cap && pl.c_lo_off <= cap, "dppo_dbg_gemm: planes exceed the scratch buffers");
         __half* a_hi = reinterpret_cast<__half*>(c->ws.scratch[0]);
         __half* c_hi = reinterpret_cast<__half*>(c->ws.scratch[1]);
-        if (int r = th_split_planes(A, (long long)M * K, a_hi, a_hi + pl.a_lo_off, st)) return r;
-        if (int r = th_pack_one(B, c->ws.partial, N, K, K, 0, st)) return r;
+        if (int r = th_split_planes(A, (long long)M * K, a_hi, a_hi + pl.a_lo_off, st, terms)) return r;
+        if (int r = th_pack_one(B, c->ws.partial, N, K, K, 0, st, terms)) return r;
         if (mode == 95) {
             if (int r = th_gemm(1, M, N, K, c->ws.scratch[0], nullptr, K, c->ws.partial, nullptr, c->ws.scratch[1], nullptr, N, nullptr,
                                 nullptr, 0, mask, 1, st, nullptr, nullptr, nullptr, &pl)) return r;
@@ -1235,7 +1260,7 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
                                 nullptr, relu, nullptr, 1, st, nullptr, nullptr,
                                 mode == 92 ? reinterpret_cast<long long*>(bias_out) : nullptr, &pl)) return r;
         }
-        return th_join_planes(c_hi, c_hi + pl.c_lo_off, (long long)M * N, C, st);
+        return th_join_planes(c_hi, c_hi + pl.c_lo_off, (long long)M * N, C, st, terms);
     }
     if (mode == 96 || mode == 97 || mode == 98) {
         // persistent fp16-split product (tc_gemm_h.cu): Bt[N,K] is packed into an fp16 hi|lo tile image first (scratch from
@@ -1247,11 +1272,14 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         else if ((long long)c->ws.stage_floats >= need) scratch = c->ws.stage;
         else if ((long long)c->cfg.max_rows * (c->shape.hmax() > 0 ? c->shape.hmax() : 1) >= need) scratch = c->ws.scratch[0];
         DPPO_REQUIRE(scratch != nullptr, "dppo_dbg_gemm: the workspace has no %lld-float scratch for the weight image", need);
-        if (int r = th_pack_one(B, scratch, N, K, K, 0, st)) return r;
+        if (int r = th_pack_one(B, scratch, N, K, K, 0, st, terms)) return r;
+        ThPlanes pl{};
+        pl.terms = terms;
         if (mode == 97)
-            return th_gemm(1, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, nullptr, nullptr, 0, mask, 1, st);
+            return th_gemm(1, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, nullptr, nullptr, 0, mask, 1, st, nullptr, nullptr,
+                           nullptr, &pl);
         return th_gemm(0, M, N, K, A, nullptr, K, scratch, nullptr, C, nullptr, N, bias, nullptr, relu, nullptr, 1, st,
-                       nullptr, nullptr, mode == 98 ? reinterpret_cast<long long*>(bias_out) : nullptr);
+                       nullptr, nullptr, mode == 98 ? reinterpret_cast<long long*>(bias_out) : nullptr, &pl);
     }
     if (mode == 48 || mode == 49) {
         // weight-image product (the tf32 path of the update): Bt[N,K] is packed into a smem-tile image first (scratch from

@@ -239,12 +239,12 @@ long long th_image_floats(int N, int K);
 long long th_bits_words(long long rows, int N);
 int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
-                   cudaStream_t st);
-int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st);
+                   cudaStream_t st, int terms = 2);
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms = 2);
 // Activations kept as two fp16 planes (x ~= hi + lo / 2^11, the split of tc_gemm_h.cu) instead of one fp32 matrix: the
 // consumer's TMA writes the MMA operand tiles directly, no converter warps.  A "planes" pointer is the hi plane (passed
 // through the float* parameter), the lo plane starts *_lo_off fp16 elements after it, leading dimensions count fp16 elements.
-struct ThPlanes { int a_planes, c_planes; long long a_lo_off, c_lo_off; };
+struct ThPlanes { int a_planes, c_planes; long long a_lo_off, c_lo_off; int terms; };   // terms: 0 / 2 = fp16 hi + lo, 1 = one bf16 plane (no lo)
 int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, int lda, const float* img0, const float* img1,
             float* C0, float* C1, int ldc, const float* bias0, const float* bias1, int relu, const float* mask, int nets,
             cudaStream_t st, uint32_t* bits_out0 = nullptr, const uint32_t* bits_in = nullptr,
@@ -253,8 +253,8 @@ bool th_dw_supported(const float* X, int ldx, const float* G, int ldg);
 // x_planes / g_planes: that operand is a pair of fp16 planes (ThPlanes convention: a = X, c = G)
 int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int ldg, float* C, int ldc, float* bias_out,
                int slices, long long slice_stride, int accumulate, cudaStream_t st, const ThPlanes* planes = nullptr);
-int th_split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t st);
-int th_join_planes(const void* hi, const void* lo, long long n, float* dst, cudaStream_t st);
+int th_split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t st, int terms = 2);
+int th_join_planes(const void* hi, const void* lo, long long n, float* dst, cudaStream_t st, int terms = 2);
 // tensor-core gemm modes whose dW runs on the tf32 TMA kernel with the 512-row accumulation bound
 inline bool tc_mode(int gemm_mode) { return gemm_mode == DPPO_GEMM_TF32X3 || gemm_mode == DPPO_GEMM_FP16X2; }
 int tc_colsum(const float* G, int rows, int N, int ld, int slabs, float* out, long long slab_stride, int accumulate,

@@ -37,15 +37,15 @@ struct DwArgs {
 // XP / GP: the X / G operand is stored as fp16 hi | lo planes (written by the forward / dX epilogues of tc_gemm_h.cu): TMA
 // boxes {64 fp16 features x 32 rows, SWIZZLE_128B} ARE the MN-major operand atoms, so that operand needs no raw slot and no
 // converter pass; the bias gradient (column sums of G) is then read back from the operand tiles by the otherwise idle warps.
-template <int BN, bool XP, bool GP>
+template <int BN, bool XP, bool GP, int T = 2>
 struct DwPlan {
     static constexpr int kARaw = XP ? 0 : 32 * BM * 4;   // 4 boxes of {32 features x 32 rows} fp32
     static constexpr int kBRaw = GP ? 0 : 32 * BN * 4;
     static constexpr int kRawSlot = kARaw + kBRaw;
     static constexpr int kAHalf = 32 * BM * 2;           // fp16 hi (or lo) operand tile: BM/64 atoms x 32 k-rows x 128 B
     static constexpr int kBHalf = 32 * BN * 2;
-    static constexpr int kOpSlot = 2 * (kAHalf + kBHalf);
-    static constexpr int kPlaneBytes = (XP ? 2 * kAHalf : 0) + (GP ? 2 * kBHalf : 0);   // what TMA writes into an operand slot
+    static constexpr int kOpSlot = T * (kAHalf + kBHalf);           // [X hi | X lo | G hi | G lo] (one-term mode: [X | G], bf16)
+    static constexpr int kPlaneBytes = (XP ? T * kAHalf : 0) + (GP ? T * kBHalf : 0);   // what TMA writes into an operand slot
     static constexpr int kPC = BN < kDwPC ? BN : kDwPC;
     static constexpr int kPhases = BN / kPC;
     static constexpr int kStaging = BM * kPC * 4;
@@ -64,12 +64,14 @@ struct DwPlan {
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
-// D = f32, A = B = fp16, both MN-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n) {
-    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// D = f32, A = B = fp16 (or bf16), both MN-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int n, bool bf16 = false) {
+    return (1u << 4) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
 }
 
 // one 8-feature unit (k-row `k`, box `box`, unit `j` of the box): raw fp32 -> hi / lo chunk of the MN-major operand tile
+template <int T>
 __device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_tile, uint32_t lo_tile, int box, int j, int k,
                                                 float (&csum)[8], bool sum) {
     const uint32_t rbase = raw_op + (uint32_t)box * 4096u + (uint32_t)k * 128u;
@@ -79,21 +81,25 @@ __device__ __forceinline__ void dw_convert_unit(uint32_t raw_op, uint32_t hi_til
         csum[0] += a.x; csum[1] += a.y; csum[2] += a.z; csum[3] += a.w;
         csum[4] += b.x; csum[5] += b.y; csum[6] += b.z; csum[7] += b.w;
     }
+    const int c = (box & 1) * 4 + j;                                  // 16-B chunk of the 64-feature atom
+    const uint32_t off = (uint32_t)(box >> 1) * 4096u + (uint32_t)k * 128u + (uint32_t)((c ^ (k & 7)) << 4);
+    if (T == 1) {
+        sts128(hi_tile + off, make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w)));
+        return;
+    }
     uint4 h, l;
     split2(a.x, a.y, h.x, l.x); split2(a.z, a.w, h.y, l.y);
     split2(b.x, b.y, h.z, l.z); split2(b.z, b.w, h.w, l.w);
-    const int c = (box & 1) * 4 + j;                                  // 16-B chunk of the 64-feature atom
-    const uint32_t off = (uint32_t)(box >> 1) * 4096u + (uint32_t)k * 128u + (uint32_t)((c ^ (k & 7)) << 4);
     sts128(hi_tile + off, h);
     sts128(lo_tile + off, l);
 }
 
 struct DwMaps { CUtensorMap x, xl, g, gl; };          // fp32 matrix or hi plane, lo plane
 
-template <int BN, bool XP, bool GP>
+template <int BN, bool XP, bool GP, int T>
 __global__ void __launch_bounds__(kThreads, 1)
 h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles) {
-    using P = DwPlan<BN, XP, GP>;
+    using P = DwPlan<BN, XP, GP, T>;
     constexpr int kDwRaw = P::kDwRaw > 0 ? P::kDwRaw : 1, kDwOp = P::kDwOp;
     constexpr bool kConv = !(XP && GP);                  // some operand still arrives as fp32 and is converted here
     extern __shared__ __align__(1024) uint8_t smem[];         // SWIZZLE_128B boxes and UMMA tiles need 1024-B alignment
@@ -141,7 +147,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
         fence_barrier_init();
     }
     if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
-    constexpr uint32_t kTmemCols = 2 * BN;
+    constexpr uint32_t kTmemCols = (T * BN) < 32 ? 32 : T * BN;
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
@@ -169,7 +175,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                 const int rs = (int)(it % kDwRaw), os = (int)(it % kDwOp);
                 const uint32_t raw = raw_ring + rs * P::kRawSlot;
                 const uint32_t op = op_ring + os * P::kOpSlot;
-                const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+                const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + T * P::kAHalf, b_lo = b_hi + P::kBHalf;
                 if (kConv) {
                     mbar_wait(&raw_full[rs], (uint32_t)((it / kDwRaw) & 1));
                     mbar_wait(&op_empty[os], (uint32_t)(((it / kDwOp) & 1) ^ 1));
@@ -177,14 +183,14 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
 #pragma unroll
                         for (int u = 0; u < kAPairs; ++u) {
                             const int p = warp + u * kMoverWarps;
-                            dw_convert_unit(raw, a_hi, a_lo, p >> 2, p & 3, k, dummy, false);
+                            dw_convert_unit<T>(raw, a_hi, a_lo, p >> 2, p & 3, k, dummy, false);
                         }
                     }
                     if (!GP) {
 #pragma unroll
                         for (int u = 0; u < kBPairs; ++u) {
                             const int p = warp + u * kMoverWarps;
-                            dw_convert_unit(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, csum[u], want_bias);
+                            dw_convert_unit<T>(raw + P::kARaw, b_hi, b_lo, p >> 2, p & 3, k, csum[u], want_bias);
                         }
                     }
                     fence_proxy_async();
@@ -201,14 +207,24 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                         for (int u = 0; u < kBPairs; ++u) {
                             const int p = warp + u * kMoverWarps;          // columns [8p, 8p + 8): atom p / 8, chunk p % 8
                             const uint32_t off = (uint32_t)(p >> 3) * 4096u + (uint32_t)k * 128u + (uint32_t)((((p & 7) ^ k) & 7) << 4);
-                            const uint4 h = lds128(b_hi + off), l = lds128(b_lo + off);
-                            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                            const uint4 h = lds128(b_hi + off);
+                            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                            if (T == 1) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-                                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-                                csum[u][2 * e] += fmaf(lf.x, kLoInv, hf.x);
-                                csum[u][2 * e + 1] += fmaf(lf.y, kLoInv, hf.y);
+                                for (int e = 0; e < 4; ++e) {
+                                    csum[u][2 * e] += __uint_as_float(hw[e] << 16);
+                                    csum[u][2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u);
+                                }
+                            } else {
+                                const uint4 l = lds128(b_lo + off);
+                                const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                                    const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                                    csum[u][2 * e] += fmaf(lf.x, kLoInv, hf.x);
+                                    csum[u][2 * e + 1] += fmaf(lf.y, kLoInv, hf.y);
+                                }
                             }
                         }
                         fence_proxy_async();       // the refill of this slot is an async-proxy write behind these generic reads
@@ -284,21 +300,21 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     const int os = (int)(cp.it % kDwOp);
                     if (mbar_test(&op_empty[os], (uint32_t)(((cp.it / kDwOp) & 1) ^ 1))) {
                         const uint32_t op = op_ring + os * P::kOpSlot;
-                        const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+                        const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + T * P::kAHalf, b_lo = b_hi + P::kBHalf;
                         mbar_arrive_expect_tx(&op_full[os], (uint32_t)P::kPlaneBytes);
                         const int row = cp.k0 + cp.kb * kKB;
                         if (XP) {
 #pragma unroll
                             for (int b = 0; b < BM / 64; ++b) {
                                 tma_load_2d(a_hi + b * 4096, &maps.x, cp.mt * BM + b * 64, row, &op_full[os]);
-                                tma_load_2d(a_lo + b * 4096, &maps.xl, cp.mt * BM + b * 64, row, &op_full[os]);
+                                if (T == 2) tma_load_2d(a_lo + b * 4096, &maps.xl, cp.mt * BM + b * 64, row, &op_full[os]);
                             }
                         }
                         if (GP) {
 #pragma unroll
                             for (int b = 0; b < BN / 64; ++b) {
                                 tma_load_2d(b_hi + b * 4096, &maps.g, cp.nt * BN + b * 64, row, &op_full[os]);
-                                tma_load_2d(b_lo + b * 4096, &maps.gl, cp.nt * BN + b * 64, row, &op_full[os]);
+                                if (T == 2) tma_load_2d(b_lo + b * 4096, &maps.gl, cp.nt * BN + b * 64, row, &op_full[os]);
                             }
                         }
                         advance(cp);
@@ -309,7 +325,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_mn(BN);
+            constexpr uint32_t idesc = make_idesc_f16_mn(BN, T == 1);
             constexpr uint32_t kLbo = 4096u, kSbo = 1024u, kStep = 2048u;     // MN atoms / 8-row k groups / one UMMA_K = 16 rows
             long long it = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -322,20 +338,22 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     mbar_wait(&op_full[os], (uint32_t)((it / kDwOp) & 1));
                     tc_fence_after();
                     const uint32_t op = op_ring + os * P::kOpSlot;
-                    const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + 2 * P::kAHalf, b_lo = b_hi + P::kBHalf;
+                    const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + T * P::kAHalf, b_lo = b_hi + P::kBHalf;
 #pragma unroll
                     for (int k = 0; k < kKB / 16; ++k) {
                         const uint64_t da_hi = make_sdesc(a_hi + k * kStep, kLbo, kSbo, kLayoutSW128);
                         const uint64_t da_lo = make_sdesc(a_lo + k * kStep, kLbo, kSbo, kLayoutSW128);
                         const uint64_t db_hi = make_sdesc(b_hi + k * kStep, kLbo, kSbo, kLayoutSW128);
                         const uint64_t db_lo = make_sdesc(b_lo + k * kStep, kLbo, kSbo, kLayoutSW128);
-                        umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                        umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                        if (T == 2) {
+                            umma_f16(tmem_base + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                            umma_f16(tmem_base + BN, da_hi, db_lo, idesc, 1u);
+                        }
                         umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | k) != 0);
                     }
                     umma_commit(&op_empty[os]);
                 }
-                if (g.fold && nkb > 0) fold_issue<BN>(tmem_base, smem_base + P::kFoldOff);
+                if (T == 2 && g.fold && nkb > 0) fold_issue<BN>(tmem_base, smem_base + P::kFoldOff);
                 umma_commit(acc_full);                 // fires at once when the slice holds no rows (nkb == 0)
             }
             tc_fence_before();
@@ -369,7 +387,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     uint32_t v[32];
                     if (nkb > 0) {
                         tmem_ld32(acc + (uint32_t)col, v);
-                        if (!g.fold) {
+                        if (T == 2 && !g.fold) {
                             uint32_t w2[32];
                             tmem_ld32(acc + (uint32_t)(BN + col), w2);
 #pragma unroll
@@ -441,28 +459,33 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
     }
 }
 
-template <int BN, bool XP, bool GP>
+template <int BN, bool XP, bool GP, int T>
 static int launch_dw(const DwMaps& maps, DwArgs& g, cudaStream_t st) {
-    using P = DwPlan<BN, XP, GP>;
+    using P = DwPlan<BN, XP, GP, T>;
     g.tiles_m = (g.M + BM - 1) / BM;
     g.tiles_n = (g.N + BN - 1) / BN;
     const long long total = (long long)g.tiles_m * g.tiles_n * g.slices;
     DPPO_REQUIRE(total < (1ll << 30), "h_dw: too many work items");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_dw_kernel<BN, XP, GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_dw_kernel<BN, XP, GP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);
-    h_dw_kernel<BN, XP, GP><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
+    h_dw_kernel<BN, XP, GP, T><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
+template <int BN, int T>
+static int launch_dw_t(const DwMaps& maps, int xp, int gp, DwArgs& g, cudaStream_t st) {
+    if (xp && gp) return launch_dw<BN, true, true, T>(maps, g, st);
+    if (xp) return launch_dw<BN, true, false, T>(maps, g, st);
+    if (gp) return launch_dw<BN, false, true, T>(maps, g, st);
+    return launch_dw<BN, false, false, T>(maps, g, st);
+}
 template <int BN>
-static int launch_dw_bn(const DwMaps& maps, int xp, int gp, DwArgs& g, cudaStream_t st) {
-    if (xp && gp) return launch_dw<BN, true, true>(maps, g, st);
-    if (xp) return launch_dw<BN, true, false>(maps, g, st);
-    if (gp) return launch_dw<BN, false, true>(maps, g, st);
-    return launch_dw<BN, false, false>(maps, g, st);
+static int launch_dw_bn(const DwMaps& maps, int xp, int gp, int terms, DwArgs& g, cudaStream_t st) {
+    if (terms == 1) return launch_dw_t<BN, 1>(maps, xp, gp, g, st);
+    return launch_dw_t<BN, 2>(maps, xp, gp, g, st);
 }
 
 }  // namespace th
@@ -479,11 +502,12 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     th::DwMaps maps;
     memset(&maps, 0, sizeof(maps));
     const int xp = planes && planes->a_planes, gp = planes && planes->c_planes;
+    const int terms = (planes && planes->terms == 1) ? 1 : 2;
     if (xp) {
         const __half* hi = reinterpret_cast<const __half*>(X);
         DPPO_REQUIRE(ldx % 8 == 0 && th::aligned16(hi) && planes->a_lo_off % 8 == 0, "h_dw: fp16 planes need 16-byte aligned rows");
         DPPO_REQUIRE(th::h_make_map16(&maps.x, hi, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
-                     th::h_make_map16(&maps.xl, hi + planes->a_lo_off, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B),
+                     (terms == 1 || th::h_make_map16(&maps.xl, hi + planes->a_lo_off, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)),
                      "cuTensorMapEncodeTiled failed for the X planes [%d x %d] ld %d", K, M, ldx);
     } else {
         DPPO_REQUIRE(th::h_make_map(&maps.x, X, K, M, ldx, 32), "cuTensorMapEncodeTiled failed for X [%d x %d] ld %d", K, M, ldx);
@@ -492,7 +516,7 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
         const __half* hi = reinterpret_cast<const __half*>(G);
         DPPO_REQUIRE(ldg % 8 == 0 && th::aligned16(hi) && planes->c_lo_off % 8 == 0, "h_dw: fp16 planes need 16-byte aligned rows");
         DPPO_REQUIRE(th::h_make_map16(&maps.g, hi, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
-                     th::h_make_map16(&maps.gl, hi + planes->c_lo_off, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B),
+                     (terms == 1 || th::h_make_map16(&maps.gl, hi + planes->c_lo_off, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)),
                      "cuTensorMapEncodeTiled failed for the G planes [%d x %d] ld %d", K, N, ldg);
     } else {
         DPPO_REQUIRE(th::h_make_map(&maps.g, G, K, N, ldg, 32), "cuTensorMapEncodeTiled failed for G [%d x %d] ld %d", K, N, ldg);
@@ -507,9 +531,9 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     if (kps == 0) kps = th::kKB;
     g.k_per_slice = kps; g.slices = slices;
     g.vecC = (ldc % 4 == 0) && th::aligned16(C) && (slice_stride % 4 == 0);
-    if (N > 128) return th::launch_dw_bn<256>(maps, xp, gp, g, st);
-    if (N > 64) return th::launch_dw_bn<128>(maps, xp, gp, g, st);
-    return th::launch_dw_bn<64>(maps, xp, gp, g, st);
+    if (N > 128) return th::launch_dw_bn<256>(maps, xp, gp, terms, g, st);
+    if (N > 64) return th::launch_dw_bn<128>(maps, xp, gp, terms, g, st);
+    return th::launch_dw_bn<64>(maps, xp, gp, terms, g, st);
 }
 
 }  // namespace dppo

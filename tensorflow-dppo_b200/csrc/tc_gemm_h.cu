@@ -53,6 +53,7 @@ struct HArgs {
     int tiles_n, nets, relu, vecA, vecC, bits_wpr;
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
+    int terms;                         // 2 = fp16 hi + lo operands (three MMAs per product), 1 = bf16 operands (one MMA)
     int fold;                          // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
     int dbg;                           // DPPO_H_DBG: timing-only ablations (WRONG results), tools/h_ablate.py
 };
@@ -67,18 +68,20 @@ enum { C_STG = 0,        // st.global write-out (fp32)
        C_TMA = 1,        // fp32 boxes by TMA store
        C_PLANES = 2 };   // fp16 hi | lo planes by TMA store (the next product's A_PLANES operand, the dW kernel's plane operands)
 
-template <int BN, int AMODE = A_RAW>
+// T = terms per operand: 2 = fp16 hi + lo (fp32-accurate, three MMAs per product), 1 = one bf16 (DPPO_GEMM_BF16, one MMA)
+template <int BN, int AMODE = A_RAW, int T = 2>
 struct HPlan {
-    static constexpr int kBSlots = 3;
+    static constexpr int kBSlots = T == 1 ? 4 : 3;
     // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight.
     // With fp16 planes there is no raw ring and no converter hand-off: its bytes go to a deeper operand ring.
-    static constexpr int kASlots = AMODE == A_PLANES ? (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8))
-                                                     : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
-    static constexpr int kRSlots = AMODE == A_PLANES ? 0 : (BN >= 256 ? 2 : (BN >= 128 ? 4 : 6));
+    static constexpr int kASlots2 = AMODE == A_PLANES ? (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8))
+                                                      : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
+    static constexpr int kASlots = T == 1 ? (2 * kASlots2 > 8 ? 8 : 2 * kASlots2) : kASlots2;    // (half-size slots in one-term mode)
+    static constexpr int kRSlots = AMODE == A_PLANES ? 0 : (BN >= 256 ? (T == 1 ? 3 : 2) : (BN >= 128 ? 4 : 6));
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
-    static constexpr int kASlot = 2 * kAHalf;
+    static constexpr int kASlot = T * kAHalf;
     static constexpr int kBHalf = BN * 64;
-    static constexpr int kBSlot = 2 * kBHalf;
+    static constexpr int kBSlot = T * kBHalf;
     static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
     static constexpr int kPhases = BN / kPhaseCols;
     static constexpr int kStaging = BM * kPhaseCols * 4;
@@ -87,7 +90,8 @@ struct HPlan {
     static constexpr int kBOff = kRawOff + kRSlots * kRawSlot;
     static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
-    static constexpr int kFoldOff = kBarOff + 256;            // the two fold patterns (tc_h.cuh)
+    static constexpr int kFoldOff = kBarOff + 512;            // the two fold patterns (tc_h.cuh)
+    static_assert((2 * kASlots + 2 * kBSlots + 2 * kRSlots + 4) * 8 + 4 <= 512, "barrier block");
     static constexpr int kBiasOff = kFoldOff + kFoldBytes;    // the tile's bias vector (TMA write-out epilogue)
     static constexpr int kBytes = kBiasOff + BN * 4;
     static_assert(kStgOff % 1024 == 0, "staging boxes are SWIZZLE_128B");
@@ -144,6 +148,22 @@ __device__ __forceinline__ void mover_store(const MoverRegs& r, uint32_t hi_tile
     mover_store_split(o, hi_tile, lo_tile, tid);
 }
 
+// one-term mode: the two units as bf16 (round to nearest) into the single operand tile
+__device__ __forceinline__ void mover_pack_bf16(const MoverRegs& r, OperandRegs& o) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float4 a = r.v[j][0], b = r.v[j][1];
+        o.h[j] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    }
+}
+__device__ __forceinline__ void mover_store_packed(const OperandRegs& o, uint32_t tile, int tid) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int row = (tid >> 2) + j * 64, c = tid & 3;
+        sts128(tile + (uint32_t)row * 64u + (uint32_t)((c ^ ((row >> 1) & 3)) << 4), o.h[j]);     // SWIZZLE_64B
+    }
+}
+
 // timing ablation: the same stores without the fp32 -> fp16 split (bit patterns, wrong values)
 __device__ __forceinline__ void mover_store_raw(const MoverRegs& r, uint32_t hi_tile, uint32_t lo_tile, int tid) {
 #pragma unroll
@@ -169,18 +189,18 @@ __device__ __forceinline__ void raw_load(MoverRegs& r, uint32_t raw_tile, int ti
 
 // The accumulators of a tile: main (hi.hi) and correction (lo.hi + hi.lo, scaled 2^11), BN columns each.  Tiles of up to 128
 // columns leave room for TWO such stages in the 512 TMEM columns: the MMAs of tile i+1 run while tile i is drained.
-template <int BN> struct HAcc { static constexpr int kStages = BN >= 256 ? 1 : 2; };
+template <int BN, int T> struct HAcc { static constexpr int kStages = (T == 2 && BN >= 256) ? 1 : 2; };
 
 // the tensor maps of one launch: [net] x {fp32 matrix or hi plane, lo plane}
 struct HMaps { CUtensorMap a[2], al[2], c[2], cl[2]; };
 
-template <int BN, int EPI, int AMODE, int CMODE>
+template <int BN, int EPI, int AMODE, int CMODE, int T>
 __global__ void __launch_bounds__(kThreads, 1)
 h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles) {
-    using P = HPlan<BN, AMODE>;
+    using P = HPlan<BN, AMODE, T>;
     constexpr bool TMA_A = (AMODE == A_RAW);
     constexpr bool TMA_C = (CMODE != C_STG);
-    constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots, kAcc = HAcc<BN>::kStages;
+    constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots, kAcc = HAcc<BN, T>::kStages;
     extern __shared__ __align__(1024) uint8_t smem[];         // SWIZZLE_128B boxes and UMMA tiles need 1024-B alignment
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t a_ring = smem_base, raw_ring = smem_base + P::kRawOff, b_ring = smem_base + P::kBOff;
@@ -213,7 +233,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
         fence_barrier_init();
     }
     if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
-    constexpr uint32_t kStageCols = 2 * BN;         // [0,BN) main, [BN,2BN) correction
+    constexpr uint32_t kStageCols = T * BN;         // [0,BN) main, [BN,2BN) correction (two-term mode)
     constexpr uint32_t kTmemCols = kAcc * kStageCols;
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
@@ -250,14 +270,15 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                 // barrier arrive alone does not keep it behind this thread's still outstanding generic-proxy reads.
                 // Releasing straight after issuing the loads let TMA overwrite rows that had not been read yet (seen as
                 // "k-block kb+2 instead of kb" in rows of a tile's first k-blocks whenever the epilogue kept the LSU busy).
-                mover_split(r, o);
+                if (T == 2) mover_split(r, o); else mover_pack_bf16(r, o);
                 if (!(g.dbg & DBG_NO_A) && !old_order) {
                     fence_proxy_async();
                     warp_arrive(&raw_empty[rs], lane);
                 }
                 mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
                 const uint32_t slot = a_ring + sa * P::kASlot;
-                if (g.dbg & DBG_NO_SPLIT) mover_store_raw(r, slot, slot + P::kAHalf, tid);
+                if (T == 1) mover_store_packed(o, slot, tid);
+                else if (g.dbg & DBG_NO_SPLIT) mover_store_raw(r, slot, slot + P::kAHalf, tid);
                 else mover_store_split(o, slot, slot + P::kAHalf, tid);
                 if (!(g.dbg & DBG_NO_FENCE)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
                 warp_arrive(&full_a[sa], lane);
@@ -281,7 +302,8 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                         const int sa = (int)(it % kASlots);
                         mbar_wait(&empty_a[sa], (uint32_t)(((it / kASlots) & 1) ^ 1));
                         const uint32_t slot = a_ring + sa * P::kASlot;
-                        mover_store(ra[j], slot, slot + P::kAHalf, tid);
+                        if (T == 1) { OperandRegs o1; mover_pack_bf16(ra[j], o1); mover_store_packed(o1, slot, tid); }
+                        else mover_store(ra[j], slot, slot + P::kAHalf, tid);
                         fence_proxy_async();
                         warp_arrive(&full_a[sa], lane);
                         if (it + kPrefetch < total_it) issue(ra[j], it + kPrefetch);
@@ -304,11 +326,11 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
             start(pb); start(pa);
             if (g.dbg & DBG_NO_W) pb.i = my_tiles;
             if (AMODE == A_LDG || (g.dbg & DBG_NO_A)) pa.i = my_tiles;
-            const uint8_t* img_base[2] = {g.Bimg[0] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes,
-                                          g.Bimg[1] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes};
+            const uint8_t* img0 = g.Bimg[0] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes;
+            const uint8_t* img1 = g.Bimg[1] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes;
             while (pb.i < my_tiles || pa.i < my_tiles) {
                 if (pb.i < my_tiles && mbar_test(&empty_b[pb.slot], pb.phase)) {
-                    const uint8_t* img = img_base[pb.net] + ((size_t)pb.nt * nkb + (size_t)pb.kb) * P::kBSlot;
+                    const uint8_t* img = (pb.net ? img1 : img0) + ((size_t)pb.nt * nkb + (size_t)pb.kb) * P::kBSlot;
                     mbar_arrive_expect_tx(&full_b[pb.slot], (uint32_t)P::kBSlot);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"(b_ring + pb.slot * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[pb.slot]))
@@ -320,7 +342,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                         const uint32_t slot = a_ring + pa.slot * P::kASlot;
                         mbar_arrive_expect_tx(&full_a[pa.slot], (uint32_t)P::kASlot);
                         tma_load_2d(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
-                        tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                        if (T == 2) tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
                         advance(pa, kASlots);
                     }
                 } else if (AMODE == A_RAW) {
@@ -335,7 +357,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BN);
+            constexpr uint32_t idesc = make_idesc_f16(BN, BM, T == 1);
             int sa = 0, sb = 0;
             uint32_t pha = 0u, phb = 0u;
             for (int i = 0; i < my_tiles; ++i) {
@@ -356,7 +378,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                         const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
-                        if (!(g.dbg & DBG_ONE_MMA)) {
+                        if (T == 2 && !(g.dbg & DBG_ONE_MMA)) {
                             umma_f16(acc + BN, da_lo, db_hi, idesc, (kb | k) != 0);
                             umma_f16(acc + BN, da_hi, db_lo, idesc, 1u);
                         }
@@ -367,7 +389,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     if (++sa == kASlots) { sa = 0; pha ^= 1u; }
                     if (++sb == kBSlots) { sb = 0; phb ^= 1u; }
                 }
-                if (g.fold) fold_issue<BN>(acc, smem_base + P::kFoldOff);
+                if (T == 2 && g.fold) fold_issue<BN>(acc, smem_base + P::kFoldOff);
                 umma_commit(&acc_full[as]);                 // accumulators of tile i complete
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 1] = clock64();
             }
@@ -425,7 +447,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     epi_bar();
                 }
                 uint32_t v[32];
-                if (!g.fold) {
+                if (T == 2 && !g.fold) {
                     uint32_t w2[32];
                     tmem_ld32x2(acc + (uint32_t)col, v, acc + (uint32_t)(BN + col), w2);
 #pragma unroll
@@ -480,6 +502,14 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
                         sts128f(buf + row_off + (uint32_t)(((j4 ^ r) & 7) << 4), make_float4(f[j4 * 4 + 0], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]));
+                } else if (T == 1) {
+                    // one bf16 plane: 64 B of this row in the {64 bf16 x 128 rows} SWIZZLE_128B box
+                    const uint32_t hb = stg + (gsp % kBufs) * (uint32_t)(BM * 64 * 4) + row_off;
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        sts128(hb + (uint32_t)((((ch * 4 + j4) ^ r) & 7) << 4),
+                               make_uint4(pack_bf16(f[j4 * 8 + 0], f[j4 * 8 + 1]), pack_bf16(f[j4 * 8 + 2], f[j4 * 8 + 3]),
+                                          pack_bf16(f[j4 * 8 + 4], f[j4 * 8 + 5]), pack_bf16(f[j4 * 8 + 6], f[j4 * 8 + 7])));
                 } else {
                     // fp16 planes: 64 B of this row in the hi box and in the lo box ({64 fp16 x 128 rows}, SWIZZLE_128B); the split
                     // is the one the next product's converters would have applied to the fp32 value, so results do not change
@@ -505,7 +535,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                         if (n0 + 32 < g.N && !(g.dbg & DBG_NO_STORE)) tma_store_2d(mapC, b0 + (uint32_t)(BM * 128), n0 + 32, mt * BM);
                     } else if (n0 < g.N && !(g.dbg & DBG_NO_STORE)) {
                         tma_store_2d(mapC, b0, n0, mt * BM);
-                        tma_store_2d(mapCl, b0 + (uint32_t)(BM * 128), n0, mt * BM);
+                        if (T == 2) tma_store_2d(mapCl, b0 + (uint32_t)(BM * 128), n0, mt * BM);
                     }
                     bulk_commit();
                 }
@@ -546,7 +576,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     const int col = p * PC + ch * kDrainCols + cb;
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)col, v);
-                    if (!g.fold) {                                  // warp-uniform: main + correction / 2^11 here, not on the tensor core
+                    if (T == 2 && !g.fold) {                        // warp-uniform: main + correction / 2^11 here, not on the tensor core
                         uint32_t w2[32];
                         tmem_ld32(acc + (uint32_t)(BN + col), w2);
 #pragma unroll
@@ -647,7 +677,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
 
 // ---- weight images: per (n-tile, k-block) the fp16 hi tile then the lo tile, K-major SWIZZLE_64B, exactly as the MMA
 // reads them from shared memory -> one cp.async.bulk per k-block ----
-struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn; };
+struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn, terms; };
 struct HImgPlan { int n; HImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
 
 __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
@@ -668,16 +698,22 @@ __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
             v[q] = (n < e.N && k < e.K) ? (e.transposed ? __ldg(e.src + (size_t)k * e.ld + n) : __ldg(e.src + (size_t)n * e.ld + k)) : 0.f;
         }
         uint4 h, l;
-        split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
+        if (e.terms == 1) {
+            h = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            l = h;
+        } else {
+            split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
+        }
         const size_t ntiles = (size_t)((e.N + e.bn - 1) / e.bn);
-        const size_t half = (size_t)e.bn * 64;                  // a tile image = [hi (bn rows x 64 B) | lo]
-        const size_t replica_bytes = ntiles * kbs * 2 * half;
+        const size_t half = (size_t)e.bn * 64;                  // a tile image = [hi (bn rows x 64 B) | lo]  (one-term mode: hi only)
+        const size_t tile_bytes = (size_t)e.terms * half;
+        const size_t replica_bytes = ntiles * kbs * tile_bytes;
         const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
 #pragma unroll
         for (int rep = 0; rep < kImgReplicas; ++rep) {
-            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * 2 * half;
+            uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * tile_bytes;
             *reinterpret_cast<uint4*>(tile + off) = h;
-            *reinterpret_cast<uint4*>(tile + half + off) = l;
+            if (e.terms == 2) *reinterpret_cast<uint4*>(tile + half + off) = l;
         }
     }
 }
@@ -689,19 +725,24 @@ static bool tmac_enabled() {
     return v == 1;
 }
 
-template <int BN, int EPI, int AMODE, int CMODE>
-static int launch_h2(const HMaps& maps, HArgs& g, cudaStream_t st) {
-    using P = HPlan<BN, AMODE>;
+template <int BN, int EPI, int AMODE, int CMODE, int T>
+static int launch_h3(const HMaps& maps, HArgs& g, cudaStream_t st) {
+    using P = HPlan<BN, AMODE, T>;
     const long long total = (long long)((g.M + BM - 1) / BM) * g.tiles_n * g.nets;
     DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, AMODE, CMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, AMODE, CMODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
     const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
     ProfScope ps(KK_TC_GEMM, st);
-    h_gemm_kernel<BN, EPI, AMODE, CMODE><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
+    h_gemm_kernel<BN, EPI, AMODE, CMODE, T><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
     DPPO_LAUNCH_CHECK();
     return 0;
+}
+template <int BN, int EPI, int AMODE, int CMODE>
+static int launch_h2(const HMaps& maps, HArgs& g, cudaStream_t st) {
+    if (g.terms == 1) return launch_h3<BN, EPI, AMODE, CMODE, 1>(maps, g, st);
+    return launch_h3<BN, EPI, AMODE, CMODE, 2>(maps, g, st);
 }
 
 template <int BN, int EPI, int AMODE>
@@ -723,7 +764,7 @@ static int launch_h(HArgs& g, const ThPlanes& pl, cudaStream_t st) {
             const __half* hi = reinterpret_cast<const __half*>(g.A[n]);
             DPPO_REQUIRE(g.lda % 8 == 0 && aligned16(hi) && pl.a_lo_off % 8 == 0, "h_gemm: fp16 planes need 16-byte aligned rows");
             DPPO_REQUIRE(h_make_map16(&maps.a[n], hi, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B) &&
-                         h_make_map16(&maps.al[n], hi + pl.a_lo_off, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B),
+                         (g.terms == 1 || h_make_map16(&maps.al[n], hi + pl.a_lo_off, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B)),
                          "cuTensorMapEncodeTiled failed for the A planes [%d x %d]", g.M, g.K);
         }
         amode = A_PLANES;
@@ -738,7 +779,7 @@ static int launch_h(HArgs& g, const ThPlanes& pl, cudaStream_t st) {
             __half* hi = reinterpret_cast<__half*>(g.C[n]);
             DPPO_REQUIRE(g.ldc % 8 == 0 && aligned16(hi) && pl.c_lo_off % 8 == 0, "h_gemm: fp16 planes need 16-byte aligned rows");
             DPPO_REQUIRE(h_make_map16(&maps.c[n], hi, g.M, g.N, g.ldc, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
-                         h_make_map16(&maps.cl[n], hi + pl.c_lo_off, g.M, g.N, g.ldc, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B),
+                         (g.terms == 1 || h_make_map16(&maps.cl[n], hi + pl.c_lo_off, g.M, g.N, g.ldc, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B)),
                          "cuTensorMapEncodeTiled failed for the C planes [%d x %d]", g.M, g.N);
         }
         cmode = C_PLANES;
@@ -753,18 +794,24 @@ static int launch_h(HArgs& g, const ThPlanes& pl, cudaStream_t st) {
 }
 
 // ---- fp32 <-> fp16 hi | lo planes (the split the converters apply; tests and one-off conversions) ----
-__global__ void split_planes_kernel(const float* __restrict__ src, long long n, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void split_planes_kernel(const float* __restrict__ src, long long n, __half* __restrict__ hi, __half* __restrict__ lo, int terms) {
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (long long)gridDim.x * blockDim.x * 2) {
         const float a = src[i], b = (i + 1 < n) ? src[i + 1] : 0.f;
         uint32_t h, l;
+        if (terms == 1) {                                    // one bf16 plane
+            h = pack_bf16(a, b);
+            if (i + 1 < n) *reinterpret_cast<uint32_t*>(hi + i) = h;
+            else hi[i] = __ushort_as_half((unsigned short)(h & 0xffffu));
+            continue;
+        }
         split2(a, b, h, l);
         if (i + 1 < n) { *reinterpret_cast<uint32_t*>(hi + i) = h; *reinterpret_cast<uint32_t*>(lo + i) = l; }
         else { hi[i] = __ushort_as_half((unsigned short)(h & 0xffffu)); lo[i] = __ushort_as_half((unsigned short)(l & 0xffffu)); }
     }
 }
-__global__ void join_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n, float* __restrict__ dst) {
+__global__ void join_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n, float* __restrict__ dst, int terms) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dst[i] = fmaf(__half2float(lo[i]), kLoInv, __half2float(hi[i]));
+        dst[i] = terms == 1 ? __uint_as_float((uint32_t)__half_as_ushort(hi[i]) << 16) : fmaf(__half2float(lo[i]), kLoInv, __half2float(hi[i]));
 }
 
 }  // namespace th
@@ -779,10 +826,10 @@ static int th_wide_min_k() {
 }
 static inline int th_bn_for(int n, int k) { return n > 128 ? (k >= th_wide_min_k() ? 256 : 128) : (n > 64 ? 128 : 64); }
 
-// bytes of one replica of the weight image of B[N,K]
-static long long th_image_replica_bytes(int N, int K) {
+// bytes of one replica of the weight image of B[N,K] (terms = 2: fp16 hi | lo tiles, 1: bf16 tiles)
+static long long th_image_replica_bytes(int N, int K, int terms = 2) {
     const int bn = th_bn_for(N, K);
-    return (long long)((N + bn - 1) / bn) * ((K + th::kKB - 1) / th::kKB) * bn * 64 * 2;
+    return (long long)((N + bn - 1) / bn) * ((K + th::kKB - 1) / th::kKB) * bn * 64 * terms;
 }
 long long th_image_floats(int N, int K) { return th::kImgReplicas * th_image_replica_bytes(N, K) / 4; }
 long long th_bits_words(long long rows, int N) { return rows * ((N + 31) / 32); }
@@ -791,14 +838,14 @@ long long th_bits_words(long long rows, int N) { return rows * ((N + 31) / 32); 
 // (img_* are arrays of L+1 device pointers; nullptr = skip).
 int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
-                   cudaStream_t st) {
+                   cudaStream_t st, int terms) {
     th::HImgPlan p; p.n = 0;
     long long units = 0;
     auto add = [&](const float* src, float* dst, int N, int K, int ld, int transposed) {
         if (!src || !dst) return;
         th::HImgEntry& e = p.e[p.n];
         e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed;
-        e.bn = th_bn_for(N, K);
+        e.bn = th_bn_for(N, K); e.terms = terms == 1 ? 1 : 2;
         units += (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
         p.unit_end[p.n++] = units;
     };
@@ -820,10 +867,11 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
 }
 
 // one image from a [N,K] (transposed = 0) or [K,N] (transposed = 1) matrix with row stride ld
-int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st) {
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms) {
     th::HImgPlan p; p.n = 1;
     th::HImgEntry& e = p.e[0];
     e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N, K);
+    e.terms = terms == 1 ? 1 : 2;
     const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
     p.unit_end[0] = units;
     int grid = (int)((units + 255) / 256);
@@ -852,7 +900,8 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     ThPlanes pl{};
     if (planes) pl = *planes;
     g.bits_wpr = (N + 31) / 32;
-    g.img_replica_bytes = th_image_replica_bytes(N, K);
+    g.terms = pl.terms == 1 ? 1 : 2;
+    g.img_replica_bytes = th_image_replica_bytes(N, K, g.terms);
     g.timeline = timeline;
     g.fold = th::fold_enabled() ? 1 : 0;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
@@ -870,21 +919,21 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
 }
 
 // x[n] fp32 -> hi[n] | lo[n] fp16 planes and back (x ~= hi + lo / 2^11)
-int th_split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t st) {
+int th_split_planes(const float* src, long long n, void* hi, void* lo, cudaStream_t st, int terms) {
     if (n <= 0) return 0;
     long long blocks = (n / 2 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     ProfScope ps(KK_MISC, st);
-    th::split_planes_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(src, n, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo));
+    th::split_planes_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(src, n, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), terms);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
-int th_join_planes(const void* hi, const void* lo, long long n, float* dst, cudaStream_t st) {
+int th_join_planes(const void* hi, const void* lo, long long n, float* dst, cudaStream_t st, int terms) {
     if (n <= 0) return 0;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     ProfScope ps(KK_MISC, st);
-    th::join_planes_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), n, dst);
+    th::join_planes_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __half*>(hi), reinterpret_cast<const __half*>(lo), n, dst, terms);
     DPPO_LAUNCH_CHECK();
     return 0;
 }

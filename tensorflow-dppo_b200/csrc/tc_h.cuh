@@ -4,6 +4,7 @@
 #include "tc_ptx.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace dppo {
@@ -28,9 +29,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// D = f32, A = B = fp16 (format 0), both K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = BM) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// D = f32, A = B = fp16 (format 0) or bf16 (format 1), both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = BM, bool bf16 = false) {
+    return (1u << 4) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // shared-memory accesses by 32-bit shared-space address (a pointer derived from the aligned dynamic buffer is a GENERIC
 // pointer to the compiler, which then emits generic LD/ST)
@@ -75,6 +76,12 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ONE-TERM mode (DPPO_GEMM_BF16, config 4): every operand is a single bf16 (round to nearest), one MMA per product
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // ---- folding the correction accumulator into the main one ON THE TENSOR CORE ---------------------------------------

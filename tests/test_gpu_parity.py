@@ -991,6 +991,44 @@ def test_h_dw_fp16_planes(M, N, Kr, mode):
     assert torch.equal(got, got0)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (1000, 256, 376), (777, 256, 256), (129, 200, 40), (4096, 64, 256),
+                                   (300, 128, 64), (3000, 1024, 1024)])
+def test_h_gemm_one_term_bf16(M, N, K):
+    """The persistent kernels in their one-term mode (DPPO_GEMM_BF16 at config 4): bf16 operands, one MMA per product,
+    double-buffered TMEM.  fp32 in / out (converters, modes 196 / 197): exact vs an fp64 product of the bf16-rounded operands;
+    planes in / out (194 / 195): the result is additionally rounded to one bf16 plane."""
+    rng = np.random.default_rng(M * 5 + N * 3 + K + 1)
+    eng = _engine(376, (1024, 1024), 17, max(M, 8192), gemm_mode=1)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bt = (rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32); mask = rng.standard_normal((M, N)).astype(np.float32)
+    ref = _bf16(A) @ _bf16(Bt).T
+    got = eng.dbg_gemm(196, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    assert rel_err(got, np.maximum(ref + bias, 0)) < 3e-6
+    got = eng.dbg_gemm(197, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    assert rel_err(got, ref * (mask > 0)) < 3e-6
+    got = eng.dbg_gemm(194, dev(A), dev(Bt), M, N, K, bias=dev(bias), relu=True).cpu().numpy()
+    want = np.maximum(ref + bias, 0)
+    assert np.array_equal(got, _bf16(got).astype(np.float32)) and rel_err(got, want) < 4e-3        # one bf16 rounding of C
+    got = eng.dbg_gemm(195, dev(A), dev(Bt), M, N, K, mask=dev(mask)).cpu().numpy()
+    assert rel_err(got, ref * (mask > 0)) < 4e-3
+
+
+@pytest.mark.parametrize("mode", [199, 201, 202, 203])
+@pytest.mark.parametrize("M,N,Kr", [(128, 256, 32), (376, 256, 1000), (256, 40, 2048), (120, 64, 333), (256, 256, 4096),
+                                    (1024, 1024, 2048)])
+def test_h_dw_one_term_bf16(M, N, Kr, mode):
+    """tc_dw_h.cu in one-term mode: bf16 operands (fp32 converted by the converter warps, or bf16 planes), fp32 accumulate."""
+    rng = np.random.default_rng(M + 3 * N + 7 * Kr + 1)
+    eng = _engine(376, (1024, 1024), 17, 8192, gemm_mode=1)
+    X = rng.standard_normal((Kr, M)).astype(np.float32)
+    G = rng.standard_normal((Kr, N)).astype(np.float32)
+    got, bias = eng.dbg_gemm(mode, dev(X), dev(G), M, N, Kr, want_bias_out=True)
+    assert rel_err(got.cpu().numpy(), _bf16(X).T @ _bf16(G)) < 3e-6
+    g_seen = _bf16(G) if mode in (201, 203) else G.astype(np.float64)      # planes hold the rounded values
+    assert rel_err(bias.cpu().numpy(), g_seen.sum(0)) < 3e-6
+
+
 @pytest.mark.parametrize("obs,hidden,A,T,N", [(376, (256, 256), 17, 64, 48), (17, (256, 256), 6, 128, 16), (24, (64,), 4, 100, 9),
                                              (376, (1024, 1024, 1024, 1024), 17, 32, 16)])
 def test_fp16x2_planes_equal_fp32_activations(obs, hidden, A, T, N, monkeypatch):
