@@ -41,6 +41,7 @@ namespace th {
 
 constexpr int kPrefetch = 3;                                 // activation k-blocks in flight per mover thread
 constexpr int kImgReplicas = 8;                              // copies of every weight image (spreads the hot L2 lines)
+constexpr int kPeerSlots = 8;                                // CTA pairs: ring of "the peer's slots are full" barriers in the leader
 
 enum { EPI_NN = 0, EPI_NT = 1 };
 
@@ -69,18 +70,28 @@ enum { C_STG = 0,        // st.global write-out (fp32)
        C_PLANES = 2 };   // fp16 hi | lo planes by TMA store (the next product's A_PLANES operand, the dW kernel's plane operands)
 
 // T = terms per operand: 2 = fp16 hi + lo (fp32-accurate, three MMAs per product), 1 = one bf16 (DPPO_GEMM_BF16, one MMA)
-template <int BN, int AMODE = A_RAW, int T = 2>
+// PAIR: two CTAs of a cluster work on a 256-row super-tile with cta_group::2 MMAs (M = 256): each CTA streams its own 128
+// activation rows and HALF of the weight tile's rows, so the weight bytes an SM pulls from L2 halve -- the single-CTA kernel
+// is bound by exactly that (48 KB per k-block at ~46 B/clk against 768 MMA cycles).  The leader (cluster rank 0) issues every
+// MMA once both CTAs' slots are full -- every TMA load of either CTA counts its bytes on the LEADER's full barrier
+// (cp.async.bulk.tensor .cta_group::2; a software relay of the peer's barriers cost ~900 cycles per remote arrive and left
+// the pair slower than two single CTAs) --, releases slots and publishes accumulators with multicast commits; each CTA drains
+// its own TMEM rows.  Pairs take fp16-plane (TMA-written) activation operands only.
+template <int BN, int AMODE = A_RAW, int T = 2, bool PAIR = false>
 struct HPlan {
-    static constexpr int kBSlots = T == 1 ? 4 : 3;
+    // (a pair runs ONE ring: the activation and weight slots of a k-block are released together by a single multicast commit)
+    static constexpr int kPairSlots = AMODE == A_PLANES ? (T == 1 ? 8 : 5) : (T == 1 ? 4 : 3);
+    static constexpr int kBSlots = PAIR ? kPairSlots : (T == 1 ? 4 : 3);
     // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight.
     // With fp16 planes there is no raw ring and no converter hand-off: its bytes go to a deeper operand ring.
     static constexpr int kASlots2 = AMODE == A_PLANES ? (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8))
                                                       : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
-    static constexpr int kASlots = T == 1 ? (2 * kASlots2 > 8 ? 8 : 2 * kASlots2) : kASlots2;    // (half-size slots in one-term mode)
-    static constexpr int kRSlots = AMODE == A_PLANES ? 0 : (BN >= 256 ? (T == 1 ? 3 : 2) : (BN >= 128 ? 4 : 6));
+    static constexpr int kASlots = PAIR ? kPairSlots : (T == 1 ? (2 * kASlots2 > 8 ? 8 : 2 * kASlots2) : kASlots2);    // (half-size slots in one-term mode)
+    static constexpr int kRSlots = AMODE == A_PLANES ? 0 : (PAIR ? kPairSlots : (BN >= 256 ? (T == 1 ? 3 : 2) : (BN >= 128 ? 4 : 6)));
     static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
     static constexpr int kASlot = T * kAHalf;
-    static constexpr int kBHalf = BN * 64;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;        // a CTA of a pair holds half of the weight tile's rows
+    static constexpr int kBHalf = kBRows * 64;
     static constexpr int kBSlot = T * kBHalf;
     static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
     static constexpr int kPhases = BN / kPhaseCols;
@@ -91,7 +102,7 @@ struct HPlan {
     static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
     static constexpr int kFoldOff = kBarOff + 512;            // the two fold patterns (tc_h.cuh)
-    static_assert((2 * kASlots + 2 * kBSlots + 2 * kRSlots + 4) * 8 + 4 <= 512, "barrier block");
+    static_assert((2 * kASlots + 2 * kBSlots + 2 * kRSlots + 4 + kPeerSlots) * 8 + 4 <= 512, "barrier block");
     static constexpr int kBiasOff = kFoldOff + kFoldBytes;    // the tile's bias vector (TMA write-out epilogue)
     static constexpr int kBytes = kBiasOff + BN * 4;
     static_assert(kStgOff % 1024 == 0, "staging boxes are SWIZZLE_128B");
@@ -192,12 +203,12 @@ __device__ __forceinline__ void raw_load(MoverRegs& r, uint32_t raw_tile, int ti
 template <int BN, int T> struct HAcc { static constexpr int kStages = (T == 2 && BN >= 256) ? 1 : 2; };
 
 // the tensor maps of one launch: [net] x {fp32 matrix or hi plane, lo plane}
-struct HMaps { CUtensorMap a[2], al[2], c[2], cl[2]; };
+struct HMaps { CUtensorMap a[2], al[2], c[2], cl[2], b[2]; };      // b: the weight images as [rows of 64 B] (CTA pairs only)
 
-template <int BN, int EPI, int AMODE, int CMODE, int T>
+template <int BN, int EPI, int AMODE, int CMODE, int T, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles) {
-    using P = HPlan<BN, AMODE, T>;
+    using P = HPlan<BN, AMODE, T, PAIR>;
     constexpr bool TMA_A = (AMODE == A_RAW);
     constexpr bool TMA_C = (CMODE != C_STG);
     constexpr int kBSlots = P::kBSlots, kASlots = P::kASlots, kRSlots = P::kRSlots, kAcc = HAcc<BN, T>::kStages;
@@ -213,29 +224,36 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
     uint64_t* raw_empty = raw_full + kRSlots;
     uint64_t* acc_full = raw_empty + kRSlots;
     uint64_t* acc_empty = acc_full + kAcc;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+    uint64_t* peer_full = acc_empty + kAcc;         // PAIR, leader only: "the peer's slots of iteration it are full"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + kPeerSlots);
     float* s_bias = reinterpret_cast<float*>(smem + P::kBiasOff);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (g.K + kKB - 1) / kKB;
-    const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int t_begin = (int)blockIdx.x * per_cta;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int n_groups = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;         // a group = one CTA, or one CTA pair
+    const int group = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    const int per_cta = (total_tiles + n_groups - 1) / n_groups;
+    const int t_begin = group * per_cta;
     const int t_end = min(total_tiles, t_begin + per_cta);
     const int my_tiles = max(0, t_end - t_begin);
     const long long total_it = (long long)my_tiles * nkb;
 
     if (tid == 0) {
         if (smem_base & 1023u) __trap();
-        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], AMODE == A_PLANES ? 1 : kMoverWarps); mbar_init(&empty_a[s], 1); }
+        // (pair: the leader's two streams -- activations, weights -- each post the bytes of BOTH CTAs on full_a)
+        for (int s = 0; s < kASlots; ++s) { mbar_init(&full_a[s], PAIR ? 2 : (AMODE == A_PLANES ? 1 : kMoverWarps)); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < kRSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kMoverWarps); }
-        for (int s = 0; s < kAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+        for (int s = 0; s < kAcc; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps); }
+        for (int s = 0; s < kPeerSlots; ++s) mbar_init(&peer_full[s], 1);
         fence_barrier_init();
     }
+    if (PAIR) cluster_sync_all();                   // both CTAs' barriers exist before anything arrives on them remotely
     if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
     constexpr uint32_t kStageCols = T * BN;         // [0,BN) main, [BN,2BN) correction (two-term mode)
     constexpr uint32_t kTmemCols = kAcc * kStageCols;
-    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == kMmaWarp) { if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -245,6 +263,12 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
     auto decode = [&](int t, int& mt, int& net, int& nt) {
         nt = t % g.tiles_n; t /= g.tiles_n;
         net = t % g.nets; mt = t / g.nets;
+        if (PAIR) mt = mt * 2 + (int)rank;          // the pair's 256-row super-tile: rank r takes rows [r*128, r*128+128)
+    };
+    // the epilogue's "this tile has left TMEM": in a pair both CTAs report to the leader, whose MMA thread waits for it
+    auto release_acc = [&](int as) {
+        if (PAIR && rank != 0) mbar_arrive_remote(mapa_u32(smem_u32(&acc_empty[as]), 0));
+        else mbar_arrive(&acc_empty[as]);
     };
 
     if (warp < kMoverWarps) {
@@ -326,23 +350,45 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
             start(pb); start(pa);
             if (g.dbg & DBG_NO_W) pb.i = my_tiles;
             if (AMODE == A_LDG || (g.dbg & DBG_NO_A)) pa.i = my_tiles;
-            const uint8_t* img0 = g.Bimg[0] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes;
-            const uint8_t* img1 = g.Bimg[1] + (size_t)(blockIdx.x % kImgReplicas) * g.img_replica_bytes;
+            uint32_t full_leader[PAIR ? kASlots : 1];              // pair: the leader's full barriers (cluster addresses)
+            if (PAIR) {
+#pragma unroll
+                for (int s2 = 0; s2 < kASlots; ++s2) full_leader[s2] = mapa_u32(smem_u32(&full_a[s2]), 0);
+            }
+            const uint8_t* img0 = g.Bimg[0] + (size_t)(group % kImgReplicas) * g.img_replica_bytes;
+            const uint8_t* img1 = g.Bimg[1] + (size_t)(group % kImgReplicas) * g.img_replica_bytes;
             while (pb.i < my_tiles || pa.i < my_tiles) {
-                if (pb.i < my_tiles && mbar_test(&empty_b[pb.slot], pb.phase)) {
-                    const uint8_t* img = (pb.net ? img1 : img0) + ((size_t)pb.nt * nkb + (size_t)pb.kb) * P::kBSlot;
-                    mbar_arrive_expect_tx(&full_b[pb.slot], (uint32_t)P::kBSlot);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(b_ring + pb.slot * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[pb.slot]))
-                                 : "memory");
+                if (pb.i < my_tiles && mbar_test(PAIR ? &empty_a[pb.slot] : &empty_b[pb.slot], pb.phase)) {
+                    // image of (n-tile, k-block): [hi tile (BN rows x 64 B) | lo tile]; a CTA of a pair takes its half of the rows of each
+                    const uint8_t* img = (pb.net ? img1 : img0) + ((size_t)pb.nt * nkb + (size_t)pb.kb) * (size_t)(T * BN * 64);
+                    if (PAIR) {
+                        // rows of 64 B in the image tensor: replica, then (n-tile, k-block) tiles of T x BN rows; this CTA's half
+                        if (rank == 0) mbar_arrive_expect_tx(&full_a[pb.slot], 2u * (uint32_t)P::kBSlot);
+                        const int row0 = (int)(((size_t)(group % kImgReplicas) * g.img_replica_bytes) / 64) +
+                                         (pb.nt * nkb + pb.kb) * (T * BN) + (int)rank * (BN / 2);
+#pragma unroll
+                        for (int t = 0; t < T; ++t)
+                            tma_load_2d_pair(b_ring + pb.slot * P::kBSlot + t * P::kBHalf, &maps.b[pb.net], 0, row0 + t * BN, full_leader[pb.slot]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_b[pb.slot], (uint32_t)P::kBSlot);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(b_ring + pb.slot * P::kBSlot), "l"(img), "r"((uint32_t)P::kBSlot), "r"(smem_u32(&full_b[pb.slot]))
+                                     : "memory");
+                    }
                     advance(pb, kBSlots);
                 }
                 if (AMODE == A_PLANES) {
                     if (pa.i < my_tiles && mbar_test(&empty_a[pa.slot], pa.phase)) {
                         const uint32_t slot = a_ring + pa.slot * P::kASlot;
-                        mbar_arrive_expect_tx(&full_a[pa.slot], (uint32_t)P::kASlot);
-                        tma_load_2d(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
-                        if (T == 2) tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                        if (PAIR) {
+                            if (rank == 0) mbar_arrive_expect_tx(&full_a[pa.slot], 2u * (uint32_t)P::kASlot);
+                            tma_load_2d_pair(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, full_leader[pa.slot]);
+                            if (T == 2) tma_load_2d_pair(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, full_leader[pa.slot]);
+                        } else {
+                            mbar_arrive_expect_tx(&full_a[pa.slot], (uint32_t)P::kASlot);
+                            tma_load_2d(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                            if (T == 2) tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                        }
                         advance(pa, kASlots);
                     }
                 } else if (AMODE == A_RAW) {
@@ -355,20 +401,35 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
             }
         }
     } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BN, BM, T == 1);
+        // ================= MMA issuer (one thread; in a pair: the leader issues, the peer relays its full barriers) ==========
+        if (PAIR && rank != 0) {
+            // (the peer issues nothing: its loads report to the leader's barriers by themselves)
+        } else if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BN, PAIR ? 2 * BM : BM, T == 1);
+            static_assert(!PAIR || (kASlots == kBSlots && AMODE == A_PLANES), "a pair runs one ring, fed by TMA alone");
             int sa = 0, sb = 0;
             uint32_t pha = 0u, phb = 0u;
             for (int i = 0; i < my_tiles; ++i) {
                 const int as = i % kAcc;
                 const uint32_t acc = tmem_base + (uint32_t)as * kStageCols;
-                mbar_wait(&acc_empty[as], (uint32_t)(((i / kAcc) & 1) ^ 1));      // the epilogue has read tile i - kAcc out of this stage
+                // the epilogue (of both CTAs of a pair) has read tile i - kAcc out of this stage
+                if (PAIR) mbar_wait_cluster(&acc_empty[as], (uint32_t)(((i / kAcc) & 1) ^ 1));
+                else mbar_wait(&acc_empty[as], (uint32_t)(((i / kAcc) & 1) ^ 1));
                 tc_fence_after();
                 if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 0] = clock64();
+                const bool tl = g.timeline && blockIdx.x == 0 && i < 16;      // cycles this tile's MMA thread spent waiting, per barrier kind
+                long long w_a = 0, w_b = 0, w_p = 0, t0 = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (!(AMODE == A_PLANES && (g.dbg & DBG_NO_A))) mbar_wait(&full_a[sa], pha);
-                    if (!(g.dbg & DBG_NO_W)) mbar_wait(&full_b[sb], phb);
+                    if (tl) t0 = clock64();
+                    if (PAIR) {                                       // one barrier: both CTAs' activation and weight bytes
+                        mbar_wait_cluster(&full_a[sa], pha);
+                        if (tl) w_p += clock64() - t0;
+                    } else {
+                        if (!(AMODE == A_PLANES && (g.dbg & DBG_NO_A))) mbar_wait(&full_a[sa], pha);
+                        if (tl) { const long long t1 = clock64(); w_a += t1 - t0; t0 = t1; }
+                        if (!(g.dbg & DBG_NO_W)) mbar_wait(&full_b[sb], phb);
+                        if (tl) { const long long t1 = clock64(); w_b += t1 - t0; t0 = t1; }
+                    }
                     tc_fence_after();
                     const uint32_t a_hi = a_ring + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
                     const uint32_t b_hi = b_ring + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
@@ -378,20 +439,28 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                         const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
                         const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
-                        if (T == 2 && !(g.dbg & DBG_ONE_MMA)) {
-                            umma_f16(acc + BN, da_lo, db_hi, idesc, (kb | k) != 0);
-                            umma_f16(acc + BN, da_hi, db_lo, idesc, 1u);
+                        if (PAIR) {
+                            if (T == 2 && !(g.dbg & DBG_ONE_MMA)) {
+                                umma_f16_pair(acc + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                                umma_f16_pair(acc + BN, da_hi, db_lo, idesc, 1u);
+                            }
+                            umma_f16_pair(acc, da_hi, db_hi, idesc, (kb | k) != 0);
+                        } else {
+                            if (T == 2 && !(g.dbg & DBG_ONE_MMA)) {
+                                umma_f16(acc + BN, da_lo, db_hi, idesc, (kb | k) != 0);
+                                umma_f16(acc + BN, da_hi, db_lo, idesc, 1u);
+                            }
+                            umma_f16(acc, da_hi, db_hi, idesc, (kb | k) != 0);
                         }
-                        umma_f16(acc, da_hi, db_hi, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_a[sa]);
-                    umma_commit(&empty_b[sb]);
+                    if (PAIR) umma_commit_pair(&empty_a[sa]);      // the k-block's slots (one ring: sa == sb) are free in BOTH CTAs
+                    else { umma_commit(&empty_a[sa]); umma_commit(&empty_b[sb]); }
                     if (++sa == kASlots) { sa = 0; pha ^= 1u; }
                     if (++sb == kBSlots) { sb = 0; phb ^= 1u; }
                 }
                 if (T == 2 && g.fold) fold_issue<BN>(acc, smem_base + P::kFoldOff);
-                umma_commit(&acc_full[as]);                 // accumulators of tile i complete
-                if (g.timeline && blockIdx.x == 0 && i < 16) g.timeline[i * 8 + 1] = clock64();
+                if (PAIR) umma_commit_pair(&acc_full[as]); else umma_commit(&acc_full[as]);     // accumulators of tile i complete
+                if (tl) { g.timeline[i * 8 + 1] = clock64(); g.timeline[i * 8 + 5] = w_a; g.timeline[i * 8 + 6] = w_b; g.timeline[i * 8 + 7] = w_p; }
             }
             tc_fence_before();
         }
@@ -458,7 +527,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                 if (sp == kSubs - 1) {                            // every column of this tile is out of TMEM
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[as]);
+                    if (lane == 0) release_acc(as);
                     if (g.timeline && blockIdx.x == 0 && i < 16 && t0) g.timeline[i * 8 + 3] = clock64();
                 }
                 // this thread's 32 finished columns
@@ -594,7 +663,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                 if (p == P::kPhases - 1) {                         // every column of this tile is out of TMEM
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[as]);
+                    if (lane == 0) release_acc(as);
                     if (g.timeline && blockIdx.x == 0 && i < 16 && ew == 0 && lane == 0) g.timeline[i * 8 + 3] = clock64();
                 }
                 // NT: the mask words of this warp's rows are requested before the barrier
@@ -668,10 +737,11 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();       // the leader's MMAs read the peer's shared memory and signal its barriers until the very end
+    else __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -725,19 +795,71 @@ static bool tmac_enabled() {
     return v == 1;
 }
 
-template <int BN, int EPI, int AMODE, int CMODE, int T>
-static int launch_h3(const HMaps& maps, HArgs& g, cudaStream_t st) {
-    using P = HPlan<BN, AMODE, T>;
-    const long long total = (long long)((g.M + BM - 1) / BM) * g.tiles_n * g.nets;
+// DPPO_H_PAIR=0: keep every product on single CTAs (A/B switch for measurements; default: pairs where they apply)
+static bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DPPO_H_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+template <int BN, int EPI, int AMODE, int CMODE, int T, bool PAIR>
+static int launch_h4(const HMaps& maps, HArgs& g, cudaStream_t st) {
+    using P = HPlan<BN, AMODE, T, PAIR>;
+    const int tiles_m = (g.M + BM - 1) / BM;
+    const long long total = (long long)(PAIR ? (tiles_m + 1) / 2 : tiles_m) * g.tiles_n * g.nets;     // (super-)tiles
     DPPO_REQUIRE(total < (1ll << 30), "h_gemm: too many tiles");
     static PerDeviceOnce configured;
     if (configured.need())
-        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, AMODE, CMODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
-    const int grid = (int)(total < kPlanSMs ? total : kPlanSMs);
+        DPPO_CHECK_CUDA(cudaFuncSetAttribute(h_gemm_kernel<BN, EPI, AMODE, CMODE, T, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytes));
+    int cap = PAIR ? kPlanSMs / 2 : kPlanSMs;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    if (PAIR) {
+        cfg.gridDim = dim3(kPlanSMs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = P::kBytes; cfg.stream = st;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        // the persistent grid = the pairs that can be resident at once (a GPC with an odd number of usable SMs leaves one unpaired)
+        static int max_clusters[16] = {0};
+        int dev = 0;
+        DPPO_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 16) {
+            if (max_clusters[dev] == 0) {
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, h_gemm_kernel<BN, EPI, AMODE, CMODE, T, PAIR>, &cfg) != cudaSuccess || n < 1) {
+                    (void)cudaGetLastError();
+                    n = kPlanSMs / 2;
+                }
+                max_clusters[dev] = n;
+                if (getenv("DPPO_H_VERBOSE")) fprintf(stderr, "h_gemm pair<%d,%d,%d,%d,%d>: cudaOccupancyMaxActiveClusters = %d\n", BN, EPI, AMODE, CMODE, T, n);
+            }
+            if (max_clusters[dev] < cap) cap = max_clusters[dev];
+        }
+    }
+    const int groups = (int)(total < cap ? total : cap);
     ProfScope ps(KK_TC_GEMM, st);
-    h_gemm_kernel<BN, EPI, AMODE, CMODE, T><<<grid, kThreads, P::kBytes, st>>>(maps, g, (int)total);
-    DPPO_LAUNCH_CHECK();
+    if (PAIR) {
+        cfg.gridDim = dim3(2 * groups);
+        DPPO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, h_gemm_kernel<BN, EPI, AMODE, CMODE, T, PAIR>, maps, g, (int)total));
+    } else {
+        h_gemm_kernel<BN, EPI, AMODE, CMODE, T, PAIR><<<groups, kThreads, P::kBytes, st>>>(maps, g, (int)total);
+        DPPO_LAUNCH_CHECK();
+    }
     return 0;
+}
+template <int BN, int EPI, int AMODE, int CMODE, int T>
+static int launch_h3(const HMaps& maps, HArgs& g, cudaStream_t st) {
+    // pairs: the 256-wide tiles whose operands arrive by TMA and leave by TMA (the L2-bound products); at least two row blocks
+    if (BN == 256 && AMODE == A_PLANES && CMODE != C_STG && g.M > BM && pair_enabled()) {
+        HMaps m2 = maps;
+        for (int n = 0; n < g.nets; ++n) {
+            const long long rows = (long long)kImgReplicas * g.img_replica_bytes / 64;
+            DPPO_REQUIRE(rows < (1ll << 31) && h_make_map16(&m2.b[n], g.Bimg[n], (int)rows, 32, 32, 32, BN / 2, CU_TENSOR_MAP_SWIZZLE_NONE),
+                         "cuTensorMapEncodeTiled failed for the weight image (%lld rows)", rows);
+        }
+        return launch_h4<BN, EPI, AMODE, CMODE, T, (BN == 256 && AMODE == A_PLANES && CMODE != C_STG)>(m2, g, st);
+    }
+    return launch_h4<BN, EPI, AMODE, CMODE, T, false>(maps, g, st);
 }
 template <int BN, int EPI, int AMODE, int CMODE>
 static int launch_h2(const HMaps& maps, HArgs& g, cudaStream_t st) {

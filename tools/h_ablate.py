@@ -11,6 +11,8 @@ eng = DppoEngine(376, 17, (256, 256), 131072, gemm_mode=1)
 A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); bias = torch.randn(N, device="cuda")
 PL = os.environ.get("H_PLANES", "0") == "1"          # activation operand and result as fp16 hi | lo planes (modes 94 / 92)
 m_run, m_tl = (94, 92) if PL else (96, 98)
+if os.environ.get("H_TERMS", "2") == "1":            # one-term (bf16) mode of the same kernels
+    m_run, m_tl = m_run + 100, m_tl + 100
 for _ in range(3):
     eng.dbg_gemm(m_run, A, B, M, N, K, bias=bias, relu=True)
 torch.cuda.synchronize()
@@ -24,4 +26,4 @@ torch.cuda.synchronize()
 t = tl.cpu().numpy().reshape(16, 8)
 i = int(os.environ.get('H_TILE', '3'))
 print(("planes " if PL else "fp32   ") + f"DPPO_H_DBG={os.environ.get('DPPO_H_DBG', '0'):>3s} M={M} N={N} K={K}: {us:7.1f} us | tile {i}: mainloop {t[i,1]-t[i,0]:6d}  acc {t[i,2]-t[i,1]:5d}  "
-      f"tmem hold {t[i,3]-t[i,2]:6d}  write2 {t[i,4]-t[i,3]:6d}  period {t[i+1,0]-t[i,0]:6d}", flush=True)
+      f"tmem hold {t[i,3]-t[i,2]:6d}  write2 {t[i,4]-t[i,3]:6d}  period {t[i+1,0]-t[i,0]:6d} | mma thread waits: A {t[i,5]:6d} W {t[i,6]:6d} peer {t[i,7]:6d}", flush=True)
