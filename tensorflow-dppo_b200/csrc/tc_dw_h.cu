@@ -531,8 +531,11 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     if (kps == 0) kps = th::kKB;
     g.k_per_slice = kps; g.slices = slices;
     g.vecC = (ldc % 4 == 0) && th::aligned16(C) && (slice_stride % 4 == 0);
-    if (N > 128) return th::launch_dw_bn<256>(maps, xp, gp, terms, g, st);
-    if (N > 64) return th::launch_dw_bn<128>(maps, xp, gp, terms, g, st);
+    // few rows (minibatches): latency-bound -- narrow tiles give more work items and the deepest rings
+    static int small_k = -1;
+    if (small_k < 0) { const char* e = getenv("DPPO_H_SMALL_M"); small_k = e ? atoi(e) : 2048; if (small_k < 0) small_k = 0; }
+    if (N > 128 && K > small_k) return th::launch_dw_bn<256>(maps, xp, gp, terms, g, st);
+    if (N > 64 && K > small_k) return th::launch_dw_bn<128>(maps, xp, gp, terms, g, st);
     return th::launch_dw_bn<64>(maps, xp, gp, terms, g, st);
 }
 

@@ -946,11 +946,21 @@ static int th_wide_min_k() {
     if (v < 0) { const char* e = getenv("DPPO_H_WIDE_MINK"); v = e ? atoi(e) : 65; if (v < 0) v = 0; }
     return v;
 }
-static inline int th_bn_for(int n, int k) { return n > 128 ? (k >= th_wide_min_k() ? 256 : 128) : (n > 64 ? 128 : 64); }
+// Few row blocks (minibatches of a few hundred rows, the strong-scaling slices): the product is latency-bound, not
+// throughput-bound -- 64-wide tiles give four times the CTAs and the deepest operand rings (DPPO_H_SMALL_M overrides the bound).
+static int th_small_m() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DPPO_H_SMALL_M"); v = e ? atoi(e) : 2048; if (v < 0) v = 0; }
+    return v;
+}
+static inline int th_bn_for(int n, int k, int m = 1 << 30) {
+    if (m <= th_small_m()) return 64;
+    return n > 128 ? (k >= th_wide_min_k() ? 256 : 128) : (n > 64 ? 128 : 64);
+}
 
 // bytes of one replica of the weight image of B[N,K] (terms = 2: fp16 hi | lo tiles, 1: bf16 tiles)
-static long long th_image_replica_bytes(int N, int K, int terms = 2) {
-    const int bn = th_bn_for(N, K);
+static long long th_image_replica_bytes(int N, int K, int terms = 2, int M = 1 << 30) {
+    const int bn = th_bn_for(N, K, M);
     return (long long)((N + bn - 1) / bn) * ((K + th::kKB - 1) / th::kKB) * bn * 64 * terms;
 }
 long long th_image_floats(int N, int K) { return th::kImgReplicas * th_image_replica_bytes(N, K) / 4; }
@@ -960,14 +970,14 @@ long long th_bits_words(long long rows, int N) { return rows * ((N + 31) / 32); 
 // (img_* are arrays of L+1 device pointers; nullptr = skip).
 int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
-                   cudaStream_t st, int terms) {
+                   cudaStream_t st, int terms, int rows) {
     th::HImgPlan p; p.n = 0;
     long long units = 0;
     auto add = [&](const float* src, float* dst, int N, int K, int ld, int transposed) {
         if (!src || !dst) return;
         th::HImgEntry& e = p.e[p.n];
         e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed;
-        e.bn = th_bn_for(N, K); e.terms = terms == 1 ? 1 : 2;
+        e.bn = th_bn_for(N, K, rows); e.terms = terms == 1 ? 1 : 2;
         units += (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
         p.unit_end[p.n++] = units;
     };
@@ -989,10 +999,10 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
 }
 
 // one image from a [N,K] (transposed = 0) or [K,N] (transposed = 1) matrix with row stride ld
-int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms) {
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms, int rows) {
     th::HImgPlan p; p.n = 1;
     th::HImgEntry& e = p.e[0];
-    e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N, K);
+    e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N, K, rows);
     e.terms = terms == 1 ? 1 : 2;
     const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
     p.unit_end[0] = units;
@@ -1023,13 +1033,13 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     if (planes) pl = *planes;
     g.bits_wpr = (N + 31) / 32;
     g.terms = pl.terms == 1 ? 1 : 2;
-    g.img_replica_bytes = th_image_replica_bytes(N, K, g.terms);
+    g.img_replica_bytes = th_image_replica_bytes(N, K, g.terms, M);
     g.timeline = timeline;
     g.fold = th::fold_enabled() ? 1 : 0;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     g.vecA = !pl.a_planes && (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = !pl.c_planes && (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));
-    const int bn = th_bn_for(N, K);
+    const int bn = th_bn_for(N, K, M);
     if (epi_nt) {
         if (bn == 256) return th::launch_h<256, th::EPI_NT>(g, pl, st);
         if (bn == 128) return th::launch_h<128, th::EPI_NT>(g, pl, st);
