@@ -106,6 +106,18 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
         } else {
             if (sl < 1) sl = 1;
             if (sl > kMaxSplitK) sl = kMaxSplitK;
+            if (cfg->gemm_mode == DPPO_GEMM_BF16 && cfg->max_rows >= 65536) {
+                // the persistent dW kernel (one-term mode of tc_dw_h.cu) walks tiles x slices work items on 148 CTAs: pick the
+                // slice count (<= 40, >= 2048 rows each) that leaves the last wave fullest (config 4: 32 tiles x 37 slices = 8 waves)
+                const int t2 = ((in + 127) / 128) * ((out + 255) / 256);
+                int best = sl; double best_w = 1e30;
+                for (int c2 = 4; c2 <= 40 && (long long)c2 * 2048 <= cfg->max_rows; ++c2) {
+                    const long long items = (long long)t2 * c2;
+                    const double waste = (double)((items + kPlanSMs - 1) / kPlanSMs * kPlanSMs) / (double)items;
+                    if (waste < best_w - 0.01) { best_w = waste; best = c2; }
+                }
+                sl = best;
+            }
         }
         s->slices[l] = sl;
         s->region[l] = (((int64_t)in * out + out) + 3) & ~3LL;
