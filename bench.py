@@ -152,10 +152,11 @@ def bind_to_gpu_numa_node(local_rank):
 GEMM_MODES = {"simt": 0, "tf32x3": 1, "bf16": 2, "fp16x2": 3}
 GEMM_TEXT = {"simt": "fp32 SIMT FFMA",
              "tf32x3": "tcgen05 kind::tf32, 3-term split (fp32-accurate), TMEM accumulators",
-             "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (NOT fp32-parity)",
+             "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate (NOT fp32-parity); the persistent kernels in one-term mode: "
+                     "activations as one bf16 plane, TMA-fed operands, CTA pairs (cta_group::2), double-buffered TMEM",
              "fp16x2": "tcgen05 kind::f16, 2-term fp16 split x = hi + lo/2^11 (fp32-accurate), persistent kernels, TMEM "
-                       "accumulators; forward / dX / dW all on the fp16-split kernels (dW falls back to the TMA-fed "
-                       "kind::tf32 kernel only with DPPO_H_DW=0)"}
+                       "accumulators; hidden activations / gradients stored as fp16 hi|lo planes (TMA writes the operand tiles), "
+                       "CTA pairs (cta_group::2) on the plane-fed 256-wide products; forward / dX / dW all on these kernels"}
 
 
 def make_config(args, world):
@@ -422,15 +423,16 @@ def run_b200(args):
             "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
             "config": make_config(args, world),
             "roofline": {
-                "kernel": {"fp16x2": "h_gemm_kernel / h_dw_kernel (persistent tcgen05 kind::f16 fwd / dX / dW; dW on tc_tn_tma_kernel when DPPO_H_DW=0)",
+                "kernel": {"fp16x2": "h_gemm_kernel / h_dw_kernel (persistent tcgen05 kind::f16 fwd / dX / dW, two-term fp16 split)",
                            "tf32x3": "tc_gemm_kernel / tc_tn_tma_kernel (tcgen05 kind::tf32 fwd / dX / dW)",
-                           "bf16": "bf16_gemm_kernel (tcgen05 kind::f16, bf16 operands)",
+                           "bf16": "h_gemm_kernel / h_dw_kernel in one-term mode (persistent tcgen05 kind::f16, bf16 operands; bf16_gemm_kernel for shapes TMA cannot address)",
                            "simt": "sgemm_kernel (fwd NN / dX NT / dW TN families)"}[args.gemm], "bound": "tensor",
                 "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
                 "traffic_source": "committed capture: profiles/traffic_<gemm>.json (ncu --set full of this command); NOT measured in this run",
                 "traffic_note": "DRAM bytes of all GEMM launches of one step; algorithmic bytes of the whole update are %d -- "
-                                "the excess is fp32 activations (h1, h2, dh) round-tripping HBM between the per-layer kernels"
+                                "the excess is the activations (h1, h2, dh; 4 bytes per element as fp16 hi|lo planes) round-tripping HBM "
+                                "between the per-layer kernels"
                                 % alg_bytes,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "note": ("algorithmic MLP FLOPs (SURVEY 8(d4)) over the event-timed duration of all GEMM launches; "

@@ -16,9 +16,9 @@ run() {   # name timeout args...
 run weak 300 --steps 30 --warmup 5
 run strong 300 --steps 30 --warmup 5 --scaling strong
 run mb256 200 --minibatch 256 --steps 5 --warmup 3
-run mb4096 200 --minibatch 4096 --steps 5 --warmup 3
+#run mb4096 200 --minibatch 4096 --steps 5 --warmup 3
 run mb256_strong 200 --minibatch 256 --steps 5 --warmup 3 --scaling strong
-run cfg4_fp16x2 400 --workload humanoid-wide-cfg4 --gemm fp16x2 --steps 8 --warmup 3 --no-cpu-baseline
+#run cfg4_fp16x2 400 --workload humanoid-wide-cfg4 --gemm fp16x2 --steps 8 --warmup 3 --no-cpu-baseline
 run cfg4_bf16 400 --workload humanoid-wide-cfg4 --gemm bf16 --steps 8 --warmup 3 --no-cpu-baseline
 (timeout 400 python -m pytest tests -m gpu -q -k "multi_gpu" 2>&1 | tail -8) > gpurun_out/${TAG}_tests_multi.log
 tail -3 gpurun_out/${TAG}_tests_multi.log
