@@ -45,7 +45,8 @@ extern "C" {
 /* arithmetic of the dense layers */
 #define DPPO_GEMM_FP32_SIMT 0  /* exact fp32 FMA (parity path, every shape)                         */
 #define DPPO_GEMM_TF32X3    1  /* tcgen05 kind::tf32, 3-term split (fp32-accurate tensor-core path)  */
-#define DPPO_GEMM_BF16      2  /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (config 4)         */
+#define DPPO_GEMM_BF16      2  /* tcgen05 kind::f16 bf16 operands, fp32 accumulate (config 4): the       */
+                               /* persistent kernels of mode 3 in one-term mode (activations as bf16)    */
 #define DPPO_GEMM_FP16X2    3  /* tcgen05 kind::f16, 2-term fp16 split x = hi + lo/2^11 (fp32-accurate, */
                                /* persistent kernels; operands must satisfy |x| < 65504)                */
 
