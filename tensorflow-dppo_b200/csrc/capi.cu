@@ -466,6 +466,13 @@ static int reduce_and_apply(dppo_ctx* c, const int* active, int rows, float* par
         return peer_allreduce_adam(c, params_pi, (adam_m && adam_v) ? adam_m : nullptr, adam_v, step, lr, beta1, beta2, eps,
                                    grad_out, st, sp, counter);
     }
+    if (!(c->nccl_comm && c->world > 1) && adam_m && adam_v) {
+        // one rank: the gradient is final when finalize_kernel has summed the slices -- Adam is applied in the same kernel
+        // (sp: the graph-replayed minibatch loop reads its step size from the step record there)
+        AdamFused f{params_pi, adam_m, adam_v, step, lr, beta1, beta2, eps};
+        return launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
+                               grad_out, nullptr, st, nullptr, sp, counter, 1.0f / grad_prescale(c, rows), &f);
+    }
     if (int r = launch_finalize(c->shape, active, c->ws.partial, c->ws.loss_part, tiles, c->cfg.entcoeff, c->cfg.vcoeff,
                                 grad_out, nullptr, st, nullptr, nullptr, nullptr, 1.0f / grad_prescale(c, rows))) return r;
     if (c->nccl_comm && c->world > 1)

@@ -276,10 +276,12 @@ int launch_value_pairwise(const NetShape& s, const float* out_pi, const float* o
                           int row_off, int T, int groups, int tile0, float inv_B, float clip, float vcoeff, float* d_out,
                           double* loss_part, cudaStream_t st);
 // active[l] = number of split-K slices the dW launches of this update actually wrote (<= s.slices[l])
+// fused: single-rank updates apply the TF-Adam step of every parameter inside finalize_kernel (no separate adam_kernel pass)
+struct AdamFused { float* params; float* m; float* v; int step; float lr, b1, b2, eps; };
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st,
                     float* grad_out_alt = nullptr, const StepParams* sp = nullptr, const int* counter = nullptr,
-                    float grad_scale = 1.0f);
+                    float grad_scale = 1.0f, const AdamFused* fused = nullptr);
 int launch_split_heads(const NetShape& s, const float* out, int rows, float* v_out, float* pd_out,
                        cudaStream_t st);
 int launch_adam(float* params, const float* grad, float* m, float* v, int64_t n, int step, float lr,

@@ -397,13 +397,24 @@ struct FinalizePlan {
     int slices[kMaxLayers + 1];
 };
 
+// one TF-1.x Adam step of one parameter (PPO.py:20,53), shared by adam_kernel and the fused finalize + Adam tail
+__device__ __forceinline__ void adam_update(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long long i, float gi,
+                                            float lr_t, float b1, float b2, float eps) {
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+}
+struct AdamTail { float* p; float* m; float* v; float lr_t, b1, b2, eps; };     // p == nullptr: finalize only
+
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ partial, FinalizePlan plan, long long n_params,
                                 long long head_off, int H, int W, const double* __restrict__ loss_part, int n_tiles,
                                 float entcoeff, float vcoeff, float* __restrict__ grad_out,
                                 float* __restrict__ losses_out, float* __restrict__ grad_out_alt,
-                                const StepParams* __restrict__ sp, const int* __restrict__ counter, float grad_scale) {
+                                const StepParams* __restrict__ sp, const int* __restrict__ counter, float grad_scale, AdamTail adam) {
     const int P = 1 + W;                     // W = policy-head width (2A or ncat)
-    if (sp && sp[*counter].peer_sel) grad_out = grad_out_alt;      // graph replay: the exchange buffer half of this step
+    if (sp && grad_out_alt && sp[*counter].peer_sel) grad_out = grad_out_alt;      // graph replay: the exchange buffer half of this step
+    if (adam.p && sp) adam.lr_t = sp[*counter].lr_t;
     // A block owns 32 consecutive parameters.  Warp w streams slices w, w+8, ... of them: every load instruction
     // is one full 128-byte line (32 lanes x consecutive parameters of ONE slice), 8 lines in flight per warp; the 8
     // warps' sums are then combined in a fixed order through shared memory -> deterministic and DRAM-friendly.
@@ -449,7 +460,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                     pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + (long long)W * H + (c - 1));
                 }
             }
-            grad_out[pub] = t * grad_scale;      // 1 / the power of two the loss kernel put on d_out (fp16-split mode), else 1
+            const float gi = t * grad_scale;     // 1 / the power of two the loss kernel put on d_out (fp16-split mode), else 1
+            grad_out[pub] = gi;
+            // single-rank updates: the optimiser step of this parameter right here (no second pass over the gradient)
+            if (adam.p) adam_update(adam.p, adam.m, adam.v, pub, gi, adam.lr_t, adam.b1, adam.b2, adam.eps);
         }
         __syncthreads();
     }
@@ -482,9 +496,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     }
 }
 
+double adam_lr_t(float lr, float b1, float b2, int step);
+
 int launch_finalize(const NetShape& s, const int* active, const float* partial, const double* loss_part, int n_loss_tiles,
                     float entcoeff, float vcoeff, float* grad_out, float* losses_out, cudaStream_t st, float* grad_out_alt,
-                    const StepParams* sp, const int* counter, float grad_scale) {
+                    const StepParams* sp, const int* counter, float grad_scale, const AdamFused* fused) {
     FinalizePlan plan;
     plan.n_regions = s.L + 1;
     for (int l = 0; l <= s.L; ++l) {
@@ -495,9 +511,16 @@ int launch_finalize(const NetShape& s, const int* active, const float* partial, 
     int grid = (int)((s.n_params + 31) / 32);
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
+    AdamTail adam{};
+    if (fused && fused->params) {
+        DPPO_REQUIRE(fused->step >= 1, "dppo_adam_apply: step=%d must be >= 1 (t after increment)", fused->step);
+        adam.p = fused->params; adam.m = fused->m; adam.v = fused->v;
+        adam.lr_t = (float)adam_lr_t(fused->lr, fused->b1, fused->b2, fused->step);
+        adam.b1 = fused->b1; adam.b2 = fused->b2; adam.eps = fused->eps;
+    }
     ProfScope ps(KK_FINALIZE, st);
     finalize_kernel<<<grid, 256, 0, st>>>(partial, plan, s.n_params, (long long)s.w_off[s.L], H, s.pdw, loss_part,
-                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out, grad_out_alt, sp, counter, grad_scale);
+                                          n_loss_tiles, entcoeff, vcoeff, grad_out, losses_out, grad_out_alt, sp, counter, grad_scale, adam);
     DPPO_LAUNCH_CHECK();
     return 0;
 }
@@ -539,13 +562,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             const StepParams* __restrict__ sp, const int* __restrict__ counter) {
     if (sp) lr_t = sp[*counter].lr_t;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i];
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
-    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        adam_update(p, m, v, i, g[i], lr_t, b1, b2, eps);
 }
 
 double adam_lr_t(float lr, float b1, float b2, int step) {

@@ -1200,7 +1200,8 @@ def test_chief_train_runs_the_fused_host_call_and_equals_the_engine_path():
     torch.cuda.synchronize()
     assert chief.ppo._t == K and len(chief.ppo.step_losses) == K
     counts = {k: c for k, (c, _) in eng.profile_read().items()}
-    assert counts["adam"] == K and counts["loss"] == K                     # K steps on the device from one call
+    # K steps on the device from one call (one rank: the Adam step runs inside finalize_kernel, no adam_kernel launch)
+    assert counts["finalize"] == K and counts["loss"] == K and counts["adam"] == 0
     # the same K steps through the separate entry points
     s = dev(np.concatenate([b[0] for b in batches])); a = dev(np.concatenate([b[1] for b in batches]))
     adv = dev(np.concatenate([b[2] for b in batches]).reshape(-1)); etr = dev(np.concatenate([b[3] for b in batches]).reshape(-1))
