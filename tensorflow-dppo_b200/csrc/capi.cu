@@ -179,6 +179,11 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     w.loss_part = (double*)take(tiles * kLossSlots * sizeof(double));
     w.gae_adv = (float*)take(R * sizeof(float));
     w.gae_ret = (float*)take(R * sizeof(float));
+    if (cfg->gemm_mode == DPPO_GEMM_FP16X2 && s.obs % 4 != 0) {
+        // observation rows whose pitch TMA cannot address (obs_dim 3, 17, ...): the dense layers read a re-pitched copy
+        w.obs_ld = (s.obs + 3) & ~3;
+        w.obs_pad = (float*)take(R * (size_t)w.obs_ld * sizeof(float));
+    }
     w.stage_floats = R * ((size_t)s.obs + s.acols + 3);
     w.stage = (float*)take(w.stage_floats * sizeof(float));
     w.step_params = (StepParams*)take((size_t)kMaxGraphSteps * sizeof(StepParams));
@@ -215,6 +220,14 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
     const int nets = params_old ? 2 : 1;
     if (int r = launch_pack_heads(s, params_pi, params_old, w.head_pi, w.head_old, st)) return r;
     const float* in0 = obs; const float* in1 = obs;
+    int ld0 = s.obs;                                     // pitch of the layer-0 operand
+    if (w.obs_pad && th_terms(c) && c->use_h_dw) {
+        // obs_dim % 4 != 0: re-pitch the rows once so that TMA feeds layer 1's forward and dW like any other shape (the pad
+        // columns are never read: the tensor maps end at obs_dim and zero-fill beyond it)
+        DPPO_CHECK_CUDA(cudaMemcpy2DAsync(w.obs_pad, (size_t)w.obs_ld * 4, obs, (size_t)s.obs * 4, (size_t)s.obs * 4, (size_t)rows,
+                                          cudaMemcpyDeviceToDevice, st));
+        in0 = in1 = w.obs_pad; ld0 = w.obs_ld;
+    }
     if (c->cfg.gemm_mode == DPPO_GEMM_BF16 && th_terms(c) == 0) {
         // bf16 tensor cores: B operand K-major = transposed kernels (fp32 in HBM, rounded to bf16 by the movers)
         if (int r = tc_transpose_weights(s, params_pi, w.head_pi, w.wt_pi, params_old, w.head_old, w.wt_old, st)) return r;
@@ -252,7 +265,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             pl.terms = terms;
             pl.a_planes = planes && l > 0; pl.a_lo_off = R * in;
             pl.c_planes = planes && !head; pl.c_lo_off = R * out;
-            if (int r = th_gemm(0, rows, out, in, in0, in1, in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
+            if (int r = th_gemm(0, rows, out, in, in0, in1, l == 0 ? ld0 : in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
                                 head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st,
                                 head ? nullptr : w.act_bits[l], nullptr, nullptr, &pl)) return r;
             in0 = o0; in1 = o1;
@@ -301,7 +314,7 @@ static void active_slices(const dppo_ctx* c, int rows, int* active) {
         if (tc_mode(c->cfg.gemm_mode)) {
             // <= 512 rows per TMEM accumulation chain (64 truncating adds of a K = 8 tf32 MMA); the fp16 dW kernel covers
             // K = 16 per MMA, so 1024 rows are the same 64 adds -- half the partial slices to write and to sum
-            const bool h_dw = c->cfg.gemm_mode == DPPO_GEMM_FP16X2 && c->use_h_dw && s.in_dim(l) % 4 == 0 &&
+            const bool h_dw = c->cfg.gemm_mode == DPPO_GEMM_FP16X2 && c->use_h_dw && (s.in_dim(l) % 4 == 0 || (l == 0 && c->ws.obs_pad)) &&
                               (l == s.L ? s.Pld : s.out_dim(l)) % 4 == 0;
             const int chain = h_dw ? 1024 : 512;
             int want = (rows + chain - 1) / chain;
@@ -375,9 +388,13 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
     const bool planes = h_planes(c);
     // dW_l (+ db_l) into layer l's split-K partial region
     // (tmp: a free [rows, hmax] buffer -- planes mode joins dY back to fp32 there when layer 0's obs rows cannot be read by TMA)
+    // layer 0 of the fp16x2 mode reads the re-pitched observation rows forward_nets prepared (obs_dim % 4 != 0)
+    const bool obs_padded = w.obs_pad && terms && c->use_h_dw;
     auto dense_dw = [&](int l, const float* x_in, const float* dY, float* tmp) -> int {
         const int in = s.in_dim(l), out = s.out_dim(l);
         const int ldy = (l == s.L) ? s.Pld : out;
+        int ldx = in;
+        if (l == 0 && obs_padded) { x_in = w.obs_pad; ldx = w.obs_ld; }
         float* p = w.partial + s.part_off[l];
         if (bf16) {
             if (int r = bf16_gemm_tn_splitk(in, out, rows, x_in, in, dY, ldy, p, out, active[l], s.region[l], accumulate, st))
@@ -389,8 +406,8 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
             pl.terms = terms;
             pl.a_planes = l > 0; pl.a_lo_off = (long long)c->cfg.max_rows * in;
             pl.c_planes = l < s.L; pl.c_lo_off = (long long)c->cfg.max_rows * out;
-            if ((pl.a_planes || th_dw_supported(x_in, in, x_in, in)) && (pl.c_planes || th_dw_supported(dY, ldy, dY, ldy)))
-                return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,
+            if ((pl.a_planes || th_dw_supported(x_in, ldx, x_in, ldx)) && (pl.c_planes || th_dw_supported(dY, ldy, dY, ldy)))
+                return th_gemm_dw(in, out, rows, x_in, ldx, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,
                                   st, &pl);
             // obs rows TMA cannot address (obs_dim 3, 17, ...): the tf32 kernels below take fp32 operands
             DPPO_REQUIRE(pl.c_planes && tmp != nullptr, "fp16 planes: layer %d has an fp32 operand TMA cannot address", l);
@@ -398,12 +415,13 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
             if (int r = th_join_planes(hi, hi + pl.c_lo_off, (long long)rows * out, tmp, st, terms)) return r;
             dY = tmp;
         }
-        if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, in, dY, ldy)) {    // persistent fp16-split kernel, bias column sums fused
+        if (fp16x2 && c->use_h_dw && th_dw_supported(x_in, ldx, dY, ldy)) {    // persistent fp16-split kernel, bias column sums fused
             ThPlanes pl{};
             pl.terms = terms;
-            return th_gemm_dw(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate, st,
+            return th_gemm_dw(in, out, rows, x_in, ldx, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate, st,
                               &pl);
         }
+        if (l == 0 && obs_padded) x_in = obs;                 // (the fallbacks below take the caller's rows)
         if (tcore) {
             if (tc_tn_tma_supported(x_in, in, dY, ldy))       // TMA-fed kernel, bias column sums fused
                 return tc_gemm_tn_tma(in, out, rows, x_in, in, dY, ldy, p, out, p + (size_t)in * out, active[l],

@@ -99,6 +99,8 @@ struct Workspace {
     double* loss_part;   // [loss_tiles_max, kLossSlots]
     float* gae_adv;      // [max_rows] used by dppo_update_host
     float* gae_ret;      // [max_rows]
+    float* obs_pad;      // fp16x2 mode, obs_dim % 4 != 0: the rows of the current block re-pitched to a multiple of 4 floats (TMA)
+    int obs_ld;          // its pitch in floats (0: not used)
     float* stage;        // device staging for dppo_update_host: obs|act|rew|predv|done
     size_t stage_floats;
     StepParams* step_params;   // [kMaxGraphSteps] per-step records of the graph-replayed minibatch loop
