@@ -249,7 +249,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
         // current parameters
         const int terms = th_terms(c);
         if (int r = th_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
-                                   w.img_dx_pi, st, terms, rows)) return r;
+                                   w.img_dx_pi, st, terms, rows, h_planes(c) ? 1 : 0)) return r;
         // hidden activations live as fp16 hi | lo planes (h_planes): the epilogue that produces them applies the split the
         // consumer's converter warps would apply, so every later product reads its operand tiles straight from TMA
         const bool planes = h_planes(c);
@@ -1288,7 +1288,7 @@ int dppo_dbg_gemm(dppo_ctx* c, int mode, int M, int N, int K, const float* A, co
         __half* a_hi = reinterpret_cast<__half*>(c->ws.scratch[0]);
         __half* c_hi = reinterpret_cast<__half*>(c->ws.scratch[1]);
         if (int r = th_split_planes(A, (long long)M * K, a_hi, a_hi + pl.a_lo_off, st, terms)) return r;
-        if (int r = th_pack_one(B, c->ws.partial, N, K, K, 0, st, terms, M)) return r;
+        if (int r = th_pack_one(B, c->ws.partial, N, K, K, 0, st, terms, M, 1)) return r;
         if (mode == 95) {
             if (int r = th_gemm(1, M, N, K, c->ws.scratch[0], nullptr, K, c->ws.partial, nullptr, c->ws.scratch[1], nullptr, N, nullptr,
                                 nullptr, 0, mask, 1, st, nullptr, nullptr, nullptr, &pl)) return r;

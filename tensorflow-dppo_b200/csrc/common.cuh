@@ -241,8 +241,9 @@ long long th_image_floats(int N, int K);
 long long th_bits_words(long long rows, int N);
 int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
-                   cudaStream_t st, int terms = 2, int rows = 1 << 30);     // rows: of the products these images feed (tile width)
-int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms = 2, int rows = 1 << 30);
+                   cudaStream_t st, int terms = 2, int rows = 1 << 30, int planes = 0);     // rows / planes: of the products these images feed
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms = 2, int rows = 1 << 30,
+                int a_planes = 0);
 // Activations kept as two fp16 planes (x ~= hi + lo / 2^11, the split of tc_gemm_h.cu) instead of one fp32 matrix: the
 // consumer's TMA writes the MMA operand tiles directly, no converter warps.  A "planes" pointer is the hi plane (passed
 // through the float* parameter), the lo plane starts *_lo_off fp16 elements after it, leading dimensions count fp16 elements.

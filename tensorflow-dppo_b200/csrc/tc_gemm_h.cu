@@ -77,21 +77,28 @@ enum { C_STG = 0,        // st.global write-out (fp32)
 // (cp.async.bulk.tensor .cta_group::2; a software relay of the peer's barriers cost ~900 cycles per remote arrive and left
 // the pair slower than two single CTAs) --, releases slots and publishes accumulators with multicast commits; each CTA drains
 // its own TMEM rows.  Pairs take fp16-plane (TMA-written) activation operands only.
+// k-block: 32 reduction elements (64-byte fp16 rows, SWIZZLE_64B); the one-term mode on plane operands takes 64 (128-byte bf16
+// rows, SWIZZLE_128B): its two MMAs per 32 elements left the per-k-block costs (barrier round trip, commit, TMA issue) in charge
+template <int AMODE, int T> struct HKb { static constexpr int kKb = (T == 1 && AMODE == A_PLANES) ? 64 : 32; };
+
 template <int BN, int AMODE = A_RAW, int T = 2, bool PAIR = false>
 struct HPlan {
+    static constexpr int kKb = HKb<AMODE, T>::kKb;
+    static constexpr int kRowBytes = kKb * 2;               // one operand row of a k-block
+    static constexpr int kSz = (T == 1 && kKb == 32) ? 1 : 2;   // slot size class: half-size slots only for one-term 32-element k-blocks
     // (a pair runs ONE ring: the activation and weight slots of a k-block are released together by a single multicast commit)
-    static constexpr int kPairSlots = AMODE == A_PLANES ? (T == 1 ? 8 : 5) : (T == 1 ? 4 : 3);
-    static constexpr int kBSlots = PAIR ? kPairSlots : (T == 1 ? 4 : 3);
+    static constexpr int kPairSlots = AMODE == A_PLANES ? (kSz == 1 ? 8 : 5) : (kSz == 1 ? 4 : 3);
+    static constexpr int kBSlots = PAIR ? kPairSlots : (kSz == 1 ? 4 : 3);
     // raw (TMA) ring depth: whatever shared memory is left -- narrow tiles have short k-blocks and need more boxes in flight.
     // With fp16 planes there is no raw ring and no converter hand-off: its bytes go to a deeper operand ring.
     static constexpr int kASlots2 = AMODE == A_PLANES ? (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8))
                                                       : (BN >= 256 ? 2 : (BN >= 128 ? 3 : 4));   // operand ring: latency-bound when k-blocks are short
-    static constexpr int kASlots = PAIR ? kPairSlots : (T == 1 ? (2 * kASlots2 > 8 ? 8 : 2 * kASlots2) : kASlots2);    // (half-size slots in one-term mode)
+    static constexpr int kASlots = PAIR ? kPairSlots : (kSz == 1 ? (2 * kASlots2 > 8 ? 8 : 2 * kASlots2) : kASlots2);    // (half-size slots in one-term mode)
     static constexpr int kRSlots = AMODE == A_PLANES ? 0 : (PAIR ? kPairSlots : (BN >= 256 ? (T == 1 ? 3 : 2) : (BN >= 128 ? 4 : 6)));
-    static constexpr int kAHalf = BM * 64;                   // hi (or lo) activation tile: 128 rows x 64 B
+    static constexpr int kAHalf = BM * kRowBytes;            // hi (or lo) activation tile: 128 rows x 64 B (128 B: 64-element k-blocks)
     static constexpr int kASlot = T * kAHalf;
     static constexpr int kBRows = PAIR ? BN / 2 : BN;        // a CTA of a pair holds half of the weight tile's rows
-    static constexpr int kBHalf = kBRows * 64;
+    static constexpr int kBHalf = kBRows * kRowBytes;
     static constexpr int kBSlot = T * kBHalf;
     static constexpr int kPhaseCols = BN < 128 ? BN : 128;   // columns staged per epilogue phase
     static constexpr int kPhases = BN / kPhaseCols;
@@ -229,7 +236,8 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
     float* s_bias = reinterpret_cast<float*>(smem + P::kBiasOff);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nkb = (g.K + kKB - 1) / kKB;
+    constexpr int KB = P::kKb;                                // reduction elements per k-block
+    const int nkb = (g.K + KB - 1) / KB;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const int n_groups = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;         // a group = one CTA, or one CTA pair
     const int group = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
@@ -313,7 +321,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
             auto issue = [&](MoverRegs& r, long long it) {
                 int mt, net, nt;
                 decode(t_begin + (int)(it / nkb), mt, net, nt);
-                mover_load(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * kKB, g.K, g.vecA, tid);
+                mover_load(r, g.A[net], g.lda, mt * BM, g.M, (int)(it % nkb) * KB, g.K, g.vecA, tid);
             };
 #pragma unroll
             for (int j = 0; j < kPrefetch; ++j)
@@ -360,11 +368,11 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
             while (pb.i < my_tiles || pa.i < my_tiles) {
                 if (pb.i < my_tiles && mbar_test(PAIR ? &empty_a[pb.slot] : &empty_b[pb.slot], pb.phase)) {
                     // image of (n-tile, k-block): [hi tile (BN rows x 64 B) | lo tile]; a CTA of a pair takes its half of the rows of each
-                    const uint8_t* img = (pb.net ? img1 : img0) + ((size_t)pb.nt * nkb + (size_t)pb.kb) * (size_t)(T * BN * 64);
+                    const uint8_t* img = (pb.net ? img1 : img0) + ((size_t)pb.nt * nkb + (size_t)pb.kb) * (size_t)(T * BN * P::kRowBytes);
                     if (PAIR) {
                         // rows of 64 B in the image tensor: replica, then (n-tile, k-block) tiles of T x BN rows; this CTA's half
                         if (rank == 0) mbar_arrive_expect_tx(&full_a[pb.slot], 2u * (uint32_t)P::kBSlot);
-                        const int row0 = (int)(((size_t)(group % kImgReplicas) * g.img_replica_bytes) / 64) +
+                        const int row0 = (int)(((size_t)(group % kImgReplicas) * g.img_replica_bytes) / P::kRowBytes) +
                                          (pb.nt * nkb + pb.kb) * (T * BN) + (int)rank * (BN / 2);
 #pragma unroll
                         for (int t = 0; t < T; ++t)
@@ -382,19 +390,19 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                         const uint32_t slot = a_ring + pa.slot * P::kASlot;
                         if (PAIR) {
                             if (rank == 0) mbar_arrive_expect_tx(&full_a[pa.slot], 2u * (uint32_t)P::kASlot);
-                            tma_load_2d_pair(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, full_leader[pa.slot]);
-                            if (T == 2) tma_load_2d_pair(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, full_leader[pa.slot]);
+                            tma_load_2d_pair(slot, &maps.a[pa.net], pa.kb * KB, pa.mt * BM, full_leader[pa.slot]);
+                            if (T == 2) tma_load_2d_pair(slot + P::kAHalf, &maps.al[pa.net], pa.kb * KB, pa.mt * BM, full_leader[pa.slot]);
                         } else {
                             mbar_arrive_expect_tx(&full_a[pa.slot], (uint32_t)P::kASlot);
-                            tma_load_2d(slot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
-                            if (T == 2) tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * kKB, pa.mt * BM, &full_a[pa.slot]);
+                            tma_load_2d(slot, &maps.a[pa.net], pa.kb * KB, pa.mt * BM, &full_a[pa.slot]);
+                            if (T == 2) tma_load_2d(slot + P::kAHalf, &maps.al[pa.net], pa.kb * KB, pa.mt * BM, &full_a[pa.slot]);
                         }
                         advance(pa, kASlots);
                     }
                 } else if (AMODE == A_RAW) {
                     if (pa.i < my_tiles && mbar_test(&raw_empty[pa.slot], pa.phase)) {
                         mbar_arrive_expect_tx(&raw_full[pa.slot], (uint32_t)P::kRawSlot);
-                        tma_load_2d(raw_ring + pa.slot * P::kRawSlot, &maps.a[pa.net], pa.kb * kKB, pa.mt * BM, &raw_full[pa.slot]);
+                        tma_load_2d(raw_ring + pa.slot * P::kRawSlot, &maps.a[pa.net], pa.kb * KB, pa.mt * BM, &raw_full[pa.slot]);
                         advance(pa, kRSlots > 0 ? kRSlots : 1);
                     }
                 }
@@ -433,12 +441,14 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     tc_fence_after();
                     const uint32_t a_hi = a_ring + sa * P::kASlot, a_lo = a_hi + P::kAHalf;
                     const uint32_t b_hi = b_ring + sb * P::kBSlot, b_lo = b_hi + P::kBHalf;
+                    // K-major tiles: 64-byte rows / SWIZZLE_64B / 512-byte 8-row groups, or 128-byte rows / SWIZZLE_128B / 1024
+                    constexpr uint32_t kSbo = KB == 64 ? 1024u : 512u, kLay = KB == 64 ? kLayoutSW128 : kLayoutSW64;
 #pragma unroll
-                    for (int k = 0; k < kKB / 16; ++k) {
-                        const uint64_t da_hi = make_sdesc(a_hi + k * 32, 0, 512, kLayoutSW64);
-                        const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, 512, kLayoutSW64);
-                        const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, 512, kLayoutSW64);
-                        const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, 512, kLayoutSW64);
+                    for (int k = 0; k < KB / 16; ++k) {
+                        const uint64_t da_hi = make_sdesc(a_hi + k * 32, 0, kSbo, kLay);
+                        const uint64_t da_lo = make_sdesc(a_lo + k * 32, 0, kSbo, kLay);
+                        const uint64_t db_hi = make_sdesc(b_hi + k * 32, 0, kSbo, kLay);
+                        const uint64_t db_lo = make_sdesc(b_lo + k * 32, 0, kSbo, kLay);
                         if (PAIR) {
                             if (T == 2 && !(g.dbg & DBG_ONE_MMA)) {
                                 umma_f16_pair(acc + BN, da_lo, db_hi, idesc, (kb | k) != 0);
@@ -747,7 +757,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
 
 // ---- weight images: per (n-tile, k-block) the fp16 hi tile then the lo tile, K-major SWIZZLE_64B, exactly as the MMA
 // reads them from shared memory -> one cp.async.bulk per k-block ----
-struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn, terms; };
+struct HImgEntry { const float* src; uint8_t* dst; int N, K, ld, transposed, bn, terms, kb; };      // kb: 32 or 64 elements per k-block
 struct HImgPlan { int n; HImgEntry e[3 * (kMaxLayers + 1)]; long long unit_end[3 * (kMaxLayers + 1)]; };
 
 __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
@@ -756,11 +766,12 @@ __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
         while (u >= p.unit_end[i]) ++i;
         const HImgEntry e = p.e[i];
         long long r_ = u - (i ? p.unit_end[i - 1] : 0);
-        const int c = (int)(r_ % 4); r_ /= 4;                  // 16-B chunk (8 fp16) of the 64-B row
+        const int cpr = e.kb / 8;                              // 16-B chunks (8 elements) per row: 4 (64-B rows) or 8 (128-B rows)
+        const int c = (int)(r_ % cpr); r_ /= cpr;
         const int r = (int)(r_ % e.bn); r_ /= e.bn;           // row within the tile
-        const int kbs = (e.K + kKB - 1) / kKB;
+        const int kbs = (e.K + e.kb - 1) / e.kb;
         const int kb = (int)(r_ % kbs), nt = (int)(r_ / kbs);
-        const int n = nt * e.bn + r, k0 = kb * kKB + c * 8;
+        const int n = nt * e.bn + r, k0 = kb * e.kb + c * 8;
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -775,10 +786,11 @@ __global__ void pack_images_h_kernel(HImgPlan p, long long total_units) {
             split2(v[0], v[1], h.x, l.x); split2(v[2], v[3], h.y, l.y); split2(v[4], v[5], h.z, l.z); split2(v[6], v[7], h.w, l.w);
         }
         const size_t ntiles = (size_t)((e.N + e.bn - 1) / e.bn);
-        const size_t half = (size_t)e.bn * 64;                  // a tile image = [hi (bn rows x 64 B) | lo]  (one-term mode: hi only)
+        const size_t half = (size_t)e.bn * (e.kb * 2);          // a tile image = [hi (bn rows x 64 | 128 B) | lo]  (one-term mode: hi only)
         const size_t tile_bytes = (size_t)e.terms * half;
         const size_t replica_bytes = ntiles * kbs * tile_bytes;
-        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+        const uint32_t off = e.kb == 64 ? (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4)               // SWIZZLE_128B
+                                        : (uint32_t)r * 64u + (uint32_t)((c ^ ((r >> 1) & 3)) << 4);       // SWIZZLE_64B
 #pragma unroll
         for (int rep = 0; rep < kImgReplicas; ++rep) {
             uint8_t* tile = e.dst + rep * replica_bytes + ((size_t)nt * kbs + kb) * tile_bytes;
@@ -853,8 +865,9 @@ static int launch_h3(const HMaps& maps, HArgs& g, cudaStream_t st) {
     if (BN == 256 && AMODE == A_PLANES && CMODE != C_STG && g.M > BM && pair_enabled()) {
         HMaps m2 = maps;
         for (int n = 0; n < g.nets; ++n) {
-            const long long rows = (long long)kImgReplicas * g.img_replica_bytes / 64;
-            DPPO_REQUIRE(rows < (1ll << 31) && h_make_map16(&m2.b[n], g.Bimg[n], (int)rows, 32, 32, 32, BN / 2, CU_TENSOR_MAP_SWIZZLE_NONE),
+            constexpr int KB = HKb<AMODE, T>::kKb;
+            const long long rows = (long long)kImgReplicas * g.img_replica_bytes / (KB * 2);
+            DPPO_REQUIRE(rows < (1ll << 31) && h_make_map16(&m2.b[n], g.Bimg[n], (int)rows, KB, KB, KB, BN / 2, CU_TENSOR_MAP_SWIZZLE_NONE),
                          "cuTensorMapEncodeTiled failed for the weight image (%lld rows)", rows);
         }
         return launch_h4<BN, EPI, AMODE, CMODE, T, (BN == 256 && AMODE == A_PLANES && CMODE != C_STG)>(m2, g, st);
@@ -885,7 +898,9 @@ static int launch_h(HArgs& g, const ThPlanes& pl, cudaStream_t st) {
         for (int n = 0; n < g.nets; ++n) {
             const __half* hi = reinterpret_cast<const __half*>(g.A[n]);
             DPPO_REQUIRE(g.lda % 8 == 0 && aligned16(hi) && pl.a_lo_off % 8 == 0, "h_gemm: fp16 planes need 16-byte aligned rows");
-            DPPO_REQUIRE(h_make_map16(&maps.a[n], hi, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B) &&
+            // (one-term mode: 64-element k-blocks = 128-byte rows, SWIZZLE_128B)
+            DPPO_REQUIRE((g.terms == 1 ? h_make_map16(&maps.a[n], hi, g.M, g.K, g.lda, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                                       : h_make_map16(&maps.a[n], hi, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B)) &&
                          (g.terms == 1 || h_make_map16(&maps.al[n], hi + pl.a_lo_off, g.M, g.K, g.lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B)),
                          "cuTensorMapEncodeTiled failed for the A planes [%d x %d]", g.M, g.K);
         }
@@ -959,35 +974,43 @@ static inline int th_bn_for(int n, int k, int m = 1 << 30) {
 }
 
 // bytes of one replica of the weight image of B[N,K] (terms = 2: fp16 hi | lo tiles, 1: bf16 tiles)
-static long long th_image_replica_bytes(int N, int K, int terms = 2, int M = 1 << 30) {
+static long long th_image_replica_bytes(int N, int K, int terms = 2, int M = 1 << 30, int kb = 32) {
     const int bn = th_bn_for(N, K, M);
-    return (long long)((N + bn - 1) / bn) * ((K + th::kKB - 1) / th::kKB) * bn * 64 * terms;
+    return (long long)((N + bn - 1) / bn) * ((K + kb - 1) / kb) * bn * (kb * 2) * terms;
 }
-long long th_image_floats(int N, int K) { return th::kImgReplicas * th_image_replica_bytes(N, K) / 4; }
+// (allocation: the two-term image with 32-element k-blocks, or the one-term image with 64-element ones if that pads K further)
+long long th_image_floats(int N, int K) {
+    const long long a = th_image_replica_bytes(N, K, 2, 1 << 30, 32), b = th_image_replica_bytes(N, K, 1, 1 << 30, 64);
+    return th::kImgReplicas * (a > b ? a : b) / 4;
+}
+// elements per k-block of a product: 64 for the one-term mode on plane operands (HKb), else 32
+static inline int th_kb_for(int terms, int a_planes) { return (terms == 1 && a_planes) ? 64 : 32; }
 long long th_bits_words(long long rows, int N) { return rows * ((N + 31) / 32); }
 
 // Every weight image of one update: forward images of pi (and oldpi) from W_l^T, dX images of pi from W_l
 // (img_* are arrays of L+1 device pointers; nullptr = skip).
 int th_pack_images(const NetShape& s, const float* params_pi, const float* head_pi, const float* params_old,
                    const float* head_old, float* const* img_fwd_pi, float* const* img_fwd_old, float* const* img_dx_pi,
-                   cudaStream_t st, int terms, int rows) {
+                   cudaStream_t st, int terms, int rows, int planes) {
     th::HImgPlan p; p.n = 0;
     long long units = 0;
-    auto add = [&](const float* src, float* dst, int N, int K, int ld, int transposed) {
+    auto add = [&](const float* src, float* dst, int N, int K, int ld, int transposed, int a_planes) {
         if (!src || !dst) return;
         th::HImgEntry& e = p.e[p.n];
         e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed;
-        e.bn = th_bn_for(N, K, rows); e.terms = terms == 1 ? 1 : 2;
-        units += (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
+        e.bn = th_bn_for(N, K, rows); e.terms = terms == 1 ? 1 : 2; e.kb = th_kb_for(e.terms, a_planes);
+        units += (long long)((N + e.bn - 1) / e.bn) * ((K + e.kb - 1) / e.kb) * e.bn * (e.kb / 8);
         p.unit_end[p.n++] = units;
     };
     for (int l = 0; l <= s.L; ++l) {
         const int in = s.in_dim(l), out = s.out_dim(l);
         const float* w_pi = (l == s.L) ? head_pi : params_pi + s.w_off[l];
         const float* w_old = (l == s.L) ? head_old : (params_old ? params_old + s.w_off[l] : nullptr);
-        add(w_pi, img_fwd_pi[l], out, in, out, 1);                 // forward: B[n=out][k=in] = W[k][n]
-        add(params_old ? w_old : nullptr, img_fwd_old[l], out, in, out, 1);
-        if (l > 0) add(w_pi, img_dx_pi[l], in, out, out, 0);      // dX:      B[n=in][k=out] = W[n][k]
+        // (a_planes: the activation operand of the product this image feeds is stored as planes -- forward of a layer above the
+        //  first, dX of a hidden layer's gradient; it decides the k-block length of the one-term mode, th_kb_for)
+        add(w_pi, img_fwd_pi[l], out, in, out, 1, planes && l > 0);                 // forward: B[n=out][k=in] = W[k][n]
+        add(params_old ? w_old : nullptr, img_fwd_old[l], out, in, out, 1, planes && l > 0);
+        if (l > 0) add(w_pi, img_dx_pi[l], in, out, out, 0, planes && l < s.L);     // dX:      B[n=in][k=out] = W[n][k]
     }
     if (p.n == 0) return 0;
     int grid = (int)((units + 255) / 256);
@@ -999,12 +1022,12 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
 }
 
 // one image from a [N,K] (transposed = 0) or [K,N] (transposed = 1) matrix with row stride ld
-int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms, int rows) {
+int th_pack_one(const float* src, float* dst, int N, int K, int ld, int transposed, cudaStream_t st, int terms, int rows, int a_planes) {
     th::HImgPlan p; p.n = 1;
     th::HImgEntry& e = p.e[0];
     e.src = src; e.dst = reinterpret_cast<uint8_t*>(dst); e.N = N; e.K = K; e.ld = ld; e.transposed = transposed; e.bn = th_bn_for(N, K, rows);
-    e.terms = terms == 1 ? 1 : 2;
-    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + th::kKB - 1) / th::kKB) * e.bn * 4;
+    e.terms = terms == 1 ? 1 : 2; e.kb = th_kb_for(e.terms, a_planes);
+    const long long units = (long long)((N + e.bn - 1) / e.bn) * ((K + e.kb - 1) / e.kb) * e.bn * (e.kb / 8);
     p.unit_end[0] = units;
     int grid = (int)((units + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
@@ -1033,7 +1056,7 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     if (planes) pl = *planes;
     g.bits_wpr = (N + 31) / 32;
     g.terms = pl.terms == 1 ? 1 : 2;
-    g.img_replica_bytes = th_image_replica_bytes(N, K, g.terms, M);
+    g.img_replica_bytes = th_image_replica_bytes(N, K, g.terms, M, th_kb_for(g.terms, pl.a_planes));
     g.timeline = timeline;
     g.fold = th::fold_enabled() ? 1 : 0;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
