@@ -37,13 +37,19 @@ struct DwArgs {
 // XP / GP: the X / G operand is stored as fp16 hi | lo planes (written by the forward / dX epilogues of tc_gemm_h.cu): TMA
 // boxes {64 fp16 features x 32 rows, SWIZZLE_128B} ARE the MN-major operand atoms, so that operand needs no raw slot and no
 // converter pass; the bias gradient (column sums of G) is then read back from the operand tiles by the otherwise idle warps.
+// rows per k-block: 32; the one-term mode on two plane operands takes 64 (its two MMAs per 32 rows left the per-k-block costs --
+// barrier round trip, commit, twelve TMA boxes -- in charge)
+template <bool XP, bool GP, int T> struct DwKb { static constexpr int kRows = (T == 1 && XP && GP) ? 64 : 32; };
+
 template <int BN, bool XP, bool GP, int T = 2>
 struct DwPlan {
+    static constexpr int kRows = DwKb<XP, GP, T>::kRows;
     static constexpr int kARaw = XP ? 0 : 32 * BM * 4;   // 4 boxes of {32 features x 32 rows} fp32
     static constexpr int kBRaw = GP ? 0 : 32 * BN * 4;
     static constexpr int kRawSlot = kARaw + kBRaw;
-    static constexpr int kAHalf = 32 * BM * 2;           // fp16 hi (or lo) operand tile: BM/64 atoms x 32 k-rows x 128 B
-    static constexpr int kBHalf = 32 * BN * 2;
+    static constexpr int kAHalf = kRows * BM * 2;        // fp16 hi (or lo) operand tile: BM/64 atoms x kRows k-rows x 128 B
+    static constexpr int kBHalf = kRows * BN * 2;
+    static constexpr int kAtom = kRows * 128;            // bytes of one 64-feature atom column (the MN stride of the UMMA descriptor)
     static constexpr int kOpSlot = T * (kAHalf + kBHalf);           // [X hi | X lo | G hi | G lo] (one-term mode: [X | G], bf16)
     static constexpr int kPlaneBytes = (XP ? T * kAHalf : 0) + (GP ? T * kBHalf : 0);   // what TMA writes into an operand slot
     static constexpr int kPC = BN < kDwPC ? BN : kDwPC;
@@ -102,6 +108,8 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
     using P = DwPlan<BN, XP, GP, T>;
     constexpr int kDwRaw = P::kDwRaw > 0 ? P::kDwRaw : 1, kDwOp = P::kDwOp;
     constexpr bool kConv = !(XP && GP);                  // some operand still arrives as fp32 and is converted here
+    constexpr int KR = P::kRows;                         // rows per k-block
+    constexpr uint32_t kAtom = (uint32_t)P::kAtom;
     extern __shared__ __align__(1024) uint8_t smem[];         // SWIZZLE_128B boxes and UMMA tiles need 1024-B alignment
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t raw_ring = smem_base, op_ring = smem_base + P::kOpOff, stg = smem_base + P::kStgOff;
@@ -131,7 +139,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
         mt = r / g.tiles_n; nt = r - mt * g.tiles_n;
         k0 = slice * g.k_per_slice;
         const int k1 = min(g.K, k0 + g.k_per_slice);
-        nkb = max(0, (k1 - k0 + kKB - 1) / kKB);
+        nkb = max(0, (k1 - k0 + KR - 1) / KR);
     };
 
     if (tid == 0) {
@@ -204,9 +212,12 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     mbar_wait(&op_full[os], (uint32_t)((it / kDwOp) & 1));
                     if (want_bias) {
 #pragma unroll
+                        for (int hr = 0; hr < KR / 32; ++hr)
+#pragma unroll
                         for (int u = 0; u < kBPairs; ++u) {
                             const int p = warp + u * kMoverWarps;          // columns [8p, 8p + 8): atom p / 8, chunk p % 8
-                            const uint32_t off = (uint32_t)(p >> 3) * 4096u + (uint32_t)k * 128u + (uint32_t)((((p & 7) ^ k) & 7) << 4);
+                            const int kr = k + hr * 32;                    // k-row of this lane in this half of the k-block
+                            const uint32_t off = (uint32_t)(p >> 3) * kAtom + (uint32_t)kr * 128u + (uint32_t)((((p & 7) ^ kr) & 7) << 4);
                             const uint4 h = lds128(b_hi + off);
                             const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
                             if (T == 1) {
@@ -283,7 +294,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     if (mbar_test(&raw_empty[rs], (uint32_t)(((cr.it / kDwRaw) & 1) ^ 1))) {
                         const uint32_t raw = raw_ring + rs * P::kRawSlot;
                         mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)P::kRawSlot);
-                        const int row = cr.k0 + cr.kb * kKB;
+                        const int row = cr.k0 + cr.kb * KR;
                         if (!XP) {
 #pragma unroll
                             for (int b = 0; b < BM / 32; ++b) tma_load_2d(raw + b * 4096, &maps.x, cr.mt * BM + b * 32, row, &raw_full[rs]);
@@ -302,19 +313,19 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                         const uint32_t op = op_ring + os * P::kOpSlot;
                         const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + T * P::kAHalf, b_lo = b_hi + P::kBHalf;
                         mbar_arrive_expect_tx(&op_full[os], (uint32_t)P::kPlaneBytes);
-                        const int row = cp.k0 + cp.kb * kKB;
+                        const int row = cp.k0 + cp.kb * KR;
                         if (XP) {
 #pragma unroll
                             for (int b = 0; b < BM / 64; ++b) {
-                                tma_load_2d(a_hi + b * 4096, &maps.x, cp.mt * BM + b * 64, row, &op_full[os]);
-                                if (T == 2) tma_load_2d(a_lo + b * 4096, &maps.xl, cp.mt * BM + b * 64, row, &op_full[os]);
+                                tma_load_2d(a_hi + b * kAtom, &maps.x, cp.mt * BM + b * 64, row, &op_full[os]);
+                                if (T == 2) tma_load_2d(a_lo + b * kAtom, &maps.xl, cp.mt * BM + b * 64, row, &op_full[os]);
                             }
                         }
                         if (GP) {
 #pragma unroll
                             for (int b = 0; b < BN / 64; ++b) {
-                                tma_load_2d(b_hi + b * 4096, &maps.g, cp.nt * BN + b * 64, row, &op_full[os]);
-                                if (T == 2) tma_load_2d(b_lo + b * 4096, &maps.gl, cp.nt * BN + b * 64, row, &op_full[os]);
+                                tma_load_2d(b_hi + b * kAtom, &maps.g, cp.nt * BN + b * 64, row, &op_full[os]);
+                                if (T == 2) tma_load_2d(b_lo + b * kAtom, &maps.gl, cp.nt * BN + b * 64, row, &op_full[os]);
                             }
                         }
                         advance(cp);
@@ -326,7 +337,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16_mn(BN, T == 1);
-            constexpr uint32_t kLbo = 4096u, kSbo = 1024u, kStep = 2048u;     // MN atoms / 8-row k groups / one UMMA_K = 16 rows
+            constexpr uint32_t kLbo = kAtom, kSbo = 1024u, kStep = 2048u;     // MN atoms / 8-row k groups / one UMMA_K = 16 rows
             long long it = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 int slice, mt, nt, nkb, k0;
@@ -340,7 +351,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     const uint32_t op = op_ring + os * P::kOpSlot;
                     const uint32_t a_hi = op, a_lo = op + P::kAHalf, b_hi = op + T * P::kAHalf, b_lo = b_hi + P::kBHalf;
 #pragma unroll
-                    for (int k = 0; k < kKB / 16; ++k) {
+                    for (int k = 0; k < KR / 16; ++k) {
                         const uint64_t da_hi = make_sdesc(a_hi + k * kStep, kLbo, kSbo, kLayoutSW128);
                         const uint64_t da_lo = make_sdesc(a_lo + k * kStep, kLbo, kSbo, kLayoutSW128);
                         const uint64_t db_hi = make_sdesc(b_hi + k * kStep, kLbo, kSbo, kLayoutSW128);
@@ -506,7 +517,7 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     if (xp) {
         const __half* hi = reinterpret_cast<const __half*>(X);
         DPPO_REQUIRE(ldx % 8 == 0 && th::aligned16(hi) && planes->a_lo_off % 8 == 0, "h_dw: fp16 planes need 16-byte aligned rows");
-        DPPO_REQUIRE(th::h_make_map16(&maps.x, hi, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+        DPPO_REQUIRE(th::h_make_map16(&maps.x, hi, K, M, ldx, 64, (terms == 1 && gp) ? 64 : 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
                      (terms == 1 || th::h_make_map16(&maps.xl, hi + planes->a_lo_off, K, M, ldx, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)),
                      "cuTensorMapEncodeTiled failed for the X planes [%d x %d] ld %d", K, M, ldx);
     } else {
@@ -515,7 +526,7 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     if (gp) {
         const __half* hi = reinterpret_cast<const __half*>(G);
         DPPO_REQUIRE(ldg % 8 == 0 && th::aligned16(hi) && planes->c_lo_off % 8 == 0, "h_dw: fp16 planes need 16-byte aligned rows");
-        DPPO_REQUIRE(th::h_make_map16(&maps.g, hi, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+        DPPO_REQUIRE(th::h_make_map16(&maps.g, hi, K, N, ldg, 64, (terms == 1 && xp) ? 64 : 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
                      (terms == 1 || th::h_make_map16(&maps.gl, hi + planes->c_lo_off, K, N, ldg, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)),
                      "cuTensorMapEncodeTiled failed for the G planes [%d x %d] ld %d", K, N, ldg);
     } else {
@@ -527,8 +538,9 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     g.fold = th::fold_enabled() ? 1 : 0;
     if (slices < 1) slices = 1;
     int kps = (K + slices - 1) / slices;
-    kps = ((kps + th::kKB - 1) / th::kKB) * th::kKB;
-    if (kps == 0) kps = th::kKB;
+    const int kr = (terms == 1 && xp && gp) ? 64 : 32;          // rows per k-block (th::DwKb)
+    kps = ((kps + kr - 1) / kr) * kr;
+    if (kps == 0) kps = kr;
     g.k_per_slice = kps; g.slices = slices;
     g.vecC = (ldc % 4 == 0) && th::aligned16(C) && (slice_stride % 4 == 0);
     // few rows (minibatches): latency-bound -- narrow tiles give more work items and the deepest rings
