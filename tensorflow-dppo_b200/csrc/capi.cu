@@ -108,13 +108,14 @@ int make_shape(const dppo_config* cfg, NetShape* s) {
             if (sl > kMaxSplitK) sl = kMaxSplitK;
             if (cfg->gemm_mode == DPPO_GEMM_BF16 && cfg->max_rows >= 65536) {
                 // the persistent dW kernel (one-term mode of tc_dw_h.cu) walks tiles x slices work items on 148 CTAs: pick the
-                // slice count (<= 40, >= 2048 rows each) that leaves the last wave fullest (config 4: 32 tiles x 37 slices = 8 waves)
+                // smallest slice count (<= 40, >= 2048 rows each) whose last wave is within 3 % of the fullest (config 4: 32 tiles x 9
+                // slices = 288 items = 1.95 waves)
                 const int t2 = ((in + 127) / 128) * ((out + 255) / 256);
                 int best = sl; double best_w = 1e30;
                 for (int c2 = 4; c2 <= 40 && (long long)c2 * 2048 <= cfg->max_rows; ++c2) {
                     const long long items = (long long)t2 * c2;
                     const double waste = (double)((items + kPlanSMs - 1) / kPlanSMs * kPlanSMs) / (double)items;
-                    if (waste < best_w - 0.01) { best_w = waste; best = c2; }
+                    if (waste < best_w - 0.03) { best_w = waste; best = c2; }      // (fewer slices unless > 3 % fuller: finalize streams them all)
                 }
                 sl = best;
             }
@@ -179,6 +180,10 @@ static size_t carve(const dppo_config* cfg, const NetShape& s, char* base, Works
     w.loss_part = (double*)take(tiles * kLossSlots * sizeof(double));
     w.gae_adv = (float*)take(R * sizeof(float));
     w.gae_ret = (float*)take(R * sizeof(float));
+    if (cfg->gemm_mode == DPPO_GEMM_BF16 && s.obs % 8 == 0)
+        // one-term mode: the observations are rounded to bf16 ONCE per row block (they feed pi's and oldpi's first layer and
+        // layer 1's dW) -- as a plane they take the TMA-fed, pair, 64-element k-block path like every hidden activation
+        w.obs_pl = (float*)take(R * (size_t)s.obs * 2);
     if (cfg->gemm_mode == DPPO_GEMM_FP16X2 && s.obs % 4 != 0) {
         // observation rows whose pitch TMA cannot address (obs_dim 3, 17, ...): the dense layers read a re-pitched copy
         w.obs_ld = (s.obs + 3) & ~3;
@@ -249,11 +254,16 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
         // current parameters
         const int terms = th_terms(c);
         if (int r = th_pack_images(s, params_pi, w.head_pi, params_old, w.head_old, w.img_fwd_pi, w.img_fwd_old,
-                                   w.img_dx_pi, st, terms, rows, h_planes(c) ? 1 : 0)) return r;
+                                   w.img_dx_pi, st, terms, rows, h_planes(c) ? (terms == 1 && w.obs_pl ? 2 : 1) : 0)) return r;
         // hidden activations live as fp16 hi | lo planes (h_planes): the epilogue that produces them applies the split the
         // consumer's converter warps would apply, so every later product reads its operand tiles straight from TMA
         const bool planes = h_planes(c);
         const long long R = c->cfg.max_rows;
+        const bool obs_plane = planes && terms == 1 && w.obs_pl != nullptr;
+        if (obs_plane) {
+            if (int r = th_split_planes(obs, (long long)rows * s.obs, w.obs_pl, nullptr, st, 1)) return r;
+            in0 = in1 = w.obs_pl;
+        }
         for (int l = 0; l <= s.L; ++l) {
             const bool head = (l == s.L);
             float* o0 = head ? w.out_pi : w.act_pi[l];
@@ -263,7 +273,7 @@ static int forward_nets(dppo_ctx* c, const float* params_pi, const float* params
             const float* b1 = head ? w.head_old + (size_t)in * out : (params_old ? params_old + s.b_off[l] : nullptr);
             ThPlanes pl{};
             pl.terms = terms;
-            pl.a_planes = planes && l > 0; pl.a_lo_off = R * in;
+            pl.a_planes = planes && (l > 0 || obs_plane); pl.a_lo_off = R * in;
             pl.c_planes = planes && !head; pl.c_lo_off = R * out;
             if (int r = th_gemm(0, rows, out, in, in0, in1, l == 0 ? ld0 : in, w.img_fwd_pi[l], w.img_fwd_old[l], o0, o1,
                                 head ? s.Pld : out, b0, b1, head ? 0 : 1, nullptr, nets, st,
@@ -404,7 +414,8 @@ static int loss_grad_rows(dppo_ctx* c, const float* params_pi, const float* para
         if (planes) {                                       // X = a hidden activation, G = a hidden gradient: fp16 planes
             ThPlanes pl{};
             pl.terms = terms;
-            pl.a_planes = l > 0; pl.a_lo_off = (long long)c->cfg.max_rows * in;
+            pl.a_planes = l > 0 || (terms == 1 && w.obs_pl != nullptr); pl.a_lo_off = (long long)c->cfg.max_rows * in;
+            if (l == 0 && pl.a_planes) x_in = w.obs_pl;       // the bf16 plane forward_nets made of this row block
             pl.c_planes = l < s.L; pl.c_lo_off = (long long)c->cfg.max_rows * out;
             if ((pl.a_planes || th_dw_supported(x_in, ldx, x_in, ldx)) && (pl.c_planes || th_dw_supported(dY, ldy, dY, ldy)))
                 return th_gemm_dw(in, out, rows, x_in, ldx, dY, ldy, p, out, p + (size_t)in * out, active[l], s.region[l], accumulate,

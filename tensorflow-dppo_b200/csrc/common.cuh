@@ -99,6 +99,7 @@ struct Workspace {
     double* loss_part;   // [loss_tiles_max, kLossSlots]
     float* gae_adv;      // [max_rows] used by dppo_update_host
     float* gae_ret;      // [max_rows]
+    float* obs_pl;       // bf16 mode (one-term kernels): the observations of the current row block as ONE bf16 plane [rows, obs]
     float* obs_pad;      // fp16x2 mode, obs_dim % 4 != 0: the rows of the current block re-pitched to a multiple of 4 floats (TMA)
     int obs_ld;          // its pitch in floats (0: not used)
     float* stage;        // device staging for dppo_update_host: obs|act|rew|predv|done

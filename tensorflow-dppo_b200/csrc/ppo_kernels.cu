@@ -395,6 +395,7 @@ struct FinalizePlan {
     long long region[kMaxLayers + 1];     // slice stride of region l
     long long part_off[kMaxLayers + 1];   // where region l's slices start in the partial buffer
     int slices[kMaxLayers + 1];
+    int few;                      // every region has <= 20 slices: thread-per-parameter summation (finalize_kernel)
 };
 
 // one TF-1.x Adam step of one parameter (PPO.py:20,53), shared by adam_kernel and the fused finalize + Adam tail
@@ -420,6 +421,44 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     // warps' sums are then combined in a fixed order through shared memory -> deterministic and DRAM-friendly.
     __shared__ float red[8][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // publish parameter i (head rows are stored transposed in the partials: see pack_heads_kernel) + the optional Adam step
+    auto publish = [&](long long i, float t) {
+        long long pub = i;
+        if (i >= head_off) {
+            const long long r = i - head_off;
+            if (r < (long long)H * P) {
+                const int kk = (int)(r / P), c = (int)(r % P);
+                pub = head_off + (c == 0 ? kk : (long long)H + 1 + (long long)kk * W + (c - 1));
+            } else {
+                const int c = (int)(r - (long long)H * P);
+                pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + (long long)W * H + (c - 1));
+            }
+        }
+        const float gi = t * grad_scale;     // 1 / the power of two the loss kernel put on d_out (fp16-split mode), else 1
+        grad_out[pub] = gi;
+        // single-rank updates: the optimiser step of this parameter right here (no second pass over the gradient)
+        if (adam.p) adam_update(adam.p, adam.m, adam.v, pub, gi, adam.lr_t, adam.b1, adam.b2, adam.eps);
+    };
+    if (plan.few) {
+        // few slices (config 4: 9 - 18 of a 3.6 M-parameter net): thread = parameter, the slices summed in order -- every load
+        // instruction of a warp is one 128-byte line and 256 of them are in flight per block (the layout below would leave
+        // seven of its eight warps with a single line each)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += (long long)gridDim.x * blockDim.x) {
+            int l = 0;
+            while (l + 1 < plan.n_regions && i >= plan.w_off[l + 1]) ++l;
+            const float* src = partial + plan.part_off[l] + (i - plan.w_off[l]);
+            const long long rg = plan.region[l];
+            const int ns = plan.slices[l];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int k = 0;
+            for (; k + 3 < ns; k += 4) {
+                a0 += __ldg(src + (size_t)(k + 0) * rg); a1 += __ldg(src + (size_t)(k + 1) * rg);
+                a2 += __ldg(src + (size_t)(k + 2) * rg); a3 += __ldg(src + (size_t)(k + 3) * rg);
+            }
+            for (; k < ns; ++k) a0 += __ldg(src + (size_t)k * rg);
+            publish(i, (a0 + a1) + (a2 + a3));
+        }
+    } else
     for (long long i0 = (long long)blockIdx.x * 32; i0 < n_params; i0 += (long long)gridDim.x * 32) {
         const long long i = i0 + lane;
         float s = 0.f;
@@ -449,21 +488,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
         if (warp == 0 && i < n_params) {
             const float t = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
                             ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
-            long long pub = i;
-            if (i >= head_off) {
-                const long long r = i - head_off;
-                if (r < (long long)H * P) {
-                    const int kk = (int)(r / P), c = (int)(r % P);
-                    pub = head_off + (c == 0 ? kk : (long long)H + 1 + (long long)kk * W + (c - 1));
-                } else {
-                    const int c = (int)(r - (long long)H * P);
-                    pub = head_off + (c == 0 ? (long long)H : (long long)H + 1 + (long long)W * H + (c - 1));
-                }
-            }
-            const float gi = t * grad_scale;     // 1 / the power of two the loss kernel put on d_out (fp16-split mode), else 1
-            grad_out[pub] = gi;
-            // single-rank updates: the optimiser step of this parameter right here (no second pass over the gradient)
-            if (adam.p) adam_update(adam.p, adam.m, adam.v, pub, gi, adam.lr_t, adam.b1, adam.b2, adam.eps);
+            publish(i, t);
         }
         __syncthreads();
     }
@@ -507,6 +532,10 @@ int launch_finalize(const NetShape& s, const int* active, const float* partial, 
         plan.w_off[l] = s.w_off[l]; plan.region[l] = s.region[l];
         plan.part_off[l] = s.part_off[l]; plan.slices[l] = active ? active[l] : s.slices[l];
     }
+    plan.few = 1;
+    for (int l = 0; l <= s.L; ++l)
+        if (plan.slices[l] > 20) plan.few = 0;
+    if (s.n_params < (1 << 18)) plan.few = 0;            // (small nets: either way is a few microseconds)
     const int H = s.in_dim(s.L);
     int grid = (int)((s.n_params + 31) / 32);
     if (grid > 148 * 16) grid = 148 * 16;

@@ -1008,8 +1008,9 @@ int th_pack_images(const NetShape& s, const float* params_pi, const float* head_
         const float* w_old = (l == s.L) ? head_old : (params_old ? params_old + s.w_off[l] : nullptr);
         // (a_planes: the activation operand of the product this image feeds is stored as planes -- forward of a layer above the
         //  first, dX of a hidden layer's gradient; it decides the k-block length of the one-term mode, th_kb_for)
-        add(w_pi, img_fwd_pi[l], out, in, out, 1, planes && l > 0);                 // forward: B[n=out][k=in] = W[k][n]
-        add(params_old ? w_old : nullptr, img_fwd_old[l], out, in, out, 1, planes && l > 0);
+        // (planes == 2: the observations are a plane too -- one-term mode, capi.cu: obs_pl)
+        add(w_pi, img_fwd_pi[l], out, in, out, 1, planes && (l > 0 || planes == 2));                 // forward: B[n=out][k=in] = W[k][n]
+        add(params_old ? w_old : nullptr, img_fwd_old[l], out, in, out, 1, planes && (l > 0 || planes == 2));
         if (l > 0) add(w_pi, img_dx_pi[l], in, out, out, 0, planes && l < s.L);     // dX:      B[n=in][k=out] = W[n][k]
     }
     if (p.n == 0) return 0;
