@@ -31,7 +31,6 @@ struct DwArgs {
     int ldc, k_per_slice, slices, accumulate, vecC;
     int tiles_m, tiles_n;
     long long slice_stride;
-    int fold;                     // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
 };
 
 // XP / GP: the X / G operand is stored as fp16 hi | lo planes (written by the forward / dX epilogues of tc_gemm_h.cu): TMA
@@ -56,7 +55,7 @@ struct DwPlan {
     static constexpr int kPhases = BN / kPC;
     static constexpr int kStaging = BM * kPC * 4;
     // ring depth (raw and operand rings alike): what shared memory allows, at most 4
-    static constexpr int kRoom = 232448 - 256 - kFoldBytes - kStaging;
+    static constexpr int kRoom = 232448 - 256 - kStaging;
     static constexpr int kFit = kRoom / (kOpSlot + kRawSlot);
     static constexpr int kDepth = kFit > 4 ? 4 : kFit;
     static_assert(kDepth >= 2, "two slots per ring at least");
@@ -65,8 +64,7 @@ struct DwPlan {
     static constexpr int kOpOff = kDepth * kRawSlot;
     static constexpr int kStgOff = kOpOff + kDwOp * kOpSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
-    static constexpr int kFoldOff = kBarOff + 256;
-    static constexpr int kBytes = kBarOff + 256 + kFoldBytes;
+    static constexpr int kBytes = kBarOff + 256;
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
@@ -154,7 +152,6 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
         mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
         fence_barrier_init();
     }
-    if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
     constexpr uint32_t kTmemCols = (T * BN) < 32 ? 32 : T * BN;
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
@@ -364,7 +361,6 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     }
                     umma_commit(&op_empty[os]);
                 }
-                if (T == 2 && g.fold && nkb > 0) fold_issue<BN>(tmem_base, smem_base + P::kFoldOff);
                 umma_commit(acc_full);                 // fires at once when the slice holds no rows (nkb == 0)
             }
             tc_fence_before();
@@ -398,7 +394,7 @@ h_dw_kernel(const __grid_constant__ DwMaps maps, const DwArgs g, int total_tiles
                     uint32_t v[32];
                     if (nkb > 0) {
                         tmem_ld32(acc + (uint32_t)col, v);
-                        if (T == 2 && !g.fold) {
+                        if (T == 2) {
                             uint32_t w2[32];
                             tmem_ld32(acc + (uint32_t)(BN + col), w2);
 #pragma unroll
@@ -535,7 +531,6 @@ int th_gemm_dw(int M, int N, int K, const float* X, int ldx, const float* G, int
     th::DwArgs g{};
     g.C = C; g.bias_out = bias_out; g.M = M; g.N = N; g.K = K; g.ldc = ldc; g.accumulate = accumulate;
     g.slice_stride = slice_stride;
-    g.fold = th::fold_enabled() ? 1 : 0;
     if (slices < 1) slices = 1;
     int kps = (K + slices - 1) / slices;
     const int kr = (terms == 1 && xp && gp) ? 64 : 32;          // rows per k-block (th::DwKb)

@@ -55,7 +55,6 @@ struct HArgs {
     long long img_replica_bytes;
     long long* timeline;               // optional: clock64 stamps of CTA 0 (tools/h_microbench.py)
     int terms;                         // 2 = fp16 hi + lo operands (three MMAs per product), 1 = bf16 operands (one MMA)
-    int fold;                          // fold the correction accumulator into the main one with tensor-core MMAs (tc_h.cuh)
     int dbg;                           // DPPO_H_DBG: timing-only ablations (WRONG results), tools/h_ablate.py
 };
 enum { DBG_NO_A = 1, DBG_NO_SPLIT = 2, DBG_ONE_MMA = 4, DBG_NO_W = 8, DBG_NO_STORE = 16, DBG_NO_FENCE = 32,
@@ -108,9 +107,8 @@ struct HPlan {
     static constexpr int kBOff = kRawOff + kRSlots * kRawSlot;
     static constexpr int kStgOff = kBOff + kBSlots * kBSlot;
     static constexpr int kBarOff = kStgOff + kStaging;
-    static constexpr int kFoldOff = kBarOff + 512;            // the two fold patterns (tc_h.cuh)
     static_assert((2 * kASlots + 2 * kBSlots + 2 * kRSlots + 4 + kPeerSlots) * 8 + 4 <= 512, "barrier block");
-    static constexpr int kBiasOff = kFoldOff + kFoldBytes;    // the tile's bias vector (TMA write-out epilogue)
+    static constexpr int kBiasOff = kBarOff + 512;            // the tile's bias vector (TMA write-out epilogue)
     static constexpr int kBytes = kBiasOff + BN * 4;
     static_assert(kStgOff % 1024 == 0, "staging boxes are SWIZZLE_128B");
     static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
@@ -258,7 +256,6 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
         fence_barrier_init();
     }
     if (PAIR) cluster_sync_all();                   // both CTAs' barriers exist before anything arrives on them remotely
-    if (g.fold) { fold_init(smem + P::kFoldOff, tid); fence_proxy_async(); }
     constexpr uint32_t kStageCols = T * BN;         // [0,BN) main, [BN,2BN) correction (two-term mode)
     constexpr uint32_t kTmemCols = kAcc * kStageCols;
     if (warp == kMmaWarp) { if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols); }
@@ -468,7 +465,6 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     if (++sa == kASlots) { sa = 0; pha ^= 1u; }
                     if (++sb == kBSlots) { sb = 0; phb ^= 1u; }
                 }
-                if (T == 2 && g.fold) fold_issue<BN>(acc, smem_base + P::kFoldOff);
                 if (PAIR) umma_commit_pair(&acc_full[as]); else umma_commit(&acc_full[as]);     // accumulators of tile i complete
                 if (tl) { g.timeline[i * 8 + 1] = clock64(); g.timeline[i * 8 + 5] = w_a; g.timeline[i * 8 + 6] = w_b; g.timeline[i * 8 + 7] = w_p; }
             }
@@ -526,7 +522,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     epi_bar();
                 }
                 uint32_t v[32];
-                if (T == 2 && !g.fold) {
+                if (T == 2) {
                     uint32_t w2[32];
                     tmem_ld32x2(acc + (uint32_t)col, v, acc + (uint32_t)(BN + col), w2);
 #pragma unroll
@@ -655,7 +651,7 @@ h_gemm_kernel(const __grid_constant__ HMaps maps, const HArgs g, int total_tiles
                     const int col = p * PC + ch * kDrainCols + cb;
                     uint32_t v[32];
                     tmem_ld32(acc + (uint32_t)col, v);
-                    if (T == 2 && !g.fold) {                        // warp-uniform: main + correction / 2^11 here, not on the tensor core
+                    if (T == 2) {                        // main + correction / 2^11
                         uint32_t w2[32];
                         tmem_ld32(acc + (uint32_t)(BN + col), w2);
 #pragma unroll
@@ -1059,7 +1055,6 @@ int th_gemm(int epi_nt, int M, int N, int K, const float* A0, const float* A1, i
     g.terms = pl.terms == 1 ? 1 : 2;
     g.img_replica_bytes = th_image_replica_bytes(N, K, g.terms, M, th_kb_for(g.terms, pl.a_planes));
     g.timeline = timeline;
-    g.fold = th::fold_enabled() ? 1 : 0;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPPO_H_DBG"); dbg = e ? atoi(e) : 0; } g.dbg = dbg; }
     g.vecA = !pl.a_planes && (lda % 4 == 0) && th::aligned16(A0) && (nets < 2 || th::aligned16(A1));
     g.vecC = !pl.c_planes && (ldc % 4 == 0) && th::aligned16(C0) && (nets < 2 || th::aligned16(C1));

@@ -139,44 +139,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// ---- folding the correction accumulator into the main one ON THE TENSOR CORE ---------------------------------------
-// Draining TMEM costs ~64 B/clk per SM; a 128 x 256 tile's two fp32 accumulators are 256 KB = 4 k cycles during which no MMA
-// can run.  The correction accumulator only contributes corr * 2^-11, for which 10 mantissa bits are plenty, so the MMA thread
-// finishes every tile with   main[:, c:c+16) += tf32(corr[:, c:c+8)) . P0 + tf32(corr[:, c+8:c+16)) . P1
-// (A operand read straight from TMEM, P0 = 2^-11 [I8 | 0], P1 = 2^-11 [0 | I8] as 16 x 8 K-major no-swizzle tiles) and the
-// epilogue reads the main accumulator only.
-constexpr int kFoldBytes = 1024;                   // P0 | P1, 512 B each
-__device__ __forceinline__ void fold_init(uint8_t* p, int tid) {
-    // element (n, k) of a pattern at  (n / 8) * 256 + (k / 4) * 128 + (n % 8) * 16 + (k % 4) * 4   (SBO 256, LBO 128)
-    if (tid < 256) {
-        const int pat = tid >> 7, e = tid & 127, n = e >> 3, k = e & 7;
-        const float v = (n == k + 8 * pat) ? (1.0f / 2048.0f) : 0.0f;
-        *reinterpret_cast<float*>(p + pat * 512 + (n >> 3) * 256 + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4) = v;
-    }
-}
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc) : "memory");
-}
-// issue the fold of a BN-wide tile (one thread, after the tile's last product MMA)
-template <int BN>
-__device__ __forceinline__ void fold_issue(uint32_t tmem_base, uint32_t pat_smem) {
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // tf32, N = 16
-    const uint64_t d0 = make_sdesc(pat_smem, 128, 256, 0), d1 = make_sdesc(pat_smem + 512, 128, 256, 0);
-#pragma unroll
-    for (int c = 0; c < BN; c += 16) {
-        umma_tf32_ts(tmem_base + c, tmem_base + BN + c, d0, idesc);
-        umma_tf32_ts(tmem_base + c, tmem_base + BN + c + 8, d1, idesc);
-    }
-}
-inline bool fold_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DPPO_H_FOLD"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
 // ---- TMA stores (shared -> global, bulk async-group completion) and split TMEM loads ----
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
